@@ -1,0 +1,115 @@
+// Shared helpers for the sm_100a kernels of libr2n2_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/r2n2_b200.h"
+
+namespace r2n2 {
+
+void set_error(const char* fmt, ...);
+
+#define R2N2_CHECK_ARG(cond, code, ...)      \
+  do {                                       \
+    if (!(cond)) {                           \
+      r2n2::set_error(__VA_ARGS__);          \
+      return (code);                         \
+    }                                        \
+  } while (0)
+
+#define R2N2_CHECK_LAUNCH(name)                                                  \
+  do {                                                                           \
+    cudaError_t e__ = cudaPeekAtLastError();                                     \
+    if (e__ != cudaSuccess) {                                                    \
+      r2n2::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+      return R2N2_ERR_CUDA;                                                      \
+    }                                                                            \
+  } while (0)
+
+constexpr float kLeak = 0.01f;  // LeakyReLU leakiness, lib/layers.py:630
+
+// ---- 4-element vector load/store with conversion to/from float -------------------------
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  static __device__ __forceinline__ void store(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    uint2 raw = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : kLeak * v; }
+__device__ __forceinline__ float lrelu_slope(float a) { return a > 0.f ? 1.f : kLeak; }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// dispatch on dtype code
+#define R2N2_DISPATCH_DTYPE(dtype, T, ...)                 \
+  if ((dtype) == R2N2_F32) {                               \
+    using T = float;                                       \
+    __VA_ARGS__                                            \
+  } else if ((dtype) == R2N2_BF16) {                       \
+    using T = __nv_bfloat16;                               \
+    __VA_ARGS__                                            \
+  } else {                                                 \
+    r2n2::set_error("bad dtype code %d", (int)(dtype));    \
+    return R2N2_ERR_BAD_DTYPE;                             \
+  }
+
+}  // namespace r2n2

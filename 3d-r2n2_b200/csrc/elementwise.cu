@@ -1,0 +1,918 @@
+// Bandwidth-bound kernels of the 3D-R2N2 hot path (sm_100a): layout transforms, 2x2 max-pool,
+// Unpool3D, LeakyReLU/residual helpers, conv-GRU / conv-LSTM gate math, fused voxel
+// softmax-cross-entropy (fwd+bwd), bias gradients, Adam/SGD, voxel IoU counts.
+// All kernels: channels-last tensors, 128-bit (fp32) / 64-bit (bf16) vector accesses along the
+// channel axis, grid-stride loops sized in multiples of the SM count, fp32 math.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace r2n2 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int grid_for(long long work_items, int block) {
+  long long b = (work_items + block - 1) / block;
+  long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ layout: NCHW -> NHWC(pad)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C,
+                                    int H, int W, int Cpad, int Wpad, int xoff) {
+  long long total = (long long)N * H * Wpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int wp = (int)(i % Wpad);
+    long long t = i / Wpad;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    int w = wp - xoff;
+    T* out = y + i * Cpad;
+    bool in = (w >= 0 && w < W);
+    for (int c = 0; c < Cpad; ++c) {
+      float v = 0.f;
+      if (in && c < C) v = x[(((long long)n * C + c) * H + h) * W + w];
+      out[c] = from_float<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ max pool 2x2/2 pad 1
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                   T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+  int C4 = C >> 2;
+  long long total = (long long)N * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    long long t = i / C4;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      int h = 2 * ho - 1 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        int w = 2 * wo - 1 + dx;
+        if (w < 0 || w >= W) continue;
+        long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
+        float4 v = Vec4<T>::load(a + off);
+        if (b) {
+          float4 u = Vec4<T>::load(b + off);
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    Vec4<T>::store(y + i * 4, m);
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                   const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
+                                   int W, int C, int Ho, int Wo, int lrelu_mask) {
+  int C4 = C >> 2;
+  long long total = (long long)N * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    long long t = i / C4;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float4 s[4], av[4];
+    bool valid[4];
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
+      valid[k] = (h >= 0 && h < H && w >= 0 && w < W);
+      if (!valid[k]) continue;
+      long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
+      float4 v = Vec4<T>::load(a + off);
+      av[k] = v;
+      if (b) {
+        float4 u = Vec4<T>::load(b + off);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;  // same fp32 sums the forward compared
+      }
+      s[k] = v;
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    float4 g = Vec4<T>::load(dy + i * 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
+      long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
+      float4 o;
+      o.x = (s[k].x == m.x) ? g.x : 0.f;
+      o.y = (s[k].y == m.y) ? g.y : 0.f;
+      o.z = (s[k].z == m.z) ? g.z : 0.f;
+      o.w = (s[k].w == m.w) ? g.w : 0.f;
+      if (lrelu_mask) {
+        o.x *= lrelu_slope(av[k].x); o.y *= lrelu_slope(av[k].y);
+        o.z *= lrelu_slope(av[k].z); o.w *= lrelu_slope(av[k].w);
+      }
+      Vec4<T>::store(dx + off, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Unpool3D (zero stuffing x2)
+template <typename T>
+__global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                  T* __restrict__ y, int B, int D, int H, int W, int C) {
+  int C4 = C >> 2;
+  int D2 = 2 * D, H2 = 2 * H, W2 = 2 * W;
+  long long total = (long long)B * D2 * H2 * W2 * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    long long t = i / C4;
+    int x = (int)(t % W2); t /= W2;
+    int yy = (int)(t % H2); t /= H2;
+    int z = (int)(t % D2);
+    int n = (int)(t / D2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (((x | yy | z) & 1) == 0) {
+      long long off = ((((long long)n * D + (z >> 1)) * H + (yy >> 1)) * W + (x >> 1)) * C + c4 * 4;
+      v = Vec4<T>::load(a + off);
+      if (b) {
+        float4 u = Vec4<T>::load(b + off);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+    }
+    Vec4<T>::store(y + i * 4, v);
+  }
+}
+
+template <typename T>
+__global__ void unpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int D,
+                                  int H, int W, int C) {
+  int C4 = C >> 2;
+  long long total = (long long)B * D * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4);
+    long long t = i / C4;
+    int x = (int)(t % W); t /= W;
+    int yy = (int)(t % H); t /= H;
+    int z = (int)(t % D);
+    int n = (int)(t / D);
+    long long off =
+        ((((long long)n * 2 * D + 2 * z) * 2 * H + 2 * yy) * 2 * W + 2 * x) * C + c4 * 4;
+    Vec4<T>::store(dx + i * 4, Vec4<T>::load(dy + off));
+  }
+}
+
+// ------------------------------------------------------------------ pointwise helpers
+template <typename T>
+__global__ void add_kernel(const T* a, const T* b, T* y,
+                           long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 u = Vec4<T>::load(a + i * 4), v = Vec4<T>::load(b + i * 4);
+    Vec4<T>::store(y + i * 4, make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w));
+  }
+}
+
+template <typename T>
+__global__ void lrelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = Vec4<T>::load(x + i * 4);
+    Vec4<T>::store(y + i * 4, make_float4(lrelu(v.x), lrelu(v.y), lrelu(v.z), lrelu(v.w)));
+  }
+}
+
+template <typename T>
+__global__ void lrelu_bwd_kernel(const T* a, const T* dy,
+                                 const T* addend, T* dx, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 av = Vec4<T>::load(a + i * 4), g = Vec4<T>::load(dy + i * 4);
+    float4 o = make_float4(g.x * lrelu_slope(av.x), g.y * lrelu_slope(av.y),
+                           g.z * lrelu_slope(av.z), g.w * lrelu_slope(av.w));
+    if (addend) {
+      float4 e = Vec4<T>::load(addend + i * 4);
+      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+    }
+    Vec4<T>::store(dx + i * 4, o);
+  }
+}
+
+// SigmoidLayer / TanhLayer / ComplementLayer / EltwiseMultiplyLayer (lib/layers.py:217-225,649-676)
+template <typename T>
+__global__ void eltwise_kernel(int op, const T* __restrict__ a, const T* __restrict__ b,
+                               T* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = Vec4<T>::load(a + i * 4);
+    float4 o;
+    if (op == R2N2_ELT_SIGMOID) {
+      o = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+    } else if (op == R2N2_ELT_TANH) {
+      o = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    } else if (op == R2N2_ELT_COMPLEMENT) {
+      o = make_float4(1.f - v.x, 1.f - v.y, 1.f - v.z, 1.f - v.w);
+    } else {
+      float4 u = Vec4<T>::load(b + i * 4);
+      o = make_float4(v.x * u.x, v.y * u.y, v.z * u.z, v.w * u.w);
+    }
+    Vec4<T>::store(y + i * 4, o);
+  }
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, long long n) {
+  long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    Vec4<T>::store(d + i * 4, *reinterpret_cast<const float4*>(s + i * 4));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long long j = (n4 << 2) + threadIdx.x;
+    d[j] = from_float<T>(s[j]);
+  }
+}
+
+// ------------------------------------------------------------------ conv-GRU gate math
+// hidden grid rows: pr = b*64 + pos ; 128 channels -> 32 float4 groups per row
+template <typename T>
+__global__ void gru_ur_fwd_kernel(const T* __restrict__ conv_ur, const T* __restrict__ xp_ur,
+                                  const float* __restrict__ bias, const T* __restrict__ h,
+                                  T* __restrict__ u, T* __restrict__ r, T* __restrict__ rh,
+                                  long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pr = i >> 5;
+    int c = (int)(i & 31) * 4;
+    float4 au = Vec4<T>::load(xp_ur + pr * 256 + c);
+    float4 ar = Vec4<T>::load(xp_ur + pr * 256 + 128 + c);
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (conv_ur) {
+      float4 cu = Vec4<T>::load(conv_ur + pr * 256 + c);
+      float4 cr = Vec4<T>::load(conv_ur + pr * 256 + 128 + c);
+      au.x += cu.x; au.y += cu.y; au.z += cu.z; au.w += cu.w;
+      ar.x += cr.x; ar.y += cr.y; ar.z += cr.z; ar.w += cr.w;
+      hv = Vec4<T>::load(h + pr * 128 + c);
+    }
+    float4 bu = *reinterpret_cast<const float4*>(bias + c);
+    float4 br = *reinterpret_cast<const float4*>(bias + 128 + c);
+    float4 uo = make_float4(sigmoidf_(au.x + bu.x), sigmoidf_(au.y + bu.y),
+                            sigmoidf_(au.z + bu.z), sigmoidf_(au.w + bu.w));
+    float4 ro = make_float4(sigmoidf_(ar.x + br.x), sigmoidf_(ar.y + br.y),
+                            sigmoidf_(ar.z + br.z), sigmoidf_(ar.w + br.w));
+    Vec4<T>::store(u + pr * 128 + c, uo);
+    Vec4<T>::store(r + pr * 128 + c, ro);
+    Vec4<T>::store(rh + pr * 128 + c,
+                   make_float4(ro.x * hv.x, ro.y * hv.y, ro.z * hv.z, ro.w * hv.w));
+  }
+}
+
+template <typename T>
+__global__ void gru_out_fwd_kernel(const T* __restrict__ conv_c, const T* __restrict__ xp_c,
+                                   const float* __restrict__ bias, const T* __restrict__ u,
+                                   const T* __restrict__ h, T* __restrict__ cc,
+                                   T* __restrict__ hn, long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long off = i * 4;
+    int c = (int)(i & 31) * 4;
+    float4 a = Vec4<T>::load(xp_c + off);
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (conv_c) {
+      float4 cv = Vec4<T>::load(conv_c + off);
+      a.x += cv.x; a.y += cv.y; a.z += cv.z; a.w += cv.w;
+      hv = Vec4<T>::load(h + off);
+    }
+    float4 bv = *reinterpret_cast<const float4*>(bias + c);
+    float4 uv = Vec4<T>::load(u + off);
+    float4 cv = make_float4(tanhf(a.x + bv.x), tanhf(a.y + bv.y), tanhf(a.z + bv.z),
+                            tanhf(a.w + bv.w));
+    Vec4<T>::store(cc + off, cv);
+    Vec4<T>::store(hn + off, make_float4(uv.x * hv.x + (1.f - uv.x) * cv.x,
+                                         uv.y * hv.y + (1.f - uv.y) * cv.y,
+                                         uv.z * hv.z + (1.f - uv.z) * cv.z,
+                                         uv.w * hv.w + (1.f - uv.w) * cv.w));
+  }
+}
+
+template <typename T>
+__global__ void gru_out_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u,
+                                   const T* __restrict__ cc, const T* __restrict__ h,
+                                   T* __restrict__ da_ur, T* __restrict__ da_c,
+                                   T* __restrict__ dh_prev, long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pr = i >> 5;
+    int c = (int)(i & 31) * 4;
+    long long off = i * 4;
+    float4 g = Vec4<T>::load(dh + off), uv = Vec4<T>::load(u + off), cv = Vec4<T>::load(cc + off);
+    float4 hv = h ? Vec4<T>::load(h + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dac, dau, dhp;
+#define R2N2_GRU_BWD(e)                                   \
+  dac.e = g.e * (1.f - uv.e) * (1.f - cv.e * cv.e);       \
+  dau.e = g.e * (hv.e - cv.e) * uv.e * (1.f - uv.e);      \
+  dhp.e = g.e * uv.e;
+    R2N2_GRU_BWD(x) R2N2_GRU_BWD(y) R2N2_GRU_BWD(z) R2N2_GRU_BWD(w)
+#undef R2N2_GRU_BWD
+    Vec4<T>::store(da_c + off, dac);
+    Vec4<T>::store(da_ur + pr * 256 + c, dau);
+    Vec4<T>::store(dh_prev + off, dhp);
+  }
+}
+
+template <typename T>
+__global__ void gru_r_bwd_kernel(const T* __restrict__ d_rh, const T* __restrict__ h,
+                                 const T* __restrict__ r, T* __restrict__ da_ur,
+                                 T* __restrict__ dh_prev, long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pr = i >> 5;
+    int c = (int)(i & 31) * 4;
+    long long off = i * 4;
+    float4 g = Vec4<T>::load(d_rh + off), hv = Vec4<T>::load(h + off), rv = Vec4<T>::load(r + off);
+    float4 dp = Vec4<T>::load(dh_prev + off);
+    float4 dar = make_float4(g.x * hv.x * rv.x * (1.f - rv.x), g.y * hv.y * rv.y * (1.f - rv.y),
+                             g.z * hv.z * rv.z * (1.f - rv.z), g.w * hv.w * rv.w * (1.f - rv.w));
+    dp.x += g.x * rv.x; dp.y += g.y * rv.y; dp.z += g.z * rv.z; dp.w += g.w * rv.w;
+    Vec4<T>::store(da_ur + pr * 256 + 128 + c, dar);
+    Vec4<T>::store(dh_prev + off, dp);
+  }
+}
+
+// ------------------------------------------------------------------ conv-LSTM gate math
+template <typename T>
+__global__ void lstm_fwd_kernel(const T* __restrict__ conv, const T* __restrict__ xp,
+                                const float* __restrict__ bias, const T* __restrict__ s,
+                                T* __restrict__ fig, T* __restrict__ sn, T* __restrict__ hn,
+                                long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pr = i >> 5;
+    int c = (int)(i & 31) * 4;
+    float4 a[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      a[k] = Vec4<T>::load(xp + pr * 384 + k * 128 + c);
+      if (conv) {
+        float4 cv = Vec4<T>::load(conv + pr * 384 + k * 128 + c);
+        a[k].x += cv.x; a[k].y += cv.y; a[k].z += cv.z; a[k].w += cv.w;
+      }
+      float4 bv = *reinterpret_cast<const float4*>(bias + k * 128 + c);
+      a[k].x += bv.x; a[k].y += bv.y; a[k].z += bv.z; a[k].w += bv.w;
+    }
+    float4 sv = s ? Vec4<T>::load(s + pr * 128 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 f = make_float4(sigmoidf_(a[0].x), sigmoidf_(a[0].y), sigmoidf_(a[0].z), sigmoidf_(a[0].w));
+    float4 ig = make_float4(sigmoidf_(a[1].x), sigmoidf_(a[1].y), sigmoidf_(a[1].z), sigmoidf_(a[1].w));
+    float4 g = make_float4(tanhf(a[2].x), tanhf(a[2].y), tanhf(a[2].z), tanhf(a[2].w));
+    float4 so = make_float4(f.x * sv.x + ig.x * g.x, f.y * sv.y + ig.y * g.y,
+                            f.z * sv.z + ig.z * g.z, f.w * sv.w + ig.w * g.w);
+    Vec4<T>::store(fig + pr * 384 + c, f);
+    Vec4<T>::store(fig + pr * 384 + 128 + c, ig);
+    Vec4<T>::store(fig + pr * 384 + 256 + c, g);
+    Vec4<T>::store(sn + pr * 128 + c, so);
+    Vec4<T>::store(hn + pr * 128 + c, make_float4(tanhf(so.x), tanhf(so.y), tanhf(so.z), tanhf(so.w)));
+  }
+}
+
+template <typename T>
+__global__ void lstm_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ ds_in,
+                                const T* __restrict__ fig, const T* __restrict__ s,
+                                const T* __restrict__ hn, T* __restrict__ da,
+                                T* __restrict__ ds_prev, long long rows) {
+  long long total = rows * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long pr = i >> 5;
+    int c = (int)(i & 31) * 4;
+    long long off = pr * 128 + c;
+    float4 g = Vec4<T>::load(dh + off), hv = Vec4<T>::load(hn + off);
+    float4 dsi = ds_in ? Vec4<T>::load(ds_in + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sv = s ? Vec4<T>::load(s + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 f = Vec4<T>::load(fig + pr * 384 + c), ig = Vec4<T>::load(fig + pr * 384 + 128 + c),
+           gg = Vec4<T>::load(fig + pr * 384 + 256 + c);
+    float4 daf, dai, dag, dsp;
+#define R2N2_LSTM_BWD(e)                                        \
+  {                                                             \
+    float dst = g.e * (1.f - hv.e * hv.e) + dsi.e;              \
+    daf.e = dst * sv.e * f.e * (1.f - f.e);                     \
+    dai.e = dst * gg.e * ig.e * (1.f - ig.e);                   \
+    dag.e = dst * ig.e * (1.f - gg.e * gg.e);                   \
+    dsp.e = dst * f.e;                                          \
+  }
+    R2N2_LSTM_BWD(x) R2N2_LSTM_BWD(y) R2N2_LSTM_BWD(z) R2N2_LSTM_BWD(w)
+#undef R2N2_LSTM_BWD
+    Vec4<T>::store(da + pr * 384 + c, daf);
+    Vec4<T>::store(da + pr * 384 + 128 + c, dai);
+    Vec4<T>::store(da + pr * 384 + 256 + c, dag);
+    Vec4<T>::store(ds_prev + off, dsp);
+  }
+}
+
+// ------------------------------------------------------------------ voxel softmax + CE (fwd+bwd)
+template <typename TD>
+__global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const float* __restrict__ y,
+                                    float* __restrict__ pred, float* __restrict__ loss_sum,
+                                    TD* __restrict__ dlogits, long long nvox_total, int nv,
+                                    float grad_scale) {
+  const long long plane = (long long)nv * nv;  // one (y,x) plane
+  float local = 0.f;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox_total;
+       v += (long long)gridDim.x * blockDim.x) {
+    // v = ((b*nv + z)*nv + yy)*nv + xx ; reference layout offset of channel c:
+    long long bz = v / plane;
+    long long yx = v - bz * plane;
+    long long ref0 = (bz * 2) * plane + yx;
+    float2 x = *reinterpret_cast<const float2*>(logits + v * 2);
+    float e0 = expf(x.x), e1 = expf(x.y);  // no max subtraction: lib/layers.py:585-589
+    float s = e0 + e1;
+    float inv = 1.f / s;
+    float p0 = e0 * inv, p1 = e1 * inv;
+    float y0 = 0.f, y1 = 0.f;
+    if (y) {
+      y0 = y[ref0];
+      y1 = y[ref0 + plane];
+    }
+    if (pred) {
+      pred[ref0] = p0;
+      pred[ref0 + plane] = p1;
+    }
+    if (loss_sum) local += -(y0 * x.x + y1 * x.y) + logf(s);
+    if (dlogits) {
+      dlogits[v * 2] = from_float<TD>((p0 - y0) * grad_scale);
+      dlogits[v * 2 + 1] = from_float<TD>((p1 - y1) * grad_scale);
+    }
+  }
+  if (loss_sum) {
+    __shared__ float red[32];
+    local = warp_sum(local);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) red[wid] = local;
+    __syncthreads();
+    if (wid == 0) {
+      float t = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(loss_sum, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bias gradient (column sums)
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
+                                 int C, long long rows_per_block) {
+  __shared__ float red[8][33];
+  int cx = threadIdx.x, ry = threadIdx.y;
+  int c = blockIdx.x * 32 + cx;
+  long long r0 = blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) acc += to_float<T>(dy[r * C + c]);
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    atomicAdd(db + c, t);
+  }
+}
+
+// ------------------------------------------------------------------ weight transpose (+cast)
+// w[Cout][taps][Cin] -> wt[Cin][taps-1-t][Cout]
+template <typename T>
+__global__ void weight_transpose_kernel(const float* __restrict__ w, T* __restrict__ wt, int Cout,
+                                        int taps, int Cin) {
+  __shared__ float tile[32][33];
+  int t = blockIdx.z;
+  int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int co = co0 + j, ci = ci0 + threadIdx.x;
+    tile[j][threadIdx.x] =
+        (co < Cout && ci < Cin) ? w[((long long)co * taps + t) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int ci = ci0 + j, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout)
+      wt[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = from_float<T>(tile[threadIdx.x][j]);
+  }
+}
+
+// ------------------------------------------------------------------ optimisers
+template <typename TM, bool kMirror>
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, TM* __restrict__ mirror,
+                            long long n, long long n_decay, float lr_t, float b1, float b2,
+                            float eps, float wd, float gscale) {
+  long long n4 = (n + 3) >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long base = i * 4;
+    if (base + 3 < n) {
+      float4 pv = *reinterpret_cast<float4*>(p + base);
+      float4 gv = *reinterpret_cast<const float4*>(g + base);
+      float4 mv = *reinterpret_cast<float4*>(m + base);
+      float4 vv = *reinterpret_cast<float4*>(v + base);
+      float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float rg = gp[e] * gscale;
+        if (base + e < n_decay) rg += wd * pp[e];
+        mp[e] = b1 * mp[e] + (1.f - b1) * rg;
+        vp[e] = b2 * vp[e] + (1.f - b2) * rg * rg;
+        pp[e] = pp[e] - lr_t * mp[e] / (sqrtf(vp[e]) + eps);
+      }
+      *reinterpret_cast<float4*>(p + base) = pv;
+      *reinterpret_cast<float4*>(m + base) = mv;
+      *reinterpret_cast<float4*>(v + base) = vv;
+      if (kMirror) Vec4<TM>::store(mirror + base, pv);
+    } else {
+      for (long long j = base; j < n; ++j) {
+        float rg = g[j] * gscale;
+        if (j < n_decay) rg += wd * p[j];
+        float mm = b1 * m[j] + (1.f - b1) * rg;
+        float vv = b2 * v[j] + (1.f - b2) * rg * rg;
+        float pn = p[j] - lr_t * mm / (sqrtf(vv) + eps);
+        m[j] = mm; v[j] = vv; p[j] = pn;
+        if (kMirror) mirror[j] = from_float<TM>(pn);
+      }
+    }
+  }
+}
+
+template <typename TM, bool kMirror>
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                           float* __restrict__ vel, TM* __restrict__ mirror, long long n,
+                           long long n_decay, float lr, float mom, float wd, float gscale) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    float rg = g[j] * gscale;
+    if (j < n_decay) rg += wd * p[j];
+    float add = mom * vel[j] - lr * rg;   // lib/solver.py:68-70
+    vel[j] = add;
+    float pn = p[j] + add;
+    p[j] = pn;
+    if (kMirror) mirror[j] = from_float<TM>(pn);
+  }
+}
+
+// ------------------------------------------------------------------ voxel IoU counts
+__global__ void voxel_eval_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                  float thresh, unsigned long long* __restrict__ counts, int nv) {
+  int b = blockIdx.y;
+  long long plane = (long long)nv * nv;
+  long long nvox = plane * nv;
+  unsigned int c[5] = {0, 0, 0, 0, 0};
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox;
+       v += (long long)gridDim.x * blockDim.x) {
+    long long z = v / plane, yx = v - z * plane;
+    long long o0 = ((b * (long long)nv + z) * 2) * plane + yx;
+    bool occ = pred[o0 + plane] >= thresh;
+    bool g1 = gt[o0 + plane] != 0.f, g0 = gt[o0] != 0.f;
+    c[0] += (occ != g1); c[1] += (occ && g1); c[2] += (occ || g1);
+    c[3] += (occ && g0); c[4] += (!occ && g1);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    unsigned int t = c[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(counts + b * 5 + k, (unsigned long long)t);
+  }
+}
+
+}  // namespace r2n2
+
+using namespace r2n2;
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* r2n2_version(void) { return "r2n2_b200 0.1 (sm_100a)"; }
+const char* r2n2_last_error(void) { return r2n2::g_err; }
+
+int r2n2_fill_zero(void* p, long long bytes, void* stream) {
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+  R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "fill_zero: %s", cudaGetErrorString(e));
+  return R2N2_OK;
+}
+
+int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, int Wpad,
+                      int xoff, int out_dtype, void* stream) {
+  R2N2_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && Wpad >= W + xoff && xoff >= 0,
+                 R2N2_ERR_BAD_SHAPE, "nchw_to_nhwc: bad shape");
+  long long total = (long long)N * H * Wpad;
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, (T*)y, N, C, H, W, Cpad, Wpad, xoff);
+  })
+  R2N2_CHECK_LAUNCH("nchw_to_nhwc");
+  return R2N2_OK;
+}
+
+int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int dtype,
+                       void* stream) {
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
+                 "maxpool2d_fwd: C must be a positive multiple of 4 (got %d)", C);
+  int Ho = H / 2 + 1, Wo = W / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C >> 2);
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
+  })
+  R2N2_CHECK_LAUNCH("maxpool2d_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
+                       int C, int lrelu_mask, int dtype, void* stream) {
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
+                 "maxpool2d_bwd: C must be a positive multiple of 4 (got %d)", C);
+  int Ho = H / 2 + 1, Wo = W / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C >> 2);
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
+  })
+  R2N2_CHECK_LAUNCH("maxpool2d_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,
+                      int dtype, void* stream) {
+  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
+                 "unpool3d_fwd: bad shape");
+  long long total = (long long)B * D * H * W * 8 * (C >> 2);
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    unpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, (T*)y, B, D, H, W, C);
+  })
+  R2N2_CHECK_LAUNCH("unpool3d_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_unpool3d_bwd(const void* dy, void* dx, int B, int D, int H, int W, int C, int dtype,
+                      void* stream) {
+  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
+                 "unpool3d_bwd: bad shape");
+  long long total = (long long)B * D * H * W * (C >> 2);
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    unpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dy, (T*)dx, B, D, H, W, C);
+  })
+  R2N2_CHECK_LAUNCH("unpool3d_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "add: n must be a multiple of 4");
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    add_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
+                                                                           (T*)y, n >> 2);
+  })
+  R2N2_CHECK_LAUNCH("add");
+  return R2N2_OK;
+}
+
+int r2n2_lrelu_fwd(const void* x, void* y, long long n, int dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "lrelu_fwd: n must be a multiple of 4");
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    lrelu_fwd_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y,
+                                                                                 n >> 2);
+  })
+  R2N2_CHECK_LAUNCH("lrelu_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, long long n,
+                   int dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "lrelu_bwd: n must be a multiple of 4");
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    lrelu_bwd_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)dy, (const T*)addend, (T*)dx, n >> 2);
+  })
+  R2N2_CHECK_LAUNCH("lrelu_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int dtype,
+                 void* stream) {
+  R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "eltwise: n must be a multiple of 4");
+  R2N2_CHECK_ARG(op >= R2N2_ELT_SIGMOID && op <= R2N2_ELT_MUL, R2N2_ERR_UNSUPPORTED, "eltwise: bad op %d", op);
+  R2N2_CHECK_ARG(op != R2N2_ELT_MUL || b, R2N2_ERR_BAD_SHAPE, "eltwise: MUL needs two operands");
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    eltwise_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
+        op, (const T*)a, (const T*)b, (T*)y, n >> 2);
+  })
+  R2N2_CHECK_LAUNCH("eltwise");
+  return R2N2_OK;
+}
+
+int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0, R2N2_ERR_BAD_SHAPE, "cast: n <= 0");
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    cast_kernel<T><<<grid_for((n >> 2) + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, n);
+  })
+  R2N2_CHECK_LAUNCH("cast");
+  return R2N2_OK;
+}
+
+int r2n2_gru_gates_ur_fwd(const void* conv_ur, const void* xp_ur, const float* bias_ur,
+                          const void* h, void* u, void* r, void* rh, int B, int dtype,
+                          void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_ur_fwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    gru_ur_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)conv_ur, (const T*)xp_ur, bias_ur, (const T*)h, (T*)u, (T*)r, (T*)rh, rows);
+  })
+  R2N2_CHECK_LAUNCH("gru_gates_ur_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_gru_gates_out_fwd(const void* conv_c, const void* xp_c, const float* bias_c, const void* u,
+                           const void* h, void* c, void* h_new, int B, int dtype, void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_out_fwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    gru_out_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)conv_c, (const T*)xp_c, bias_c, (const T*)u, (const T*)h, (T*)c, (T*)h_new, rows);
+  })
+  R2N2_CHECK_LAUNCH("gru_gates_out_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_gru_gates_out_bwd(const void* dh, const void* u, const void* c, const void* h, void* da_ur,
+                           void* da_c, void* dh_prev, int B, int dtype, void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_out_bwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    gru_out_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dh, (const T*)u, (const T*)c, (const T*)h, (T*)da_ur, (T*)da_c, (T*)dh_prev, rows);
+  })
+  R2N2_CHECK_LAUNCH("gru_gates_out_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_gru_gates_r_bwd(const void* d_rh, const void* h, const void* r, void* da_ur,
+                         void* dh_prev, int B, int dtype, void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_r_bwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    gru_r_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)d_rh, (const T*)h, (const T*)r, (T*)da_ur, (T*)dh_prev, rows);
+  })
+  R2N2_CHECK_LAUNCH("gru_gates_r_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_lstm_gates_fwd(const void* conv_fig, const void* xp_fig, const float* bias_fig,
+                        const void* s, void* fig, void* s_new, void* h_new, int B, int dtype,
+                        void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "lstm_gates_fwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    lstm_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)conv_fig, (const T*)xp_fig, bias_fig, (const T*)s, (T*)fig, (T*)s_new, (T*)h_new,
+        rows);
+  })
+  R2N2_CHECK_LAUNCH("lstm_gates_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_lstm_gates_bwd(const void* dh, const void* ds_in, const void* fig, const void* s,
+                        const void* h_new, void* da_fig, void* ds_prev, int B, int dtype,
+                        void* stream) {
+  R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "lstm_gates_bwd: B <= 0");
+  long long rows = (long long)B * 64;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    lstm_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)dh, (const T*)ds_in, (const T*)fig, (const T*)s, (const T*)h_new, (T*)da_fig,
+        (T*)ds_prev, rows);
+  })
+  R2N2_CHECK_LAUNCH("lstm_gates_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_softmax_ce3d(const float* logits, const float* y, float* pred, float* loss_sum,
+                      void* dlogits, int B, int nv, float grad_scale, int ddtype, void* stream) {
+  R2N2_CHECK_ARG(B > 0 && nv > 0, R2N2_ERR_BAD_SHAPE, "softmax_ce3d: bad shape");
+  long long total = (long long)B * nv * nv * nv;
+  R2N2_DISPATCH_DTYPE(ddtype, T, {
+    softmax_ce3d_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        logits, y, pred, loss_sum, (T*)dlogits, total, nv, grad_scale);
+  })
+  R2N2_CHECK_LAUNCH("softmax_ce3d");
+  return R2N2_OK;
+}
+
+int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, int accumulate,
+                   void* stream) {
+  R2N2_CHECK_ARG(rows > 0 && C > 0, R2N2_ERR_BAD_SHAPE, "bias_grad: bad shape");
+  if (!accumulate) cudaMemsetAsync(db, 0, sizeof(float) * C, (cudaStream_t)stream);
+  int gx = (C + 31) / 32;
+  long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
+  long long gy = rows / 64;
+  if (gy < 1) gy = 1;
+  if (gy > want) gy = want;
+  long long rpb = (rows + gy - 1) / gy;
+  gy = (rows + rpb - 1) / rpb;
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    bias_grad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        (const T*)dy, db, rows, C, rpb);
+  })
+  R2N2_CHECK_LAUNCH("bias_grad");
+  return R2N2_OK;
+}
+
+int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin, int out_dtype,
+                          void* stream) {
+  R2N2_CHECK_ARG(Cout > 0 && taps > 0 && Cin > 0 && taps <= 65535, R2N2_ERR_BAD_SHAPE,
+                 "weight_transpose: bad shape");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps);
+  R2N2_CHECK_ARG(grid.y <= 65535, R2N2_ERR_BAD_SHAPE, "weight_transpose: Cout too large");
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    weight_transpose_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, (T*)wt, Cout,
+                                                                                taps, Cin);
+  })
+  R2N2_CHECK_LAUNCH("weight_transpose");
+  return R2N2_OK;
+}
+
+int r2n2_adam(float* p, const float* g, float* m, float* v, void* p_mirror, long long n,
+              long long n_decay, float lr_t, float beta1, float beta2, float eps, float wd,
+              float grad_scale, int mirror_dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && n_decay >= 0 && n_decay <= n, R2N2_ERR_BAD_SHAPE, "adam: bad sizes");
+  int grid = grid_for((n + 3) >> 2, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p_mirror) {
+    adam_kernel<float, false><<<grid, 256, 0, st>>>(p, g, m, v, nullptr, n, n_decay, lr_t, beta1,
+                                                    beta2, eps, wd, grad_scale);
+  } else if (mirror_dtype == R2N2_BF16) {
+    adam_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_mirror, n,
+                                                           n_decay, lr_t, beta1, beta2, eps, wd,
+                                                           grad_scale);
+  } else {
+    R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "adam: mirror dtype must be bf16");
+  }
+  R2N2_CHECK_LAUNCH("adam");
+  return R2N2_OK;
+}
+
+int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, long long n_decay,
+             float lr, float momentum, float wd, float grad_scale, int mirror_dtype, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && n_decay >= 0 && n_decay <= n, R2N2_ERR_BAD_SHAPE, "sgd: bad sizes");
+  int grid = grid_for(n, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p_mirror) {
+    sgd_kernel<float, false><<<grid, 256, 0, st>>>(p, g, vel, nullptr, n, n_decay, lr, momentum, wd,
+                                                   grad_scale);
+  } else if (mirror_dtype == R2N2_BF16) {
+    sgd_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(p, g, vel, (__nv_bfloat16*)p_mirror, n,
+                                                          n_decay, lr, momentum, wd, grad_scale);
+  } else {
+    R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "sgd: mirror dtype must be bf16");
+  }
+  R2N2_CHECK_LAUNCH("sgd");
+  return R2N2_OK;
+}
+
+int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long* counts, int B,
+                    int nv, void* stream) {
+  R2N2_CHECK_ARG(B > 0 && nv > 0, R2N2_ERR_BAD_SHAPE, "voxel_eval: bad shape");
+  cudaMemsetAsync(counts, 0, sizeof(long long) * 5 * B, (cudaStream_t)stream);
+  long long nvox = (long long)nv * nv * nv;
+  int gx = (int)((nvox + 255) / 256);
+  if (gx > 64) gx = 64;
+  voxel_eval_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+      pred, gt, thresh, (unsigned long long*)counts, nv);
+  R2N2_CHECK_LAUNCH("voxel_eval");
+  return R2N2_OK;
+}
+
+}  // extern "C"

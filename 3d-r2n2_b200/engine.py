@@ -1,0 +1,551 @@
+"""Fused executor for the three networks of the hot path (GRUNet, ResidualGRUNet and the
+3D-conv-LSTM variant of the residual net).
+
+Same arithmetic as the reference graphs (models/gru_net.py:63-144, models/res_gru_net.py:78-204),
+re-scheduled B200-first:
+  * everything that does not depend on h_{t-1} (the 2-D encoder, fc7 and the FCConv3DLayer
+    x-projections dot(f, Wx), lib/layers.py:502-503) is hoisted out of the theano.scan recurrence
+    and run ONCE over all T*B views;
+  * the update/reset gates share one 3-D convolution of h (Cout=256) and one x-projection GEMM;
+  * AddLayer + PoolLayer / AddLayer + Unpool3DLayer pairs are single kernels; bias + LeakyReLU
+    (+ residual add, + LeakyReLU' in the backward) live in the GEMM epilogues;
+  * all parameters, gradients and Adam moments live in ONE flat fp32 buffer each (packed
+    layouts), so the optimiser is one launch and the data-parallel all-reduce a few big buckets.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from . import packing as pk
+from .ops import Act, Param, Ctx
+
+N_CONVFILTER = [96, 128, 256, 256, 256, 256]
+N_FC = 1024
+N_DECONV = [128, 128, 128, 64, 32, 2]
+N_GRU_VOX = 4
+HID_POS = N_GRU_VOX ** 3          # 64 cells
+HID_C = N_DECONV[0]               # 128 channels
+
+NETS = ('GRUNet', 'ResidualGRUNet', 'ResidualLSTMNet')
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class RefWeight:
+    """One parameter tensor of the reference's `net.params` list (weights.npy order):
+    knows how to move between the reference layout and its packed view in the flat store."""
+
+    def __init__(self, name, ref_shape, is_bias, view, to_packed, to_ref):
+        self.name, self.ref_shape, self.is_bias = name, tuple(ref_shape), is_bias
+        self.view = view              # fp32 torch view (possibly strided) into the flat store
+        self._to_packed, self._to_ref = to_packed, to_ref
+
+    def set_value(self, arr):
+        t = torch.as_tensor(np.asarray(arr, dtype=np.float32))
+        if tuple(t.shape) != self.ref_shape:
+            raise ValueError('%s: expected shape %s, got %s' % (self.name, self.ref_shape, tuple(t.shape)))
+        self.view.copy_(self._to_packed(t.to(self.view.device)).reshape(self.view.shape))
+
+    def get_value(self, src=None):
+        v = self.view if src is None else src
+        return self._to_ref(v).reshape(self.ref_shape).cpu().numpy()
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / moment buffers.  Non-bias segments first (L2 decay
+    applies to [0, n_decay)), biases after.  Segments are 64-element aligned."""
+
+    def __init__(self, device, mirror_dtype=None):
+        self.device = device
+        self.mirror_dtype = mirror_dtype
+        self._plan = []           # (name, numel, is_bias)
+        self.offsets = {}
+        self.version = 0
+        self.p = self.g = self.m = self.v = self.mirror = None
+
+    def plan(self, name, numel, is_bias):
+        self._plan.append((name, int(numel), bool(is_bias)))
+
+    def allocate(self):
+        off = 0
+        for want_bias in (False, True):
+            for name, numel, is_bias in self._plan:
+                if is_bias == want_bias:
+                    self.offsets[name] = (off, numel)
+                    off += _round_up(numel, 64)
+            if not want_bias:
+                self.n_decay = off
+        self.n = off
+        self.p = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.g = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        if self.mirror_dtype is not None:
+            self.mirror = torch.zeros(self.n, dtype=self.mirror_dtype, device=self.device)
+
+    def seg(self, name, buf=None):
+        off, numel = self.offsets[name]
+        return (self.p if buf is None else buf)[off:off + numel]
+
+    def ensure_moments(self):
+        if self.m is None:
+            self.m = torch.zeros_like(self.p)
+            self.v = torch.zeros_like(self.p)
+
+    def touch(self):
+        """Parameters changed (set_value / optimiser step): refresh the operand mirrors lazily."""
+        self.version += 1
+
+    def refresh_mirror(self):
+        if self.mirror is not None and self.p.is_cuda:
+            ops.cast(self.p, self.mirror)
+
+
+class Engine:
+    def __init__(self, net_name, batch_size, device='cuda', compute='fp32', conv_algo=None,
+                 wgrad_algo=None, img=127, n_vox=32, params_only=False):
+        if net_name not in NETS:
+            raise ValueError('unknown network %r' % (net_name,))
+        self.params_only = params_only      # host-side parameter bookkeeping only (CPU tests)
+        if not params_only:
+            if not torch.cuda.is_available():
+                raise RuntimeError('r2n2_b200.Engine needs a CUDA device (no CPU fallback exists)')
+            L.load()
+        self.net_name = net_name
+        self.B = int(batch_size)
+        self.img, self.n_vox = img, n_vox
+        self.device = torch.device(device)
+        self.compute = compute
+        self.dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[compute]
+        if conv_algo is None:
+            conv_algo = L.ALGO_SIMT if compute == 'fp32' else L.ALGO_UMMA
+        self.algo = conv_algo
+        self.wgrad_algo = conv_algo if wgrad_algo is None else wgrad_algo
+        self.residual = net_name != 'GRUNet'
+        self.lstm = net_name == 'ResidualLSTMNet'
+        self.n_gates = 3
+        # channel padding of the RGB input: 4 for the fp32 SIMT path, 16 for tensor-core K tiles
+        self.cin_pad = 4 if self.algo == L.ALGO_SIMT else 16
+        self.store = ParamStore(self.device, None if self.dtype == torch.float32 else self.dtype)
+        self.P = {}
+        self.weights = []      # RefWeight list in reference creation order
+        self._define()
+        self.ctx = None
+        self.last = None
+
+    # ------------------------------------------------------------------ parameter definition
+    def _define(self):
+        c, d = N_CONVFILTER, N_DECONV
+        st = self.store
+        defs = []        # deferred (after allocate) construction of Params / RefWeights
+
+        def conv2(name, cout, cin, k, cin_pad=None):
+            cp = cin_pad or cin
+            st.plan(name + '.W', cout * k * k * cp, False)
+            st.plan(name + '.b', cout, True)
+            defs.append(('conv2', name, cout, cin, k, cp))
+
+        def conv3(name, cout, cin, k):
+            st.plan(name + '.W', cout * k ** 3 * cin, False)
+            st.plan(name + '.b', cout, True)
+            defs.append(('conv3', name, cout, cin, k, cin))
+
+        if self.residual:
+            conv2('conv1a', c[0], 3, 7, self.cin_pad); conv2('conv1b', c[0], c[0], 3)
+            conv2('conv2a', c[1], c[0], 3); conv2('conv2b', c[1], c[1], 3); conv2('conv2c', c[1], c[0], 1)
+            conv2('conv3a', c[2], c[1], 3); conv2('conv3b', c[2], c[2], 3); conv2('conv3c', c[2], c[1], 1)
+            conv2('conv4a', c[3], c[2], 3); conv2('conv4b', c[3], c[3], 3)
+            conv2('conv5a', c[4], c[3], 3); conv2('conv5b', c[4], c[4], 3); conv2('conv5c', c[4], c[3], 1)
+            conv2('conv6a', c[5], c[4], 3); conv2('conv6b', c[5], c[5], 3)
+        else:
+            cin = 3
+            for i in range(6):
+                conv2('conv%d' % (i + 1), c[i], cin, 7 if i == 0 else 3, self.cin_pad if i == 0 else None)
+                cin = c[i]
+        st.plan('fc7.W', N_FC * c[5] * 9, False)
+        st.plan('fc7.b', N_FC, True)
+        defs.append(('fc7',))
+        # recurrent unit: gate groups that read the same input share one conv / one GEMM
+        if self.lstm:
+            self.gate_names = ['t_x_s_forget', 't_x_s_input', 't_x_s_cell']
+            self.groups = [('fig', [0, 1, 2])]
+        else:
+            self.gate_names = ['t_x_s_update', 't_x_s_reset', 't_x_rs']
+            self.groups = [('ur', [0, 1]), ('c', [2])]
+        for gname, members in self.groups:
+            ng = len(members)
+            st.plan('rnn.Wh_' + gname, ng * HID_C * 27 * HID_C, False)
+            st.plan('rnn.Wx_' + gname, HID_POS * ng * HID_C * N_FC, False)
+            st.plan('rnn.b_' + gname, ng * HID_C, True)
+        defs.append(('rnn',))
+        if self.residual:
+            conv3('conv7a', d[1], d[0], 3); conv3('conv7b', d[1], d[1], 3)
+            conv3('conv8a', d[2], d[1], 3); conv3('conv8b', d[2], d[2], 3)
+            conv3('conv9a', d[3], d[2], 3); conv3('conv9b', d[3], d[3], 3); conv3('conv9c', d[3], d[2], 1)
+            conv3('conv10a', d[4], d[3], 3); conv3('conv10b', d[4], d[4], 3); conv3('conv10c', d[4], d[4], 3)
+            conv3('conv11', d[5], d[4], 3)
+        else:
+            conv3('conv7', d[1], d[0], 3); conv3('conv8', d[2], d[1], 3); conv3('conv9', d[3], d[2], 3)
+            conv3('conv10', d[4], d[3], 3); conv3('conv11', d[5], d[4], 3)
+        st.allocate()
+
+        def mk_param(seg, cout, taps, cin):
+            p = Param(st.seg(seg), st.seg(seg, st.g),
+                      None if st.mirror is None else st.seg(seg, st.mirror), cout, taps, cin, st)
+            self.P[seg] = p
+            return p
+
+        def mk_bias(seg, n):
+            p = Param(st.seg(seg), st.seg(seg, st.g), None, n, 1, 1, st)
+            self.P[seg] = p
+            return p
+
+        for dfn in defs:
+            kind = dfn[0]
+            if kind == 'conv2':
+                _, name, cout, cin, k, cp = dfn
+                mk_param(name + '.W', cout, k * k, cp)
+                mk_bias(name + '.b', cout)
+                vw = st.seg(name + '.W').view(cout, k, k, cp)
+                self.weights.append(RefWeight(
+                    name + '.W', (cout, cin, k, k), False, vw,
+                    lambda t, cp=cp: pk.pack_conv2d(t, cp), lambda v, cin=cin: pk.unpack_conv2d(v, cin)))
+                self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
+                                              lambda t: t, lambda v: v))
+            elif kind == 'conv3':
+                _, name, cout, cin, k, _ = dfn
+                mk_param(name + '.W', cout, k ** 3, cin)
+                mk_bias(name + '.b', cout)
+                vw = st.seg(name + '.W').view(cout, k, k, k, cin)
+                self.weights.append(RefWeight(name + '.W', (cout, k, cin, k, k), False, vw,
+                                              pk.pack_conv3d, pk.unpack_conv3d))
+                self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
+                                              lambda t: t, lambda v: v))
+            elif kind == 'fc7':
+                n_in = N_CONVFILTER[5] * 9
+                mk_param('fc7.W', N_FC, 1, n_in)
+                mk_bias('fc7.b', N_FC)
+                chw = (N_CONVFILTER[5], 3, 3)
+                self.weights.append(RefWeight('fc7.W', (n_in, N_FC), False,
+                                              st.seg('fc7.W').view(N_FC, n_in),
+                                              lambda t: pk.pack_fc(t, chw), lambda v: pk.unpack_fc(v, chw)))
+                self.weights.append(RefWeight('fc7.b', (N_FC,), True, st.seg('fc7.b'),
+                                              lambda t: t, lambda v: v))
+            elif kind == 'rnn':
+                slot = {}
+                for gname, members in self.groups:
+                    ng = len(members)
+                    mk_param('rnn.Wh_' + gname, ng * HID_C, 27, HID_C)
+                    mk_param('rnn.Wx_' + gname, HID_POS * ng * HID_C, 1, N_FC)
+                    mk_bias('rnn.b_' + gname, ng * HID_C)
+                    wh = st.seg('rnn.Wh_' + gname).view(ng, HID_C, 3, 3, 3, HID_C)
+                    wx = st.seg('rnn.Wx_' + gname).view(HID_POS, ng, HID_C, N_FC)
+                    bb = st.seg('rnn.b_' + gname).view(ng, HID_C)
+                    for j, gi in enumerate(members):
+                        slot[gi] = (wh[j], wx[:, j], bb[j])
+                g4 = N_GRU_VOX
+                for gi, lname in enumerate(self.gate_names):
+                    wh, wx, bb = slot[gi]
+                    self.weights.append(RefWeight(lname + '.Wh', (HID_C, 3, HID_C, 3, 3), False, wh,
+                                                  pk.pack_conv3d, pk.unpack_conv3d))
+                    self.weights.append(RefWeight(
+                        lname + '.Wx', (N_FC, HID_POS * HID_C), False, wx,
+                        lambda t: pk.pack_fcconv_wx(t, g4, HID_C, g4, g4),
+                        lambda v: pk.unpack_fcconv_wx(v, g4, HID_C, g4, g4)))
+                    self.weights.append(RefWeight(lname + '.b', (HID_C,), True, bb,
+                                                  lambda t: t, lambda v: v))
+
+    # ------------------------------------------------------------------ parameter I/O
+    def set_params(self, arrays):
+        """arrays: list in the reference's weights.npy order (models/net.py:60-86)."""
+        if len(arrays) != len(self.weights):
+            raise ValueError('expected %d parameter tensors, got %d' % (len(self.weights), len(arrays)))
+        for w, a in zip(self.weights, arrays):
+            w.set_value(a)
+        self.params_changed()
+
+    def get_params(self):
+        return [w.get_value() for w in self.weights]
+
+    def get_grads(self):
+        """Gradients in reference layout / order (tensor.grad(loss, params), models/net.py:58)."""
+        out = []
+        for w in self.weights:
+            off = w.view.storage_offset() - self.store.p.storage_offset()
+            gview = torch.as_strided(self.store.g, w.view.shape, w.view.stride(), off)
+            out.append(w.get_value(gview))
+        return out
+
+    def params_changed(self):
+        self.store.touch()
+        self.store.refresh_mirror()
+
+    # ------------------------------------------------------------------ recurrent composites
+    def _xproj(self, ctx, f, TB):
+        """Hoisted FCConv3DLayer x-projections (lib/layers.py:502-503) for all T*B views."""
+        xps = {}
+        for gname, members in self.groups:
+            n = HID_POS * len(members) * HID_C
+            xp = ctx.empty(TB * n, f.data)
+            ops.conv_fwd(f.data, self.P['rnn.Wx_' + gname].operand(), None, None, None, xp,
+                         (TB, 1, 1, 1, N_FC), n, (1, 1, 1), 0, ctx.algo)
+            xps[gname] = xp
+        return xps
+
+    def _rnn_param_grads(self, ctx, f, dxp, hin, T, B):
+        """Weight gradients of the recurrent unit, batched over all time steps, and dL/df."""
+        TB = T * B
+        g4 = N_GRU_VOX
+        first = None
+        for idx, (gname, members) in enumerate(self.groups):
+            ng = len(members)
+            cg = ng * HID_C
+            Wh, Wx, bb = self.P['rnn.Wh_' + gname], self.P['rnn.Wx_' + gname], self.P['rnn.b_' + gname]
+            d = dxp[gname]                                     # [T,B,64,cg]
+            ops.bias_grad(d, bb.grad, cg, bb.grad_written); bb.grad_written = True
+            if T > 1:                                          # step 0 has h == 0: no conv term
+                ops.conv_wgrad(hin[gname][:(T - 1) * B * HID_POS * HID_C], d[B * HID_POS * cg:],
+                               Wh.grad, ((T - 1) * B, g4, g4, g4, HID_C), cg, (3, 3, 3),
+                               ctx.wgrad_algo, Wh.grad_written)
+                Wh.grad_written = True
+            ops.conv_wgrad(f.data, d, Wx.grad, (TB, 1, 1, 1, N_FC), HID_POS * cg, (1, 1, 1),
+                           ctx.wgrad_algo, Wx.grad_written)
+            Wx.grad_written = True
+            if idx < len(self.groups) - 1:
+                first = ctx.empty(TB * N_FC, f.data)
+                ops.conv_fwd(d, Wx.operand_t(), None, None, None, first,
+                             (TB, 1, 1, 1, HID_POS * cg), N_FC, (1, 1, 1), 0, ctx.algo)
+            else:
+                # last group: fuse the accumulation and fc7's LeakyReLU' into the epilogue
+                self._dgrad_fc(ctx, f, d, Wx, HID_POS * cg, first)
+
+    def _dgrad_fc(self, ctx, f, d, Wx, kdim, extra):
+        TB = f.geom[0]
+        flags, res, mask = 0, None, None
+        if f.n_recv > 0:
+            raise RuntimeError('fc7 output has an unexpected second consumer')
+        if extra is not None:
+            flags |= L.EPI_RESIDUAL
+            res = extra
+        if f.lrelu_out and f.n_cons == 1:
+            flags |= L.EPI_MASK
+            mask = f.data
+            f.grad_preact = True
+        out = extra if extra is not None else ctx.empty(TB * N_FC, f.data)
+        ops.conv_fwd(d, Wx.operand_t(), None, mask, res, out, (TB, 1, 1, 1, kdim), N_FC, (1, 1, 1),
+                     flags, ctx.algo)
+        f.grad, f.grad_shared = out, False
+        f.n_recv += 1
+
+    def gru_sequence(self, ctx, f, T, B):
+        """theano.scan over views of the GRU update (models/res_gru_net.py:128-160):
+        u = sigmoid(conv(h;Wh_u) + f.Wx_u + b_u), r likewise, c = tanh(conv(r*h;Wh_c) + f.Wx_c + b_c),
+        h <- u*h + (1-u)*c.   Returns (h_T Act, update gates [T,B,64,128])."""
+        g4 = N_GRU_VOX
+        hn = HID_POS * HID_C
+        P = self.P
+        xps = self._xproj(ctx, f, T * B)
+        xp_ur, xp_c = xps['ur'], xps['c']
+        u = ctx.empty(T * B * hn, f.data); r = ctx.empty(T * B * hn, f.data)
+        rh = ctx.empty(T * B * hn, f.data); c = ctx.empty(T * B * hn, f.data)
+        h = ctx.empty(T * B * hn, f.data)
+        sl = lambda buf, t, width=hn: buf[t * B * width:(t + 1) * B * width]
+        geom_h = (B, g4, g4, g4, HID_C)
+        for t in range(T):
+            if t == 0:
+                ops.gru_ur_fwd(None, sl(xp_ur, 0, 2 * hn), P['rnn.b_ur'].data, None, sl(u, 0), sl(r, 0),
+                               sl(rh, 0), B)
+                ops.gru_out_fwd(None, sl(xp_c, 0), P['rnn.b_c'].data, sl(u, 0), None, sl(c, 0),
+                                sl(h, 0), B)
+                continue
+            hp = sl(h, t - 1)
+            a_ur = ctx.empty(B * 2 * hn, f.data)
+            ops.conv_fwd(hp, P['rnn.Wh_ur'].operand(), None, None, None, a_ur, geom_h, 2 * HID_C,
+                         (3, 3, 3), 0, ctx.algo)
+            ops.gru_ur_fwd(a_ur, sl(xp_ur, t, 2 * hn), P['rnn.b_ur'].data, hp, sl(u, t), sl(r, t),
+                           sl(rh, t), B)
+            a_c = ctx.empty(B * hn, f.data)
+            ops.conv_fwd(sl(rh, t), P['rnn.Wh_c'].operand(), None, None, None, a_c, geom_h, HID_C,
+                         (3, 3, 3), 0, ctx.algo)
+            ops.gru_out_fwd(a_c, sl(xp_c, t), P['rnn.b_c'].data, sl(u, t), hp, sl(c, t), sl(h, t), B)
+        h_last = Act(sl(h, T - 1), geom_h, requires_grad=ctx.training)
+        if ctx.training:
+            ctx.consume(f)
+
+            def bwd():
+                if h_last.grad is None:
+                    return
+                dxp_ur = torch.zeros(T * B * 2 * hn, dtype=ctx.dtype, device=f.data.device)
+                dxp_c = ctx.empty(T * B * hn, f.data)
+                dh = h_last.grad
+                geom_ur = (B, g4, g4, g4, 2 * HID_C)
+                for t in range(T - 1, -1, -1):
+                    hp = sl(h, t - 1) if t > 0 else None
+                    dh_prev = ctx.empty(B * hn, f.data)
+                    ops.gru_out_bwd(dh, sl(u, t), sl(c, t), hp, sl(dxp_ur, t, 2 * hn), sl(dxp_c, t),
+                                    dh_prev, B)
+                    if t == 0:
+                        break
+                    d_rh = ctx.empty(B * hn, f.data)
+                    ops.conv_fwd(sl(dxp_c, t), P['rnn.Wh_c'].operand_t(), None, None, None, d_rh,
+                                 geom_h, HID_C, (3, 3, 3), 0, ctx.algo)
+                    ops.gru_r_bwd(d_rh, hp, sl(r, t), sl(dxp_ur, t, 2 * hn), dh_prev, B)
+                    ops.conv_fwd(sl(dxp_ur, t, 2 * hn), P['rnn.Wh_ur'].operand_t(), None, None, dh_prev,
+                                 dh_prev, geom_ur, HID_C, (3, 3, 3), L.EPI_RESIDUAL, ctx.algo)
+                    dh = dh_prev
+                self._rnn_param_grads(ctx, f, {'ur': dxp_ur, 'c': dxp_c}, {'ur': h, 'c': rh[B * hn:]},
+                                      T, B)
+                h_last.grad = None
+            ctx.tape.append(bwd)
+        return h_last, u
+
+    def lstm_sequence(self, ctx, f, T, B):
+        """3D-conv-LSTM variant (no reference code exists):
+        f,i = sigmoid(.), g = tanh(.), all three FCConv3D terms read h_{t-1};
+        s <- f*s + i*g ; h <- tanh(s).  Returns (h_T Act, input gates [T,B,64,128] strided)."""
+        g4 = N_GRU_VOX
+        hn = HID_POS * HID_C
+        P = self.P
+        xp = self._xproj(ctx, f, T * B)['fig']
+        fig = ctx.empty(T * B * 3 * hn, f.data)
+        s = ctx.empty(T * B * hn, f.data); h = ctx.empty(T * B * hn, f.data)
+        sl = lambda buf, t, width=hn: buf[t * B * width:(t + 1) * B * width]
+        geom_h = (B, g4, g4, g4, HID_C)
+        for t in range(T):
+            a = None
+            if t > 0:
+                a = ctx.empty(B * 3 * hn, f.data)
+                ops.conv_fwd(sl(h, t - 1), P['rnn.Wh_fig'].operand(), None, None, None, a, geom_h,
+                             3 * HID_C, (3, 3, 3), 0, ctx.algo)
+            ops.lstm_fwd(a, sl(xp, t, 3 * hn), P['rnn.b_fig'].data, sl(s, t - 1) if t > 0 else None,
+                         sl(fig, t, 3 * hn), sl(s, t), sl(h, t), B)
+        h_last = Act(sl(h, T - 1), geom_h, requires_grad=ctx.training)
+        if ctx.training:
+            ctx.consume(f)
+
+            def bwd():
+                if h_last.grad is None:
+                    return
+                dxp = ctx.empty(T * B * 3 * hn, f.data)
+                dh, ds = h_last.grad, None
+                geom_3 = (B, g4, g4, g4, 3 * HID_C)
+                for t in range(T - 1, -1, -1):
+                    ds_prev = ctx.empty(B * hn, f.data)
+                    ops.lstm_bwd(dh, ds, sl(fig, t, 3 * hn), sl(s, t - 1) if t > 0 else None, sl(h, t),
+                                 sl(dxp, t, 3 * hn), ds_prev, B)
+                    if t == 0:
+                        break
+                    dh = ctx.empty(B * hn, f.data)
+                    ops.conv_fwd(sl(dxp, t, 3 * hn), P['rnn.Wh_fig'].operand_t(), None, None, None, dh,
+                                 geom_3, HID_C, (3, 3, 3), 0, ctx.algo)
+                    ds = ds_prev
+                self._rnn_param_grads(ctx, f, {'fig': dxp}, {'fig': h}, T, B)
+                h_last.grad = None
+            ctx.tape.append(bwd)
+        gates_i = fig.view(T, B, HID_POS, 3, HID_C)[:, :, :, 1]
+        return h_last, gates_i
+
+    # ------------------------------------------------------------------ whole network
+    def forward(self, x, y=None, training=False, want_pred=True):
+        """x: CUDA fp32 (T,B,3,H,W); y: CUDA fp32 (B,nv,2,nv,nv) or None.
+        Returns dict(pred (B,nv,2,nv,nv), loss (0-d CUDA tensor or None), update_gates)."""
+        T, B = int(x.shape[0]), int(x.shape[1])
+        if B != self.B:
+            raise ValueError('batch size is static (lib/layers.py:304-308): built for %d, got %d'
+                             % (self.B, B))
+        if tuple(x.shape[2:]) != (3, self.img, self.img):
+            raise ValueError('expected views of shape (3,%d,%d), got %s' % (self.img, self.img, tuple(x.shape[2:])))
+        if training and y is None:
+            raise ValueError('training needs ground-truth voxels')
+        TB = T * B
+        ctx = Ctx(self.dtype, self.algo, self.wgrad_algo, training)
+        self.ctx = ctx
+        if training:
+            for p in self.P.values():
+                p.grad_written = False
+        P = self.P
+        x = x.contiguous()
+        xin = ctx.empty(TB * self.img * self.img * self.cin_pad, x)
+        ops.nchw_to_nhwc(x.view(TB, 3, self.img, self.img), xin, self.cin_pad)
+        a = Act(xin, (TB, 1, self.img, self.img, self.cin_pad))
+
+        def c2(name, inp, lrelu, residual=None):
+            k = 7 if name in ('conv1a', 'conv1') else (1 if name.endswith('c') else 3)
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (1, k, k), lrelu, residual)
+
+        def c3(name, inp, lrelu, residual=None, out_dtype=None):
+            k = 1 if name == 'conv9c' else 3
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (k, k, k), lrelu, residual, out_dtype)
+
+        # ---- encoder over all T*B views (hoisted out of the scan) ----------------------------
+        if self.residual:
+            pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
+            pool2 = ctx.pool(c2('conv2c', pool1, False), c2('conv2b', c2('conv2a', pool1, True), True))
+            pool3 = ctx.pool(c2('conv3c', pool2, False), c2('conv3b', c2('conv3a', pool2, True), True))
+            pool4 = ctx.pool(c2('conv4b', c2('conv4a', pool3, True), True))
+            pool5 = ctx.pool(c2('conv5c', pool4, False), c2('conv5b', c2('conv5a', pool4, True), True))
+            pool6 = ctx.pool(pool5, c2('conv6b', c2('conv6a', pool5, True), True))
+        else:
+            t_ = a
+            for i in range(6):       # conv -> pool -> lrelu == conv -> lrelu -> pool (monotone)
+                t_ = ctx.pool(c2('conv%d' % (i + 1), t_, True))
+            pool6 = t_
+        flat = ctx.reshape(pool6, (TB, 1, 1, 1, N_CONVFILTER[5] * 9))
+        f = ctx.conv(flat, P['fc7.W'], P['fc7.b'], (1, 1, 1), True)
+
+        # ---- recurrence ---------------------------------------------------------------------
+        if self.lstm:
+            h, gates = self.lstm_sequence(ctx, f, T, B)
+        else:
+            h, gates = self.gru_sequence(ctx, f, T, B)
+
+        # ---- decoder ------------------------------------------------------------------------
+        if self.residual:
+            unpool7 = ctx.unpool(h)
+            rect7 = c3('conv7b', c3('conv7a', unpool7, True), True)
+            unpool8 = ctx.unpool(unpool7, rect7)                      # unpool(res7)
+            rect8 = c3('conv8b', c3('conv8a', unpool8, True), True)
+            unpool9 = ctx.unpool(unpool8, rect8)                      # unpool(res8)
+            rect9 = c3('conv9b', c3('conv9a', unpool9, True), True)
+            res9 = c3('conv9c', unpool9, False, residual=rect9)
+            rect10a = c3('conv10a', res9, True)
+            rect10 = c3('conv10b', rect10a, True)
+            res10 = c3('conv10c', rect10a, False, residual=rect10)
+            logits = c3('conv11', res10, False, out_dtype=torch.float32)
+        else:
+            t_ = c3('conv7', ctx.unpool(h), True)
+            t_ = c3('conv8', ctx.unpool(t_), True)
+            t_ = c3('conv9', ctx.unpool(t_), True)
+            t_ = c3('conv10', t_, True)
+            logits = c3('conv11', t_, False, out_dtype=torch.float32)
+
+        # ---- SoftmaxWithLoss3D --------------------------------------------------------------
+        nv = self.n_vox
+        pred = torch.empty(B, nv, 2, nv, nv, dtype=torch.float32, device=x.device) if want_pred else None
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=x.device) if y is not None else None
+        dlogits = None
+        if training:
+            dlogits = ctx.empty(B * nv ** 3 * 2, x)
+        ops.softmax_ce3d(logits.data, None if y is None else y.contiguous(), pred, loss_sum, dlogits,
+                         B, nv, 1.0 / (B * nv ** 3))
+        if training:
+            logits.grad, logits.n_recv = dlogits, 1
+        loss = None if loss_sum is None else loss_sum[0] / float(B * nv ** 3)
+        g5 = N_GRU_VOX
+        gates_ref = gates.reshape(T, B, g5, g5, g5, HID_C).permute(0, 1, 2, 5, 3, 4)
+        self.last = dict(pred=pred, loss=loss, update_gates=gates_ref, logits=logits.data)
+        return self.last
+
+    def backward(self):
+        """Reverse pass over the tape: fills the flat gradient buffer (store.g)."""
+        ctx = self.ctx
+        if ctx is None or not ctx.training:
+            raise RuntimeError('backward() needs a preceding forward(training=True)')
+        ctx.backward()
+        for p in self.P.values():
+            if not p.grad_written:
+                p.grad.zero_()
+        self.ctx = None

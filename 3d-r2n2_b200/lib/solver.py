@@ -1,0 +1,155 @@
+"""Mirror of lib/solver.py: ADAM / SGD update rules and the Solver train / test surface.
+
+The reference compiles `theano.function([x, y], loss, updates=...)`; here one training step is
+engine.forward(training) -> engine.backward() -> [NCCL all-reduce of the flat gradient buffer] ->
+one fused optimiser kernel over the flat parameter buffer (r2n2_adam / r2n2_sgd).
+numpy in / numpy out, like the reference.
+"""
+import math
+import os
+import sys
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .config import cfg
+from .. import ops
+
+
+def max_or_nan(params):
+    """lib/solver.py:12-17"""
+    nan_or_max_param = 0.0
+    for param_idx, param in enumerate(params):
+        nan_or_max_param = np.max(np.abs(param.val.get_value()))
+        print('param %d : %f' % (param_idx, nan_or_max_param))
+    return nan_or_max_param
+
+
+class Solver(object):
+
+    def __init__(self, net, dist_group=None):
+        self.net = net
+        self.lr = np.float32(1)
+        self.iteration = np.float32(0)     # lib/solver.py:79: float32, starts from 0
+        self._policy = None
+        self.grad_sync = None              # set by parallel.DataParallel (all-reduce of store.g)
+        self.compile_model(cfg.TRAIN.POLICY)
+
+    def compile_model(self, policy=cfg.TRAIN.POLICY):
+        """lib/solver.py:85-97"""
+        if policy not in ('sgd', 'adam'):
+            sys.exit('Error: Unimplemented optimization policy')
+        self._policy = policy
+        self.beta_1, self.beta_2, self.epsilon = 0.9, 0.999, 1e-8   # lib/solver.py:20
+        self.w_decay = cfg.TRAIN.WEIGHT_DECAY
+        self.momentum = cfg.TRAIN.MOMENTUM
+
+    def set_lr(self, lr):
+        self.lr = np.float32(lr)
+
+    # ---- one optimisation step -----------------------------------------------------------
+    def _apply_updates(self, grad_scale=1.0):
+        st = self.net.engine.store
+        if self._policy == 'adam':
+            # lib/solver.py:24-25: lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t), t float32
+            t = float(self.iteration)
+            lr_t = float(self.lr) * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+            st.ensure_moments()
+            ops.adam(st.p, st.g, st.m, st.v, st.mirror, st.n_decay, lr_t, self.beta_1, self.beta_2,
+                     self.epsilon, self.w_decay, grad_scale)
+        else:
+            if st.m is None:
+                st.m = torch.zeros_like(st.p)
+            ops.sgd(st.p, st.g, st.m, st.mirror, st.n_decay, float(self.lr), self.momentum,
+                    self.w_decay, grad_scale)
+        st.touch()
+
+    def _step(self, x, y):
+        out = self.net.forward_backward(x, y)
+        scale = 1.0
+        if self.grad_sync is not None:
+            scale = self.grad_sync(self.net.engine.store.g)
+        self._apply_updates(scale)
+        return out['loss']
+
+    @property
+    def train_loss(self):
+        """lib/solver.py:102-109: a property returning the compiled step; the iteration counter is
+        bumped on ACCESS, before the call (first step has t = 1)."""
+        self.iteration = np.float32(self.iteration + 1)
+
+        def fn(x, y):
+            return float(self._step(x, y))
+        return fn
+
+    def train_step_device(self, x_dev, y_dev):
+        """Same step with inputs already on the device; returns the loss as a 0-d CUDA tensor
+        (no host sync).  Used by bench.py for the HBM-resident `value` measurement."""
+        self.iteration = np.float32(self.iteration + 1)
+        return self._step(x_dev, y_dev)
+
+    def train(self, train_queue, val_queue=None):
+        ''' Given data queues, train the network (lib/solver.py:111-186) '''
+        save_dir = os.path.join(cfg.DIR.OUT_PATH)
+        if not os.path.exists(save_dir):
+            os.makedirs(save_dir)
+        training_losses = []
+        start_iter = 0
+        if cfg.TRAIN.RESUME_TRAIN:
+            self.net.load(cfg.CONST.WEIGHTS)
+            start_iter = cfg.TRAIN.INITIAL_ITERATION
+        lr = cfg.TRAIN.DEFAULT_LEARNING_RATE
+        lr_steps = [int(k) for k in cfg.TRAIN.LEARNING_RATES.keys()]
+        print('Set the learning rate to %f.' % lr)
+        self.set_lr(lr)
+        for train_ind in range(start_iter, cfg.TRAIN.NUM_ITERATION + 1):
+            batch_img, batch_voxel = train_queue.get()
+            if self.net.is_x_tensor4:
+                batch_img = batch_img[0]
+            loss = self.train_loss(batch_img, batch_voxel)
+            training_losses.append(loss)
+            if train_ind in lr_steps:
+                self.set_lr(float(cfg.TRAIN.LEARNING_RATES[str(train_ind)]))
+                print('Learing rate decreased to %f: ' % self.lr)
+            if train_ind % cfg.TRAIN.PRINT_FREQ == 0:
+                print('%s Iter: %d Loss: %f' % (datetime.now(), train_ind, loss))
+            if train_ind % cfg.TRAIN.VALIDATION_FREQ == 0 and val_queue is not None:
+                val_losses = []
+                for i in range(cfg.TRAIN.NUM_VALIDATION_ITERATIONS):
+                    batch_img, batch_voxel = val_queue.get()
+                    _, val_loss, _ = self.test_output(batch_img, batch_voxel)
+                    val_losses.append(val_loss)
+                print('%s Test loss: %f' % (datetime.now(), np.mean(val_losses)))
+            if train_ind % cfg.TRAIN.NAN_CHECK_FREQ == 0:
+                max_param = max_or_nan(self.net.params)
+                if np.isnan(max_param):
+                    print('NAN detected')
+                    break
+            if train_ind % cfg.TRAIN.SAVE_FREQ == 0 and not train_ind == 0:
+                self.save(training_losses, save_dir, train_ind)
+            if loss > cfg.TRAIN.LOSS_LIMIT:
+                print("Cost exceeds the threshold. Stop training")
+                break
+        return training_losses
+
+    def save(self, training_losses, save_dir, step):
+        ''' lib/solver.py:188-205 '''
+        save_path = os.path.join(save_dir, 'weights.%d' % (step))
+        self.net.save(save_path)
+        symlink_path = os.path.join(save_dir, 'weights.npy')
+        if os.path.lexists(symlink_path):
+            os.remove(symlink_path)
+        os.symlink("%s.npy" % os.path.abspath(save_path), symlink_path)
+        with open(os.path.join(save_dir, 'loss.%d.txt' % step), 'w') as f:
+            f.write('\n'.join([str(l) for l in training_losses]))
+
+    def test_output(self, x, y=None):
+        '''lib/solver.py:207-240: returns (prediction, activations) or
+        (prediction, loss, activations), all numpy.'''
+        out = self.net.forward(x, y)
+        prediction = out['pred'].cpu().numpy()
+        activations = [out['update_gates'].float().contiguous().cpu().numpy()]
+        if y is None:
+            return prediction, activations
+        return prediction, float(out['loss']), activations

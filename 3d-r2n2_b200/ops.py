@@ -1,0 +1,466 @@
+"""Host-side op layer: thin wrappers that turn torch CUDA tensors into C-ABI calls
+(include/r2n2_b200.h) plus a minimal reverse-mode tape so that the reference's
+`tensor.grad(loss, params)` (models/net.py:58) has an equivalent.
+
+torch is used for device memory and streams only: every FLOP and every byte moved on the
+hot path goes through libr2n2_b200.so.  There is no CPU path here: tensors must be CUDA
+tensors and the library must load.
+"""
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+launch_count = 0  # number of r2n2_* kernels launched by this process (bench.py reports it)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    L.call(name, *args)
+
+
+def _check(t, dtype=None):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError('r2n2_b200 ops need CUDA tensors (there is no CPU fallback)')
+    if not t.is_contiguous():
+        raise RuntimeError('r2n2_b200 ops need contiguous tensors, got strides %s' % (t.stride(),))
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError('dtype mismatch: expected %s got %s' % (dtype, t.dtype))
+
+
+# ======================================================================= raw op wrappers
+def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
+    """geom = (N,D,H,W,Cin) of x; k=(kd,kh,kw); y preallocated [N,D,H,W,cout]."""
+    N, D, H, W, Cin = geom
+    for t in (x, w, bias, mask_src, residual, y):
+        _check(t)
+    assert x.numel() == N * D * H * W * Cin, (x.shape, geom)
+    assert w.numel() == cout * k[0] * k[1] * k[2] * Cin, (w.shape, cout, k, Cin)
+    assert y.numel() == N * D * H * W * cout
+    assert w.dtype == x.dtype
+    _call('r2n2_conv_fwd', _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(residual), _ptr(y),
+          N, D, H, W, Cin, cout, k[0], k[1], k[2], flags, _DT[x.dtype], _DT[y.dtype], algo,
+          _stream())
+    return y
+
+
+def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate):
+    N, D, H, W, Cin = geom
+    for t in (x, dy, dw):
+        _check(t)
+    assert dw.dtype == torch.float32 and x.dtype == dy.dtype
+    assert x.numel() == N * D * H * W * Cin and dy.numel() == N * D * H * W * cout
+    assert dw.numel() == cout * k[0] * k[1] * k[2] * Cin
+    _call('r2n2_conv_wgrad', _ptr(x), _ptr(dy), _ptr(dw), N, D, H, W, Cin, cout, k[0], k[1], k[2],
+          _DT[x.dtype], algo, 1 if accumulate else 0, _stream())
+
+
+def bias_grad(dy, db, C, accumulate):
+    _check(dy), _check(db, torch.float32)
+    _call('r2n2_bias_grad', _ptr(dy), _ptr(db), dy.numel() // C, C, _DT[dy.dtype],
+          1 if accumulate else 0, _stream())
+
+
+def weight_transpose(w, wt, cout, taps, cin):
+    _check(w, torch.float32), _check(wt)
+    _call('r2n2_weight_transpose', _ptr(w), _ptr(wt), cout, taps, cin, _DT[wt.dtype], _stream())
+
+
+def cast(src, dst):
+    _check(src, torch.float32), _check(dst)
+    _call('r2n2_cast', _ptr(src), _ptr(dst), src.numel(), _DT[dst.dtype], _stream())
+
+
+def nchw_to_nhwc(x, y, cpad, wpad=None, xoff=0):
+    N, C, H, W = x.shape
+    _check(x, torch.float32), _check(y)
+    wpad = wpad or W
+    assert y.numel() == N * H * wpad * cpad
+    _call('r2n2_nchw_to_nhwc', _ptr(x), _ptr(y), N, C, H, W, cpad, wpad, xoff, _DT[y.dtype],
+          _stream())
+    return y
+
+
+def maxpool_fwd(a, b, y, N, H, W, C):
+    _check(a), _check(b), _check(y)
+    _call('r2n2_maxpool2d_fwd', _ptr(a), _ptr(b), _ptr(y), N, H, W, C, _DT[a.dtype], _stream())
+
+
+def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask):
+    for t in (a, b, dy, dx):
+        _check(t)
+    _call('r2n2_maxpool2d_bwd', _ptr(a), _ptr(b), _ptr(dy), _ptr(dx), N, H, W, C,
+          1 if lrelu_mask else 0, _DT[a.dtype], _stream())
+
+
+def unpool_fwd(a, b, y, B, D, H, W, C):
+    _check(a), _check(b), _check(y)
+    _call('r2n2_unpool3d_fwd', _ptr(a), _ptr(b), _ptr(y), B, D, H, W, C, _DT[a.dtype], _stream())
+
+
+def unpool_bwd(dy, dx, B, D, H, W, C):
+    _check(dy), _check(dx)
+    _call('r2n2_unpool3d_bwd', _ptr(dy), _ptr(dx), B, D, H, W, C, _DT[dy.dtype], _stream())
+
+
+def add(a, b, y):
+    _check(a), _check(b), _check(y)
+    _call('r2n2_add', _ptr(a), _ptr(b), _ptr(y), a.numel(), _DT[a.dtype], _stream())
+
+
+def lrelu_fwd(x, y):
+    _check(x), _check(y)
+    _call('r2n2_lrelu_fwd', _ptr(x), _ptr(y), x.numel(), _DT[x.dtype], _stream())
+
+
+def lrelu_bwd(a, dy, addend, dx):
+    for t in (a, dy, addend, dx):
+        _check(t)
+    _call('r2n2_lrelu_bwd', _ptr(a), _ptr(dy), _ptr(addend), _ptr(dx), a.numel(), _DT[a.dtype],
+          _stream())
+
+
+def eltwise(op, a, b, y):
+    _check(a), _check(b), _check(y)
+    _call('r2n2_eltwise', op, _ptr(a), _ptr(b), _ptr(y), a.numel(), _DT[a.dtype], _stream())
+
+
+def gru_ur_fwd(conv_ur, xp_ur, bias_ur, h, u, r, rh, B):
+    _call('r2n2_gru_gates_ur_fwd', _ptr(conv_ur), _ptr(xp_ur), _ptr(bias_ur), _ptr(h), _ptr(u),
+          _ptr(r), _ptr(rh), B, _DT[xp_ur.dtype], _stream())
+
+
+def gru_out_fwd(conv_c, xp_c, bias_c, u, h, c, h_new, B):
+    _call('r2n2_gru_gates_out_fwd', _ptr(conv_c), _ptr(xp_c), _ptr(bias_c), _ptr(u), _ptr(h),
+          _ptr(c), _ptr(h_new), B, _DT[xp_c.dtype], _stream())
+
+
+def gru_out_bwd(dh, u, c, h, da_ur, da_c, dh_prev, B):
+    _call('r2n2_gru_gates_out_bwd', _ptr(dh), _ptr(u), _ptr(c), _ptr(h), _ptr(da_ur), _ptr(da_c),
+          _ptr(dh_prev), B, _DT[dh.dtype], _stream())
+
+
+def gru_r_bwd(d_rh, h, r, da_ur, dh_prev, B):
+    _call('r2n2_gru_gates_r_bwd', _ptr(d_rh), _ptr(h), _ptr(r), _ptr(da_ur), _ptr(dh_prev), B,
+          _DT[d_rh.dtype], _stream())
+
+
+def lstm_fwd(conv, xp, bias, s, fig, s_new, h_new, B):
+    _call('r2n2_lstm_gates_fwd', _ptr(conv), _ptr(xp), _ptr(bias), _ptr(s), _ptr(fig), _ptr(s_new),
+          _ptr(h_new), B, _DT[xp.dtype], _stream())
+
+
+def lstm_bwd(dh, ds_in, fig, s, h_new, da, ds_prev, B):
+    _call('r2n2_lstm_gates_bwd', _ptr(dh), _ptr(ds_in), _ptr(fig), _ptr(s), _ptr(h_new), _ptr(da),
+          _ptr(ds_prev), B, _DT[dh.dtype], _stream())
+
+
+def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale):
+    _check(logits, torch.float32), _check(y, torch.float32), _check(pred, torch.float32)
+    _check(loss_sum, torch.float32), _check(dlogits)
+    dd = _DT[dlogits.dtype] if dlogits is not None else L.F32
+    _call('r2n2_softmax_ce3d', _ptr(logits), _ptr(y), _ptr(pred), _ptr(loss_sum), _ptr(dlogits), B,
+          nv, float(grad_scale), dd, _stream())
+
+
+def adam(p, g, m, v, mirror, n_decay, lr_t, b1, b2, eps, wd, grad_scale):
+    for t in (p, g, m, v):
+        _check(t, torch.float32)
+    _check(mirror)
+    _call('r2n2_adam', _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mirror), p.numel(), n_decay,
+          float(lr_t), float(b1), float(b2), float(eps), float(wd), float(grad_scale),
+          _DT[mirror.dtype] if mirror is not None else L.F32, _stream())
+
+
+def sgd(p, g, vel, mirror, n_decay, lr, momentum, wd, grad_scale):
+    for t in (p, g, vel):
+        _check(t, torch.float32)
+    _call('r2n2_sgd', _ptr(p), _ptr(g), _ptr(vel), _ptr(mirror), p.numel(), n_decay, float(lr),
+          float(momentum), float(wd), float(grad_scale),
+          _DT[mirror.dtype] if mirror is not None else L.F32, _stream())
+
+
+def voxel_eval(pred, gt, thresh):
+    """lib/voxel.py:4-11 on the GPU: returns int64 tensor [B,5]."""
+    _check(pred, torch.float32), _check(gt, torch.float32)
+    B, nv = pred.shape[0], pred.shape[1]
+    counts = torch.empty(B, 5, dtype=torch.int64, device=pred.device)
+    _call('r2n2_voxel_eval', _ptr(pred), _ptr(gt), float(thresh), _ptr(counts), B, nv, _stream())
+    return counts
+
+
+# ======================================================================= tape machinery
+class Act:
+    """An activation on the tape: channels-last data + gradient bookkeeping."""
+    __slots__ = ('data', 'geom', 'grad', 'n_cons', 'n_recv', 'lrelu_out', 'grad_preact',
+                 'grad_shared', 'requires_grad')
+
+    def __init__(self, data, geom, requires_grad=False, lrelu_out=False):
+        self.data = data
+        self.geom = tuple(int(g) for g in geom)   # (N, D, H, W, C)
+        self.grad = None
+        self.n_cons = 0          # consumers registered in the forward pass
+        self.n_recv = 0          # gradient contributions received so far in the backward pass
+        self.lrelu_out = lrelu_out      # data = LeakyReLU(z): sign(data) == sign(z)
+        self.grad_preact = False        # grad already multiplied by LeakyReLU'(z)
+        self.grad_shared = False        # grad buffer aliased by another Act: no in-place edits
+        self.requires_grad = requires_grad
+
+
+class Param:
+    """A packed parameter tensor used as a GEMM operand.
+    data: fp32 master [cout, taps, cin] (contiguous view into the flat store)
+    grad: fp32, same shape.  mirror: compute-dtype copy (bf16 path) or None.
+    wt:   [cin, taps(reversed), cout] compute-dtype copy for the data-gradient GEMM."""
+
+    def __init__(self, data, grad, mirror, cout, taps, cin, store=None):
+        self.data, self.grad, self.mirror = data, grad, mirror
+        self.cout, self.taps, self.cin = cout, taps, cin
+        self.store = store
+        self.wt = None
+        self.wt_version = -1
+        self.grad_written = False
+
+    def operand(self):
+        return self.mirror if self.mirror is not None else self.data
+
+    def operand_t(self):
+        ver = self.store.version if self.store is not None else 0
+        if self.wt is None or self.wt_version != ver:
+            dt = self.mirror.dtype if self.mirror is not None else torch.float32
+            if self.wt is None:
+                self.wt = torch.empty(self.cin * self.taps * self.cout, dtype=dt,
+                                      device=self.data.device)
+            weight_transpose(self.data, self.wt, self.cout, self.taps, self.cin)
+            self.wt_version = ver
+        return self.wt
+
+
+class Ctx:
+    """Execution context: compute dtype, conv algorithms, training flag and the tape."""
+
+    def __init__(self, dtype=torch.float32, algo=L.ALGO_SIMT, wgrad_algo=None, training=False):
+        self.dtype = dtype
+        self.algo = algo
+        self.wgrad_algo = algo if wgrad_algo is None else wgrad_algo
+        self.training = training
+        self.tape = []
+
+    # ---- helpers -------------------------------------------------------------------------
+    def empty(self, numel, like, dtype=None):
+        return torch.empty(int(numel), dtype=dtype or self.dtype, device=like.device)
+
+    def consume(self, x):
+        if self.training and x.requires_grad:
+            x.n_cons += 1
+
+    def accumulate(self, x, g, shared=False):
+        """Add gradient tensor g into x.grad (taking ownership of g when it is the first)."""
+        if not x.requires_grad:
+            return
+        if x.n_recv == 0:
+            x.grad, x.grad_shared = g, shared
+        elif x.grad_shared:
+            new = torch.empty_like(x.grad)
+            add(x.grad, g, new)
+            x.grad, x.grad_shared = new, False
+        else:
+            add(x.grad, g, x.grad)
+        x.n_recv += 1
+
+    def ensure_preact(self, out):
+        """out.grad currently holds dL/d(out); turn it into dL/dz where out = LeakyReLU(z)."""
+        if out.lrelu_out and not out.grad_preact:
+            dst = torch.empty_like(out.grad) if out.grad_shared else out.grad
+            lrelu_bwd(out.data, out.grad, None, dst)
+            out.grad, out.grad_shared, out.grad_preact = dst, False, True
+
+    def dgrad_into(self, x, dy, W, k, extra=None):
+        """x.grad (+)= conv_T(dy; W), fusing the pending accumulation (RESIDUAL) and, when this is
+        the last contribution to a LeakyReLU output, the LeakyReLU' mask (MASK)."""
+        if not x.requires_grad:
+            return
+        N, D, H, Wd, Cin = x.geom
+        flags = 0
+        res = None
+        out_buf = None
+        if x.n_recv > 0:
+            res = x.grad
+            out_buf = torch.empty_like(x.grad) if x.grad_shared else x.grad
+            flags |= L.EPI_RESIDUAL
+            if extra is not None:
+                add(extra, res, extra)
+                res = extra
+        elif extra is not None:
+            res = extra
+            flags |= L.EPI_RESIDUAL
+        if out_buf is None:
+            out_buf = self.empty(x.data.numel(), x.data)
+        last = (x.n_recv == x.n_cons - 1)
+        mask = None
+        if x.lrelu_out and last:
+            flags |= L.EPI_MASK
+            mask = x.data
+            x.grad_preact = True
+        conv_fwd(dy, W.operand_t(), None, mask, res, out_buf, (N, D, H, Wd, W.cout), Cin, k,
+                 flags, self.algo)
+        x.grad, x.grad_shared = out_buf, False
+        x.n_recv += 1
+
+    def weight_grads(self, x_data, dy, geom, W, b, k):
+        conv_wgrad(x_data, dy, W.grad, geom, W.cout, k, self.wgrad_algo, W.grad_written)
+        W.grad_written = True
+        if b is not None:
+            bias_grad(dy, b.grad, W.cout, b.grad_written)
+            b.grad_written = True
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+    # ---- differentiable ops --------------------------------------------------------------
+    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None):
+        """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw)."""
+        N, D, H, Wd, Cin = x.geom
+        assert Cin == W.cin and k[0] * k[1] * k[2] == W.taps, (x.geom, W.cin, W.taps, k)
+        assert not (lrelu and residual is not None)
+        cout = W.cout
+        y = self.empty(N * D * H * Wd * cout, x.data, out_dtype)
+        flags = (L.EPI_BIAS if b is not None else 0) | (L.EPI_LRELU if lrelu else 0)
+        if residual is not None:
+            flags |= L.EPI_RESIDUAL
+        conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
+                 None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
+        out = Act(y, (N, D, H, Wd, cout), requires_grad=self.training, lrelu_out=lrelu)
+        if self.training:
+            self.consume(x)
+            if residual is not None:
+                self.consume(residual)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                self.ensure_preact(out)
+                dy = out.grad
+                self.weight_grads(x.data, dy, x.geom, W, b, k)
+                self.dgrad_into(x, dy, W, k)
+                if residual is not None:
+                    self.accumulate(residual, dy)   # hand the buffer over (we are done with it)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def pool(self, a, b=None):
+        """2x2/2 max-pool (pad 1) of a (+ b)."""
+        N, D, H, W, C = a.geom
+        assert D == 1
+        Ho, Wo = H // 2 + 1, W // 2 + 1
+        y = self.empty(N * Ho * Wo * C, a.data)
+        maxpool_fwd(a.data, None if b is None else b.data, y, N, H, W, C)
+        out = Act(y, (N, 1, Ho, Wo, C), requires_grad=self.training,
+                  lrelu_out=(b is None and a.lrelu_out))
+        if self.training:
+            self.consume(a)
+            if b is not None:
+                self.consume(b)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                # max commutes with the monotone LeakyReLU, so pool(lrelu(z)) passes the mask on
+                fuse = (b is None and a.lrelu_out and a.n_recv == 0 and a.n_cons == 1
+                        and not out.grad_preact)
+                dx = torch.empty_like(a.data)
+                maxpool_bwd(a.data, None if b is None else b.data, out.grad, dx, N, H, W, C, fuse)
+                if b is None:
+                    if out.grad_preact:         # mask already applied downstream (on the max)
+                        assert a.n_cons == 1
+                        a.grad_preact = True
+                    elif fuse:
+                        a.grad_preact = True
+                    self.accumulate(a, dx)
+                else:
+                    self.accumulate(a, dx, shared=b.requires_grad)
+                    self.accumulate(b, dx, shared=a.requires_grad)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def unpool(self, a, b=None):
+        """Unpool3D x2 (zero stuffing) of a (+ b)."""
+        B, D, H, W, C = a.geom
+        y = self.empty(B * D * H * W * 8 * C, a.data)
+        unpool_fwd(a.data, None if b is None else b.data, y, B, D, H, W, C)
+        out = Act(y, (B, 2 * D, 2 * H, 2 * W, C), requires_grad=self.training)
+        if self.training:
+            self.consume(a)
+            if b is not None:
+                self.consume(b)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                dx = torch.empty_like(a.data)
+                unpool_bwd(out.grad, dx, B, D, H, W, C)
+                if b is None:
+                    self.accumulate(a, dx)
+                else:
+                    self.accumulate(a, dx, shared=b.requires_grad)
+                    self.accumulate(b, dx, shared=a.requires_grad)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def reshape(self, x, geom):
+        """FlattenLayer: reinterpret the (contiguous, channels-last) buffer with a new geometry."""
+        geom = tuple(int(g) for g in geom)
+        assert x.n_cons == 0 and x.data.numel() == geom[0] * geom[1] * geom[2] * geom[3] * geom[4]
+        x.geom = geom
+        return x
+
+    def add_act(self, a, b):
+        """AddLayer as a standalone op (only used by the layer-by-layer path)."""
+        y = torch.empty_like(a.data)
+        add(a.data, b.data, y)
+        out = Act(y, a.geom, requires_grad=self.training)
+        if self.training:
+            self.consume(a), self.consume(b)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                self.accumulate(a, out.grad, shared=b.requires_grad)
+                self.accumulate(b, out.grad, shared=a.requires_grad)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def lrelu(self, x):
+        """Standalone LeakyReLU (layer-by-layer path; the fused path folds it into conv)."""
+        y = torch.empty_like(x.data)
+        lrelu_fwd(x.data, y)
+        out = Act(y, x.geom, requires_grad=self.training, lrelu_out=True)
+        if self.training:
+            self.consume(x)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                self.ensure_preact(out)
+                self.accumulate(x, out.grad)
+                out.grad = None
+            self.tape.append(bwd)
+        return out

@@ -1,0 +1,192 @@
+/*
+ * r2n2_b200.h -- C ABI of the B200-native 3D-R2N2 hot path (libr2n2_b200.so).
+ *
+ * The reference (chrischoy/3D-R2N2) has no FFI: its layers call Theano ops inline.  Each
+ * entry point below therefore replaces one Theano call site of lib/layers.py /
+ * lib/solver.py / lib/voxel.py (cited per function, paths relative to the reference root);
+ * the Python mirror of the reference's layer API (3d-r2n2_b200/lib/layers.py) binds them
+ * through ctypes exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless stated.
+ *   - the library never allocates, frees or retains caller memory; all work is enqueued on
+ *     the caller's stream (cudaStream_t passed as void*); no implicit synchronisation.
+ *   - every function returns 0 on success or a negative R2N2_ERR_* code; the message is
+ *     available from r2n2_last_error() (thread-local).
+ *   - activations are CHANNELS-LAST: 2-D tensors [N,H,W,C], 3-D tensors [B,D,H,W,C]
+ *     (a 2-D tensor is the D==1 case).  The Python layer exposes them with the reference's
+ *     logical shapes ((N,C,H,W) / (B,D,C,H,W)) as stride-permuted views.
+ *   - dtype codes: R2N2_F32 = 0, R2N2_BF16 = 1.
+ *   - convolution weights are PACKED: w[Cout][kd][kh][kw][Cin], already flipped so that the
+ *     kernel computes a correlation  y[p,co] = sum_{tap,ci} x[p+tap-centre,ci] * w[co,tap,ci]
+ *     (Theano's conv2d / conv3d2d.conv3d are true convolutions; the flip happens once, at
+ *     Weight.set_value time, see 3d-r2n2_b200/lib/layers.py:pack_*).
+ */
+#ifndef R2N2_B200_H
+#define R2N2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2N2_F32 0
+#define R2N2_BF16 1
+
+#define R2N2_OK 0
+#define R2N2_ERR_BAD_SHAPE (-1)
+#define R2N2_ERR_BAD_DTYPE (-2)
+#define R2N2_ERR_BAD_ALIGN (-3)
+#define R2N2_ERR_WORKSPACE (-4)
+#define R2N2_ERR_CUDA (-5)
+#define R2N2_ERR_UNSUPPORTED (-6)
+
+/* conv epilogue flags: v = acc; BIAS: v += bias[co]; LRELU: v = v>0?v:0.01v;
+ * RESIDUAL: v += residual[p,co]; MASK: v *= (mask_src[p,co] > 0 ? 1 : 0.01)   (in that order) */
+#define R2N2_EPI_BIAS 1
+#define R2N2_EPI_LRELU 2
+#define R2N2_EPI_RESIDUAL 4
+#define R2N2_EPI_MASK 8
+
+/* conv algorithms */
+#define R2N2_ALGO_SIMT 0  /* fp32 FFMA implicit GEMM: the exact-fp32 parity path            */
+#define R2N2_ALGO_UMMA 1  /* tcgen05 + TMA implicit GEMM, bf16 operands, fp32 TMEM accumulate */
+
+const char* r2n2_version(void);
+const char* r2n2_last_error(void);
+
+/* ---- dense contractions -------------------------------------------------------------
+ * r2n2_conv_fwd: 'same' stride-1 N-d convolution as an implicit GEMM (M = N*D*H*W pixels,
+ * N = Cout, K = kd*kh*kw*Cin).  Replaces tensor.nnet.conv2d (lib/layers.py:322-333),
+ * conv3d2d.conv3d (lib/layers.py:441-442, 504) and, with D=H=W=1, k=1, tensor.dot
+ * (lib/layers.py:159-161, 502-503).  The same entry point computes data gradients when
+ * given the transposed/flipped weights from r2n2_weight_transpose (tensor.grad,
+ * models/net.py:58).  mask_src / residual / y have dtype out_dtype; x / w have in_dtype. */
+int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* mask_src,
+                  const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                  int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
+                  void* stream);
+
+/* r2n2_conv_wgrad: dw[co][tap][ci] (+)= sum_p dy[p,co] * x[p+tap-centre,ci]  (fp32 output in
+ * packed layout).  tensor.grad of the call sites above w.r.t. W / Wh / Wx. */
+int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
+                    int Cout, int kd, int kh, int kw, int dtype, int algo, int accumulate,
+                    void* stream);
+
+/* r2n2_bias_grad: db[c] (+)= sum_rows dy[row,c].  Gradient of the `+ b.dimshuffle(...)`
+ * terms (lib/layers.py:161,333,442,505). */
+int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, int accumulate,
+                   void* stream);
+
+/* w[Cout][taps][Cin] (fp32 master) -> wt[Cin][taps reversed][Cout] in out_dtype: the operand
+ * r2n2_conv_fwd needs to compute the data gradient. */
+int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin, int out_dtype,
+                          void* stream);
+
+/* fp32 -> out_dtype copy (bf16 operand mirrors of the fp32 master weights). */
+int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream);
+
+/* ---- bandwidth-bound kernels ----------------------------------------------------------
+ * input images: x (N,C,H,W) fp32 as delivered by lib/data_process.py:133-148 -> channels-last
+ * [N,H,Wpad,Cpad] in out_dtype; pixels are written at column offset xoff, everything else is
+ * zero (Wpad=W, xoff=0 for the plain case). */
+int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, int Wpad,
+                      int xoff, int out_dtype, void* stream);
+
+/* PoolLayer (lib/layers.py:349-353): 2x2/2 max pool, pad 1 (-inf), floor.  If b != NULL the
+ * pooled tensor is a+b (the AddLayer that precedes the pool in models/res_gru_net.py:92-93). */
+int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int dtype,
+                       void* stream);
+/* gradient to every maximal element of each (non-overlapping) window, as Theano does;
+ * lrelu_mask: additionally multiply by LeakyReLU'(a) (a is then a LeakyReLU output). */
+int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
+                       int C, int lrelu_mask, int dtype, void* stream);
+
+/* Unpool3DLayer (lib/layers.py:375-385): y[B,2D,2H,2W,C], value at the even corner, zeros
+ * elsewhere; input is a+b if b != NULL (AddLayer res7/res8, models/res_gru_net.py:171-178). */
+int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,
+                      int dtype, void* stream);
+int r2n2_unpool3d_bwd(const void* dy, void* dx, int B, int D, int H, int W, int C, int dtype,
+                      void* stream);
+
+/* AddLayer (lib/layers.py:214) and LeakyReLU backward (lib/layers.py:641-643):
+ * y = a + b ;  dx = dy * (a > 0 ? 1 : 0.01) (+ addend if not NULL). */
+int r2n2_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream);
+int r2n2_lrelu_fwd(const void* x, void* y, long long n, int dtype, void* stream);
+int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, long long n,
+                   int dtype, void* stream);
+
+/* SigmoidLayer / TanhLayer / ComplementLayer (1-x) / EltwiseMultiplyLayer (a*b) as standalone
+ * kernels (lib/layers.py:649-676, 217-225) for the layer-by-layer API; the fused GRU kernels
+ * below are what the networks use. */
+#define R2N2_ELT_SIGMOID 0
+#define R2N2_ELT_TANH 1
+#define R2N2_ELT_COMPLEMENT 2
+#define R2N2_ELT_MUL 3
+int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int dtype,
+                 void* stream);
+
+/* 3-D conv GRU gate math (models/res_gru_net.py:130-151; lib/layers.py:217-225,649-676).
+ * Hidden grid h: [B,64,128] (= (B,4,4,4,128) channels-last).
+ *   ur_fwd : u = sigmoid(conv_ur[...,0:128] + xp_ur[...,0:128] + b[0:128]),
+ *            r = sigmoid(conv_ur[...,128:256] + xp_ur[...,128:256] + b[128:256]), rh = r*h
+ *            (conv_ur may be NULL: first step, h == 0)
+ *   out_fwd: c = tanh(conv_c + xp_c + b_c);  h_new = u*h + (1-u)*c
+ *   out_bwd: da_c = dh*(1-u)*(1-c^2); da_u = dh*(h-c)*u*(1-u) -> da_ur[...,0:128];
+ *            dh_prev = dh*u
+ *   r_bwd  : da_r = d_rh*h*r*(1-r) -> da_ur[...,128:256];  dh_prev += d_rh*r            */
+int r2n2_gru_gates_ur_fwd(const void* conv_ur, const void* xp_ur, const float* bias_ur,
+                          const void* h, void* u, void* r, void* rh, int B, int dtype,
+                          void* stream);
+int r2n2_gru_gates_out_fwd(const void* conv_c, const void* xp_c, const float* bias_c, const void* u,
+                           const void* h, void* c, void* h_new, int B, int dtype, void* stream);
+int r2n2_gru_gates_out_bwd(const void* dh, const void* u, const void* c, const void* h, void* da_ur,
+                           void* da_c, void* dh_prev, int B, int dtype, void* stream);
+int r2n2_gru_gates_r_bwd(const void* d_rh, const void* h, const void* r, void* da_ur,
+                         void* dh_prev, int B, int dtype, void* stream);
+
+/* 3-D conv LSTM variant (no reference code: lib/layers.py:508-575 is a stub; built from
+ * imgs/lstm.png / README.md:36-38): gates a = conv + xp + b laid out [B,64,384] = (f,i,g):
+ *   f = sigmoid(a_f), i = sigmoid(a_i), g = tanh(a_g); s_new = f*s + i*g; h_new = tanh(s_new)
+ *   bwd: ds_tot = dh*(1-h_new^2) + ds_in; da_f = ds_tot*s*f(1-f); da_i = ds_tot*g*i(1-i);
+ *        da_g = ds_tot*i*(1-g^2); ds_prev = ds_tot*f                                      */
+int r2n2_lstm_gates_fwd(const void* conv_fig, const void* xp_fig, const float* bias_fig,
+                        const void* s, void* fig, void* s_new, void* h_new, int B, int dtype,
+                        void* stream);
+int r2n2_lstm_gates_bwd(const void* dh, const void* ds_in, const void* fig, const void* s,
+                        const void* h_new, void* da_fig, void* ds_prev, int B, int dtype,
+                        void* stream);
+
+/* SoftmaxWithLoss3D (lib/layers.py:583-601), fused forward(+backward):
+ *   logits  [B,nv,nv,nv,2] fp32 channels-last (conv11 output)
+ *   y       (B,nv,2,nv,nv) fp32 reference layout, may be NULL (lib/solver.py:222-226 feeds 0)
+ *   pred    (B,nv,2,nv,nv) fp32 reference layout, may be NULL  = exp(x)/sum_c exp(x)
+ *   loss_sum: 1 float, ACCUMULATES sum_vox(-sum_c y_c x_c + log sum_c exp x_c), may be NULL
+ *   dlogits [B,nv,nv,nv,2] in ddtype, may be NULL                = (p - y) * grad_scale   */
+int r2n2_softmax_ce3d(const float* logits, const float* y, float* pred, float* loss_sum,
+                      void* dlogits, int B, int nv, float grad_scale, int ddtype, void* stream);
+
+/* ADAM (lib/solver.py:20-48) over one flat fp32 buffer; the first n_decay elements are
+ * non-bias parameters (L2 term g += wd*p), the rest biases.  g is multiplied by grad_scale
+ * first (1/world after the NCCL sum).  p_mirror (may be NULL) receives p in mirror_dtype. */
+int r2n2_adam(float* p, const float* g, float* m, float* v, void* p_mirror, long long n,
+              long long n_decay, float lr_t, float beta1, float beta2, float eps, float wd,
+              float grad_scale, int mirror_dtype, void* stream);
+/* SGD with momentum (lib/solver.py:51-71) */
+int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, long long n_decay,
+             float lr, float momentum, float wd, float grad_scale, int mirror_dtype, void* stream);
+
+/* evaluate_voxel_prediction (lib/voxel.py:4-11): pred, gt (B,nv,2,nv,nv) fp32; counts[B][5] =
+ * {xor, intersection, union, false-pos, false-neg} at pred[:,:,1] >= thresh (int64, zeroed here) */
+int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long* counts, int B,
+                    int nv, void* stream);
+
+/* [rows][cols] element-type transpose-free helpers used by the host mirror */
+int r2n2_fill_zero(void* p, long long bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2N2_B200_H */

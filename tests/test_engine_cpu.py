@@ -1,0 +1,111 @@
+"""Host-logic tests (no GPU): the engine's scheduling -- hoisted encoder, fused gate groups,
+tape / gradient accumulation / LeakyReLU'-mask fusion, packed parameter layouts, Adam over the
+flat store -- executed with the C-ABI calls routed to tests/emu.py (a torch-CPU emulation of
+the documented kernel semantics) and compared with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import r2n2_b200  # noqa: F401
+from r2n2_b200 import ops, packing as pk
+from r2n2_b200.engine import Engine
+from oracle import ref_torch as rt
+import emu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.mark.parametrize('net_name,T', [('GRUNet', 2), ('ResidualGRUNet', 2), ('ResidualLSTMNet', 2),
+                                        ('GRUNet', 1)])
+def test_engine_forward_backward_matches_oracle(monkeypatch, net_name, T):
+    emu.install(monkeypatch, ops)
+    B = 1
+    params = rt.init_params(net_name, seed=0)
+    x, y = rt.synthetic_batch(T, B)
+    eng = Engine(net_name, B, device='cpu', compute='fp32', conv_algo=0, params_only=True)
+    eng.set_params(params)
+    # parameter round trip through the packed store
+    for a, b in zip(eng.get_params(), params):
+        assert np.array_equal(a, b)
+    out = eng.forward(torch.as_tensor(x), torch.as_tensor(y), training=True)
+    eng.backward()
+    grads = eng.get_grads()
+
+    ref = rt.RefNet(net_name, params, dtype=torch.float64)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    assert np.abs(out['pred'].numpy() - rout['pred'].detach().numpy()).max() < 1e-5
+    assert abs(float(out['loss']) - float(rout['loss'])) < 1e-5
+    assert np.abs(out['update_gates'].numpy() - rout['update_gates'].detach().numpy()).max() < 1e-5
+    for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
+        assert g.shape == tuple(rg.shape), name
+        assert _rel(g, rg.numpy()) < 2e-4, (name, _rel(g, rg.numpy()))
+
+
+def test_solver_adam_steps_match_oracle(monkeypatch):
+    """3 Adam steps through Solver (lib/solver.py:20-48,102-109 semantics)."""
+    emu.install(monkeypatch, ops)
+    from r2n2_b200.lib.solver import Solver
+    B, T = 1, 1
+    params = rt.init_params('GRUNet', seed=1)
+    x, y = rt.synthetic_batch(T, B)
+
+    class FakeNet:
+        compute_grad = True
+        is_x_tensor4 = False
+
+        def __init__(self):
+            self.engine = Engine('GRUNet', B, device='cpu', compute='fp32', conv_algo=0, params_only=True)
+            self.engine.set_params(params)
+
+        def forward_backward(self, xx, yy):
+            out = self.engine.forward(torch.as_tensor(xx), torch.as_tensor(yy), training=True, want_pred=False)
+            self.engine.backward()
+            return out
+
+    net = FakeNet()
+    s = Solver(net)
+    s.set_lr(1e-3)
+    ref = rt.RefNet('GRUNet', params, dtype=torch.float64)
+    radam = rt.RefAdam(ref, lr=1e-3)
+    for it in range(3):
+        l = s.train_loss(x, y)
+        rl, _ = radam.step(x, y)
+        assert abs(l - rl) < 1e-5 * max(1, abs(rl)), (it, l, rl)
+    assert float(s.iteration) == 3.0
+    for (name, _, _), a, b in zip(ref.spec, net.engine.get_params(), ref.P):
+        # Adam's update is ~lr*sign(g) for the first steps: elements whose gradient is at the
+        # fp32 noise floor may differ by O(lr); everything else must agree tightly.
+        d = np.abs(a - b.detach().numpy())
+        assert d.max() < 3 * 1e-3 and np.quantile(d, 0.99) < 2e-5 and d.mean() < 2e-6, (name, d.max())
+
+
+def test_packing_round_trips():
+    r = np.random.RandomState(0)
+    w2 = torch.tensor(r.randn(5, 3, 7, 7), dtype=torch.float32)
+    assert torch.equal(pk.unpack_conv2d(pk.pack_conv2d(w2, 4), 3), w2)
+    assert pk.pack_conv2d(w2, 4)[..., 3].abs().sum() == 0
+    w3 = torch.tensor(r.randn(4, 3, 6, 3, 3), dtype=torch.float32)
+    assert torch.equal(pk.unpack_conv3d(pk.pack_conv3d(w3)), w3)
+    wf = torch.tensor(r.randn(2 * 3 * 3, 7), dtype=torch.float32)
+    assert torch.equal(pk.unpack_fc(pk.pack_fc(wf, (2, 3, 3)), (2, 3, 3)), wf)
+    wx = torch.tensor(r.randn(6, 2 * 5 * 2 * 2), dtype=torch.float32)
+    assert torch.equal(pk.unpack_fcconv_wx(pk.pack_fcconv_wx(wx, 2, 5, 2, 2), 2, 5, 2, 2), wx)
+
+
+def test_store_layout_and_reference_order():
+    import json, os
+    s = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_structure.json')))
+    for name in ('GRUNet', 'ResidualGRUNet'):
+        eng = Engine(name, 2, device='cpu', params_only=True)
+        ref = s['nets'][name]['params']
+        assert len(eng.weights) == len(ref)
+        for w, rp in zip(eng.weights, ref):
+            assert list(w.ref_shape) == rp['shape'] and w.is_bias == rp['is_bias'], w.name
+        st = eng.store
+        # non-bias segments first, then biases; 64-element aligned; decay boundary between them
+        for nm, (off, n) in st.offsets.items():
+            assert off % 64 == 0
+            assert (off < st.n_decay) == (not nm.endswith(('.b',)) and '.b_' not in nm), nm
