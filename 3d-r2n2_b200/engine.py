@@ -135,6 +135,8 @@ class Engine:
         self._define()
         self.ctx = None
         self.last = None
+        self.progress = None       # callback(stage) fired when a backward stage's grads are final
+        self._marks = (0, 0)
 
     # ------------------------------------------------------------------ parameter definition
     def _define(self):
@@ -471,6 +473,7 @@ class Engine:
         xin = ctx.empty(TB * self.img * self.img * self.cin_pad, x)
         ops.nchw_to_nhwc(x.view(TB, 3, self.img, self.img), xin, self.cin_pad)
         a = Act(xin, (TB, 1, self.img, self.img, self.cin_pad))
+        a.useful = 3.0 / self.cin_pad          # RGB padded with zero channels
 
         def c2(name, inp, lrelu, residual=None):
             k = 7 if name in ('conv1a', 'conv1') else (1 if name.endswith('c') else 3)
@@ -495,12 +498,16 @@ class Engine:
             pool6 = t_
         flat = ctx.reshape(pool6, (TB, 1, 1, 1, N_CONVFILTER[5] * 9))
         f = ctx.conv(flat, P['fc7.W'], P['fc7.b'], (1, 1, 1), True)
+        mark_enc = len(ctx.tape)
 
         # ---- recurrence ---------------------------------------------------------------------
         if self.lstm:
             h, gates = self.lstm_sequence(ctx, f, T, B)
         else:
             h, gates = self.gru_sequence(ctx, f, T, B)
+
+        mark_rnn = len(ctx.tape)
+        self._marks = (mark_enc, mark_rnn)
 
         # ---- decoder ------------------------------------------------------------------------
         if self.residual:
@@ -544,8 +551,40 @@ class Engine:
         ctx = self.ctx
         if ctx is None or not ctx.training:
             raise RuntimeError('backward() needs a preceding forward(training=True)')
-        ctx.backward()
-        for p in self.P.values():
+        mark_enc, mark_rnn = self._marks
+        tape = ctx.tape
+        for i in range(len(tape) - 1, -1, -1):
+            tape[i]()
+            if i == mark_rnn:
+                self._finalize_stage('decoder')
+            if i == mark_enc:
+                self._finalize_stage('rnn')
+        ctx.tape = []
+        self._finalize_stage('encoder')
+        self.ctx = None
+
+    def stage_segments(self):
+        """Non-bias store segments per backward stage, in the order their gradients become final."""
+        dec, rnn, enc = [], [], []
+        for name in self.P:
+            if name.endswith('.b') or '.b_' in name:
+                continue
+            if name.startswith('rnn.'):
+                rnn.append(name)
+            elif name.startswith('conv') and int(''.join(ch for ch in name.split('.')[0][4:] if ch.isdigit())) >= 7:
+                dec.append(name)
+            else:
+                enc.append(name)
+        return {'decoder': dec, 'rnn': rnn, 'encoder': enc}
+
+    def _finalize_stage(self, stage):
+        names = self.stage_segments()[stage]
+        if stage == 'encoder':      # biases ride with the last stage
+            names = names + [n for n in self.P if n.endswith('.b') or '.b_' in n]
+        for n in names:
+            p = self.P[n]
             if not p.grad_written:
                 p.grad.zero_()
-        self.ctx = None
+                p.grad_written = True
+        if self.progress is not None:
+            self.progress(stage)

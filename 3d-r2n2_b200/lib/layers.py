@@ -23,6 +23,7 @@ from ..ops import Act, Param, Ctx
 trainable_params = []          # lib/layers.py:10 (module-global, never cleared: quirk 13)
 _rng = np.random.RandomState()  # lib/layers.py:31 uses an unseeded RandomState per Weight
 _ctx = None
+DEVICE = 'cuda'              # the kernels only run on CUDA; tests of the host logic override it
 
 
 def get_trainable_params():
@@ -125,7 +126,7 @@ class Weight(object):
     def param(self, ctx):
         if self._param is not None and self._param_dtype == ctx.dtype:
             return self._param
-        t = torch.as_tensor(self.np_values).cuda()
+        t = torch.as_tensor(self.np_values).to(DEVICE)
         kind = self._kind
         if kind is None or kind[0] == 'bias':
             p, cout, taps, cin = t.contiguous(), t.numel(), 1, 1
@@ -168,7 +169,7 @@ def _as_act(t, shape, ctx):
         t = torch.as_tensor(t)
     if not isinstance(t, torch.Tensor):
         raise ValueError('InputLayer needs a numpy array or torch tensor, got %r' % type(t))
-    t = t.cuda()
+    t = t.to(DEVICE)
     if tuple(t.shape) != tuple(shape):
         raise ValueError('InputLayer: tensor shape %s does not match declared shape %s'
                          % (tuple(t.shape), tuple(shape)))

@@ -23,7 +23,7 @@ def run(net, x, y, residual):
     ctx = Ctx(net.engine.dtype, net.engine.algo, training=False)
     ly.set_context(ctx)
     n0 = len(ly.trainable_params)
-    x = torch.as_tensor(np.asarray(x, dtype=np.float32)).cuda()
+    x = torch.as_tensor(np.asarray(x, dtype=np.float32)).to(ly.DEVICE)
     batch_size, img_w, img_h = net.batch_size, net.img_w, net.img_h
     n_gru_vox = 4
     n_convfilter = [96, 128, 256, 256, 256, 256]

@@ -23,10 +23,60 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class Profiler:
+    """Optional per-launch CUDA-event timing of every C-ABI call (bench.py's roofline pass).
+    Events are recorded on the launching (current) stream; resolve() after a synchronize."""
+
+    def __init__(self):
+        self.records = []       # (name, tag, work, start_event, end_event)
+
+    def resolve(self):
+        """-> {name: dict(ms, calls, flops, bytes)} plus the raw per-launch list."""
+        table, raw = {}, []
+        for name, tag, work, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            d = table.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+            d['ms'] += ms
+            d['calls'] += 1
+            d['flops'] += work.get('flops', 0.0)
+            d['bytes'] += work.get('bytes', 0.0)
+            raw.append((name, tag, ms, work))
+        return table, raw
+
+
+profiler = None          # set to a Profiler() to time every launch
+_next_work = None        # work description (flops / bytes) attached by the wrapper about to launch
+_next_tag = ''
+
+
 def _call(name, *args):
-    global launch_count
+    global launch_count, _next_work, _next_tag
     launch_count += 1
+    if profiler is None:
+        L.call(name, *args)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     L.call(name, *args)
+    e1.record()
+    profiler.records.append((name, _next_tag, _next_work or {}, e0, e1))
+    _next_work, _next_tag = None, ''
+
+
+def _work(flops=0.0, tensors=()):
+    """Describe the launch that follows: algorithmic flops and bytes (sum of operand sizes)."""
+    global _next_work
+    if profiler is not None:
+        nbytes = 0
+        for t in tensors:
+            if t is not None:
+                nbytes += t.numel() * t.element_size()
+        _next_work = dict(flops=float(flops), bytes=float(nbytes))
+
+
+useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
+                         # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
 
 
 def _check(t, dtype=None):
@@ -50,6 +100,10 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     assert w.numel() == cout * k[0] * k[1] * k[2] * Cin, (w.shape, cout, k, Cin)
     assert y.numel() == N * D * H * W * cout
     assert w.dtype == x.dtype
+    global _next_tag
+    _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2] * useful_frac,
+          (x, w, bias, mask_src, residual, y))
+    _next_tag = 'M%dxN%dxK%d' % (N * D * H * W, cout, k[0] * k[1] * k[2] * Cin)
     _call('r2n2_conv_fwd', _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(residual), _ptr(y),
           N, D, H, W, Cin, cout, k[0], k[1], k[2], flags, _DT[x.dtype], _DT[y.dtype], algo,
           _stream())
@@ -63,23 +117,29 @@ def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate):
     assert dw.dtype == torch.float32 and x.dtype == dy.dtype
     assert x.numel() == N * D * H * W * Cin and dy.numel() == N * D * H * W * cout
     assert dw.numel() == cout * k[0] * k[1] * k[2] * Cin
+    global _next_tag
+    _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2] * useful_frac, (x, dy, dw))
+    _next_tag = 'M%dxN%dxK%d' % (cout, k[0] * k[1] * k[2] * Cin, N * D * H * W)
     _call('r2n2_conv_wgrad', _ptr(x), _ptr(dy), _ptr(dw), N, D, H, W, Cin, cout, k[0], k[1], k[2],
           _DT[x.dtype], algo, 1 if accumulate else 0, _stream())
 
 
 def bias_grad(dy, db, C, accumulate):
     _check(dy), _check(db, torch.float32)
+    _work(0.0, (dy,))
     _call('r2n2_bias_grad', _ptr(dy), _ptr(db), dy.numel() // C, C, _DT[dy.dtype],
           1 if accumulate else 0, _stream())
 
 
 def weight_transpose(w, wt, cout, taps, cin):
     _check(w, torch.float32), _check(wt)
+    _work(0.0, (w, wt))
     _call('r2n2_weight_transpose', _ptr(w), _ptr(wt), cout, taps, cin, _DT[wt.dtype], _stream())
 
 
 def cast(src, dst):
     _check(src, torch.float32), _check(dst)
+    _work(0.0, (src, dst))
     _call('r2n2_cast', _ptr(src), _ptr(dst), src.numel(), _DT[dst.dtype], _stream())
 
 
@@ -95,28 +155,33 @@ def nchw_to_nhwc(x, y, cpad, wpad=None, xoff=0):
 
 def maxpool_fwd(a, b, y, N, H, W, C):
     _check(a), _check(b), _check(y)
+    _work(0.0, (a, b, y))
     _call('r2n2_maxpool2d_fwd', _ptr(a), _ptr(b), _ptr(y), N, H, W, C, _DT[a.dtype], _stream())
 
 
 def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask):
     for t in (a, b, dy, dx):
         _check(t)
+    _work(0.0, (a, b, dy, dx))
     _call('r2n2_maxpool2d_bwd', _ptr(a), _ptr(b), _ptr(dy), _ptr(dx), N, H, W, C,
           1 if lrelu_mask else 0, _DT[a.dtype], _stream())
 
 
 def unpool_fwd(a, b, y, B, D, H, W, C):
     _check(a), _check(b), _check(y)
+    _work(0.0, (a, b, y))
     _call('r2n2_unpool3d_fwd', _ptr(a), _ptr(b), _ptr(y), B, D, H, W, C, _DT[a.dtype], _stream())
 
 
 def unpool_bwd(dy, dx, B, D, H, W, C):
     _check(dy), _check(dx)
+    _work(0.0, (dy, dx))
     _call('r2n2_unpool3d_bwd', _ptr(dy), _ptr(dx), B, D, H, W, C, _DT[dy.dtype], _stream())
 
 
 def add(a, b, y):
     _check(a), _check(b), _check(y)
+    _work(0.0, (a, b, y))
     _call('r2n2_add', _ptr(a), _ptr(b), _ptr(y), a.numel(), _DT[a.dtype], _stream())
 
 
@@ -128,6 +193,7 @@ def lrelu_fwd(x, y):
 def lrelu_bwd(a, dy, addend, dx):
     for t in (a, dy, addend, dx):
         _check(t)
+    _work(0.0, (a, dy, addend, dx))
     _call('r2n2_lrelu_bwd', _ptr(a), _ptr(dy), _ptr(addend), _ptr(dx), a.numel(), _DT[a.dtype],
           _stream())
 
@@ -138,31 +204,37 @@ def eltwise(op, a, b, y):
 
 
 def gru_ur_fwd(conv_ur, xp_ur, bias_ur, h, u, r, rh, B):
+    _work(0.0, (conv_ur, xp_ur, h, u, r, rh))
     _call('r2n2_gru_gates_ur_fwd', _ptr(conv_ur), _ptr(xp_ur), _ptr(bias_ur), _ptr(h), _ptr(u),
           _ptr(r), _ptr(rh), B, _DT[xp_ur.dtype], _stream())
 
 
 def gru_out_fwd(conv_c, xp_c, bias_c, u, h, c, h_new, B):
+    _work(0.0, (conv_c, xp_c, u, h, c, h_new))
     _call('r2n2_gru_gates_out_fwd', _ptr(conv_c), _ptr(xp_c), _ptr(bias_c), _ptr(u), _ptr(h),
           _ptr(c), _ptr(h_new), B, _DT[xp_c.dtype], _stream())
 
 
 def gru_out_bwd(dh, u, c, h, da_ur, da_c, dh_prev, B):
+    _work(0.0, (dh, u, c, h, da_c, dh_prev, dh_prev))
     _call('r2n2_gru_gates_out_bwd', _ptr(dh), _ptr(u), _ptr(c), _ptr(h), _ptr(da_ur), _ptr(da_c),
           _ptr(dh_prev), B, _DT[dh.dtype], _stream())
 
 
 def gru_r_bwd(d_rh, h, r, da_ur, dh_prev, B):
+    _work(0.0, (d_rh, h, r, dh_prev, dh_prev, d_rh))
     _call('r2n2_gru_gates_r_bwd', _ptr(d_rh), _ptr(h), _ptr(r), _ptr(da_ur), _ptr(dh_prev), B,
           _DT[d_rh.dtype], _stream())
 
 
 def lstm_fwd(conv, xp, bias, s, fig, s_new, h_new, B):
+    _work(0.0, (conv, xp, s, fig, s_new, h_new))
     _call('r2n2_lstm_gates_fwd', _ptr(conv), _ptr(xp), _ptr(bias), _ptr(s), _ptr(fig), _ptr(s_new),
           _ptr(h_new), B, _DT[xp.dtype], _stream())
 
 
 def lstm_bwd(dh, ds_in, fig, s, h_new, da, ds_prev, B):
+    _work(0.0, (dh, ds_in, fig, s, h_new, da, ds_prev))
     _call('r2n2_lstm_gates_bwd', _ptr(dh), _ptr(ds_in), _ptr(fig), _ptr(s), _ptr(h_new), _ptr(da),
           _ptr(ds_prev), B, _DT[dh.dtype], _stream())
 
@@ -171,6 +243,7 @@ def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale):
     _check(logits, torch.float32), _check(y, torch.float32), _check(pred, torch.float32)
     _check(loss_sum, torch.float32), _check(dlogits)
     dd = _DT[dlogits.dtype] if dlogits is not None else L.F32
+    _work(0.0, (logits, y, pred, dlogits))
     _call('r2n2_softmax_ce3d', _ptr(logits), _ptr(y), _ptr(pred), _ptr(loss_sum), _ptr(dlogits), B,
           nv, float(grad_scale), dd, _stream())
 
@@ -179,6 +252,7 @@ def adam(p, g, m, v, mirror, n_decay, lr_t, b1, b2, eps, wd, grad_scale):
     for t in (p, g, m, v):
         _check(t, torch.float32)
     _check(mirror)
+    _work(0.0, (p, g, m, v, p, m, v, mirror))
     _call('r2n2_adam', _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mirror), p.numel(), n_decay,
           float(lr_t), float(b1), float(b2), float(eps), float(wd), float(grad_scale),
           _DT[mirror.dtype] if mirror is not None else L.F32, _stream())
@@ -205,7 +279,7 @@ def voxel_eval(pred, gt, thresh):
 class Act:
     """An activation on the tape: channels-last data + gradient bookkeeping."""
     __slots__ = ('data', 'geom', 'grad', 'n_cons', 'n_recv', 'lrelu_out', 'grad_preact',
-                 'grad_shared', 'requires_grad')
+                 'grad_shared', 'requires_grad', 'useful')
 
     def __init__(self, data, geom, requires_grad=False, lrelu_out=False):
         self.data = data
@@ -217,6 +291,7 @@ class Act:
         self.grad_preact = False        # grad already multiplied by LeakyReLU'(z)
         self.grad_shared = False        # grad buffer aliased by another Act: no in-place edits
         self.requires_grad = requires_grad
+        self.useful = 1.0               # non-structural-zero fraction (1/8 after Unpool3D)
 
 
 class Param:
@@ -342,8 +417,11 @@ class Ctx:
         flags = (L.EPI_BIAS if b is not None else 0) | (L.EPI_LRELU if lrelu else 0)
         if residual is not None:
             flags |= L.EPI_RESIDUAL
+        global useful_frac
+        useful_frac = x.useful
         conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
                  None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
+        useful_frac = 1.0
         out = Act(y, (N, D, H, Wd, cout), requires_grad=self.training, lrelu_out=lrelu)
         if self.training:
             self.consume(x)
@@ -355,8 +433,11 @@ class Ctx:
                     return
                 self.ensure_preact(out)
                 dy = out.grad
+                global useful_frac
+                useful_frac = x.useful
                 self.weight_grads(x.data, dy, x.geom, W, b, k)
                 self.dgrad_into(x, dy, W, k)
+                useful_frac = 1.0
                 if residual is not None:
                     self.accumulate(residual, dy)   # hand the buffer over (we are done with it)
                 out.grad = None
@@ -405,6 +486,7 @@ class Ctx:
         y = self.empty(B * D * H * W * 8 * C, a.data)
         unpool_fwd(a.data, None if b is None else b.data, y, B, D, H, W, C)
         out = Act(y, (B, 2 * D, 2 * H, 2 * W, C), requires_grad=self.training)
+        out.useful = 0.125          # 7/8 structural zeros: only 1/8 of a conv's MACs are useful
         if self.training:
             self.consume(a)
             if b is not None:

@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the 3D-R2N2 hot path on B200 (contract: see the task description / DESIGN.md §5).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--compute bf16|fp32] [--batch 36] [--views 5] [--net ResidualGRUNet]
+
+Workload = BASELINE.json config[2], the configuration the headline metric is quoted on:
+ResidualGRUNet training (SoftmaxWithLoss3D + Adam), per-GPU batch 36, 5 views of 127x127 RGB ->
+32^3x2, synthetic ShapeNet-shaped data, random-init weights.  One "step" = forward + backward +
+(N>1: NCCL gradient all-reduce) + fused Adam over one batch.
+
+Printed JSON (rank 0, one line):
+  value   : samples/s, whole job, inputs resident in HBM (CUDA-event timed, max over ranks)
+  e2e     : same metric through Solver.train_loss with HOST (pinned) numpy inputs: H2D of x,y and
+            D2H of the loss inside the timed region
+  roofline: dominant kernel (implicit-GEMM conv fwd/dgrad), algorithmic (useful) FLOPs / CUDA-event
+            time of its launches, against MEASURED_PEAKS.json
+  cpu_baseline: the oracle's torch-CPU restatement of the reference graph timed on the host cores
+            on a bounded sample (kind "port": Theano itself cannot run)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'ResidualGRUNet train samples/sec (5 views, 32^3)'
+UNIT = 'samples/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--compute', default=os.environ.get('R2N2_BENCH_COMPUTE', 'auto'))
+    ap.add_argument('--net', default='ResidualGRUNet')
+    ap.add_argument('--batch', type=int, default=36)
+    ap.add_argument('--views', type=int, default=5)
+    ap.add_argument('--cpu-sample-batch', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-out', default=None, help='write the per-kernel event table here')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get('bf16_tflops_sustained', d.get('bf16_tflops')), hbm=d.get('hbm_gbs'),
+                    src='measured (MEASURED_PEAKS.json, bf16 sustained)')
+    return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+def config_dict(args, extra=None):
+    c = {'workload': '%s training step (fwd+bwd+Adam), per-GPU batch %d, %d views 127x127 RGB -> 32^3x2'
+                     % (args.net, args.batch, args.views),
+         'net': args.net, 'per_gpu_batch': args.batch, 'views': args.views,
+         'global_batch': args.batch * args.gpus, 'parallelism': 'dp%d' % args.gpus,
+         'l2': 'working set per step (activations, GBs) >> 126 MB L2; no explicit flush'}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------- CPU reference
+def cpu_reference_step(net_name, B, T, n_steps, warmup):
+    """Times training steps of the oracle's torch-CPU restatement of the reference graph
+    (oracle/ref_torch.py: per-view encoder inside the loop, dense convs on zero-stuffed tensors)."""
+    import torch
+    from oracle import ref_torch as rt
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = rt.init_params(net_name, seed=0)
+    x, y = rt.synthetic_batch(T, B)
+    net = rt.RefNet(net_name, params)
+    adam = rt.RefAdam(net, lr=1e-4)
+    times = []
+    for i in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        adam.step(x, y)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    B = args.cpu_sample_batch
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    times, cores = cpu_reference_step(args.net, B, args.views, steps, warm)
+    ms = 1e3 * sum(times) / len(times)
+    val = B / (ms / 1e3)
+    sample = ('oracle torch-CPU fp32 restatement of the reference graph, %d training steps at batch %d '
+              '(same net/views, batch reduced from %d to bound the CPU time)' % (steps, B, args.batch))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config_dict(args, {'cpu_sample_batch': B}),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.p = None
+        self.idx = gpu_index
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '200'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import r2n2_b200  # noqa: F401
+    from r2n2_b200 import ops, _lib
+    from r2n2_b200.lib.config import cfg
+    from r2n2_b200.lib.solver import Solver
+    from r2n2_b200.models import load_model
+    from r2n2_b200 import dist as r2dist
+    from oracle import ref_torch as rt      # synthetic-input generator + CPU baseline only
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    _lib.load()
+
+    compute = args.compute
+    if compute == 'auto':
+        compute = os.environ.get('R2N2_COMPUTE', 'bf16')
+    B, T = args.batch, args.views
+    cfg.CONST.BATCH_SIZE = B
+    cfg.CONST.COMPUTE = compute
+    net = load_model(args.net)(random_seed=0)
+    solver = Solver(net)
+    solver.set_lr(cfg.TRAIN.DEFAULT_LEARNING_RATE)
+    if world > 1:
+        r2dist.broadcast_params(net.engine)
+        r2dist.attach(solver)
+
+    # synthetic ShapeNet-shaped batch (different per rank), pinned host copies for the e2e leg
+    x_np, y_np = rt.synthetic_batch(T, B, seed_x=1234 + rank, seed_y=4321 + rank)
+    x_pin = torch.as_tensor(x_np).pin_memory()
+    y_pin = torch.as_tensor(y_np).pin_memory()
+    x_dev, y_dev = x_pin.cuda(), y_pin.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count - l0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms], device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, clocks
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    losses = []
+
+    def step_dev():
+        losses.append(solver.train_step_device(x_dev, y_dev))
+    ms_total, launches, clocks = timed(step_dev, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+    final_loss = float(losses[-1])
+
+    # ---- e2e: host buffers through the public API (Solver.train_loss) -----------------------
+    def step_e2e():
+        solver.train_loss(x_pin, y_pin)        # H2D x,y (pinned) ... D2H loss (float())
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e_total, _, _ = timed(step_e2e, e2e_steps, 1)
+    e2e_value = B * world / (ms_e2e_total / e2e_steps / 1e3)
+
+    # ---- roofline pass: CUDA events around every C-ABI launch of one more step (rank 0) ------
+    roofline, table_out = None, None
+    pk = peaks()
+    if rank == 0:
+        prof = ops.Profiler()
+        ops.profiler = prof
+        step_dev()
+        torch.cuda.synchronize()
+        ops.profiler = None
+        table, raw = prof.resolve()
+        tot_ms = sum(d['ms'] for d in table.values())
+        conv = table.get('r2n2_conv_fwd', dict(ms=0.0, flops=0.0, calls=0))
+        if conv['ms'] > 0:
+            ach = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
+            roofline = {'bound': 'tensor', 'kernel': 'r2n2_conv_fwd (implicit-GEMM conv/FC fwd + dgrad)',
+                        'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops'],
+                        'traffic': None, 'peak_source': pk['src'],
+                        'launches': conv['calls'], 'avg_launch_ms': conv['ms'] / max(1, conv['calls']),
+                        'share_of_step': conv['ms'] / tot_ms if tot_ms else None,
+                        'flops_counted': 'algorithmic (useful, zero-skipped unpool), summed over the launches'}
+        table_out = {k: dict(v, share=v['ms'] / tot_ms if tot_ms else 0.0,
+                             tflops=(v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['ms'] > 0 else 0.0,
+                             gbs=(v['bytes'] / (v['ms'] * 1e-3) / 1e9) if v['ms'] > 0 else 0.0)
+                     for k, v in sorted(table.items(), key=lambda kv: -kv[1]['ms'])}
+        if args.profile_out:
+            with open(args.profile_out, 'w') as f:
+                json.dump({'per_kernel': table_out, 'sum_ms': tot_ms,
+                           'launches': [(n, t, ms, w) for n, t, ms, w in raw]}, f, indent=1)
+
+    # ---- CPU baseline (rank 0, N=1 only, bounded sample) --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bc = args.cpu_sample_batch
+        times, cores = cpu_reference_step(args.net, Bc, T, 1, 1)
+        v = Bc / (sum(times) / len(times))
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': 'oracle torch-CPU fp32 restatement of the reference graph: 1 warm-up + 1 timed '
+                         'training step at batch %d, %d views (batch reduced from %d)' % (Bc, T, B)}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if compute == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': config_dict(args, {'compute': compute,
+                                             'conv_algo': 'tcgen05/TMA' if compute == 'bf16' else 'fp32 FFMA',
+                                             'final_loss': final_loss}),
+                'e2e': {'value': e2e_value, 'unit': UNIT,
+                        'h2d_bytes_per_step': int(x_pin.numel() * 4 + y_pin.numel() * 4),
+                        'd2h_bytes_per_step': 4, 'steps': e2e_steps},
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+                'per_kernel': {k: {'ms': round(v['ms'], 4), 'calls': v['calls'], 'share': round(v['share'], 4),
+                                   'tflops': round(v['tflops'], 2), 'gbs': round(v['gbs'], 1)}
+                               for k, v in (table_out or {}).items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,278 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (r2n2_b200.ops -> libr2n2_b200.so):
+each CUDA kernel against tests/emu.py (the torch-CPU statement of the header's semantics, itself
+checked against the oracle on CPU) on seeded inputs, including ragged / edge shapes."""
+import numpy as np
+import pytest
+import torch
+
+import r2n2_b200  # noqa: F401
+from r2n2_b200 import ops, _lib as L
+import emu
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _r(*shape, seed=0, scale=1.0):
+    return torch.tensor(np.random.RandomState(seed).randn(*shape) * scale, dtype=torch.float32)
+
+
+def _cmp(got, want, tol, what=''):
+    got, want = got.float().cpu(), want.float().cpu()
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item() + 1e-20
+    assert err <= tol * max(1.0, ref), '%s: max err %.3e (ref max %.3e)' % (what, err, ref)
+
+
+CONV_CASES = [
+    # N, D, H, W, Cin, Cout, k
+    (2, 1, 9, 7, 4, 96, (1, 7, 7)),       # conv1a-like: Cin padded RGB, 49 taps, ragged M
+    (3, 1, 17, 17, 96, 128, (1, 3, 3)),
+    (2, 1, 5, 5, 128, 256, (1, 1, 1)),    # 1x1 shortcut
+    (5, 1, 1, 1, 2304, 1024, (1, 1, 1)),  # fc7
+    (3, 4, 4, 4, 128, 256, (3, 3, 3)),    # GRU hidden conv (u,r fused)
+    (1, 8, 8, 8, 32, 2, (3, 3, 3)),       # conv11: Cout=2
+    (2, 6, 5, 7, 64, 64, (3, 3, 3)),      # ragged 3-D
+    (7, 1, 1, 1, 1024, 8192, (1, 1, 1)),  # x-projection slice
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('flags', [0, L.EPI_BIAS | L.EPI_LRELU, L.EPI_BIAS | L.EPI_RESIDUAL,
+                                   L.EPI_RESIDUAL | L.EPI_MASK])
+def test_conv_fwd_simt(case, flags):
+    N, D, H, W, Cin, Cout, k = case
+    taps = k[0] * k[1] * k[2]
+    P = N * D * H * W
+    x = _r(P * Cin, seed=1)
+    w = _r(Cout * taps * Cin, seed=2, scale=(2.0 / (taps * Cin)) ** 0.5)
+    b = _r(Cout, seed=3)
+    res = _r(P * Cout, seed=4)
+    mask = _r(P * Cout, seed=5)
+    want = torch.empty(P * Cout)
+    emu.conv_fwd(x, w, b, mask, res, want, (N, D, H, W, Cin), Cout, k, flags, 0)
+    y = torch.empty(P * Cout, device=DEV)
+    ops.conv_fwd(x.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV), res.to(DEV), y, (N, D, H, W, Cin),
+                 Cout, k, flags, L.ALGO_SIMT)
+    _cmp(y, want, 2e-5, 'conv_fwd simt %s flags %d' % (case, flags))
+
+
+def test_conv_fwd_in_place_residual():
+    """the backward accumulates with residual == y (same buffer)."""
+    N, D, H, W, Cin, Cout, k = 2, 1, 6, 6, 32, 32, (1, 3, 3)
+    x, w = _r(N * H * W * Cin, seed=1), _r(Cout * 9 * Cin, seed=2, scale=.1)
+    acc = _r(N * H * W * Cout, seed=3)
+    want = torch.empty_like(acc)
+    emu.conv_fwd(x, w, None, None, acc, want, (N, D, H, W, Cin), Cout, k, L.EPI_RESIDUAL, 0)
+    buf = acc.to(DEV)
+    ops.conv_fwd(x.to(DEV), w.to(DEV), None, None, buf, buf, (N, D, H, W, Cin), Cout, k,
+                 L.EPI_RESIDUAL, L.ALGO_SIMT)
+    _cmp(buf, want, 2e-5)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('accumulate', [False, True])
+def test_conv_wgrad_simt(case, accumulate):
+    N, D, H, W, Cin, Cout, k = case
+    taps = k[0] * k[1] * k[2]
+    P = N * D * H * W
+    x, dy = _r(P * Cin, seed=1), _r(P * Cout, seed=2)
+    dw0 = _r(Cout * taps * Cin, seed=3)
+    want = dw0.clone()
+    emu.conv_wgrad(x, dy, want, (N, D, H, W, Cin), Cout, k, 0, accumulate)
+    dw = dw0.to(DEV)
+    ops.conv_wgrad(x.to(DEV), dy.to(DEV), dw, (N, D, H, W, Cin), Cout, k, L.ALGO_SIMT, accumulate)
+    _cmp(dw, want, 5e-5, 'wgrad %s' % (case,))
+
+
+def test_dgrad_equals_autograd():
+    """conv_fwd with r2n2_weight_transpose'd weights is the data gradient."""
+    N, D, H, W, Cin, Cout, k = 2, 3, 4, 5, 8, 12, (3, 3, 3)
+    x = _r(N, D, H, W, Cin, seed=1).requires_grad_(True)
+    w = _r(Cout, 3, 3, 3, Cin, seed=2)
+    y = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(0, 4, 1, 2, 3), padding=1)
+    dy = _r(*y.shape, seed=3)
+    y.backward(dy)
+    wt = torch.empty(Cin * 27 * Cout, device=DEV)
+    ops.weight_transpose(w.reshape(-1).to(DEV), wt, Cout, 27, Cin)
+    dx = torch.empty(N * D * H * W * Cin, device=DEV)
+    dyl = dy.permute(0, 2, 3, 4, 1).contiguous().reshape(-1).to(DEV)
+    ops.conv_fwd(dyl, wt, None, None, None, dx, (N, D, H, W, Cout), Cin, k, 0, L.ALGO_SIMT)
+    _cmp(dx, x.grad.reshape(-1), 2e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_pool_unpool(dtype):
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    for (N, H, W, C) in [(2, 127, 127, 8), (3, 33, 33, 16), (2, 5, 5, 256), (1, 3, 3, 4), (1, 64, 64, 96)]:
+        a, b = _r(N * H * W * C, seed=1).to(dtype), _r(N * H * W * C, seed=2).to(dtype)
+        Ho, Wo = H // 2 + 1, W // 2 + 1
+        dy = _r(N * Ho * Wo * C, seed=3).to(dtype)
+        for bb in (None, b):
+            want, y = torch.empty(N * Ho * Wo * C, dtype=dtype), torch.empty(N * Ho * Wo * C, dtype=dtype, device=DEV)
+            emu.maxpool_fwd(a, bb, want, N, H, W, C)
+            ops.maxpool_fwd(a.to(DEV), None if bb is None else bb.to(DEV), y, N, H, W, C)
+            _cmp(y, want, tol, 'pool fwd')
+            for mask in (False, True):
+                wdx, dx = torch.empty_like(a), torch.empty_like(a, device=DEV)
+                emu.maxpool_bwd(a, bb, dy, wdx, N, H, W, C, mask)
+                ops.maxpool_bwd(a.to(DEV), None if bb is None else bb.to(DEV), dy.to(DEV), dx, N, H, W, C, mask)
+                _cmp(dx, wdx, tol, 'pool bwd')
+    for (B, D, H, W, C) in [(2, 4, 4, 4, 128), (1, 3, 5, 2, 8)]:
+        a, b = _r(B * D * H * W * C, seed=1).to(dtype), _r(B * D * H * W * C, seed=2).to(dtype)
+        for bb in (None, b):
+            want, y = torch.empty(a.numel() * 8, dtype=dtype), torch.empty(a.numel() * 8, dtype=dtype, device=DEV)
+            emu.unpool_fwd(a, bb, want, B, D, H, W, C)
+            ops.unpool_fwd(a.to(DEV), None if bb is None else bb.to(DEV), y, B, D, H, W, C)
+            _cmp(y, want, tol, 'unpool fwd')
+        dy = _r(a.numel() * 8, seed=5).to(dtype)
+        wdx, dx = torch.empty_like(a), torch.empty_like(a, device=DEV)
+        emu.unpool_bwd(dy, wdx, B, D, H, W, C)
+        ops.unpool_bwd(dy.to(DEV), dx, B, D, H, W, C)
+        _cmp(dx, wdx, 0.0 if dtype == torch.float32 else tol, 'unpool bwd')
+
+
+def test_pointwise_and_layout():
+    n = 4 * 1237
+    a, b = _r(n, seed=1), _r(n, seed=2)
+    for name, args in [('add', (a, b)), ('lrelu_fwd', (a,)), ('lrelu_bwd', (a, b, None)),
+                       ('lrelu_bwd', (a, b, a))]:
+        want, y = torch.empty(n), torch.empty(n, device=DEV)
+        getattr(emu, name)(*args, want)
+        getattr(ops, name)(*[None if t is None else t.to(DEV) for t in args], y)
+        _cmp(y, want, 1e-6, name)
+    for op in range(4):
+        want, y = torch.empty(n), torch.empty(n, device=DEV)
+        emu.eltwise(op, a, b, want)
+        ops.eltwise(op, a.to(DEV), b.to(DEV), y)
+        _cmp(y, want, 2e-6, 'eltwise %d' % op)
+    x = _r(3, 3, 11, 13, seed=4)
+    for cpad, wpad, xoff in [(4, None, 0), (16, None, 0), (8, 24, 3)]:
+        wp = wpad or 13
+        want, y = torch.empty(3 * 11 * wp * cpad), torch.empty(3 * 11 * wp * cpad, device=DEV)
+        emu.nchw_to_nhwc(x, want, cpad, wpad, xoff)
+        ops.nchw_to_nhwc(x.to(DEV), y, cpad, wpad, xoff)
+        _cmp(y, want, 0.0, 'nchw_to_nhwc')
+    w = _r(10, 27, 12, seed=5).reshape(-1)
+    want, wt = torch.empty(w.numel()), torch.empty(w.numel(), device=DEV)
+    emu.weight_transpose(w, want, 10, 27, 12)
+    ops.weight_transpose(w.to(DEV), wt, 10, 27, 12)
+    _cmp(wt, want, 0.0, 'weight_transpose')
+    for rows, C in [(1000, 96), (77, 2), (3, 1024), (5000, 256)]:
+        dy = _r(rows * C, seed=6)
+        for acc in (False, True):
+            want = _r(C, seed=7)
+            db = want.to(DEV)
+            emu.bias_grad(dy, want, C, acc)
+            ops.bias_grad(dy.to(DEV), db, C, acc)
+            _cmp(db, want, 2e-5, 'bias_grad')
+
+
+def test_gate_kernels():
+    B = 3
+    hn = B * 64 * 128
+    t = lambda n, s: _r(n, seed=s, scale=.7)
+    conv_ur, xp_ur, b_ur, h = t(2 * hn, 1), t(2 * hn, 2), t(256, 3), t(hn, 4)
+    for cv, hh in ((conv_ur, h), (None, None)):
+        outs_w = [torch.empty(hn) for _ in range(3)]
+        outs_g = [torch.empty(hn, device=DEV) for _ in range(3)]
+        emu.gru_ur_fwd(cv, xp_ur, b_ur, hh, *outs_w, B)
+        ops.gru_ur_fwd(None if cv is None else cv.to(DEV), xp_ur.to(DEV), b_ur.to(DEV),
+                       None if hh is None else hh.to(DEV), *outs_g, B)
+        for g, w in zip(outs_g, outs_w):
+            _cmp(g, w, 2e-6, 'gru_ur_fwd')
+    u = torch.sigmoid(t(hn, 5))
+    conv_c, xp_c, b_c = t(hn, 6), t(hn, 7), t(128, 8)
+    ow = [torch.empty(hn), torch.empty(hn)]
+    og = [torch.empty(hn, device=DEV), torch.empty(hn, device=DEV)]
+    emu.gru_out_fwd(conv_c, xp_c, b_c, u, h, *ow, B)
+    ops.gru_out_fwd(conv_c.to(DEV), xp_c.to(DEV), b_c.to(DEV), u.to(DEV), h.to(DEV), *og, B)
+    for g, w in zip(og, ow):
+        _cmp(g, w, 2e-6, 'gru_out_fwd')
+    dh, c, r = t(hn, 9), torch.tanh(t(hn, 10)), torch.sigmoid(t(hn, 11))
+    for hh in (h, None):
+        w_ur, w_c, w_p = torch.zeros(2 * hn), torch.empty(hn), torch.empty(hn)
+        g_ur, g_c, g_p = torch.zeros(2 * hn, device=DEV), torch.empty(hn, device=DEV), torch.empty(hn, device=DEV)
+        emu.gru_out_bwd(dh, u, c, hh, w_ur, w_c, w_p, B)
+        ops.gru_out_bwd(dh.to(DEV), u.to(DEV), c.to(DEV), None if hh is None else hh.to(DEV), g_ur, g_c, g_p, B)
+        d_rh = t(hn, 12)
+        emu.gru_r_bwd(d_rh, h, r, w_ur, w_p, B)
+        ops.gru_r_bwd(d_rh.to(DEV), h.to(DEV), r.to(DEV), g_ur, g_p, B)
+        for g, w in ((g_ur, w_ur), (g_c, w_c), (g_p, w_p)):
+            _cmp(g, w, 2e-6, 'gru bwd')
+    # LSTM
+    conv, xp, bb, s = t(3 * hn, 13), t(3 * hn, 14), t(384, 15), t(hn, 16)
+    for cv, ss in ((conv, s), (None, None)):
+        ow = [torch.empty(3 * hn), torch.empty(hn), torch.empty(hn)]
+        og = [torch.empty(3 * hn, device=DEV), torch.empty(hn, device=DEV), torch.empty(hn, device=DEV)]
+        emu.lstm_fwd(cv, xp, bb, ss, *ow, B)
+        ops.lstm_fwd(None if cv is None else cv.to(DEV), xp.to(DEV), bb.to(DEV), None if ss is None else ss.to(DEV), *og, B)
+        for g, w in zip(og, ow):
+            _cmp(g, w, 2e-6, 'lstm_fwd')
+        ds = t(hn, 17)
+        for dsi in (ds, None):
+            bw = [torch.empty(3 * hn), torch.empty(hn)]
+            bg = [torch.empty(3 * hn, device=DEV), torch.empty(hn, device=DEV)]
+            emu.lstm_bwd(dh, dsi, ow[0], ss, ow[2], *bw, B)
+            ops.lstm_bwd(dh.to(DEV), None if dsi is None else dsi.to(DEV), og[0], None if ss is None else ss.to(DEV), og[2], *bg, B)
+            for g, w in zip(bg, bw):
+                _cmp(g, w, 3e-6, 'lstm_bwd')
+
+
+def test_softmax_ce_adam_voxel():
+    B, nv = 3, 32
+    logits = _r(B * nv ** 3 * 2, seed=1, scale=2.0)
+    occ = np.random.RandomState(2).rand(B, nv, nv, nv) < 0.1
+    y = torch.zeros(B, nv, 2, nv, nv)
+    y[:, :, 1] = torch.tensor(occ, dtype=torch.float32)
+    y[:, :, 0] = 1 - y[:, :, 1]
+    for yy in (y, None):
+        wp, wl, wd = torch.empty(B, nv, 2, nv, nv), torch.zeros(1), torch.empty(logits.numel())
+        gp, gl, gd = torch.empty(B, nv, 2, nv, nv, device=DEV), torch.zeros(1, device=DEV), torch.empty(logits.numel(), device=DEV)
+        emu.softmax_ce3d(logits, yy, wp, wl, wd, B, nv, 0.125)
+        ops.softmax_ce3d(logits.to(DEV), None if yy is None else yy.to(DEV), gp, gl, gd, B, nv, 0.125)
+        _cmp(gp, wp, 2e-6, 'softmax pred')
+        _cmp(gd, wd, 2e-6, 'softmax dlogits')
+        assert abs(gl.item() - wl.item()) < 2e-5 * abs(wl.item())
+    # prediction-only (inference) call
+    gp2 = torch.empty(B, nv, 2, nv, nv, device=DEV)
+    ops.softmax_ce3d(logits.to(DEV), None, gp2, None, None, B, nv, 1.0)
+    _cmp(gp2, wp, 2e-6)
+    # Adam / SGD: ragged n, decay boundary inside a float4
+    n, nd = 10007, 5002
+    p, g = _r(n, seed=3), _r(n, seed=4)
+    wp_, wm, wv = p.clone(), torch.zeros(n), torch.zeros(n)
+    gp_, gm, gv = p.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    mir = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(1, 4):
+        lr_t = 1e-2 * (1 - 0.999 ** step) ** 0.5 / (1 - 0.9 ** step)
+        emu.adam(wp_, g, wm, wv, None, nd, lr_t, 0.9, 0.999, 1e-8, 5e-5, 0.5)
+        ops.adam(gp_, g.to(DEV), gm, gv, mir, nd, lr_t, 0.9, 0.999, 1e-8, 5e-5, 0.5)
+    _cmp(gp_, wp_, 2e-6, 'adam p'); _cmp(gm, wm, 2e-6, 'adam m'); _cmp(gv, wv, 2e-6, 'adam v')
+    _cmp(mir, wp_, 1e-2, 'adam mirror')
+    wv2, gv2 = torch.zeros(n), torch.zeros(n, device=DEV)
+    emu.sgd(wp_, g, wv2, None, nd, 0.1, 0.9, 5e-5, 1.0)
+    ops.sgd(gp_, g.to(DEV), gv2, None, nd, 0.1, 0.9, 5e-5, 1.0)
+    _cmp(gp_, wp_, 3e-6, 'sgd')
+    # voxel IoU counts against the golden fixture generated by the real lib/voxel.py
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'voxel_eval.npz'))
+    p1 = torch.tensor(z['preds1'].astype(np.float32))
+    oc = torch.tensor(np.unpackbits(z['occ'])[:p1.numel()].reshape(p1.shape).astype(np.float32))
+    pred = torch.stack([1 - p1, p1], dim=2).contiguous()
+    gt = torch.stack([1 - oc, oc], dim=2).contiguous()
+    for ti, th in enumerate(z['thresholds']):
+        counts = ops.voxel_eval(pred.to(DEV), gt.to(DEV), float(th)).cpu().numpy()
+        assert np.array_equal(counts, z['counts'][:, ti]), th
+
+
+def test_errors_are_loud():
+    x = torch.zeros(16, device=DEV)
+    with pytest.raises(L.R2N2Error):       # Cin not a multiple of 4
+        ops.conv_fwd(torch.zeros(2 * 3, device=DEV), torch.zeros(4 * 3, device=DEV), None, None, None,
+                     torch.zeros(2 * 4, device=DEV), (2, 1, 1, 1, 3), 4, (1, 1, 1), 0, L.ALGO_SIMT)
+    with pytest.raises(L.R2N2Error):       # even kernel extent
+        ops.conv_fwd(x, torch.zeros(64, device=DEV), None, None, None, x, (1, 1, 2, 2, 4), 4, (1, 2, 2), 0,
+                     L.ALGO_SIMT)
+    with pytest.raises(RuntimeError):      # CPU tensor
+        ops.add(torch.zeros(4), torch.zeros(4), torch.zeros(4))

@@ -1,0 +1,166 @@
+"""GPU parity tests of the whole hot path through the reference-facing API (models + Solver):
+forward probabilities, loss, update gates, gradients, Adam steps and IoU@0.4 against the CPU
+oracle on the same seeded inputs and weights.
+
+Tolerances (BASELINE.json north_star): fp32 path: voxel probabilities max-abs <= 1e-3 (we assert
+1e-4), IoU@0.4 identical to 3 decimals.  bf16/tcgen05 path: stated tolerance 3e-2 max-abs on
+probabilities (measured values are printed), IoU within 5e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+import r2n2_b200  # noqa: F401
+from r2n2_b200.lib.config import cfg
+from r2n2_b200.lib.solver import Solver
+from r2n2_b200.models import load_model
+from oracle import ref_torch as rt
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(net_name, B, compute='fp32', seed=0):
+    cfg.CONST.BATCH_SIZE = B
+    cfg.CONST.COMPUTE = compute
+    try:
+        net = load_model(net_name)()
+    finally:
+        cfg.CONST.COMPUTE = 'fp32'
+    params = rt.init_params(net_name, seed=seed)
+    net.engine.set_params(params)
+    return net, params
+
+
+@pytest.mark.parametrize('net_name,B,T', [('ResidualGRUNet', 2, 3), ('GRUNet', 3, 1), ('GRUNet', 2, 2),
+                                          ('ResidualLSTMNet', 2, 2)])
+def test_forward_parity_fp32(net_name, B, T):
+    net, params = _build(net_name, B)
+    x, y = rt.synthetic_batch(T, B)
+    solver = Solver(net)
+    pred, loss, acts = solver.test_output(x, y)
+    ref = rt.RefNet(net_name, params)
+    with torch.no_grad():
+        out = ref.forward(x, y)
+    rp = out['pred'].numpy()
+    err = np.abs(pred - rp).max()
+    print('%s fp32: max|dp| %.3e, loss %.6f vs %.6f' % (net_name, err, loss, float(out['loss'])))
+    assert pred.shape == (B, 32, 2, 32, 32) and acts[0].shape == (T, B, 4, 128, 4, 4)
+    assert err < 1e-4
+    assert abs(loss - float(out['loss'])) < 1e-5 * max(1.0, abs(float(out['loss'])))
+    assert np.abs(acts[0] - out['update_gates'].numpy()).max() < 1e-4
+    assert round(rt.iou(pred, y, 0.4), 3) == round(rt.iou(rp, y, 0.4), 3)
+    # y=None path: (prediction, activations), zeros fed for y (lib/solver.py:222-238)
+    p2, a2 = solver.test_output(x)
+    assert np.array_equal(p2, pred)
+
+
+def test_demo_shape_config1():
+    """BASELINE config 1: ResidualGRUNet, batch 1, 3 views (demo.py path, random-init weights)."""
+    net, params = _build('ResidualGRUNet', 1)
+    x, _ = rt.synthetic_batch(3, 1, seed_x=7)
+    pred, acts = Solver(net).test_output(x)
+    with torch.no_grad():
+        out = rt.RefNet('ResidualGRUNet', params).forward(x)
+    assert np.abs(pred - out['pred'].numpy()).max() < 1e-4
+    occ_ref = out['pred'].numpy()[0, :, 1] > 0.4          # demo.py:69
+    assert np.array_equal(pred[0, :, 1] > 0.4, occ_ref) or \
+        np.mean((pred[0, :, 1] > 0.4) != occ_ref) < 1e-4
+
+
+@pytest.mark.parametrize('net_name,B,T', [('ResidualGRUNet', 2, 2), ('GRUNet', 2, 3), ('ResidualLSTMNet', 1, 2)])
+def test_gradients_fp32(net_name, B, T):
+    net, params = _build(net_name, B)
+    x, y = rt.synthetic_batch(T, B)
+    out = net.forward_backward(x, y)
+    grads = net.get_grads()
+    ref = rt.RefNet(net_name, params, dtype=torch.float64)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    assert abs(float(out['loss']) - float(rout['loss'])) < 1e-5
+    worst = 0.0
+    for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
+        rg = rg.numpy()
+        rel = np.abs(g - rg).max() / (np.abs(rg).max() + 1e-30)
+        worst = max(worst, rel)
+        assert rel < 2e-3, (name, rel)
+    print('%s grads: worst relative max-error %.3e' % (net_name, worst))
+
+
+def test_adam_training_steps_fp32():
+    """3 Solver.train_loss steps == 3 oracle Adam steps (lib/solver.py:20-48, 102-109)."""
+    net, params = _build('ResidualGRUNet', 2)
+    x, y = rt.synthetic_batch(2, 2)
+    solver = Solver(net)
+    solver.set_lr(1e-4)
+    ref = rt.RefNet('ResidualGRUNet', params)
+    radam = rt.RefAdam(ref, lr=1e-4)
+    for it in range(3):
+        l = solver.train_loss(x, y)
+        rl, _ = radam.step(x, y)
+        assert abs(l - rl) < 2e-5 * max(1.0, abs(rl)), (it, l, rl)
+    assert float(solver.iteration) == 3.0
+    for (name, _, _), a, b in zip(ref.spec, net.engine.get_params(), ref.P):
+        d = np.abs(a - b.detach().numpy())
+        assert d.max() < 3.5e-4 and np.quantile(d, 0.99) < 5e-5, (name, d.max())
+    # save / load round trip in the reference's weights.npy format
+    import os, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        solver.save([1.0, 0.5], td, 7)
+        assert os.path.islink(os.path.join(td, 'weights.npy'))
+        net2, _ = _build('ResidualGRUNet', 2, seed=5)
+        net2.load(os.path.join(td, 'weights.npy'))
+        for a, b in zip(net.engine.get_params(), net2.engine.get_params()):
+            assert np.array_equal(a, b)
+
+
+def test_layer_api_path_matches_engine():
+    """reference-ordered, layer-by-layer graph (drop-in layer classes) == fused engine."""
+    net, params = _build('ResidualGRUNet', 1)
+    x, y = rt.synthetic_batch(2, 1)
+    out_e = net.forward(x, y)
+    out_l = net.forward_layerwise(x, y)
+    assert (out_e['pred'] - out_l['pred']).abs().max().item() < 1e-5
+    assert abs(float(out_e['loss']) - float(out_l['loss'])) < 1e-6
+    assert (out_e['update_gates'].float() - out_l['update_gates']).abs().max().item() < 1e-5
+
+
+def test_static_shapes_and_errors():
+    net, _ = _build('GRUNet', 2)
+    x, y = rt.synthetic_batch(1, 3)
+    with pytest.raises(ValueError):       # batch size is static in the graph (quirk 14)
+        Solver(net).test_output(x)
+    with pytest.raises(ValueError):
+        net.engine.set_params([np.zeros(3)])
+
+
+@pytest.mark.parametrize('net_name,B,T', [('ResidualGRUNet', 2, 3), ('GRUNet', 2, 2)])
+def test_forward_parity_bf16_umma(net_name, B, T):
+    net, params = _build(net_name, B, compute='bf16')
+    x, y = rt.synthetic_batch(T, B)
+    pred, loss, acts = Solver(net).test_output(x, y)
+    with torch.no_grad():
+        out = rt.RefNet(net_name, params).forward(x, y)
+    rp = out['pred'].numpy()
+    err = np.abs(pred - rp).max()
+    iou_a, iou_b = rt.iou(pred, y, 0.4), rt.iou(rp, y, 0.4)
+    print('%s bf16/tcgen05: max|dp| %.3e mean|dp| %.3e loss %.5f vs %.5f IoU %.4f vs %.4f'
+          % (net_name, err, np.abs(pred - rp).mean(), loss, float(out['loss']), iou_a, iou_b))
+    assert err < 3e-2                      # stated tolerance of the bf16 tensor-core path
+    assert abs(loss - float(out['loss'])) < 2e-2 * max(1.0, abs(float(out['loss'])))
+    assert abs(iou_a - iou_b) < 5e-3
+
+
+def test_gradients_bf16_umma():
+    net, params = _build('ResidualGRUNet', 2, compute='bf16')
+    x, y = rt.synthetic_batch(2, 2)
+    out = net.forward_backward(x, y)
+    grads = net.get_grads()
+    ref = rt.RefNet('ResidualGRUNet', params)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    worst = 0.0
+    for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
+        rg = rg.numpy()
+        # bf16 operands: compare direction and scale of each gradient tensor
+        cos = float((g * rg).sum() / (np.linalg.norm(g) * np.linalg.norm(rg) + 1e-30))
+        worst = min(worst, cos) if worst else cos
+        assert cos > 0.98, (name, cos)
+    print('bf16 grads: worst cosine %.4f' % worst)
