@@ -19,7 +19,9 @@ constexpr int kMaxTaps = 64;
 
 // ------------------------------------------------------------------------------------ fwd
 // Tile 128 pixels x 64 out-channels x 16 k ; 256 threads, 8x4 register tile each.
-template <typename TIn, typename TOut>
+// kVec: Cin % 4 == 0 -> 4-wide vector loads along the channel axis; otherwise scalar loads
+// (only the data gradient of conv11, whose "input" is the 2-channel dlogits, needs that).
+template <typename TIn, typename TOut, bool kVec>
 __global__ void __launch_bounds__(256)
 conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
                      const float* __restrict__ bias, const TOut* mask,
@@ -69,7 +71,23 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
     for (int j = 0; j < 2; ++j) {
       int kk = k0 + a_k8 + 4 * j;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_valid && kk < g.K) {
+      if (!kVec) {
+        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int ke = kk + e;
+          if (a_valid && ke < g.K) {
+            int tap = ke / g.Cin;
+            int ci = ke - tap * g.Cin;
+            int sz = a_z + tap_dz[tap], sy = a_y + tap_dy[tap], sx = a_x + tap_dx[tap];
+            if ((unsigned)sz < (unsigned)g.D && (unsigned)sy < (unsigned)g.H &&
+                (unsigned)sx < (unsigned)g.W)
+              t4[e] = to_float<TIn>(
+                  x[((((long long)a_n * g.D + sz) * g.H + sy) * g.W + sx) * g.Cin + ci]);
+          }
+        }
+        v = make_float4(t4[0], t4[1], t4[2], t4[3]);
+      } else if (a_valid && kk < g.K) {
         int tap = kk / g.Cin;
         int ci = kk - tap * g.Cin;
         int sz = a_z + tap_dz[tap], sy = a_y + tap_dy[tap], sx = a_x + tap_dx[tap];
@@ -83,7 +101,15 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
     }
     {
       int kk = k0 + b_k4;
-      rb = (b_valid && kk < g.K) ? Vec4<TIn>::load(b_ptr + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kVec) {
+        rb = (b_valid && kk < g.K) ? Vec4<TIn>::load(b_ptr + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (b_valid && kk + e < g.K) t4[e] = to_float<TIn>(b_ptr[kk + e]);
+        rb = make_float4(t4[0], t4[1], t4[2], t4[3]);
+      }
     }
   };
   auto store_tiles = [&](int buf) {
@@ -296,14 +322,14 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
 }
 
 static int make_geom(ConvGeom& g, int N, int D, int H, int W, int Cin, int Cout, int kd, int kh,
-                     int kw, const char* who) {
+                     int kw, const char* who, bool need_vec = true) {
   R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
                  "%s: non-positive dimension", who);
   R2N2_CHECK_ARG(kd > 0 && kh > 0 && kw > 0 && (kd & 1) && (kh & 1) && (kw & 1),
                  R2N2_ERR_BAD_SHAPE, "%s: kernel extents must be odd ('same' convolution)", who);
   R2N2_CHECK_ARG(kd * kh * kw <= kMaxTaps, R2N2_ERR_BAD_SHAPE, "%s: more than %d taps", who,
                  kMaxTaps);
-  R2N2_CHECK_ARG((Cin & 3) == 0, R2N2_ERR_BAD_ALIGN,
+  R2N2_CHECK_ARG(!need_vec || (Cin & 3) == 0, R2N2_ERR_BAD_ALIGN,
                  "%s: Cin (%d) must be a multiple of 4 (pad the channel axis)", who, Cin);
   g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
   g.kd = kd; g.kh = kh; g.kw = kw;
@@ -317,13 +343,20 @@ int conv_fwd_simt(const void* x, const void* w, const float* bias, const void* m
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
                   int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
   ConvGeom g;
-  int rc = make_geom(g, N, D, H, W, Cin, Cout, kd, kh, kw, "conv_fwd[simt]");
+  int rc = make_geom(g, N, D, H, W, Cin, Cout, kd, kh, kw, "conv_fwd[simt]", false);
   if (rc) return rc;
+  const bool vec = (Cin & 3) == 0;
   dim3 grid((unsigned)((g.P + 127) / 128), (Cout + 63) / 64);
   R2N2_CHECK_ARG(grid.y <= 65535, R2N2_ERR_BAD_SHAPE, "conv_fwd[simt]: Cout too large");
-#define R2N2_LAUNCH_FWD(TI, TO)                                                        \
-  conv_fwd_simt_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (const TI*)w, bias, \
-                                                     (const TO*)mask, (const TO*)res, (TO*)y, g, flags)
+#define R2N2_LAUNCH_FWD(TI, TO)                                                              \
+  do {                                                                                       \
+    if (vec)                                                                                 \
+      conv_fwd_simt_kernel<TI, TO, true><<<grid, 256, 0, st>>>(                              \
+          (const TI*)x, (const TI*)w, bias, (const TO*)mask, (const TO*)res, (TO*)y, g, flags); \
+    else                                                                                     \
+      conv_fwd_simt_kernel<TI, TO, false><<<grid, 256, 0, st>>>(                             \
+          (const TI*)x, (const TI*)w, bias, (const TO*)mask, (const TO*)res, (TO*)y, g, flags); \
+  } while (0)
   if (in_dtype == R2N2_F32 && out_dtype == R2N2_F32) R2N2_LAUNCH_FWD(float, float);
   else if (in_dtype == R2N2_BF16 && out_dtype == R2N2_BF16) R2N2_LAUNCH_FWD(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == R2N2_BF16 && out_dtype == R2N2_F32) R2N2_LAUNCH_FWD(__nv_bfloat16, float);

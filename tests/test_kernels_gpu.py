@@ -57,6 +57,21 @@ def test_conv_fwd_simt(case, flags):
     _cmp(y, want, 2e-5, 'conv_fwd simt %s flags %d' % (case, flags))
 
 
+def test_conv_fwd_simt_unaligned_cin():
+    """data gradient of conv11: the 'input' is the 2-channel dlogits (Cin=2, K=54)."""
+    N, D, H, W, Cin, Cout, k = 1, 8, 8, 8, 2, 32, (3, 3, 3)
+    P = N * D * H * W
+    x, w = _r(P * Cin, seed=1), _r(Cout * 27 * Cin, seed=2, scale=.2)
+    res, mask = _r(P * Cout, seed=4), _r(P * Cout, seed=5)
+    for flags in (0, L.EPI_RESIDUAL | L.EPI_MASK):
+        want = torch.empty(P * Cout)
+        emu.conv_fwd(x, w, None, mask, res, want, (N, D, H, W, Cin), Cout, k, flags, 0)
+        y = torch.empty(P * Cout, device=DEV)
+        ops.conv_fwd(x.to(DEV), w.to(DEV), None, mask.to(DEV), res.to(DEV), y, (N, D, H, W, Cin), Cout, k,
+                     flags, L.ALGO_SIMT)
+        _cmp(y, want, 2e-5, 'conv_fwd simt Cin=2')
+
+
 def test_conv_fwd_in_place_residual():
     """the backward accumulates with residual == y (same buffer)."""
     N, D, H, W, Cin, Cout, k = 2, 1, 6, 6, 32, 32, (1, 3, 3)
