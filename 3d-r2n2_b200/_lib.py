@@ -42,6 +42,7 @@ PROTOTYPES = {
     'r2n2_sgd': [_p, _p, _p, _p, _ll, _ll, _f, _f, _f, _f, _i, _p],
     'r2n2_voxel_eval': [_p, _p, _f, _p, _i, _i, _p],
     'r2n2_fill_zero': [_p, _ll, _p],
+    'r2n2_umma_error_flag': [],
 }
 
 _lib = None

@@ -1,14 +1,472 @@
-// placeholder, replaced by the tcgen05/TMA implementation
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+//   y[p, co] = epilogue( sum_{tap, ci} x[p + off(tap), ci] * w[co, tap, ci] )
+//
+// GEMM view: M = output pixels, N = Cout, K = taps * Cin.  One CTA computes a 128 x BN tile:
+//   * the M tile is a SPATIAL BOX (bw x bh x bd x bn pixels, <= 128) of the channels-last
+//     activation tensor; for every filter tap the A operand is ONE tiled-TMA box load of the
+//     shifted box -- TMA's out-of-bounds zero fill implements the 'same' zero padding, so no
+//     im2col buffer and no padded copy ever exists (the reference materialises both,
+//     lib/layers.py:304-313, 427-437);
+//   * the B operand (packed weights [Cout][taps*Cin], K contiguous) is a 2-D TMA box;
+//   * both land in shared memory in the canonical K-major swizzled layout that tcgen05.mma
+//     reads through shared-memory descriptors; accumulators live in TMEM;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = epilogue
+//     (tcgen05.ld -> bias / LeakyReLU / residual / LeakyReLU' mask -> global), connected by an
+//     mbarrier ring (full/empty per stage) and a tmem_full barrier.
+// The same kernel computes data gradients (dgrad) when fed dy and the transposed weights.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace r2n2 {
-int conv_fwd_umma(const void*, const void*, const float*, const void*, const void*, void*, int, int,
-                  int, int, int, int, int, int, int, int, int, int, cudaStream_t) {
-  set_error("conv_fwd[umma]: not built");
-  return R2N2_ERR_UNSUPPORTED;
+
+// --------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must never hang the GPU.  On timeout the CTA-wide abort flag is
+// raised (every later wait returns at once) and a global error word is set for the host.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                          int* err_word) {
+  if (*abort_flag) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL || *abort_flag) {
+      *abort_flag = 1;
+      if (err_word) atomicExch(err_word, 1);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, swizzled (canonical layouts of the tcgen05 ISA):
+//   start address >>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes,
+                                                     uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+struct UmmaConvParams {
+  int N, D, H, W, Cin, Cout;
+  int kd, kh, kw;
+  int bw, bh, bd, bn;                      // spatial box of the M tile
+  int tiles_w, tiles_h, tiles_d, tiles_n;  // number of boxes per axis
+  int BN;                                  // N tile (multiple of 16, <= 256)
+  int kbox;                                // channels per K block (16 / 32 / 64)
+  int kchunks;                             // ceil(Cin / kbox)
+  int stages;
+  int a_stage_bytes, b_stage_bytes;        // 1024-aligned
+  int tmem_cols;
+  int flags;
+  int* err_word;
+};
+
+constexpr int kUmmaThreads = 192;
+
+template <typename TOut>
+__global__ void __launch_bounds__(kUmmaThreads)
+conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
+                     const UmmaConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] [full[stages]] [empty[stages]] [tmem_full] [tmem_ptr] [abort]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int td = t % p.tiles_d; t /= p.tiles_d;
+  const int tn = t;
+  const int x0 = tw * p.bw, y0 = th * p.bh, z0 = td * p.bd, n0 = tn * p.bn;
+  const int col0 = blockIdx.y * p.BN;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int taps = p.kd * p.kh * p.kw;
+  const int nkb = taps * p.kchunks;
+  const int row_bytes = p.kbox * 2;
+  const int rows = p.bw * p.bh * p.bd * p.bn;
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(rows * row_bytes + p.BN * row_bytes);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, abort_flag, p.err_word);
+        const int tap = kb / p.kchunks;
+        const int c0 = (kb - tap * p.kchunks) * p.kbox;
+        const int tz = tap / (p.kh * p.kw);
+        const int r2 = tap - tz * p.kh * p.kw;
+        const int ty = r2 / p.kw;
+        const int tx = r2 - ty * p.kw;
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_dst = a_dst + (uint32_t)p.a_stage_bytes;
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, tx_bytes);
+        tma_load_5d(a_dst, &map_a, bar, c0, x0 + tx - (p.kw - 1) / 2, y0 + ty - (p.kh - 1) / 2,
+                    z0 + tz - (p.kd - 1) / 2, n0);
+        tma_load_2d(b_dst, &map_b, bar, tap * p.Cin + c0, col0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t layout_type = (row_bytes == 128) ? 2u : (row_bytes == 64 ? 4u : 6u);
+      const uint32_t sbo = 8u * (uint32_t)row_bytes;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
+        mbar_wait(smem_u32(&full_bar[s]), ph, abort_flag, p.err_word);
+        tc_fence_after();
+        const int c0 = (kb % p.kchunks) * p.kbox;
+        int kvalid = p.Cin - c0;
+        if (kvalid > p.kbox) kvalid = p.kbox;
+        const int nk16 = kvalid >> 4;
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + (uint32_t)p.a_stage_bytes;
+        for (int k = 0; k < nk16; ++k) {
+          const uint64_t da = make_kmajor_desc(a_addr + k * 32, sbo, layout_type);
+          const uint64_t db = make_kmajor_desc(b_addr + k * 32, sbo, layout_type);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when the MMAs retire
+      }
+      umma_commit(smem_u32(tmem_full_bar));        // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..5) =================================
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int r = row;
+    const int xi = r % p.bw; r /= p.bw;
+    const int yi = r % p.bh; r /= p.bh;
+    const int zi = r % p.bd; r /= p.bd;
+    const int ni = r;
+    const int xx = x0 + xi, yy = y0 + yi, zz = z0 + zi, nn = n0 + ni;
+    const bool valid = (row < rows) && xx < p.W && yy < p.H && zz < p.D && nn < p.N;
+    const long long pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
+    mbar_wait(smem_u32(tmem_full_bar), 0u, abort_flag, p.err_word);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
+      const int co = col0 + c;
+      if (!valid || co >= p.Cout) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 b4 = *reinterpret_cast<const float4*>(bias + co + j);
+          f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+        }
+      }
+      if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
+      }
+      const long long off = pix * p.Cout + co;
+      if (p.flags & R2N2_EPI_RESIDUAL) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 r4 = Vec4<TOut>::load(res + off + j);
+          f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+        }
+      }
+      if (p.flags & R2N2_EPI_MASK) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 m4 = Vec4<TOut>::load(mask + off + j);
+          f[j] *= lrelu_slope(m4.x); f[j + 1] *= lrelu_slope(m4.y);
+          f[j + 2] *= lrelu_slope(m4.z); f[j + 3] *= lrelu_slope(m4.w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        Vec4<TOut>::store(y + off + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int* get_err_word() {
+  static int* w = nullptr;
+  if (!w) {
+    if (cudaMalloc(&w, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(w, 0, sizeof(int));
+  }
+  return w;
+}
+
+// choose the spatial box (bw,bh,bd,bn), product <= 128, minimising the number of M tiles
+static void choose_box(int N, int D, int H, int W, int& bw, int& bh, int& bd, int& bn) {
+  long long best = -1;
+  int best_rows = 0;
+  for (int w = 1; w <= W && w <= 128; ++w) {
+    for (int h = 1; h <= H && w * h <= 128; ++h) {
+      if (h > 1 && w < W && false) continue;
+      for (int d = 1; d <= D && w * h * d <= 128; ++d) {
+        int n = 128 / (w * h * d);
+        if (n > N) n = N;
+        if (n < 1) continue;
+        long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d) *
+                          ((N + n - 1) / n);
+        int rows = w * h * d * n;
+        if (best < 0 || tiles < best || (tiles == best && rows < best_rows)) {
+          best = tiles; best_rows = rows;
+          bw = w; bh = h; bd = d; bn = n;
+        }
+      }
+    }
+  }
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
+                  const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
+  R2N2_CHECK_ARG(in_dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: operands must be bf16");
+  R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd[umma]: non-positive dimension");
+  R2N2_CHECK_ARG((kd & 1) && (kh & 1) && (kw & 1), R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd[umma]: kernel extents must be odd");
+  R2N2_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0, R2N2_ERR_UNSUPPORTED,
+                 "conv_fwd[umma]: Cin (%d) and Cout (%d) must be multiples of 16 (use ALGO_SIMT)", Cin, Cout);
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode();
+  R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled unavailable");
+
+  UmmaConvParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  choose_box(N, D, H, W, p.bw, p.bh, p.bd, p.bn);
+  p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.BN = Cout >= 128 ? 128 : Cout;
+  p.kbox = Cin >= 64 ? 64 : (Cin >= 32 ? 32 : 16);
+  p.kchunks = (Cin + p.kbox - 1) / p.kbox;
+  const int row_bytes = p.kbox * 2;
+  p.a_stage_bytes = (128 * row_bytes + 1023) / 1024 * 1024;
+  p.b_stage_bytes = (p.BN * row_bytes + 1023) / 1024 * 1024;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  p.stages = stage_bytes >= 32768 ? 3 : 4;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
+  p.flags = flags;
+  p.err_word = get_err_word();
+
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+                         (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA,
+                   "conv_fwd[umma]: cuTensorMapEncodeTiled(A) failed (%d) dims %d,%d,%d,%d,%d box %d,%d,%d,%d,%d",
+                   (int)r, Cin, W, H, D, N, p.kbox, p.bw, p.bh, p.bd, p.bn);
+  }
+  {
+    const long long K = (long long)kd * kh * kw * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA,
+                   "conv_fwd[umma]: cuTensorMapEncodeTiled(B) failed (%d) K %lld Cout %d box %d,%d", (int)r,
+                   K, Cout, p.kbox, p.BN);
+  }
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n),
+            (unsigned)((Cout + p.BN - 1) / p.BN));
+  cudaError_t e;
+  if (out_dtype == R2N2_BF16) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_fwd_umma_kernel<__nv_bfloat16>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s",
+                     cudaGetErrorString(e));
+      attr_set = true;
+    }
+    conv_fwd_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem_bytes, st>>>(
+        map_a, map_b, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
+  } else if (out_dtype == R2N2_F32) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_fwd_umma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               200 * 1024);
+      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s",
+                     cudaGetErrorString(e));
+      attr_set = true;
+    }
+    conv_fwd_umma_kernel<float><<<grid, kUmmaThreads, smem_bytes, st>>>(
+        map_a, map_b, bias, (const float*)mask, (const float*)res, (float*)y, p);
+  } else {
+    R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
+  }
+  R2N2_CHECK_LAUNCH("conv_fwd[umma]");
+  return R2N2_OK;
+}
+
+int umma_error_flag() {
+  int* w = get_err_word();
+  int h = 0;
+  if (w) cudaMemcpy(&h, w, sizeof(int), cudaMemcpyDeviceToHost);
+  return h;
+}
+
 int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int,
                     int, int, cudaStream_t) {
-  set_error("conv_wgrad[umma]: not built");
+  set_error("conv_wgrad[umma]: not implemented yet (use ALGO_SIMT)");
   return R2N2_ERR_UNSUPPORTED;
 }
+
 }  // namespace r2n2
+
+extern "C" int r2n2_umma_error_flag(void) { return r2n2::umma_error_flag(); }

@@ -75,6 +75,7 @@ def _work(flops=0.0, tensors=()):
         _next_work = dict(flops=float(flops), bytes=float(nbytes))
 
 
+WGRAD_UMMA = False       # tcgen05 weight-gradient kernel available
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
 
@@ -90,10 +91,22 @@ def _check(t, dtype=None):
         raise RuntimeError('dtype mismatch: expected %s got %s' % (dtype, t.dtype))
 
 
+def umma_ok(cin, cout):
+    """Shapes the tcgen05 kernel takes (16-element K and N granules); anything else (the RGB-free
+    conv11 with Cout=2 and its data gradient with Cin=2) runs on the fp32-FFMA kernel."""
+    return cin % 16 == 0 and cout % 16 == 0
+
+
+def umma_error_flag():
+    return L.load().r2n2_umma_error_flag()
+
+
 # ======================================================================= raw op wrappers
 def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     """geom = (N,D,H,W,Cin) of x; k=(kd,kh,kw); y preallocated [N,D,H,W,cout]."""
     N, D, H, W, Cin = geom
+    if algo == L.ALGO_UMMA and not (umma_ok(Cin, cout) and x.dtype == torch.bfloat16):
+        algo = L.ALGO_SIMT
     for t in (x, w, bias, mask_src, residual, y):
         _check(t)
     assert x.numel() == N * D * H * W * Cin, (x.shape, geom)
@@ -112,6 +125,8 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
 
 def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate):
     N, D, H, W, Cin = geom
+    if algo == L.ALGO_UMMA and not (umma_ok(Cin, cout) and x.dtype == torch.bfloat16 and WGRAD_UMMA):
+        algo = L.ALGO_SIMT
     for t in (x, dy, dw):
         _check(t)
     assert dw.dtype == torch.float32 and x.dtype == dy.dtype

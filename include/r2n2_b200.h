@@ -183,8 +183,11 @@ int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, 
 int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long* counts, int B,
                     int nv, void* stream);
 
-/* [rows][cols] element-type transpose-free helpers used by the host mirror */
 int r2n2_fill_zero(void* p, long long bytes, void* stream);
+
+/* 1 if any tcgen05 kernel launched by this process hit its bounded mbarrier wait (a pipeline
+ * protocol failure: results of that launch are garbage); synchronises the device. */
+int r2n2_umma_error_flag(void);
 
 #ifdef __cplusplus
 }

@@ -283,11 +283,63 @@ def test_softmax_ce_adam_voxel():
 
 def test_errors_are_loud():
     x = torch.zeros(16, device=DEV)
-    with pytest.raises(L.R2N2Error):       # Cin not a multiple of 4
-        ops.conv_fwd(torch.zeros(2 * 3, device=DEV), torch.zeros(4 * 3, device=DEV), None, None, None,
-                     torch.zeros(2 * 4, device=DEV), (2, 1, 1, 1, 3), 4, (1, 1, 1), 0, L.ALGO_SIMT)
+    with pytest.raises(L.R2N2Error):       # wgrad needs Cin % 4 == 0
+        ops.conv_wgrad(torch.zeros(2 * 3, device=DEV), torch.zeros(2 * 4, device=DEV),
+                       torch.zeros(4 * 3, device=DEV), (2, 1, 1, 1, 3), 4, (1, 1, 1), L.ALGO_SIMT, False)
     with pytest.raises(L.R2N2Error):       # even kernel extent
         ops.conv_fwd(x, torch.zeros(64, device=DEV), None, None, None, x, (1, 1, 2, 2, 4), 4, (1, 2, 2), 0,
                      L.ALGO_SIMT)
     with pytest.raises(RuntimeError):      # CPU tensor
         ops.add(torch.zeros(4), torch.zeros(4), torch.zeros(4))
+
+
+# ------------------------------------------------------------------ tcgen05 / TMA kernel
+UMMA_CASES = [
+    # N, D, H, W, Cin, Cout, k
+    (2, 1, 16, 16, 64, 128, (1, 3, 3)),     # exact tiles, one K block per tap
+    (3, 1, 17, 17, 96, 128, (1, 3, 3)),     # ragged box, partial K block (96 = 64 + 32)
+    (2, 1, 33, 33, 128, 256, (1, 3, 3)),    # two N tiles, two K blocks per tap
+    (2, 1, 9, 9, 16, 96, (1, 7, 7)),        # conv1a-like: Cin=16 (SW32), 49 taps, BN=96
+    (2, 1, 5, 5, 256, 256, (1, 1, 1)),      # 1x1
+    (5, 1, 1, 1, 2304, 1024, (1, 1, 1)),    # fc7: M tile mostly out of bounds
+    (3, 4, 4, 4, 128, 256, (3, 3, 3)),      # GRU hidden conv, box spans 2 samples
+    (2, 8, 8, 8, 128, 128, (3, 3, 3)),
+    (1, 16, 16, 16, 32, 32, (3, 3, 3)),     # Cin=32 (SW64), BN=32
+    (1, 8, 8, 8, 128, 64, (1, 1, 1)),       # conv9c
+    (180, 1, 1, 1, 1024, 512, (1, 1, 1)),   # x-projection slice
+    (2, 6, 5, 7, 64, 64, (3, 3, 3)),        # ragged 3-D
+]
+
+
+@pytest.mark.parametrize('case', UMMA_CASES)
+@pytest.mark.parametrize('flags,out_dtype', [(0, torch.float32), (L.EPI_BIAS | L.EPI_LRELU, torch.bfloat16),
+                                             (L.EPI_BIAS | L.EPI_RESIDUAL, torch.bfloat16),
+                                             (L.EPI_RESIDUAL | L.EPI_MASK, torch.bfloat16)])
+def test_conv_fwd_umma_bf16(case, flags, out_dtype):
+    N, D, H, W, Cin, Cout, k = case
+    taps = k[0] * k[1] * k[2]
+    P = N * D * H * W
+    bf = torch.bfloat16
+    x = _r(P * Cin, seed=1).to(bf)
+    w = _r(Cout * taps * Cin, seed=2, scale=(2.0 / (taps * Cin)) ** 0.5).to(bf)
+    b = _r(Cout, seed=3)
+    res = _r(P * Cout, seed=4).to(out_dtype)
+    mask = _r(P * Cout, seed=5).to(out_dtype)
+    want = torch.empty(P * Cout, dtype=torch.float32)
+    emu.conv_fwd(x.float(), w.float(), b, mask.float(), res.float(), want, (N, D, H, W, Cin), Cout, k, flags, 0)
+    y = torch.full((P * Cout,), float('nan'), dtype=out_dtype, device=DEV)
+    ops.conv_fwd(x.to(DEV), w.to(DEV), b.to(DEV), mask.to(DEV), res.to(DEV), y, (N, D, H, W, Cin), Cout, k,
+                 flags, L.ALGO_UMMA)
+    torch.cuda.synchronize()
+    assert ops.umma_error_flag() == 0, 'tcgen05 pipeline timed out'
+    got = y.float().cpu()
+    assert torch.isfinite(got).all(), 'unwritten / non-finite outputs: %d' % (~torch.isfinite(got)).sum().item()
+    tol = 2e-3 if out_dtype == torch.float32 else 1.2e-2       # exact bf16 products, fp32 accumulate
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item()
+    if err > tol * max(1.0, ref):
+        bad = ((got - want).abs() > tol * max(1.0, ref)).nonzero().flatten()
+        rows = torch.unique(bad // Cout)[:12].tolist()
+        cols = torch.unique(bad % Cout)[:12].tolist()
+        raise AssertionError('umma %s flags %d: max err %.3e (ref %.3e), %d bad; rows %s cols %s'
+                             % (case, flags, err, ref, bad.numel(), rows, cols))
