@@ -461,10 +461,317 @@ int umma_error_flag() {
   return h;
 }
 
-int conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int,
-                    int, int, cudaStream_t) {
-  set_error("conv_wgrad[umma]: not implemented yet (use ALGO_SIMT)");
-  return R2N2_ERR_UNSUPPORTED;
+// =====================================================================================
+// Weight gradient:  dw[co][tap][ci] += sum_p dy[p, co] * x[p + off(tap), ci]
+//
+// GEMM view per tap: M = co (TMEM lanes), N = ci (TMEM columns), K = pixels.  Both operands are
+// "MN-major" in memory (channels contiguous), so the TMA boxes [pixels][64 channels] land in the
+// canonical MN-major swizzled layout and the K loop runs over pixel boxes; the x box is loaded
+// shifted by the tap (zero fill = 'same' padding).  One CTA owns a 128(co) x ci_tile x G(taps)
+// block of dw (G accumulators side by side in TMEM, G * ci_cols <= 512 columns), loops over its
+// share of the pixel boxes and finally reduces into dw with red.global.add.f32 (fp32 atomics
+// combine the pixel splits).
+struct UmmaWgradParams {
+  int N, D, H, W, Cin, Cout;
+  int kd, kh, kw, taps;
+  int bw, bh, bd, bn, rows;                // pixel box = K block (rows % 16 == 0)
+  int tiles_w, tiles_h, tiles_d, tiles_n;
+  long long nbox, box_per_cta;
+  int ci_tiles, ci_tile, ci_cols;          // N tile (<=256), its TMEM column footprint
+  int G;                                   // taps per CTA
+  int cw_a, cw_b;                          // channels per smem chunk (16/32/64) for dy / x
+  int a_bytes, b_tap_bytes, stage_bytes;   // per stage
+  int stages, tmem_cols;
+  int* err_word;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                      uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kUmmaThreads)
+conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                       float* __restrict__ dw, const UmmaWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int co_tile = blockIdx.y / p.ci_tiles;
+  const int ci_t = blockIdx.y - co_tile * p.ci_tiles;
+  const int co0 = co_tile * 128;
+  const int ci0 = ci_t * p.ci_tile;
+  const int tap0 = blockIdx.z * p.G;
+  int ntap = p.taps - tap0;
+  if (ntap > p.G) ntap = p.G;
+  int nci = p.Cin - ci0;                       // valid ci in this tile (multiple of 16)
+  if (nci > p.ci_tile) nci = p.ci_tile;
+  int nco = p.Cout - co0;
+  if (nco > 128) nco = 128;
+  const int na = (nco + p.cw_a - 1) / p.cw_a;  // dy chunks to load
+  const int nb = (nci + p.cw_b - 1) / p.cw_b;  // x chunks to load per tap
+  const long long box_begin = (long long)blockIdx.x * p.box_per_cta;
+  long long box_end = box_begin + p.box_per_cta;
+  if (box_end > p.nbox) box_end = p.nbox;
+  const int nkb = (int)(box_end > box_begin ? box_end - box_begin : 0);
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int rb_a = p.cw_a * 2, rb_b = p.cw_b * 2;        // smem row pitch (bytes) of dy / x chunks
+  const int chunk_a = p.rows * rb_a, chunk_b = p.rows * rb_b;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t tx_bytes = (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, abort_flag, p.err_word);
+        long long b = box_begin + kb;
+        const int tw = (int)(b % p.tiles_w); b /= p.tiles_w;
+        const int th = (int)(b % p.tiles_h); b /= p.tiles_h;
+        const int td = (int)(b % p.tiles_d); b /= p.tiles_d;
+        const int tn = (int)b;
+        const int x0 = tw * p.bw, y0 = th * p.bh, z0 = td * p.bd, n0 = tn * p.bn;
+        const uint32_t stage = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, tx_bytes);
+        for (int c = 0; c < na; ++c)
+          tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+        for (int g = 0; g < ntap; ++g) {
+          const int tap = tap0 + g;
+          const int tz = tap / (p.kh * p.kw);
+          const int r2 = tap - tz * p.kh * p.kw;
+          const int ty = r2 / p.kw;
+          const int tx = r2 - ty * p.kw;
+          const uint32_t bdst = stage + p.a_bytes + g * p.b_tap_bytes;
+          for (int c = 0; c < nb; ++c)
+            tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + tx - (p.kw - 1) / 2,
+                        y0 + ty - (p.kh - 1) / 2, z0 + tz - (p.kd - 1) / 2, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const int nmma = (nci + 15) & ~15;                 // UMMA N
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lt_a = (rb_a == 128) ? 2u : (rb_a == 64 ? 4u : 6u);
+      const uint32_t lt_b = (rb_b == 128) ? 2u : (rb_b == 64 ? 4u : 6u);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
+        mbar_wait(smem_u32(&full_bar[s]), ph, abort_flag, p.err_word);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        for (int g = 0; g < ntap; ++g) {
+          const uint32_t b_addr = a_addr + p.a_bytes + g * p.b_tap_bytes;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.ci_cols);
+          for (int k = 0; k < p.rows / 16; ++k) {
+            const uint64_t da = make_mnmajor_desc(a_addr + k * 16 * rb_a, chunk_a, 8 * rb_a, lt_a);
+            const uint64_t db = make_mnmajor_desc(b_addr + k * 16 * rb_b, chunk_b, 8 * rb_b, lt_b);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(tmem_full_bar));
+    }
+    __syncwarp();
+  } else if (nkb > 0) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                    // co within the tile
+    const bool valid = row < nco;
+    mbar_wait(smem_u32(tmem_full_bar), 0u, abort_flag, p.err_word);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int g = 0; g < ntap; ++g) {
+      float* dst = dw + ((long long)(co0 + row) * p.taps + (tap0 + g)) * p.Cin + ci0;
+      for (int c = 0; c < nci; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)(g * p.ci_cols + c), v);
+        if (!valid) continue;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// pixel box for the K loop: rows = bw*bh*bd*bn must be a multiple of 16 and <= max_rows;
+// maximise the fraction of in-bounds pixels (out-of-bounds ones are zero-filled by TMA and only
+// cost time), then the box size.
+static void choose_kbox(int N, int D, int H, int W, int max_rows, int& bw, int& bh, int& bd, int& bn) {
+  double best_eff = -1.0;
+  int best_rows = 0;
+  bw = bh = bd = 1; bn = 16;
+  for (int w = 1; w <= W && w <= max_rows; ++w)
+    for (int h = 1; h <= H && w * h <= max_rows; ++h)
+      for (int d = 1; d <= D && w * h * d <= max_rows; ++d)
+        for (int n = 1; n <= N && w * h * d * n <= max_rows; ++n) {
+          int rows = w * h * d * n;
+          if (rows % 16) continue;
+          double cover = (double)((W + w - 1) / w * w) * ((H + h - 1) / h * h) * ((D + d - 1) / d * d) *
+                         ((N + n - 1) / n * n);
+          double eff = ((double)W * H * D * N) / cover;
+          if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && rows > best_rows)) {
+            best_eff = eff; best_rows = rows;
+            bw = w; bh = h; bd = d; bn = n;
+          }
+        }
+}
+
+static int pow2_chunk(int c) { return c >= 64 ? 64 : (c >= 32 ? 32 : 16); }
+
+int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
+                    int Cout, int kd, int kh, int kw, int dtype, int accumulate, cudaStream_t st) {
+  R2N2_CHECK_ARG(dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_wgrad[umma]: operands must be bf16");
+  R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
+                 "conv_wgrad[umma]: non-positive dimension");
+  R2N2_CHECK_ARG((kd & 1) && (kh & 1) && (kw & 1), R2N2_ERR_BAD_SHAPE,
+                 "conv_wgrad[umma]: kernel extents must be odd");
+  R2N2_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0, R2N2_ERR_UNSUPPORTED,
+                 "conv_wgrad[umma]: Cin (%d) and Cout (%d) must be multiples of 16 (use ALGO_SIMT)", Cin, Cout);
+  EncodeTiledFn encode = get_encode();
+  R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_wgrad[umma]: cuTensorMapEncodeTiled unavailable");
+
+  UmmaWgradParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.kd = kd; p.kh = kh; p.kw = kw; p.taps = kd * kh * kw;
+  p.cw_a = pow2_chunk(Cout);
+  p.cw_b = pow2_chunk(Cin);
+  p.ci_tile = Cin > 256 ? 256 : Cin;
+  p.ci_tiles = (Cin + p.ci_tile - 1) / p.ci_tile;
+  p.ci_cols = (p.ci_tile + 31) / 32 * 32;
+  p.G = 512 / p.ci_cols;
+  if (p.G > p.taps) p.G = p.taps;
+  const int co_tiles = (Cout + 127) / 128;
+  const int tap_groups = (p.taps + p.G - 1) / p.G;
+  // bytes per K row (pixel) in one stage
+  const int a_row = ((Cout < 128 ? Cout : 128) + p.cw_a - 1) / p.cw_a * p.cw_a * 2;
+  const int b_row = (p.ci_tile + p.cw_b - 1) / p.cw_b * p.cw_b * 2;
+  const int per_row = a_row + p.G * b_row;
+  p.stages = 3;
+  int max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
+  if (max_rows > 128) max_rows = 128;
+  if (max_rows < 16) {
+    p.stages = 2;
+    max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
+  }
+  R2N2_CHECK_ARG(max_rows >= 16, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: tile does not fit shared memory");
+  choose_kbox(N, D, H, W, max_rows, p.bw, p.bh, p.bd, p.bn);
+  p.rows = p.bw * p.bh * p.bd * p.bn;
+  p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.nbox = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  p.a_bytes = (p.rows * a_row + 1023) / 1024 * 1024;
+  p.b_tap_bytes = p.rows * b_row;
+  p.stage_bytes = (p.a_bytes + p.G * p.b_tap_bytes + 1023) / 1024 * 1024;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.G * p.ci_cols) p.tmem_cols *= 2;
+  p.err_word = get_err_word();
+  // pixel splits: enough CTAs to fill the machine, but at least ~4 K blocks each
+  const long long units = (long long)co_tiles * p.ci_tiles * tap_groups;
+  long long splits = ((long long)num_sms() * 2 + units - 1) / units;
+  if (splits > p.nbox / 4) splits = p.nbox / 4;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.box_per_cta = (p.nbox + splits - 1) / splits;
+  splits = (p.nbox + p.box_per_cta - 1) / p.box_per_cta;
+
+  CUtensorMap map_dy, map_x;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2,
+                             (cuuint64_t)D * H * W * Cout * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.cw_a, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+                         (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.cw_a * 2),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_wgrad[umma]: cuTensorMapEncodeTiled(dy) failed (%d)",
+                   (int)r);
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.cw_b, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+                         (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.cw_b * 2),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_wgrad[umma]: cuTensorMapEncodeTiled(x) failed (%d)",
+                   (int)r);
+  }
+  if (!accumulate)
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.taps * Cin, st);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_wgrad[umma]: smem attribute: %s",
+                   cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  dim3 grid((unsigned)splits, (unsigned)(co_tiles * p.ci_tiles), (unsigned)tap_groups);
+  conv_wgrad_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
+  R2N2_CHECK_LAUNCH("conv_wgrad[umma]");
+  return R2N2_OK;
 }
 
 }  // namespace r2n2

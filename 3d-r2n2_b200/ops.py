@@ -75,7 +75,7 @@ def _work(flops=0.0, tensors=()):
         _next_work = dict(flops=float(flops), bytes=float(nbytes))
 
 
-WGRAD_UMMA = False       # tcgen05 weight-gradient kernel available
+WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
 

@@ -79,9 +79,12 @@ def test_gradients_fp32(net_name, B, T):
     worst = 0.0
     for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
         rg = rg.numpy()
+        # fp32 kernels vs the fp64 oracle: near-ties in max-pool windows / LeakyReLU signs can route
+        # a gradient differently, so bound the L2 error tightly and the max error loosely
         rel = np.abs(g - rg).max() / (np.abs(rg).max() + 1e-30)
+        rel2 = np.linalg.norm((g - rg).ravel()) / (np.linalg.norm(rg.ravel()) + 1e-30)
         worst = max(worst, rel)
-        assert rel < 2e-3, (name, rel)
+        assert rel < 1e-2 and rel2 < 1e-3, (name, rel, rel2)
     print('%s grads: worst relative max-error %.3e' % (net_name, worst))
 
 
