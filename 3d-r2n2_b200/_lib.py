@@ -37,7 +37,7 @@ PROTOTYPES = {
     'r2n2_gru_gates_r_bwd': [_p, _p, _p, _p, _p, _i, _i, _p],
     'r2n2_lstm_gates_fwd': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     'r2n2_lstm_gates_bwd': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
-    'r2n2_softmax_ce3d': [_p, _p, _p, _p, _p, _i, _i, _f, _i, _p],
+    'r2n2_softmax_ce3d': [_p, _p, _p, _p, _p, _i, _i, _f, _i, _i, _p],
     'r2n2_adam': [_p, _p, _p, _p, _p, _ll, _ll, _f, _f, _f, _f, _f, _f, _i, _p],
     'r2n2_sgd': [_p, _p, _p, _p, _ll, _ll, _f, _f, _f, _f, _i, _p],
     'r2n2_voxel_eval': [_p, _p, _f, _p, _i, _i, _p],

@@ -436,7 +436,7 @@ template <typename TD>
 __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const float* __restrict__ y,
                                     float* __restrict__ pred, float* __restrict__ loss_sum,
                                     TD* __restrict__ dlogits, long long nvox_total, int nv,
-                                    float grad_scale) {
+                                    float grad_scale, int cstride) {
   const long long plane = (long long)nv * nv;  // one (y,x) plane
   float local = 0.f;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox_total;
@@ -445,7 +445,7 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
     long long bz = v / plane;
     long long yx = v - bz * plane;
     long long ref0 = (bz * 2) * plane + yx;
-    float2 x = *reinterpret_cast<const float2*>(logits + v * 2);
+    float2 x = *reinterpret_cast<const float2*>(logits + v * cstride);
     float e0 = expf(x.x), e1 = expf(x.y);  // no max subtraction: lib/layers.py:585-589
     float s = e0 + e1;
     float inv = 1.f / s;
@@ -461,8 +461,10 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
     }
     if (loss_sum) local += -(y0 * x.x + y1 * x.y) + logf(s);
     if (dlogits) {
-      dlogits[v * 2] = from_float<TD>((p0 - y0) * grad_scale);
-      dlogits[v * 2 + 1] = from_float<TD>((p1 - y1) * grad_scale);
+      TD* dl = dlogits + v * cstride;
+      dl[0] = from_float<TD>((p0 - y0) * grad_scale);
+      dl[1] = from_float<TD>((p1 - y1) * grad_scale);
+      for (int c = 2; c < cstride; ++c) dl[c] = from_float<TD>(0.f);   // padded logit channels
     }
   }
   if (loss_sum) {
@@ -820,12 +822,14 @@ int r2n2_lstm_gates_bwd(const void* dh, const void* ds_in, const void* fig, cons
 }
 
 int r2n2_softmax_ce3d(const float* logits, const float* y, float* pred, float* loss_sum,
-                      void* dlogits, int B, int nv, float grad_scale, int ddtype, void* stream) {
-  R2N2_CHECK_ARG(B > 0 && nv > 0, R2N2_ERR_BAD_SHAPE, "softmax_ce3d: bad shape");
+                      void* dlogits, int B, int nv, float grad_scale, int ddtype, int cstride,
+                      void* stream) {
+  R2N2_CHECK_ARG(B > 0 && nv > 0 && cstride >= 2 && (cstride & 1) == 0, R2N2_ERR_BAD_SHAPE,
+                 "softmax_ce3d: bad shape");
   long long total = (long long)B * nv * nv * nv;
   R2N2_DISPATCH_DTYPE(ddtype, T, {
     softmax_ce3d_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        logits, y, pred, loss_sum, (T*)dlogits, total, nv, grad_scale);
+        logits, y, pred, loss_sum, (T*)dlogits, total, nv, grad_scale, cstride);
   })
   R2N2_CHECK_LAUNCH("softmax_ce3d");
   return R2N2_OK;

@@ -129,6 +129,9 @@ class Engine:
         self.n_gates = 3
         # channel padding of the RGB input: 4 for the fp32 SIMT path, 16 for tensor-core K tiles
         self.cin_pad = 4 if self.algo == L.ALGO_SIMT else 16
+        # conv11 has 2 output channels; on the tensor-core path it is padded to one N granule (16):
+        # the extra weight rows are zero and stay zero (their gradients are exactly zero)
+        self.logit_c = 2 if self.algo == L.ALGO_SIMT else 16
         self.store = ParamStore(self.device, None if self.dtype == torch.float32 else self.dtype)
         self.P = {}
         self.weights = []      # RefWeight list in reference creation order
@@ -151,9 +154,10 @@ class Engine:
             defs.append(('conv2', name, cout, cin, k, cp))
 
         def conv3(name, cout, cin, k):
-            st.plan(name + '.W', cout * k ** 3 * cin, False)
-            st.plan(name + '.b', cout, True)
-            defs.append(('conv3', name, cout, cin, k, cin))
+            cs = self.logit_c if name == 'conv11' else cout      # stored (padded) out channels
+            st.plan(name + '.W', cs * k ** 3 * cin, False)
+            st.plan(name + '.b', cs, True)
+            defs.append(('conv3', name, cout, cin, k, cs))
 
         if self.residual:
             conv2('conv1a', c[0], 3, 7, self.cin_pad); conv2('conv1b', c[0], c[0], 3)
@@ -218,13 +222,13 @@ class Engine:
                 self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
                                               lambda t: t, lambda v: v))
             elif kind == 'conv3':
-                _, name, cout, cin, k, _ = dfn
-                mk_param(name + '.W', cout, k ** 3, cin)
-                mk_bias(name + '.b', cout)
-                vw = st.seg(name + '.W').view(cout, k, k, k, cin)
+                _, name, cout, cin, k, cs = dfn
+                mk_param(name + '.W', cs, k ** 3, cin)
+                mk_bias(name + '.b', cs)
+                vw = st.seg(name + '.W').view(cs, k, k, k, cin)[:cout]
                 self.weights.append(RefWeight(name + '.W', (cout, k, cin, k, k), False, vw,
                                               pk.pack_conv3d, pk.unpack_conv3d))
-                self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
+                self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b')[:cout],
                                               lambda t: t, lambda v: v))
             elif kind == 'fc7':
                 n_in = N_CONVFILTER[5] * 9
@@ -535,9 +539,9 @@ class Engine:
         loss_sum = torch.zeros(1, dtype=torch.float32, device=x.device) if y is not None else None
         dlogits = None
         if training:
-            dlogits = ctx.empty(B * nv ** 3 * 2, x)
+            dlogits = ctx.empty(B * nv ** 3 * self.logit_c, x)
         ops.softmax_ce3d(logits.data, None if y is None else y.contiguous(), pred, loss_sum, dlogits,
-                         B, nv, 1.0 / (B * nv ** 3))
+                         B, nv, 1.0 / (B * nv ** 3), self.logit_c)
         if training:
             logits.grad, logits.n_recv = dlogits, 1
         loss = None if loss_sum is None else loss_sum[0] / float(B * nv ** 3)

@@ -254,13 +254,13 @@ def lstm_bwd(dh, ds_in, fig, s, h_new, da, ds_prev, B):
           _ptr(ds_prev), B, _DT[dh.dtype], _stream())
 
 
-def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale):
+def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale, cstride=2):
     _check(logits, torch.float32), _check(y, torch.float32), _check(pred, torch.float32)
     _check(loss_sum, torch.float32), _check(dlogits)
     dd = _DT[dlogits.dtype] if dlogits is not None else L.F32
     _work(0.0, (logits, y, pred, dlogits))
     _call('r2n2_softmax_ce3d', _ptr(logits), _ptr(y), _ptr(pred), _ptr(loss_sum), _ptr(dlogits), B,
-          nv, float(grad_scale), dd, _stream())
+          nv, float(grad_scale), dd, cstride, _stream())
 
 
 def adam(p, g, m, v, mirror, n_decay, lr_t, b1, b2, eps, wd, grad_scale):

@@ -164,9 +164,12 @@ int r2n2_lstm_gates_bwd(const void* dh, const void* ds_in, const void* fig, cons
  *   y       (B,nv,2,nv,nv) fp32 reference layout, may be NULL (lib/solver.py:222-226 feeds 0)
  *   pred    (B,nv,2,nv,nv) fp32 reference layout, may be NULL  = exp(x)/sum_c exp(x)
  *   loss_sum: 1 float, ACCUMULATES sum_vox(-sum_c y_c x_c + log sum_c exp x_c), may be NULL
- *   dlogits [B,nv,nv,nv,2] in ddtype, may be NULL                = (p - y) * grad_scale   */
+ *   dlogits [B,nv,nv,nv,2] in ddtype, may be NULL                = (p - y) * grad_scale
+ *   cstride : channels per voxel in logits / dlogits (2, or 16 when conv11 is padded to a
+ *             tensor-core N granule; the extra channels are ignored / written as zero)      */
 int r2n2_softmax_ce3d(const float* logits, const float* y, float* pred, float* loss_sum,
-                      void* dlogits, int B, int nv, float grad_scale, int ddtype, void* stream);
+                      void* dlogits, int B, int nv, float grad_scale, int ddtype, int cstride,
+                      void* stream);
 
 /* ADAM (lib/solver.py:20-48) over one flat fp32 buffer; the first n_decay elements are
  * non-bias parameters (L2 term g += wd*p), the rest biases.  g is multiplied by grad_scale

@@ -204,8 +204,8 @@ def lstm_bwd(dh, ds_in, fig, s, h_new, da, ds_prev, B):
     ds_prev.copy_((dst * f).reshape(-1).to(ds_prev.dtype))
 
 
-def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale):
-    x = _f(logits).view(B, nv, nv, nv, 2)
+def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale, cstride=2):
+    x = _f(logits).view(B, nv, nv, nv, cstride)[..., :2]
     e = torch.exp(x)
     p = e / e.sum(-1, keepdim=True)
     yy = torch.zeros_like(x) if y is None else _f(y).view(B, nv, 2, nv, nv).permute(0, 1, 3, 4, 2)
@@ -214,7 +214,9 @@ def softmax_ce3d(logits, y, pred, loss_sum, dlogits, B, nv, grad_scale):
     if loss_sum is not None:
         loss_sum.add_((-(yy * x).sum(-1) + torch.log(e.sum(-1))).sum().to(loss_sum.dtype))
     if dlogits is not None:
-        dlogits.copy_(((p - yy) * grad_scale).reshape(-1).to(dlogits.dtype))
+        d = torch.zeros(B, nv, nv, nv, cstride, dtype=torch.float64)
+        d[..., :2] = (p - yy) * grad_scale
+        dlogits.copy_(d.reshape(-1).to(dlogits.dtype))
 
 
 def adam(p, g, m, v, mirror, n_decay, lr_t, b1, b2, eps, wd, grad_scale):

@@ -168,3 +168,34 @@ def test_layer_shapes_match_reference_fixture():
     with pytest.raises(ValueError):
         ly.InputLayer((1, 2)).output                       # lib/layers.py:88-92
     del ly.trainable_params[n0:]
+
+
+def test_engine_tensor_core_configuration_on_emulator(monkeypatch):
+    """bf16 / UMMA configuration of the engine (RGB padded to 16 channels, conv11 padded to 16
+    output channels, bf16 activations, fp32 master weights + bf16 mirrors) on the emulated ABI."""
+    emu.install(monkeypatch, ops)
+    B, T = 1, 2
+    params = rt.init_params('ResidualGRUNet', seed=0)
+    x, y = rt.synthetic_batch(T, B)
+    eng = Engine('ResidualGRUNet', B, device='cpu', compute='bf16', conv_algo=1, params_only=True)
+    assert eng.cin_pad == 16 and eng.logit_c == 16
+    eng.set_params(params)
+    eng.store.mirror.copy_(eng.store.p.to(torch.bfloat16))      # refresh_mirror is a CUDA kernel
+    for a, b in zip(eng.get_params(), params):
+        assert np.array_equal(a, b)
+    out = eng.forward(torch.as_tensor(x), torch.as_tensor(y), training=True)
+    eng.backward()
+    grads = eng.get_grads()
+    ref = rt.RefNet('ResidualGRUNet', params, dtype=torch.float64)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    assert np.abs(out['pred'].numpy() - rout['pred'].detach().numpy()).max() < 3e-2
+    for (name, shape, _), g, rg in zip(ref.spec, grads, rgrads):
+        rg = rg.numpy()
+        assert g.shape == tuple(shape)
+        cos = float((g * rg).sum() / (np.linalg.norm(g) * np.linalg.norm(rg) + 1e-30))
+        assert cos > 0.9, (name, cos)       # bf16 activations/gradients: conv1a.W is the noisiest
+    # padded conv11 rows / RGB pad channels carry exactly zero gradient
+    gW = eng.store.seg('conv11.W', eng.store.g).view(16, -1)
+    assert float(gW[2:].abs().max()) == 0.0
+    g1 = eng.store.seg('conv1a.W', eng.store.g).view(96, 7, 7, 16)
+    assert float(g1[..., 3:].abs().max()) == 0.0
