@@ -16,6 +16,7 @@
 //     mbarrier ring (full/empty per stage) and a tmem_full barrier.
 // The same kernel computes data gradients (dgrad) when fed dy and the transposed weights.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace r2n2 {
@@ -46,10 +47,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // raised (every later wait returns at once) and a global error word is set for the host.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag,
                                           int* err_word) {
+  if (mbar_try_wait(bar, parity)) return;
   if (*abort_flag) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL || *abort_flag) {
+    if (clock64() - t0 > 2000000000LL || *abort_flag) {
       *abort_flag = 1;
       if (err_word) atomicExch(err_word, 1);
       return;
@@ -115,6 +117,24 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sb
   return d;
 }
 
+// 16 consecutive output channels of one pixel: 2 x 16-byte stores (bf16) / 4 x 16-byte (fp32)
+__device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&f)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void store16(float* dst, const float (&f)[16]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+
 struct UmmaConvParams {
   int N, D, H, W, Cin, Cout;
   int kd, kh, kw;
@@ -128,6 +148,7 @@ struct UmmaConvParams {
   int tmem_cols;
   int flags;
   int* err_word;
+  long long* dbg;                          // optional [grid][8] clock64 timestamps (R2N2_UMMA_DBG=1)
 };
 
 constexpr int kUmmaThreads = 192;
@@ -150,6 +171,8 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   // tile coordinates
   int t = blockIdx.x;
@@ -181,6 +204,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   const int taps = p.kd * p.kh * p.kw;
   const int nkb = taps * p.kchunks;
@@ -189,26 +213,30 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
+    // A lone thread runs this loop: every instruction's latency is exposed, so the loop carries
+    // only counters (no divisions): nested (tz, ty, tx, chunk) iteration, incremental stage/phase.
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(rows * row_bytes + p.BN * row_bytes);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, abort_flag, p.err_word);
-        const int tap = kb / p.kchunks;
-        const int c0 = (kb - tap * p.kchunks) * p.kbox;
-        const int tz = tap / (p.kh * p.kw);
-        const int r2 = tap - tz * p.kh * p.kw;
-        const int ty = r2 / p.kw;
-        const int tx = r2 - ty * p.kw;
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_dst = a_dst + (uint32_t)p.a_stage_bytes;
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        mbar_expect_tx(bar, tx_bytes);
-        tma_load_5d(a_dst, &map_a, bar, c0, x0 + tx - (p.kw - 1) / 2, y0 + ty - (p.kh - 1) / 2,
-                    z0 + tz - (p.kd - 1) / 2, n0);
-        tma_load_2d(b_dst, &map_b, bar, tap * p.Cin + c0, col0);
-      }
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int cz = z0 - (p.kd - 1) / 2, cy = y0 - (p.kh - 1) / 2, cx = x0 - (p.kw - 1) / 2;
+      int s = 0;
+      uint32_t ph = 0;
+      int kcol = 0;                                   // tap * Cin + c0 (weights K coordinate)
+      for (int tz = 0; tz < p.kd; ++tz)
+        for (int ty = 0; ty < p.kh; ++ty)
+          for (int tx = 0; tx < p.kw; ++tx) {
+            for (int c0 = 0; c0 < p.Cin; c0 += p.kbox) {
+              mbar_wait(empty0 + 8u * s, ph ^ 1u, abort_flag, p.err_word);
+              const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+              const uint32_t bar = full0 + 8u * s;
+              mbar_expect_tx(bar, tx_bytes);
+              tma_load_5d(a_dst, &map_a, bar, c0, cx + tx, cy + ty, cz + tz, n0);
+              tma_load_2d(a_dst + (uint32_t)p.a_stage_bytes, &map_b, bar, kcol + c0, col0);
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            kcol += p.Cin;
+          }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -218,25 +246,33 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                              ((uint32_t)(128 >> 4) << 24);
       const uint32_t layout_type = (row_bytes == 128) ? 2u : (row_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-        mbar_wait(smem_u32(&full_bar[s]), ph, abort_flag, p.err_word);
-        tc_fence_after();
-        const int c0 = (kb % p.kchunks) * p.kbox;
-        int kvalid = p.Cin - c0;
-        if (kvalid > p.kbox) kvalid = p.kbox;
-        const int nk16 = kvalid >> 4;
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + (uint32_t)p.a_stage_bytes;
-        for (int k = 0; k < nk16; ++k) {
-          const uint64_t da = make_kmajor_desc(a_addr + k * 32, sbo, layout_type);
-          const uint64_t db = make_kmajor_desc(b_addr + k * 32, sbo, layout_type);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      // descriptor templates: only the 14-bit start-address field changes per MMA
+      const uint64_t desc_hi = make_kmajor_desc(0, sbo, layout_type);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int last_nk16 = (p.Cin - (p.kchunks - 1) * p.kbox) >> 4;
+      const int full_nk16 = p.kbox >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc = 0;
+      for (int tap = 0; tap < taps; ++tap)
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
+          tc_fence_after();
+          if (dbg && acc == 0) dbg[2] = clock64();
+          const int nk16 = (cc == p.kchunks - 1) ? last_nk16 : full_nk16;
+          const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
+          const uint64_t da0 = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+          const uint64_t db0 = desc_hi | (uint64_t)(((a_addr + (uint32_t)p.a_stage_bytes) & 0x3FFFF) >> 4);
+          for (int k = 0; k < nk16; ++k) {
+            umma_bf16(tmem_base, da0 + 2u * k, db0 + 2u * k, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(empty0 + 8u * s);              // frees the smem stage when the MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(smem_u32(&empty_bar[s]));      // frees the smem stage when the MMAs retire
-      }
-      umma_commit(smem_u32(tmem_full_bar));        // accumulator complete
+      if (dbg) dbg[3] = clock64();
+      umma_commit(smem_u32(tmem_full_bar));          // accumulator complete
     }
     __syncwarp();
   } else {
@@ -253,6 +289,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const long long pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
     mbar_wait(smem_u32(tmem_full_bar), 0u, abort_flag, p.err_word);
     tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
@@ -289,18 +326,23 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           f[j + 2] *= lrelu_slope(m4.z); f[j + 3] *= lrelu_slope(m4.w);
         }
       }
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        Vec4<TOut>::store(y + off + j, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+      store16(y + off, f);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[5] = clock64();
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
+  }
+  if (dbg && threadIdx.x == 0) {
+    dbg[6] = clock64();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[7] = smid;
   }
 }
 
@@ -359,6 +401,8 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
                           : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+static void umma_debug_report(const UmmaConvParams& p, dim3 grid, long long* dbg);
+
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
                   int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
@@ -392,6 +436,14 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   while (p.tmem_cols < p.BN) p.tmem_cols *= 2;
   p.flags = flags;
   p.err_word = get_err_word();
+  p.dbg = nullptr;
+  const bool want_dbg = getenv("R2N2_UMMA_DBG") != nullptr;
+  if (const char* e = getenv("R2N2_UMMA_STAGES")) p.stages = atoi(e);          // perf experiments
+  if (const char* e = getenv("R2N2_UMMA_BOX")) {
+    sscanf(e, "%d,%d,%d,%d", &p.bw, &p.bh, &p.bd, &p.bn);
+    p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
+    p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
+  }
 
   CUtensorMap map_a, map_b;
   {
@@ -425,6 +477,10 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n),
             (unsigned)((Cout + p.BN - 1) / p.BN));
   cudaError_t e;
+  if (want_dbg) {
+    cudaMalloc(&p.dbg, (size_t)grid.x * grid.y * 8 * sizeof(long long));
+    cudaMemset(p.dbg, 0, (size_t)grid.x * grid.y * 8 * sizeof(long long));
+  }
   if (out_dtype == R2N2_BF16) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -451,7 +507,36 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
   }
   R2N2_CHECK_LAUNCH("conv_fwd[umma]");
+  if (want_dbg) umma_debug_report(p, grid, p.dbg);
   return R2N2_OK;
+}
+
+// debugging aid for tools/bench_conv.py: per-CTA phase timestamps of ONE launch, summarised
+static void umma_debug_report(const UmmaConvParams& p, dim3 grid, long long* dbg) {
+  cudaDeviceSynchronize();
+  size_t n = (size_t)grid.x * grid.y;
+  long long* h = (long long*)malloc(n * 8 * sizeof(long long));
+  cudaMemcpy(h, dbg, n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  long long tmin = h[0], tmax = 0;
+  for (size_t i = 0; i < n; ++i) {
+    long long* d = h + i * 8;
+    s[0] += d[1] - d[0];   // setup (barrier init + TMEM alloc + sync)
+    s[1] += d[2] - d[1];   // first k-block arrives
+    s[2] += d[3] - d[2];   // main loop (first full -> last full)
+    s[3] += d[4] - d[3];   // last MMAs -> accumulator ready
+    s[4] += d[5] - d[4];   // epilogue
+    s[5] += d[6] - d[0];   // total CTA
+    if (d[0] < tmin) tmin = d[0];
+    if (d[6] > tmax) tmax = d[6];
+  }
+  fprintf(stderr,
+          "[umma dbg] grid %ux%u box %dx%dx%dx%d BN %d kbox %d stages %d nkb %d | avg cycles: setup %.0f "
+          "first-load %.0f mainloop %.0f drain %.0f epilogue %.0f total %.0f | span %lld\n",
+          grid.x, grid.y, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.stages, p.kd * p.kh * p.kw * p.kchunks,
+          s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[5] / n, tmax - tmin);
+  free(h);
+  cudaFree(dbg);
 }
 
 int umma_error_flag() {
@@ -513,6 +598,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   uint64_t* tmem_full_bar = bars + 2 * p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+  int* tap_off = reinterpret_cast<int*>(tmem_ptr_smem + 2);      // [G] packed (dx,dy,dz)+8
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -535,6 +621,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (box_end > p.nbox) box_end = p.nbox;
   const int nkb = (int)(box_end > box_begin ? box_end - box_begin : 0);
 
+  if (threadIdx.x < ntap) {
+    const int tap = tap0 + threadIdx.x;
+    const int tz = tap / (p.kh * p.kw);
+    const int r2 = tap - tz * p.kh * p.kw;
+    const int ty = r2 / p.kw;
+    const int tx = r2 - ty * p.kw;
+    tap_off[threadIdx.x] = (tx - (p.kw - 1) / 2 + 8) | ((ty - (p.kh - 1) / 2 + 8) << 8) |
+                           ((tz - (p.kd - 1) / 2 + 8) << 16);
+  }
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < p.stages; ++s) {
@@ -562,32 +657,40 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
 
   if (warp == 0) {
     if (lane == 0 && nkb > 0) {
+      // lean single-thread loop: incremental box coordinates, tap offsets precomputed in smem
       const uint32_t tx_bytes = (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      long long b = box_begin;
+      int tw = (int)(b % p.tiles_w); b /= p.tiles_w;
+      int th = (int)(b % p.tiles_h); b /= p.tiles_h;
+      int td = (int)(b % p.tiles_d); b /= p.tiles_d;
+      int tn = (int)b;
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, abort_flag, p.err_word);
-        long long b = box_begin + kb;
-        const int tw = (int)(b % p.tiles_w); b /= p.tiles_w;
-        const int th = (int)(b % p.tiles_h); b /= p.tiles_h;
-        const int td = (int)(b % p.tiles_d); b /= p.tiles_d;
-        const int tn = (int)b;
+        mbar_wait(empty0 + 8u * s, ph ^ 1u, abort_flag, p.err_word);
         const int x0 = tw * p.bw, y0 = th * p.bh, z0 = td * p.bd, n0 = tn * p.bn;
-        const uint32_t stage = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t stage = smem_base + (uint32_t)(s * p.stage_bytes);
+        const uint32_t bar = full0 + 8u * s;
         mbar_expect_tx(bar, tx_bytes);
         for (int c = 0; c < na; ++c)
           tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+        uint32_t bdst = stage + p.a_bytes;
         for (int g = 0; g < ntap; ++g) {
-          const int tap = tap0 + g;
-          const int tz = tap / (p.kh * p.kw);
-          const int r2 = tap - tz * p.kh * p.kw;
-          const int ty = r2 / p.kw;
-          const int tx = r2 - ty * p.kw;
-          const uint32_t bdst = stage + p.a_bytes + g * p.b_tap_bytes;
+          const int o = tap_off[g];
+          const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
           for (int c = 0; c < nb; ++c)
-            tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + tx - (p.kw - 1) / 2,
-                        y0 + ty - (p.kh - 1) / 2, z0 + tz - (p.kd - 1) / 2, n0);
+            tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + ox, y0 + oy, z0 + oz, n0);
+          bdst += p.b_tap_bytes;
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            if (++td == p.tiles_d) { td = 0; ++tn; }
+          }
         }
       }
     }
@@ -599,22 +702,35 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
                              ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lt_a = (rb_a == 128) ? 2u : (rb_a == 64 ? 4u : 6u);
       const uint32_t lt_b = (rb_b == 128) ? 2u : (rb_b == 64 ? 4u : 6u);
+      const uint64_t da_hi = make_mnmajor_desc(0, chunk_a, 8 * rb_a, lt_a);
+      const uint64_t db_hi = make_mnmajor_desc(0, chunk_b, 8 * rb_b, lt_b);
+      const uint32_t ka = (uint32_t)(16 * rb_a) >> 4, kbs = (uint32_t)(16 * rb_b) >> 4;  // desc step / K16
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int nk = p.rows >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (uint32_t)((kb / p.stages) & 1);
-        mbar_wait(smem_u32(&full_bar[s]), ph, abort_flag, p.err_word);
+        mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
+        const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+        uint32_t b_addr = a_addr + p.a_bytes;
+        uint32_t d_tmem = tmem_base;
         for (int g = 0; g < ntap; ++g) {
-          const uint32_t b_addr = a_addr + p.a_bytes + g * p.b_tap_bytes;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g * p.ci_cols);
-          for (int k = 0; k < p.rows / 16; ++k) {
-            const uint64_t da = make_mnmajor_desc(a_addr + k * 16 * rb_a, chunk_a, 8 * rb_a, lt_a);
-            const uint64_t db = make_mnmajor_desc(b_addr + k * 16 * rb_b, chunk_b, 8 * rb_b, lt_b);
-            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          const uint64_t db0 = db_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+          uint32_t a2 = acc;
+          for (int k = 0; k < nk; ++k) {
+            umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
+            a2 = 1;
           }
+          b_addr += p.b_tap_bytes;
+          d_tmem += (uint32_t)p.ci_cols;
         }
-        umma_commit(smem_u32(&empty_bar[s]));
+        acc = 1;
+        umma_commit(empty0 + 8u * s);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       umma_commit(smem_u32(tmem_full_bar));
     }
@@ -767,7 +883,7 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
                    cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 256 + 1024;
   dim3 grid((unsigned)splits, (unsigned)(co_tiles * p.ci_tiles), (unsigned)tap_groups);
   conv_wgrad_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma]");
