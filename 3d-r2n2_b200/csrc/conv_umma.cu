@@ -97,6 +97,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one elected lane of a fully converged warp (the loops below are executed by the WHOLE warp so
+// that ptxas keeps descriptors / barrier addresses in uniform registers; running them under
+// `if (lane == 0)` made every operand a vector register that needed R2UR moves per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -172,6 +184,8 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   long long* dbg = p.dbg ? p.dbg + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long* tl = (p.dbg && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0)
+                      ? p.dbg + (long long)gridDim.x * gridDim.y * 8 : nullptr;   // [kb][4] timeline
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   // tile coordinates
@@ -215,24 +229,33 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ================================ TMA producer =========================================
     // A lone thread runs this loop: every instruction's latency is exposed, so the loop carries
     // only counters (no divisions): nested (tz, ty, tx, chunk) iteration, incremental stage/phase.
-    if (lane == 0) {
+    {
       const uint32_t tx_bytes = (uint32_t)(rows * row_bytes + p.BN * row_bytes);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       const int cz = z0 - (p.kd - 1) / 2, cy = y0 - (p.kh - 1) / 2, cx = x0 - (p.kw - 1) / 2;
       int s = 0;
       uint32_t ph = 0;
+      int kbi = 0;
       int kcol = 0;                                   // tap * Cin + c0 (weights K coordinate)
       for (int tz = 0; tz < p.kd; ++tz)
         for (int ty = 0; ty < p.kh; ++ty)
           for (int tx = 0; tx < p.kw; ++tx) {
             for (int c0 = 0; c0 < p.Cin; c0 += p.kbox) {
               mbar_wait(empty0 + 8u * s, ph ^ 1u, abort_flag, p.err_word);
+              if (tl) { tl[kbi * 4 + 0] = clock64(); }
               const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
               const uint32_t bar = full0 + 8u * s;
-              mbar_expect_tx(bar, tx_bytes);
-              tma_load_5d(a_dst, &map_a, bar, c0, cx + tx, cy + ty, cz + tz, n0);
-              tma_load_2d(a_dst + (uint32_t)p.a_stage_bytes, &map_b, bar, kcol + c0, col0);
+              const int skip = (p.flags >> 16) & 3;        // perf experiment: 1 = no A loads, 2 = no B loads
+              if (elect_one()) {
+                mbar_expect_tx(bar, skip == 1 ? (uint32_t)(p.BN * row_bytes)
+                                              : (skip == 2 ? (uint32_t)(rows * row_bytes) : tx_bytes));
+                if (skip != 1) tma_load_5d(a_dst, &map_a, bar, c0, cx + tx, cy + ty, cz + tz, n0);
+                if (skip != 2)
+                  tma_load_2d(a_dst + (uint32_t)p.a_stage_bytes, &map_b, bar, kcol + c0, col0);
+              }
+              __syncwarp();
+              if (tl) { tl[kbi * 4 + 1] = clock64(); ++kbi; }
               if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
             kcol += p.Cin;
@@ -241,7 +264,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const uint32_t layout_type = (row_bytes == 128) ? 2u : (row_bytes == 64 ? 4u : 6u);
@@ -260,19 +283,26 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
           tc_fence_after();
           if (dbg && acc == 0) dbg[2] = clock64();
+          if (tl) tl[(tap * p.kchunks + cc) * 4 + 2] = clock64();
           const int nk16 = (cc == p.kchunks - 1) ? last_nk16 : full_nk16;
           const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
           const uint64_t da0 = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
           const uint64_t db0 = desc_hi | (uint64_t)(((a_addr + (uint32_t)p.a_stage_bytes) & 0x3FFFF) >> 4);
-          for (int k = 0; k < nk16; ++k) {
-            umma_bf16(tmem_base, da0 + 2u * k, db0 + 2u * k, idesc, acc);
-            acc = 1;
+          if (elect_one()) {
+            uint32_t a2 = acc;
+            for (int k = 0; k < nk16; ++k) {
+              umma_bf16(tmem_base, da0 + 2u * k, db0 + 2u * k, idesc, a2);
+              a2 = 1;
+            }
+            umma_commit(empty0 + 8u * s);            // frees the smem stage when the MMAs retire
           }
-          umma_commit(empty0 + 8u * s);              // frees the smem stage when the MMAs retire
+          __syncwarp();
+          acc = 1;
+          if (tl) tl[(tap * p.kchunks + cc) * 4 + 3] = clock64();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       if (dbg) dbg[3] = clock64();
-      umma_commit(smem_u32(tmem_full_bar));          // accumulator complete
+      if (elect_one()) umma_commit(smem_u32(tmem_full_bar));   // accumulator complete
     }
     __syncwarp();
   } else {
@@ -439,6 +469,10 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.dbg = nullptr;
   const bool want_dbg = getenv("R2N2_UMMA_DBG") != nullptr;
   if (const char* e = getenv("R2N2_UMMA_STAGES")) p.stages = atoi(e);          // perf experiments
+  if (const char* e = getenv("R2N2_UMMA_SKIP")) {
+    int v = atoi(e);
+    if (v == 1 || v == 2) p.flags |= v << 16;
+  }
   if (const char* e = getenv("R2N2_UMMA_BOX")) {
     sscanf(e, "%d,%d,%d,%d", &p.bw, &p.bh, &p.bd, &p.bn);
     p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
@@ -478,8 +512,8 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
             (unsigned)((Cout + p.BN - 1) / p.BN));
   cudaError_t e;
   if (want_dbg) {
-    cudaMalloc(&p.dbg, (size_t)grid.x * grid.y * 8 * sizeof(long long));
-    cudaMemset(p.dbg, 0, (size_t)grid.x * grid.y * 8 * sizeof(long long));
+    cudaMalloc(&p.dbg, ((size_t)grid.x * grid.y * 8 + 4 * 512) * sizeof(long long));
+    cudaMemset(p.dbg, 0, ((size_t)grid.x * grid.y * 8 + 4 * 512) * sizeof(long long));
   }
   if (out_dtype == R2N2_BF16) {
     static bool attr_set = false;
@@ -535,6 +569,17 @@ static void umma_debug_report(const UmmaConvParams& p, dim3 grid, long long* dbg
           "first-load %.0f mainloop %.0f drain %.0f epilogue %.0f total %.0f | span %lld\n",
           grid.x, grid.y, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.stages, p.kd * p.kh * p.kw * p.kchunks,
           s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[5] / n, tmax - tmin);
+  {
+    int nkb = p.kd * p.kh * p.kw * p.kchunks;
+    if (nkb > 64) nkb = 64;
+    long long tlh[4 * 64];
+    cudaMemcpy(tlh, dbg + n * 8, sizeof(long long) * 4 * nkb, cudaMemcpyDeviceToHost);
+    long long t0 = tlh[0];
+    fprintf(stderr, "[umma timeline] kb: empty-ok  tma-issued  full-seen  commit-issued (cycles from first)\n");
+    for (int i = 0; i < nkb; ++i)
+      fprintf(stderr, "[umma timeline] %2d: %7lld %7lld %7lld %7lld\n", i, tlh[i * 4] - t0, tlh[i * 4 + 1] - t0,
+              tlh[i * 4 + 2] - t0, tlh[i * 4 + 3] - t0);
+  }
   free(h);
   cudaFree(dbg);
 }
@@ -656,8 +701,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   const int chunk_a = p.rows * rb_a, chunk_b = p.rows * rb_b;
 
   if (warp == 0) {
-    if (lane == 0 && nkb > 0) {
-      // lean single-thread loop: incremental box coordinates, tap offsets precomputed in smem
+    if (nkb > 0) {
+      // warp-uniform loop: incremental box coordinates, tap offsets precomputed in smem
       const uint32_t tx_bytes = (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -673,17 +718,20 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const int x0 = tw * p.bw, y0 = th * p.bh, z0 = td * p.bd, n0 = tn * p.bn;
         const uint32_t stage = smem_base + (uint32_t)(s * p.stage_bytes);
         const uint32_t bar = full0 + 8u * s;
-        mbar_expect_tx(bar, tx_bytes);
-        for (int c = 0; c < na; ++c)
-          tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
-        uint32_t bdst = stage + p.a_bytes;
-        for (int g = 0; g < ntap; ++g) {
-          const int o = tap_off[g];
-          const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
-          for (int c = 0; c < nb; ++c)
-            tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + ox, y0 + oy, z0 + oz, n0);
-          bdst += p.b_tap_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(bar, tx_bytes);
+          for (int c = 0; c < na; ++c)
+            tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+          uint32_t bdst = stage + p.a_bytes;
+          for (int g = 0; g < ntap; ++g) {
+            const int o = tap_off[g];
+            const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
+            for (int c = 0; c < nb; ++c)
+              tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + ox, y0 + oy, z0 + oz, n0);
+            bdst += p.b_tap_bytes;
+          }
         }
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
         if (++tw == p.tiles_w) {
           tw = 0;
@@ -696,7 +744,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0) {
       const int nmma = (nci + 15) & ~15;                 // UMMA N
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -716,23 +764,26 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
         const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
-        uint32_t b_addr = a_addr + p.a_bytes;
-        uint32_t d_tmem = tmem_base;
-        for (int g = 0; g < ntap; ++g) {
-          const uint64_t db0 = db_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
-          uint32_t a2 = acc;
-          for (int k = 0; k < nk; ++k) {
-            umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
-            a2 = 1;
+        if (elect_one()) {
+          uint32_t b_addr = a_addr + p.a_bytes;
+          uint32_t d_tmem = tmem_base;
+          for (int g = 0; g < ntap; ++g) {
+            const uint64_t db0 = db_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+            uint32_t a2 = acc;
+            for (int k = 0; k < nk; ++k) {
+              umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
+              a2 = 1;
+            }
+            b_addr += p.b_tap_bytes;
+            d_tmem += (uint32_t)p.ci_cols;
           }
-          b_addr += p.b_tap_bytes;
-          d_tmem += (uint32_t)p.ci_cols;
+          umma_commit(empty0 + 8u * s);
         }
+        __syncwarp();
         acc = 1;
-        umma_commit(empty0 + 8u * s);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(smem_u32(tmem_full_bar));
+      if (elect_one()) umma_commit(smem_u32(tmem_full_bar));
     }
     __syncwarp();
   } else if (nkb > 0) {

@@ -1,14 +1,9 @@
 mkdir -p gpurun_out
-run() { echo "### $1" >> gpurun_out/exp_a.log; env $1 R2N2_UMMA_DBG=1 timeout 120 python tools/bench_conv.py --only conv2b --iters 1 --what fwd 2>&1 | grep -E "umma dbg|TF/s" | tail -2 >> gpurun_out/exp_a.log; }
-run "X=0"
-run "R2N2_UMMA_STAGES=2"
-run "R2N2_UMMA_STAGES=6"
-run "R2N2_UMMA_BOX=16,8,1,1"
-run "R2N2_UMMA_BOX=8,16,1,1"
-run "R2N2_UMMA_BOX=64,2,1,1"
-run "R2N2_UMMA_SKIP=1"
-run "R2N2_UMMA_SKIP=2"
-run "R2N2_UMMA_SKIP=3"
-run "R2N2_UMMA_SKIP=4"
-run "R2N2_UMMA_SKIP=7"
-run "R2N2_UMMA_BOX=16,8,1,1 R2N2_UMMA_STAGES=6"
+rm -f gpurun_out/exp_c.log
+run() { echo "### $1" >> gpurun_out/exp_c.log; env $1 R2N2_UMMA_DBG=1 timeout 60 python tools/bench_conv.py --only $2 --iters 1 --what fwd 2>&1 | grep -E "umma dbg|TF/s" | tail -2 | cut -c1-260 >> gpurun_out/exp_c.log; }
+run "R2N2_UMMA_SKIP=1" conv2b
+run "R2N2_UMMA_SKIP=2" conv2b
+run "R2N2_UMMA_SKIP=1 R2N2_UMMA_STAGES=6" conv2b
+run "R2N2_UMMA_SKIP=2 R2N2_UMMA_STAGES=6" conv2b
+run "R2N2_UMMA_SKIP=1" conv10b
+run "R2N2_UMMA_SKIP=2" conv10b
