@@ -46,6 +46,33 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
   }
 }
 
+// Row-packed first-layer input: y[n,h,w, kx*C + c] = x[n,c,h, w + kx - (kw-1)/2] (0 outside the
+// image, 0 for j >= kw*C).  A kh x kw convolution over C channels becomes a kh x 1 convolution over
+// Cpack channels, so the 7x7x3 first layer (K = 147) runs as 7 tensor-core K blocks of 32 instead of
+// 49 blocks of 16 zero-padded channels.
+template <typename T>
+__global__ void nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C,
+                                       int H, int W, int kw, int Cpack) {
+  long long total = (long long)N * H * W;
+  const int pad = (kw - 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    long long t = i / W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    T* out = y + i * Cpack;
+    int j = 0;
+    for (int kx = 0; kx < kw; ++kx) {
+      int sw = w + kx - pad;
+      bool in = (sw >= 0 && sw < W);
+      for (int c = 0; c < C; ++c, ++j)
+        out[j] = from_float<T>(in ? x[(((long long)n * C + c) * H + h) * W + sw] : 0.f);
+    }
+    for (; j < Cpack; ++j) out[j] = from_float<T>(0.f);
+  }
+}
+
 // ------------------------------------------------------------------ max pool 2x2/2 pad 1
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
@@ -634,6 +661,19 @@ int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int C
         x, (T*)y, N, C, H, W, Cpad, Wpad, xoff);
   })
   R2N2_CHECK_LAUNCH("nchw_to_nhwc");
+  return R2N2_OK;
+}
+
+int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, int kw, int Cpack,
+                         int out_dtype, void* stream) {
+  R2N2_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && (kw & 1) && kw * C <= Cpack, R2N2_ERR_BAD_SHAPE,
+                 "nchw_to_rowpack: bad shape");
+  long long total = (long long)N * H * W;
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    nchw_to_rowpack_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, (T*)y, N, C, H, W, kw, Cpack);
+  })
+  R2N2_CHECK_LAUNCH("nchw_to_rowpack");
   return R2N2_OK;
 }
 

@@ -132,6 +132,9 @@ class Engine:
         # conv11 has 2 output channels; on the tensor-core path it is padded to one N granule (16):
         # the extra weight rows are zero and stay zero (their gradients are exactly zero)
         self.logit_c = 2 if self.algo == L.ALGO_SIMT else 16
+        # tensor path: the 7x7x3 first layer runs on a row-packed input (7 taps x 3 channels packed
+        # into 32 channels by r2n2_nchw_to_rowpack) as a 7x1 convolution: K = 7*32 instead of 49*16
+        self.rowpack = 0 if self.algo == L.ALGO_SIMT else 32
         self.store = ParamStore(self.device, None if self.dtype == torch.float32 else self.dtype)
         self.P = {}
         self.weights = []      # RefWeight list in reference creation order
@@ -149,6 +152,11 @@ class Engine:
 
         def conv2(name, cout, cin, k, cin_pad=None):
             cp = cin_pad or cin
+            if cin_pad and self.rowpack:            # first layer, row-packed: [cout][k][rowpack]
+                st.plan(name + '.W', cout * k * self.rowpack, False)
+                st.plan(name + '.b', cout, True)
+                defs.append(('conv2rp', name, cout, cin, k, self.rowpack))
+                return
             st.plan(name + '.W', cout * k * k * cp, False)
             st.plan(name + '.b', cout, True)
             defs.append(('conv2', name, cout, cin, k, cp))
@@ -219,6 +227,17 @@ class Engine:
                 self.weights.append(RefWeight(
                     name + '.W', (cout, cin, k, k), False, vw,
                     lambda t, cp=cp: pk.pack_conv2d(t, cp), lambda v, cin=cin: pk.unpack_conv2d(v, cin)))
+                self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
+                                              lambda t: t, lambda v: v))
+            elif kind == 'conv2rp':
+                _, name, cout, cin, k, rp = dfn
+                mk_param(name + '.W', cout, k, rp)
+                mk_bias(name + '.b', cout)
+                vw = st.seg(name + '.W').view(cout, k, rp)
+                self.weights.append(RefWeight(
+                    name + '.W', (cout, cin, k, k), False, vw,
+                    lambda t, rp=rp: pk.pack_conv2d_rowpack(t, rp),
+                    lambda v, cin=cin, k=k: pk.unpack_conv2d_rowpack(v, cin, k)))
                 self.weights.append(RefWeight(name + '.b', (cout,), True, st.seg(name + '.b'),
                                               lambda t: t, lambda v: v))
             elif kind == 'conv3':
@@ -474,14 +493,21 @@ class Engine:
                 p.grad_written = False
         P = self.P
         x = x.contiguous()
-        xin = ctx.empty(TB * self.img * self.img * self.cin_pad, x)
-        ops.nchw_to_nhwc(x.view(TB, 3, self.img, self.img), xin, self.cin_pad)
-        a = Act(xin, (TB, 1, self.img, self.img, self.cin_pad))
-        a.useful = 3.0 / self.cin_pad          # RGB padded with zero channels
+        if self.rowpack:
+            xin = ctx.empty(TB * self.img * self.img * self.rowpack, x)
+            ops.nchw_to_rowpack(x.view(TB, 3, self.img, self.img), xin, 7, self.rowpack)
+            a = Act(xin, (TB, 1, self.img, self.img, self.rowpack))
+            a.useful = 21.0 / self.rowpack         # 7 taps x 3 channels of the 32 are real
+        else:
+            xin = ctx.empty(TB * self.img * self.img * self.cin_pad, x)
+            ops.nchw_to_nhwc(x.view(TB, 3, self.img, self.img), xin, self.cin_pad)
+            a = Act(xin, (TB, 1, self.img, self.img, self.cin_pad))
+            a.useful = 3.0 / self.cin_pad          # RGB padded with zero channels
 
         def c2(name, inp, lrelu, residual=None):
             k = 7 if name in ('conv1a', 'conv1') else (1 if name.endswith('c') else 3)
-            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (1, k, k), lrelu, residual)
+            kk = (1, k, 1) if (k == 7 and self.rowpack) else (1, k, k)
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, lrelu, residual)
 
         def c3(name, inp, lrelu, residual=None, out_dtype=None):
             k = 1 if name == 'conv9c' else 3

@@ -168,6 +168,14 @@ def nchw_to_nhwc(x, y, cpad, wpad=None, xoff=0):
     return y
 
 
+def nchw_to_rowpack(x, y, kw, cpack):
+    N, C, H, W = x.shape
+    _check(x, torch.float32), _check(y)
+    assert y.numel() == N * H * W * cpack
+    _call('r2n2_nchw_to_rowpack', _ptr(x), _ptr(y), N, C, H, W, kw, cpack, _DT[y.dtype], _stream())
+    return y
+
+
 def maxpool_fwd(a, b, y, N, H, W, C):
     _check(a), _check(b), _check(y)
     _work(0.0, (a, b, y))

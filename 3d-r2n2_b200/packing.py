@@ -28,6 +28,23 @@ def unpack_conv2d(w_packed, cin):
     return w_packed[..., :cin].permute(0, 3, 1, 2).flip(2, 3).contiguous()
 
 
+def pack_conv2d_rowpack(w_ref, cpack):
+    """(Cout,Cin,kh,kw) -> [Cout,kh,cpack] for a row-packed input (channel j = kx*Cin + c holds
+    x[..., w + kx - pad]): packed[co,ty,kx*Cin+c] = w_ref[co,c,kh-1-ty,kw-1-kx], zeros for j >= kw*Cin."""
+    cout, cin, kh, kw = w_ref.shape
+    p = w_ref.flip(2, 3).permute(0, 2, 3, 1).reshape(cout, kh, kw * cin)     # [co,ty,kx*cin+c]
+    out = w_ref.new_zeros(cout, kh, cpack)
+    out[..., :kw * cin] = p
+    return out
+
+
+def unpack_conv2d_rowpack(w_packed, cin, kw):
+    """[Cout,kh,cpack] -> (Cout,Cin,kh,kw)"""
+    cout, kh, _ = w_packed.shape
+    p = w_packed[..., :kw * cin].reshape(cout, kh, kw, cin)
+    return p.permute(0, 3, 1, 2).flip(2, 3).contiguous()
+
+
 def pack_conv3d(w_ref):
     """(Cout,kd,Cin,kh,kw) -> [Cout,kd,kh,kw,Cin]"""
     return w_ref.flip(1, 3, 4).permute(0, 1, 3, 4, 2).contiguous()

@@ -68,6 +68,17 @@ def config_dict(args, extra=None):
     return c
 
 
+def synthetic_batch(np, T, B, seed_x=1234, seed_y=4321, n_vox=32, img=127):
+    """ShapeNet-shaped synthetic inputs (lib/data_process.py:133-154 shapes/dtypes/ranges):
+    x (T,B,3,127,127) uniform [0,1); y (B,32,2,32,32) one-hot occupancy, ~10% occupied."""
+    x = np.random.RandomState(seed_x).uniform(0, 1, (T, B, 3, img, img)).astype(np.float32)
+    occ = np.random.RandomState(seed_y).rand(B, n_vox, n_vox, n_vox) < 0.1
+    y = np.zeros((B, n_vox, 2, n_vox, n_vox), np.float32)
+    y[:, :, 1] = occ
+    y[:, :, 0] = ~occ
+    return x, y
+
+
 # ------------------------------------------------------------------------------- CPU reference
 def cpu_reference_step(net_name, B, T, n_steps, warmup):
     """Times training steps of the oracle's torch-CPU restatement of the reference graph
@@ -165,7 +176,6 @@ def run_ours(args):
     from r2n2_b200.lib.solver import Solver
     from r2n2_b200.models import load_model
     from r2n2_b200 import dist as r2dist
-    from oracle import ref_torch as rt      # synthetic-input generator + CPU baseline only
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -191,7 +201,7 @@ def run_ours(args):
         r2dist.attach(solver)
 
     # synthetic ShapeNet-shaped batch (different per rank), pinned host copies for the e2e leg
-    x_np, y_np = rt.synthetic_batch(T, B, seed_x=1234 + rank, seed_y=4321 + rank)
+    x_np, y_np = synthetic_batch(np, T, B, seed_x=1234 + rank, seed_y=4321 + rank)
     x_pin = torch.as_tensor(x_np).pin_memory()
     y_pin = torch.as_tensor(y_np).pin_memory()
     x_dev, y_dev = x_pin.cuda(), y_pin.cuda()
@@ -241,12 +251,13 @@ def run_ours(args):
     # ---- roofline pass: CUDA events around every C-ABI launch of one more step (rank 0) ------
     roofline, table_out = None, None
     pk = peaks()
+    # every rank runs the step (it contains the gradient all-reduce); only rank 0 records events
+    prof = ops.Profiler() if rank == 0 else None
+    ops.profiler = prof
+    step_dev()
+    torch.cuda.synchronize()
+    ops.profiler = None
     if rank == 0:
-        prof = ops.Profiler()
-        ops.profiler = prof
-        step_dev()
-        torch.cuda.synchronize()
-        ops.profiler = None
         table, raw = prof.resolve()
         tot_ms = sum(d['ms'] for d in table.values())
         conv = table.get('r2n2_conv_fwd', dict(ms=0.0, flops=0.0, calls=0))

@@ -95,6 +95,12 @@ int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* str
 int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int Cpad, int Wpad,
                       int xoff, int out_dtype, void* stream);
 
+/* first-layer variant: y[n,h,w, kx*C + c] = x[n,c,h, w + kx - (kw-1)/2], zero outside the image and
+ * for channels >= kw*C, so that the kh x kw conv1 (models/res_gru_net.py:33) becomes a kh x 1
+ * convolution over Cpack channels (weights packed accordingly by the host mirror). */
+int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, int kw, int Cpack,
+                         int out_dtype, void* stream);
+
 /* PoolLayer (lib/layers.py:349-353): 2x2/2 max pool, pad 1 (-inf), floor.  If b != NULL the
  * pooled tensor is a+b (the AddLayer that precedes the pool in models/res_gru_net.py:92-93). */
 int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int dtype,

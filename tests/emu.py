@@ -80,6 +80,17 @@ def nchw_to_nhwc(x, y, cpad, wpad=None, xoff=0):
     return y
 
 
+def nchw_to_rowpack(x, y, kw, cpack):
+    N, C, H, W = x.shape
+    pad = (kw - 1) // 2
+    xp = F.pad(x, (pad, pad))
+    o = torch.zeros(N, H, W, cpack, dtype=y.dtype)
+    for kx in range(kw):
+        o[..., kx * C:(kx + 1) * C] = xp[:, :, :, kx:kx + W].permute(0, 2, 3, 1).to(y.dtype)
+    y.copy_(o.reshape(-1))
+    return y
+
+
 def _pool_in(a, b, N, H, W, C):
     s = _f(a).view(N, H, W, C)
     if b is not None:
@@ -245,7 +256,7 @@ def voxel_eval(pred, gt, thresh):
     return torch.stack([f(occ ^ g1), f(occ & g1), f(occ | g1), f(occ & g0), f(~occ & g1)], 1)
 
 
-ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'nchw_to_nhwc',
+ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'nchw_to_nhwc', 'nchw_to_rowpack',
        'maxpool_fwd', 'maxpool_bwd', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
        'eltwise', 'gru_ur_fwd', 'gru_out_fwd', 'gru_out_bwd', 'gru_r_bwd', 'lstm_fwd', 'lstm_bwd',
        'softmax_ce3d', 'adam', 'sgd', 'voxel_eval']

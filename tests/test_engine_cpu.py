@@ -197,5 +197,5 @@ def test_engine_tensor_core_configuration_on_emulator(monkeypatch):
     # padded conv11 rows / RGB pad channels carry exactly zero gradient
     gW = eng.store.seg('conv11.W', eng.store.g).view(16, -1)
     assert float(gW[2:].abs().max()) == 0.0
-    g1 = eng.store.seg('conv1a.W', eng.store.g).view(96, 7, 7, 16)
-    assert float(g1[..., 3:].abs().max()) == 0.0
+    g1 = eng.store.seg('conv1a.W', eng.store.g).view(96, 7, 32)      # row-packed first layer
+    assert eng.rowpack == 32 and float(g1[..., 21:].abs().max()) == 0.0

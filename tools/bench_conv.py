@@ -18,7 +18,7 @@ from r2n2_b200 import ops, _lib as L  # noqa: E402
 TB, B = 180, 36
 SHAPES = [
     # name, (N,D,H,W), Cin, Cout, k
-    ('conv1a', (TB, 1, 127, 127), 16, 96, (1, 7, 7)),
+    ('conv1a', (TB, 1, 127, 127), 32, 96, (1, 7, 1)),      # row-packed first layer
     ('conv1b', (TB, 1, 127, 127), 96, 96, (1, 3, 3)),
     ('conv2a', (TB, 1, 64, 64), 96, 128, (1, 3, 3)),
     ('conv2b', (TB, 1, 64, 64), 128, 128, (1, 3, 3)),
