@@ -1,0 +1,401 @@
+// Persistent tcgen05 / TMEM / TMA implicit-GEMM convolution (forward and data gradient), sm_100a.
+//
+//   y[p, co] = epilogue( sum_{tap, ci} x[p + off(tap), ci] * w[co, tap, ci] )     bf16 x bf16 -> fp32
+//
+// One CTA per SM loops over (M tile, N tile) pairs:
+//   * M tile = 128-pixel SPATIAL BOX of the channels-last tensor; for each filter tap the A operand
+//     is one tiled-TMA load of the shifted box (out-of-bounds zero fill = 'same' padding);
+//   * N tile = BN output channels (<= 256); weights [Cout][taps*Cin] come in through a 2-D TMA;
+//   * a pipeline STAGE holds NSUB (tap, channel-chunk) sub-blocks, so that one full/empty barrier
+//     round feeds NSUB * kbox/16 MMAs (the per-round wait/fence/commit overhead of the single
+//     issuing thread is ~300 cycles: it has to be amortised over >= 512 cycles of tensor work);
+//   * TWO accumulators live in TMEM (2 x BN columns): the epilogue warps drain tile i
+//     (tcgen05.ld -> bias / LeakyReLU / residual / LeakyReLU' -> 16-byte global stores) while the
+//     MMA warp already accumulates tile i+1 and the TMA warp prefetches further ahead.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.  All role loops are executed by
+// the whole warp (elect.sync around the issuing instructions) so operands stay in uniform registers.
+#include "umma.cuh"
+
+namespace r2n2 {
+
+struct FwdParams {
+  int N, D, H, W, Cin, Cout;
+  int kd, kh, kw;
+  int bw, bh, bd, bn;                      // spatial box of the M tile
+  int tiles_w, tiles_h, tiles_d, tiles_n;  // boxes per axis
+  int m_tiles, n_tiles, total_tiles;
+  int BN, bn_cols;                         // N tile and its TMEM column footprint
+  int kbox, kchunks;                       // channels per sub-block, sub-blocks per tap
+  int nsub;                                // sub-blocks per pipeline stage
+  int stages;
+  int a_bytes, b_bytes, stage_bytes;       // per sub-block A / B bytes (1024-aligned), per stage
+  int tmem_cols;
+  int flags;
+  int* err_word;
+};
+
+template <typename TOut>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
+                         const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
+  uint64_t* empty_bar = bars + p.stages;           // [stages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]       MMA -> epilogue (accumulator ready)
+  uint64_t* tempty_bar = bars + 2 * p.stages + 2;  // [2]       epilogue -> MMA (accumulator drained)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), 4);      // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int taps = p.kd * p.kh * p.kw;
+  const int nq = taps * p.kchunks;                  // sub-blocks per tile
+  const int row_bytes = p.kbox * 2;
+  const int rows = p.bw * p.bh * p.bd * p.bn;
+  const int sub_bytes = p.a_bytes + p.b_bytes;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+
+  if (warp == 0) {
+    // ================================ TMA producer =========================================
+    const uint32_t sub_tx = (uint32_t)(rows * row_bytes + p.BN * row_bytes);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int td = t % p.tiles_d; t /= p.tiles_d;
+      const int cx = tw * p.bw - (p.kw - 1) / 2, cy = th * p.bh - (p.kh - 1) / 2,
+                cz = td * p.bd - (p.kd - 1) / 2, n0 = t * p.bn;
+      const int col0 = nt * p.BN;
+      int tz = 0, ty = 0, tx = 0, c0 = 0, kcol = 0;       // current sub-block (tap, channel chunk)
+      for (int q0 = 0; q0 < nq; q0 += p.nsub) {
+        const int ns = (nq - q0 < p.nsub) ? nq - q0 : p.nsub;
+        mbar_wait(empty0 + 8u * s, ph ^ 1u, abort_flag, p.err_word);
+        const uint32_t bar = full0 + 8u * s;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(bar, sub_tx * (uint32_t)ns);
+        uint32_t dst = smem_base + (uint32_t)(s * p.stage_bytes);
+        for (int u = 0; u < ns; ++u) {
+          if (leader) {
+            tma_load_5d(dst, &map_a, bar, c0, cx + tx, cy + ty, cz + tz, n0);
+            tma_load_2d(dst + (uint32_t)p.a_bytes, &map_b, bar, kcol + c0, col0);
+          }
+          dst += (uint32_t)sub_bytes;
+          c0 += p.kbox;
+          if (c0 >= p.Cin) {
+            c0 = 0; kcol += p.Cin;
+            if (++tx == p.kw) { tx = 0; if (++ty == p.kh) { ty = 0; ++tz; } }
+          }
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===========================================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    const uint32_t layout_type = (row_bytes == 128) ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint64_t desc_hi = make_kmajor_desc(0, 8u * (uint32_t)row_bytes, layout_type);
+    const int last_nk16 = (p.Cin - (p.kchunks - 1) * p.kbox) >> 4;
+    const int full_nk16 = p.kbox >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u, abort_flag, p.err_word);   // accumulator drained
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn_cols);
+      uint32_t acc = 0;
+      int cc = 0;                                                          // channel chunk counter
+      for (int q0 = 0; q0 < nq; q0 += p.nsub) {
+        const int ns = (nq - q0 < p.nsub) ? nq - q0 : p.nsub;
+        mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
+        if (elect_one()) {
+          uint32_t addr = a_addr;
+          int c = cc;
+          uint32_t a2 = acc;
+          for (int u = 0; u < ns; ++u) {
+            const int nk16 = (c == p.kchunks - 1) ? last_nk16 : full_nk16;
+            const uint64_t da0 = desc_hi | (uint64_t)((addr & 0x3FFFF) >> 4);
+            const uint64_t db0 = desc_hi | (uint64_t)(((addr + (uint32_t)p.a_bytes) & 0x3FFFF) >> 4);
+            for (int k = 0; k < nk16; ++k) {
+              umma_bf16(d_tmem, da0 + 2u * k, db0 + 2u * k, idesc, a2);
+              a2 = 1;
+            }
+            addr += (uint32_t)sub_bytes;
+            if (++c == p.kchunks) c = 0;
+          }
+          umma_commit(empty0 + 8u * s);                 // stage free once these MMAs retire
+        }
+        __syncwarp();
+        acc = 1;
+        cc += ns;
+        while (cc >= p.kchunks) cc -= p.kchunks;
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(tfull0 + 8u * buf);  // accumulator complete
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) =================================
+    const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+    const int row = quad * 32 + lane;
+    int r = row;
+    const int xi = r % p.bw; r /= p.bw;
+    const int yi = r % p.bh; r /= p.bh;
+    const int zi = r % p.bd; r /= p.bd;
+    const int ni = r;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int nt = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int td = t % p.tiles_d; t /= p.tiles_d;
+      const int xx = tw * p.bw + xi, yy = th * p.bh + yi, zz = td * p.bd + zi, nn = t * p.bn + ni;
+      const bool valid = (row < rows) && xx < p.W && yy < p.H && zz < p.D && nn < p.N;
+      const long long pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
+      const int col0 = nt * p.BN;
+      mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);
+        const int co = col0 + c;
+        if (!valid || co >= p.Cout) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          }
+        }
+        if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
+        }
+        const long long off = pix * p.Cout + co;
+        if (p.flags & R2N2_EPI_RESIDUAL) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 r4 = Vec4<TOut>::load(res + off + j);
+            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+          }
+        }
+        if (p.flags & R2N2_EPI_MASK) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 m4 = Vec4<TOut>::load(mask + off + j);
+            f[j] *= lrelu_slope(m4.x); f[j + 1] *= lrelu_slope(m4.y);
+            f[j + 2] *= lrelu_slope(m4.z); f[j + 3] *= lrelu_slope(m4.w);
+          }
+        }
+        store16(y + off, f);
+      }
+      // this warp has finished reading the accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// choose the spatial box (bw,bh,bd,bn), product <= 128, minimising the number of M tiles
+static void choose_box_fwd(int N, int D, int H, int W, int& bw, int& bh, int& bd, int& bn) {
+  long long best = -1;
+  int best_rows = 0;
+  for (int w = 1; w <= W && w <= 128; ++w)
+    for (int h = 1; h <= H && w * h <= 128; ++h)
+      for (int d = 1; d <= D && w * h * d <= 128; ++d) {
+        int n = 128 / (w * h * d);
+        if (n > N) n = N;
+        if (n < 1) continue;
+        long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d) *
+                          ((N + n - 1) / n);
+        int rows = w * h * d * n;
+        // fewer tiles first; then the most compact box (short TMA rows hurt nothing, but a box that
+        // follows the memory order keeps the L2 footprint of the shifted taps small)
+        if (best < 0 || tiles < best || (tiles == best && (rows < best_rows))) {
+          best = tiles; best_rows = rows;
+          bw = w; bh = h; bd = d; bn = n;
+        }
+      }
+}
+
+int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void* mask,
+                     const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                     int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st);
+
+int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
+                  const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
+  if (getenv("R2N2_UMMA_V1"))          // A/B comparison with the one-tile-per-CTA kernel
+    return conv_fwd_umma_v1(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
+                            out_dtype, st);
+  R2N2_CHECK_ARG(in_dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: operands must be bf16");
+  R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd[umma]: non-positive dimension");
+  R2N2_CHECK_ARG((kd & 1) && (kh & 1) && (kw & 1), R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd[umma]: kernel extents must be odd");
+  R2N2_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0, R2N2_ERR_UNSUPPORTED,
+                 "conv_fwd[umma]: Cin (%d) and Cout (%d) must be multiples of 16 (use ALGO_SIMT)", Cin, Cout);
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode();
+  R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled unavailable");
+
+  FwdParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.kd = kd; p.kh = kh; p.kw = kw;
+  choose_box_fwd(N, D, H, W, p.bw, p.bh, p.bd, p.bn);
+  p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
+  p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+  p.BN = Cout >= 256 ? 256 : Cout;
+  if (const char* e = getenv("R2N2_UMMA_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && v <= Cout) p.BN = v; }
+  p.n_tiles = (Cout + p.BN - 1) / p.BN;
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.bn_cols = (p.BN + 31) / 32 * 32;
+  p.kbox = Cin >= 64 ? 64 : (Cin >= 32 ? 32 : 16);
+  p.kchunks = (Cin + p.kbox - 1) / p.kbox;
+  const int row_bytes = p.kbox * 2;
+  p.a_bytes = (128 * row_bytes + 1023) / 1024 * 1024;
+  p.b_bytes = (p.BN * row_bytes + 1023) / 1024 * 1024;
+  const int sub_bytes = p.a_bytes + p.b_bytes;
+  const int nq = kd * kh * kw * p.kchunks;
+  // sub-blocks per stage: aim at >= 512 cycles of MMA per barrier round, stage <= 64 KB
+  const int mma_cycles_per_sub = (p.kbox / 16) * (p.BN / 2);
+  int nsub = (512 + mma_cycles_per_sub - 1) / mma_cycles_per_sub;
+  if (nsub > 8) nsub = 8;
+  while (nsub > 1 && nsub * sub_bytes > 64 * 1024) --nsub;
+  if (nsub > nq) nsub = nq;
+  if (const char* e = getenv("R2N2_UMMA_NSUB")) { int v = atoi(e); if (v >= 1 && v <= 8) nsub = v < nq ? v : nq; }
+  p.nsub = nsub;
+  p.stage_bytes = nsub * sub_bytes;
+  int stages = (200 * 1024) / p.stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  if (const char* e = getenv("R2N2_UMMA_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 12) stages = v; }
+  p.stages = stages;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.bn_cols) p.tmem_cols *= 2;
+  p.flags = flags;
+  p.err_word = get_err_word();
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+  R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma]: pipeline does not fit smem");
+
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+                         (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA,
+                   "conv_fwd[umma]: cuTensorMapEncodeTiled(A) failed (%d) dims %d,%d,%d,%d,%d box %d,%d,%d,%d,%d",
+                   (int)r, Cin, W, H, D, N, p.kbox, p.bw, p.bh, p.bd, p.bn);
+  }
+  {
+    const long long K = (long long)kd * kh * kw * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA,
+                   "conv_fwd[umma]: cuTensorMapEncodeTiled(B) failed (%d) K %lld Cout %d box %d,%d", (int)r,
+                   K, Cout, p.kbox, p.BN);
+  }
+  int grid = num_sms();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (getenv("R2N2_UMMA_DBG"))
+    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d smem %zu\n",
+            p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages,
+            smem_bytes);
+  cudaError_t e;
+  if (out_dtype == R2N2_BF16) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_fwd_umma_persistent<__nv_bfloat16>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    conv_fwd_umma_persistent<__nv_bfloat16><<<grid, kUmmaThreads, smem_bytes, st>>>(
+        map_a, map_b, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
+  } else if (out_dtype == R2N2_F32) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_fwd_umma_persistent<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
+      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    conv_fwd_umma_persistent<float><<<grid, kUmmaThreads, smem_bytes, st>>>(
+        map_a, map_b, bias, (const float*)mask, (const float*)res, (float*)y, p);
+  } else {
+    R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
+  }
+  R2N2_CHECK_LAUNCH("conv_fwd[umma]");
+  return R2N2_OK;
+}
+
+}  // namespace r2n2
