@@ -315,16 +315,26 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.b_bytes = (p.BN * row_bytes + 1023) / 1024 * 1024;
   const int sub_bytes = p.a_bytes + p.b_bytes;
   const int nq = kd * kh * kw * p.kchunks;
-  // sub-blocks per stage: aim at >= 512 cycles of MMA per barrier round, stage <= 64 KB
+  // narrow N tiles are bound by the single MMA-issuing thread, not by the tensor pipe: run two
+  // CTAs (two issuers) per SM there; wide tiles get the whole SM (deeper stages, 2 x 256 TMEM cols)
+  // (measured, profiles/r01_umma_ctas_nsub_sweep.txt: N<=64 +40%, N=128 +5..18%; N=96 prefers one
+  // CTA with two sub-blocks per stage because a single 28 KB sub-block is < 256 MMA cycles)
+  const int sub_cycles = (p.kbox / 16) * (p.BN / 2);
+  int ctas = (p.BN <= 64 || (p.BN <= 128 && sub_cycles >= 256)) ? 2 : 1;
+  if (const char* e = getenv("R2N2_UMMA_CTAS")) { int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
+  if (2 * p.bn_cols * ctas > 512) ctas = 1;
+  const int smem_budget = (ctas == 2 ? 100 : 200) * 1024;
+  const int stage_cap = (ctas == 2 ? 48 : 64) * 1024;
+  // sub-blocks per stage: aim at >= 512 cycles of MMA per barrier round, stage <= stage_cap
   const int mma_cycles_per_sub = (p.kbox / 16) * (p.BN / 2);
   int nsub = (512 + mma_cycles_per_sub - 1) / mma_cycles_per_sub;
   if (nsub > 8) nsub = 8;
-  while (nsub > 1 && nsub * sub_bytes > 64 * 1024) --nsub;
+  while (nsub > 1 && nsub * sub_bytes > stage_cap) --nsub;
   if (nsub > nq) nsub = nq;
   if (const char* e = getenv("R2N2_UMMA_NSUB")) { int v = atoi(e); if (v >= 1 && v <= 8) nsub = v < nq ? v : nq; }
   p.nsub = nsub;
   p.stage_bytes = nsub * sub_bytes;
-  int stages = (200 * 1024) / p.stage_bytes;
+  int stages = smem_budget / p.stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   if (const char* e = getenv("R2N2_UMMA_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 12) stages = v; }
@@ -364,11 +374,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
                    "conv_fwd[umma]: cuTensorMapEncodeTiled(B) failed (%d) K %lld Cout %d box %d,%d", (int)r,
                    K, Cout, p.kbox, p.BN);
   }
-  int grid = num_sms();
+  int grid = num_sms() * ctas;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (getenv("R2N2_UMMA_DBG"))
-    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d smem %zu\n",
-            p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages,
+    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d smem %zu\n",
+            p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages, ctas,
             smem_bytes);
   cudaError_t e;
   if (out_dtype == R2N2_BF16) {
