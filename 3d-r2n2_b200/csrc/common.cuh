@@ -61,6 +61,49 @@ struct Vec4<__nv_bfloat16> {
   }
 };
 
+// ---- 16-byte vector of channels: 4 x fp32 or 8 x bf16, widened to float --------------------------
+template <typename T>
+struct Pack;
+template <>
+struct Pack<float> {
+  static constexpr int N = 4;
+  float v[4];
+  static __device__ __forceinline__ Pack load(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    Pack r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Pack<__nv_bfloat16> {
+  static constexpr int N = 8;
+  float v[8];
+  static __device__ __forceinline__ Pack load(const __nv_bfloat16* p) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    Pack r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      float2 f = __bfloat1622float2(h);
+      r.v[2 * j] = f.x; r.v[2 * j + 1] = f.y;
+    }
+    return r;
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ float to_float(T v);
 template <>

@@ -53,23 +53,29 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
 template <typename T>
 __global__ void nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C,
                                        int H, int W, int kw, int Cpack) {
-  long long total = (long long)N * H * W;
+  // one thread per (pixel, 16-byte group of packed channels): coalesced reads along w for every
+  // (kx, c), 16-byte stores
+  constexpr int PN = Pack<T>::N;
+  const int groups = Cpack / PN;
+  long long total = (long long)N * H * W * groups;
   const int pad = (kw - 1) / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int w = (int)(i % W);
-    long long t = i / W;
+    int gq = (int)(i % groups);
+    long long pix = i / groups;
+    int w = (int)(pix % W);
+    long long t = pix / W;
     int h = (int)(t % H);
     int n = (int)(t / H);
-    T* out = y + i * Cpack;
-    int j = 0;
-    for (int kx = 0; kx < kw; ++kx) {
+    Pack<T> o;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) {
+      int j = gq * PN + e;
+      int kx = j / C, c = j - kx * C;
       int sw = w + kx - pad;
-      bool in = (sw >= 0 && sw < W);
-      for (int c = 0; c < C; ++c, ++j)
-        out[j] = from_float<T>(in ? x[(((long long)n * C + c) * H + h) * W + sw] : 0.f);
+      o.v[e] = (kx < kw && sw >= 0 && sw < W) ? x[(((long long)n * C + c) * H + h) * W + sw] : 0.f;
     }
-    for (; j < Cpack; ++j) out[j] = from_float<T>(0.f);
+    o.store(y + pix * Cpack + gq * PN);
   }
 }
 
@@ -77,17 +83,20 @@ __global__ void nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restric
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                    T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
-  int C4 = C >> 2;
-  long long total = (long long)N * Ho * Wo * C4;
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
+  long long total = (long long)N * Ho * Wo * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    long long t = i / C4;
+    int cg = (int)(i % CG);
+    long long t = i / CG;
     int wo = (int)(t % Wo);
     t /= Wo;
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    Pack<T> m;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
       int h = 2 * ho - 1 + dy;
@@ -96,16 +105,18 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict_
       for (int dx = 0; dx < 2; ++dx) {
         int w = 2 * wo - 1 + dx;
         if (w < 0 || w >= W) continue;
-        long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
-        float4 v = Vec4<T>::load(a + off);
+        long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+        Pack<T> v = Pack<T>::load(a + off);
         if (b) {
-          float4 u = Vec4<T>::load(b + off);
-          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+          Pack<T> u = Pack<T>::load(b + off);
+#pragma unroll
+          for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];
         }
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
       }
     }
-    Vec4<T>::store(y + i * 4, m);
+    m.store(y + i * PN);
   }
 }
 
@@ -113,50 +124,51 @@ template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                    const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
                                    int W, int C, int Ho, int Wo, int lrelu_mask) {
-  int C4 = C >> 2;
-  long long total = (long long)N * Ho * Wo * C4;
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
+  long long total = (long long)N * Ho * Wo * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    long long t = i / C4;
+    int cg = (int)(i % CG);
+    long long t = i / CG;
     int wo = (int)(t % Wo);
     t /= Wo;
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
-    float4 s[4], av[4];
+    Pack<T> s[4], av[4], m;
     bool valid[4];
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
       valid[k] = (h >= 0 && h < H && w >= 0 && w < W);
       if (!valid[k]) continue;
-      long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
-      float4 v = Vec4<T>::load(a + off);
+      long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+      Pack<T> v = Pack<T>::load(a + off);
       av[k] = v;
       if (b) {
-        float4 u = Vec4<T>::load(b + off);
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;  // same fp32 sums the forward compared
+        Pack<T> u = Pack<T>::load(b + off);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];      // same fp32 sums the forward compared
       }
       s[k] = v;
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+#pragma unroll
+      for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
     }
-    float4 g = Vec4<T>::load(dy + i * 4);
+    Pack<T> g = Pack<T>::load(dy + i * PN);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!valid[k]) continue;
       int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
-      long long off = (((long long)n * H + h) * W + w) * C + c4 * 4;
-      float4 o;
-      o.x = (s[k].x == m.x) ? g.x : 0.f;
-      o.y = (s[k].y == m.y) ? g.y : 0.f;
-      o.z = (s[k].z == m.z) ? g.z : 0.f;
-      o.w = (s[k].w == m.w) ? g.w : 0.f;
-      if (lrelu_mask) {
-        o.x *= lrelu_slope(av[k].x); o.y *= lrelu_slope(av[k].y);
-        o.z *= lrelu_slope(av[k].z); o.w *= lrelu_slope(av[k].w);
+      long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+      Pack<T> o;
+#pragma unroll
+      for (int e = 0; e < PN; ++e) {
+        o.v[e] = (s[k].v[e] == m.v[e]) ? g.v[e] : 0.f;
+        if (lrelu_mask) o.v[e] *= lrelu_slope(av[k].v[e]);
       }
-      Vec4<T>::store(dx + off, o);
+      o.store(dx + off);
     }
   }
 }
@@ -165,46 +177,51 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict_
 template <typename T>
 __global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                   T* __restrict__ y, int B, int D, int H, int W, int C) {
-  int C4 = C >> 2;
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
   int D2 = 2 * D, H2 = 2 * H, W2 = 2 * W;
-  long long total = (long long)B * D2 * H2 * W2 * C4;
+  long long total = (long long)B * D2 * H2 * W2 * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    long long t = i / C4;
+    int cg = (int)(i % CG);
+    long long t = i / CG;
     int x = (int)(t % W2); t /= W2;
     int yy = (int)(t % H2); t /= H2;
     int z = (int)(t % D2);
     int n = (int)(t / D2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    Pack<T> v;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) v.v[e] = 0.f;
     if (((x | yy | z) & 1) == 0) {
-      long long off = ((((long long)n * D + (z >> 1)) * H + (yy >> 1)) * W + (x >> 1)) * C + c4 * 4;
-      v = Vec4<T>::load(a + off);
+      long long off = ((((long long)n * D + (z >> 1)) * H + (yy >> 1)) * W + (x >> 1)) * C + cg * PN;
+      v = Pack<T>::load(a + off);
       if (b) {
-        float4 u = Vec4<T>::load(b + off);
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        Pack<T> u = Pack<T>::load(b + off);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];
       }
     }
-    Vec4<T>::store(y + i * 4, v);
+    v.store(y + i * PN);
   }
 }
 
 template <typename T>
 __global__ void unpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int D,
                                   int H, int W, int C) {
-  int C4 = C >> 2;
-  long long total = (long long)B * D * H * W * C4;
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
+  long long total = (long long)B * D * H * W * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    long long t = i / C4;
+    int cg = (int)(i % CG);
+    long long t = i / CG;
     int x = (int)(t % W); t /= W;
     int yy = (int)(t % H); t /= H;
     int z = (int)(t % D);
     int n = (int)(t / D);
     long long off =
-        ((((long long)n * 2 * D + 2 * z) * 2 * H + 2 * yy) * 2 * W + 2 * x) * C + c4 * 4;
-    Vec4<T>::store(dx + i * 4, Vec4<T>::load(dy + off));
+        ((((long long)n * 2 * D + 2 * z) * 2 * H + 2 * yy) * 2 * W + 2 * x) * C + cg * PN;
+    Pack<T>::load(dy + off).store(dx + i * PN);
   }
 }
 
@@ -509,25 +526,47 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
 }
 
 // ------------------------------------------------------------------ bias gradient (column sums)
+// grid.x covers channel groups of 32*PN (a warp reads 512 contiguous bytes of one row), grid.y
+// splits the rows; 8 row-lanes per block, fp32 register accumulation, smem reduce, one atomic per
+// (block, channel).  Scalar tail path for C not a multiple of the vector width (conv11: C = 2).
 template <typename T>
 __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
                                  int C, long long rows_per_block) {
-  __shared__ float red[8][33];
-  int cx = threadIdx.x, ry = threadIdx.y;
-  int c = blockIdx.x * 32 + cx;
+  constexpr int PN = Pack<T>::N;
+  __shared__ float red[8][32 * PN + 1];
+  const int cx = threadIdx.x, ry = threadIdx.y;
   long long r0 = blockIdx.y * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  float acc = 0.f;
-  if (c < C)
-    for (long long r = r0 + ry; r < r1; r += 8) acc += to_float<T>(dy[r * C + c]);
-  red[ry][cx] = acc;
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    float t = 0.f;
+  float acc[PN];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][cx];
-    atomicAdd(db + c, t);
+  for (int e = 0; e < PN; ++e) acc[e] = 0.f;
+  const bool vec = (C % PN) == 0;
+  const int c0 = (blockIdx.x * 32 + cx) * PN;
+  if (vec) {
+    if (c0 < C)
+      for (long long r = r0 + ry; r < r1; r += 8) {
+        Pack<T> v = Pack<T>::load(dy + r * C + c0);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) acc[e] += v.v[e];
+      }
+  } else {
+    for (int e = 0; e < PN; ++e)
+      if (c0 + e < C)
+        for (long long r = r0 + ry; r < r1; r += 8) acc[e] += to_float<T>(dy[r * C + c0 + e]);
+  }
+#pragma unroll
+  for (int e = 0; e < PN; ++e) red[ry][cx * PN + e] = acc[e];
+  __syncthreads();
+  if (ry == 0) {
+#pragma unroll
+    for (int e = 0; e < PN; ++e) {
+      if (c0 + e >= C) continue;
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][cx * PN + e];
+      atomicAdd(db + c0 + e, t);
+    }
   }
 }
 
@@ -666,9 +705,9 @@ int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int C
 
 int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, int kw, int Cpack,
                          int out_dtype, void* stream) {
-  R2N2_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && (kw & 1) && kw * C <= Cpack, R2N2_ERR_BAD_SHAPE,
-                 "nchw_to_rowpack: bad shape");
-  long long total = (long long)N * H * W;
+  R2N2_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && (kw & 1) && kw * C <= Cpack && (Cpack % 8) == 0,
+                 R2N2_ERR_BAD_SHAPE, "nchw_to_rowpack: bad shape");
+  long long total = (long long)N * H * W * (Cpack / (out_dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
     nchw_to_rowpack_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         x, (T*)y, N, C, H, W, kw, Cpack);
@@ -679,10 +718,10 @@ int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, in
 
 int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int W, int C, int dtype,
                        void* stream) {
-  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
-                 "maxpool2d_fwd: C must be a positive multiple of 4 (got %d)", C);
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+                 R2N2_ERR_BAD_SHAPE, "maxpool2d_fwd: C must be a multiple of 4 (fp32) / 8 (bf16), got %d", C);
   int Ho = H / 2 + 1, Wo = W / 2 + 1;
-  long long total = (long long)N * Ho * Wo * (C >> 2);
+  long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
     maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
@@ -693,10 +732,10 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
 
 int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
                        int C, int lrelu_mask, int dtype, void* stream) {
-  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
-                 "maxpool2d_bwd: C must be a positive multiple of 4 (got %d)", C);
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+                 R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd: C must be a multiple of 4 (fp32) / 8 (bf16), got %d", C);
   int Ho = H / 2 + 1, Wo = W / 2 + 1;
-  long long total = (long long)N * Ho * Wo * (C >> 2);
+  long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
     maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
@@ -707,9 +746,9 @@ int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, i
 
 int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,
                       int dtype, void* stream) {
-  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
-                 "unpool3d_fwd: bad shape");
-  long long total = (long long)B * D * H * W * 8 * (C >> 2);
+  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+                 R2N2_ERR_BAD_SHAPE, "unpool3d_fwd: bad shape");
+  long long total = (long long)B * D * H * W * 8 * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
     unpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)a, (const T*)b, (T*)y, B, D, H, W, C);
@@ -720,9 +759,9 @@ int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H
 
 int r2n2_unpool3d_bwd(const void* dy, void* dx, int B, int D, int H, int W, int C, int dtype,
                       void* stream) {
-  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, R2N2_ERR_BAD_SHAPE,
-                 "unpool3d_bwd: bad shape");
-  long long total = (long long)B * D * H * W * (C >> 2);
+  R2N2_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+                 R2N2_ERR_BAD_SHAPE, "unpool3d_bwd: bad shape");
+  long long total = (long long)B * D * H * W * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
     unpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)dy, (T*)dx, B, D, H, W, C);
@@ -879,7 +918,8 @@ int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, 
                    void* stream) {
   R2N2_CHECK_ARG(rows > 0 && C > 0, R2N2_ERR_BAD_SHAPE, "bias_grad: bad shape");
   if (!accumulate) cudaMemsetAsync(db, 0, sizeof(float) * C, (cudaStream_t)stream);
-  int gx = (C + 31) / 32;
+  const int pn = (dtype == R2N2_BF16) ? 8 : 4;
+  int gx = (C + 32 * pn - 1) / (32 * pn);
   long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
   long long gy = rows / 64;
   if (gy < 1) gy = 1;

@@ -120,6 +120,8 @@ def test_dgrad_equals_autograd():
 def test_pool_unpool(dtype):
     tol = 1e-6 if dtype == torch.float32 else 1e-2
     for (N, H, W, C) in [(2, 127, 127, 8), (3, 33, 33, 16), (2, 5, 5, 256), (1, 3, 3, 4), (1, 64, 64, 96)]:
+        if dtype == torch.bfloat16 and C % 8:
+            continue                      # 16-byte channel vectors: 8 x bf16
         a, b = _r(N * H * W * C, seed=1).to(dtype), _r(N * H * W * C, seed=2).to(dtype)
         Ho, Wo = H // 2 + 1, W // 2 + 1
         dy = _r(N * Ho * Wo * C, seed=3).to(dtype)
