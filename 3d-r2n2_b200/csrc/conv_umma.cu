@@ -706,9 +706,16 @@ static void choose_kbox(int N, int D, int H, int W, int max_rows, int& bw, int& 
 
 static int pow2_chunk(int c) { return c >= 64 ? 64 : (c >= 32 ? 32 : 16); }
 
+int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
+                     int Cout, int kd, int kh, int kw, int accumulate, cudaStream_t st);
+
 int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                     int Cout, int kd, int kh, int kw, int dtype, int accumulate, cudaStream_t st) {
   R2N2_CHECK_ARG(dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_wgrad[umma]: operands must be bf16");
+  // narrow output-channel counts: co on the N side, taps stacked along M (conv_umma_wgrad2.cu)
+  if (Cout <= 64 && Cin % 16 == 0 && Cout % 16 == 0 && N > 0 && D > 0 && H > 0 && W > 0 &&
+      (kd & 1) && (kh & 1) && (kw & 1) && !getenv("R2N2_UMMA_WGRAD_V1"))
+    return conv_wgrad2_umma(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, accumulate, st);
   R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
                  "conv_wgrad[umma]: non-positive dimension");
   R2N2_CHECK_ARG((kd & 1) && (kh & 1) && (kw & 1), R2N2_ERR_BAD_SHAPE,

@@ -31,6 +31,11 @@ CASES = [
     (1, 16, 16, 16, 32, 32, (3, 3, 3)),      # Cin=Cout=32 (SW64 both)
     (1, 8, 8, 8, 128, 64, (1, 1, 1)),
     (2, 6, 5, 7, 64, 64, (3, 3, 3)),
+    (1, 8, 8, 8, 64, 32, (3, 3, 3)),         # conv10a-like (stacked taps, TS=2)
+    (1, 8, 8, 8, 32, 16, (3, 3, 3)),         # conv11-like (TS=4, Cout=16)
+    (1, 8, 8, 8, 16, 32, (3, 3, 3)),         # conv11 data-gradient operand shapes (TS=8)
+    (2, 1, 12, 12, 96, 64, (1, 3, 3)),       # Cin=96: no stacking, 32 idle lanes
+    (1, 8, 8, 8, 256, 64, (3, 3, 3)),        # two ci tiles
 ]
 
 
