@@ -680,7 +680,13 @@ static void choose_kbox(int N, int D, int H, int W, int max_rows, int& bw, int& 
           double cover = (double)((W + w - 1) / w * w) * ((H + h - 1) / h * h) * ((D + d - 1) / d * d) *
                          ((N + n - 1) / n * n);
           double eff = ((double)W * H * D * N) / cover;
-          if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && rows > best_rows)) {
+          // max in-bounds fraction, then the biggest K block, then the box that follows the memory
+          // order (long runs along x, then y): contiguous TMA rows and L2 reuse between shifted taps
+          const bool better = eff > best_eff + 1e-9 ||
+                              (eff > best_eff - 1e-9 &&
+                               (rows > best_rows ||
+                                (rows == best_rows && (w > bw || (w == bw && (h > bh || (h == bh && d > bd)))))));
+          if (better) {
             best_eff = eff; best_rows = rows;
             bw = w; bh = h; bd = d; bn = n;
           }

@@ -267,7 +267,9 @@ static void choose_box_fwd(int N, int D, int H, int W, int& bw, int& bh, int& bd
         int rows = w * h * d * n;
         // fewer tiles first; then the most compact box (short TMA rows hurt nothing, but a box that
         // follows the memory order keeps the L2 footprint of the shifted taps small)
-        if (best < 0 || tiles < best || (tiles == best && (rows < best_rows))) {
+        const bool better = best < 0 || tiles < best ||
+                            (tiles == best && (w > bw || (w == bw && (h > bh || (h == bh && d > bd)))));
+        if (better) {
           best = tiles; best_rows = rows;
           bw = w; bh = h; bd = d; bn = n;
         }
