@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, 'libr2n2_b200.so')
 
 F32, BF16 = 0, 1
 EPI_BIAS, EPI_LRELU, EPI_RESIDUAL, EPI_MASK = 1, 2, 4, 8
+CONV_UP2, CONV_DOWN2 = 16, 32
+WGRAD_ACCUMULATE, WGRAD_UP2 = 1, 2
 ALGO_SIMT, ALGO_UMMA = 0, 1
 ELT_SIGMOID, ELT_TANH, ELT_COMPLEMENT, ELT_MUL = 0, 1, 2, 3
 

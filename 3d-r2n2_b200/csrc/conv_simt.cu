@@ -414,6 +414,8 @@ int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* m
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_BIAS) || bias, R2N2_ERR_BAD_SHAPE, "conv_fwd: BIAS flag without bias");
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_RESIDUAL) || residual, R2N2_ERR_BAD_SHAPE, "conv_fwd: RESIDUAL flag without residual");
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_MASK) || mask_src, R2N2_ERR_BAD_SHAPE, "conv_fwd: MASK flag without mask_src");
+  R2N2_CHECK_ARG(algo == R2N2_ALGO_UMMA || !(flags & (R2N2_CONV_UP2 | R2N2_CONV_DOWN2)), R2N2_ERR_UNSUPPORTED,
+                 "conv_fwd: UP2 / DOWN2 need R2N2_ALGO_UMMA (materialise the unpooled tensor for ALGO_SIMT)");
   if (algo == R2N2_ALGO_SIMT)
     return conv_fwd_simt(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags,
                          in_dtype, out_dtype, (cudaStream_t)stream);
@@ -428,8 +430,10 @@ int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int 
                     void* stream) {
   using namespace r2n2;
   R2N2_CHECK_ARG(x && dy && dw, R2N2_ERR_BAD_SHAPE, "conv_wgrad: null pointer");
+  R2N2_CHECK_ARG(algo == R2N2_ALGO_UMMA || !(accumulate & R2N2_WGRAD_UP2), R2N2_ERR_UNSUPPORTED,
+                 "conv_wgrad: UP2 needs R2N2_ALGO_UMMA");
   if (algo == R2N2_ALGO_SIMT)
-    return conv_wgrad_simt(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, dtype, accumulate,
+    return conv_wgrad_simt(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, dtype, accumulate & R2N2_WGRAD_ACCUMULATE,
                            (cudaStream_t)stream);
   if (algo == R2N2_ALGO_UMMA)
     return conv_wgrad_umma(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, dtype, accumulate,

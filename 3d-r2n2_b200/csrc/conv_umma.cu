@@ -477,6 +477,8 @@ struct UmmaWgradParams {
   int cw_a, cw_b;                          // channels per smem chunk (16/32/64) for dy / x
   int a_bytes, b_tap_bytes, stage_bytes;   // per stage
   int stages, tmem_cols;
+  int up2;                                 // x is the small tensor of an UP2 conv: dy is read with stride 2,
+  int a_tap_bytes, b_off;                  //   one dy tile PER TAP (A side), one shared x tile (B side)
   int* err_word;
 };
 
@@ -551,7 +553,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (warp == 0) {
     if (nkb > 0) {
       // warp-uniform loop: incremental box coordinates, tap offsets precomputed in smem
-      const uint32_t tx_bytes = (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
+      const uint32_t tx_bytes = p.up2 ? (uint32_t)(ntap * na * chunk_a + nb * chunk_b)
+                                      : (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       long long b = box_begin;
@@ -568,15 +571,32 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const uint32_t bar = full0 + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(bar, tx_bytes);
-          for (int c = 0; c < na; ++c)
-            tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
-          uint32_t bdst = stage + p.a_bytes;
-          for (int g = 0; g < ntap; ++g) {
-            const int o = tap_off[g];
-            const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
+          if (!p.up2) {
+            for (int c = 0; c < na; ++c)
+              tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+            uint32_t bdst = stage + p.b_off;
+            for (int g = 0; g < ntap; ++g) {
+              const int o = tap_off[g];
+              const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
+              for (int c = 0; c < nb; ++c)
+                tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + ox, y0 + oy, z0 + oz, n0);
+              bdst += p.b_tap_bytes;
+            }
+          } else {
+            // zero-stuffed input: xs[o + tap] is stored only where o + tap = 2i, i.e. the small pixel i
+            // meets dy[2i - tap] -> one stride-2 dy box per tap, one shared box of the small x
+            uint32_t adst = stage;
+            for (int g = 0; g < ntap; ++g) {
+              const int o = tap_off[g];
+              const int ox = (o & 0xff) - 8, oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
+              for (int c = 0; c < na; ++c)
+                tma_load_5d(adst + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, 2 * x0 - ox, 2 * y0 - oy,
+                            2 * z0 - oz, n0);
+              adst += p.a_tap_bytes;
+            }
+            const uint32_t bdst = stage + p.b_off;
             for (int c = 0; c < nb; ++c)
-              tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0 + ox, y0 + oy, z0 + oz, n0);
-            bdst += p.b_tap_bytes;
+              tma_load_5d(bdst + c * chunk_b, &map_x, bar, ci0 + c * p.cw_b, x0, y0, z0, n0);
           }
         }
         __syncwarp();
@@ -604,25 +624,28 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       const int nk = p.rows >> 4;
+      const uint32_t a_step = p.up2 ? (uint32_t)p.a_tap_bytes : 0u;       // the operand that changes per tap
+      const uint32_t b_step = p.up2 ? 0u : (uint32_t)p.b_tap_bytes;
       int s = 0;
       uint32_t ph = 0;
       uint32_t acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
-        const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
         if (elect_one()) {
-          uint32_t b_addr = a_addr + p.a_bytes;
+          uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
+          uint32_t b_addr = a_addr + p.b_off;
           uint32_t d_tmem = tmem_base;
           for (int g = 0; g < ntap; ++g) {
+            const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
             const uint64_t db0 = db_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
             uint32_t a2 = acc;
             for (int k = 0; k < nk; ++k) {
               umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
               a2 = 1;
             }
-            b_addr += p.b_tap_bytes;
+            a_addr += a_step;
+            b_addr += b_step;
             d_tmem += (uint32_t)p.ci_cols;
           }
           umma_commit(empty0 + 8u * s);
@@ -699,11 +722,14 @@ int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int
                      int Cout, int kd, int kh, int kw, int accumulate, cudaStream_t st);
 
 int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
-                    int Cout, int kd, int kh, int kw, int dtype, int accumulate, cudaStream_t st) {
+                    int Cout, int kd, int kh, int kw, int dtype, int wflags, cudaStream_t st) {
   R2N2_CHECK_ARG(dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_wgrad[umma]: operands must be bf16");
-  // narrow output-channel counts: co on the N side, taps stacked along M (conv_umma_wgrad2.cu)
-  if (Cout <= 64 && Cin % 16 == 0 && Cout % 16 == 0 && N > 0 && D > 0 && H > 0 && W > 0 &&
-      (kd & 1) && (kh & 1) && (kw & 1) && !getenv("R2N2_UMMA_WGRAD_V1"))
+  const int accumulate = wflags & R2N2_WGRAD_ACCUMULATE;
+  const int up2 = (wflags & R2N2_WGRAD_UP2) ? 1 : 0;
+  // 1x1 convolutions with few output channels: co on the N side, channels stacked along M
+  // (conv_umma_wgrad2.cu; measured faster only there -- with 27 taps the per-tap reloads dominate)
+  if (!up2 && Cout <= 64 && kd * kh * kw == 1 && Cin % 16 == 0 && Cout % 16 == 0 && N > 0 && D > 0 && H > 0 &&
+      W > 0 && !getenv("R2N2_UMMA_WGRAD_V1"))
     return conv_wgrad2_umma(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, accumulate, st);
   R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
                  "conv_wgrad[umma]: non-positive dimension");
@@ -729,7 +755,8 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   // bytes per K row (pixel) in one stage
   const int a_row = ((Cout < 128 ? Cout : 128) + p.cw_a - 1) / p.cw_a * p.cw_a * 2;
   const int b_row = (p.ci_tile + p.cw_b - 1) / p.cw_b * p.cw_b * 2;
-  const int per_row = a_row + p.G * b_row;
+  p.up2 = up2;
+  const int per_row = up2 ? p.G * a_row + (b_row > 256 - a_row ? b_row : 256 - a_row) : a_row + p.G * b_row;
   p.stages = 3;
   int max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
   if (max_rows > 128) max_rows = 128;
@@ -745,7 +772,19 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   p.nbox = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   p.a_bytes = (p.rows * a_row + 1023) / 1024 * 1024;
   p.b_tap_bytes = p.rows * b_row;
-  p.stage_bytes = (p.a_bytes + p.G * p.b_tap_bytes + 1023) / 1024 * 1024;
+  p.a_tap_bytes = (p.rows * a_row + 1023) / 1024 * 1024;
+  if (up2) {
+    // [G dy tiles][x tile]; an M=128 MMA on a narrower dy tile reads on into the next tile / the x
+    // tile (finite data, rows discarded by the epilogue): the x tile is padded to cover that span
+    p.b_off = p.G * p.a_tap_bytes;
+    // (an M=128 MN-major A view always spans rows * 256 bytes from the start of its tile)
+    const int span = p.rows * 256 - p.a_tap_bytes;
+    const int xb = p.rows * b_row > span ? p.rows * b_row : span;
+    p.stage_bytes = (p.b_off + xb + 1023) / 1024 * 1024;
+  } else {
+    p.b_off = p.a_bytes;
+    p.stage_bytes = (p.a_bytes + p.G * p.b_tap_bytes + 1023) / 1024 * 1024;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < p.G * p.ci_cols) p.tmem_cols *= 2;
   p.err_word = get_err_word();
@@ -760,12 +799,14 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
 
   CUtensorMap map_dy, map_x;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2,
-                             (cuuint64_t)D * H * W * Cout * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.cw_a, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
-                         (cuuint32_t)p.bn};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const int sc = up2 ? 2 : 1;
+    const long long Wy = (long long)W * sc, Hy = (long long)H * sc, Dy = (long long)D * sc;
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wy, (cuuint64_t)Hy, (cuuint64_t)Dy, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wy * Cout * 2, (cuuint64_t)Hy * Wy * Cout * 2,
+                             (cuuint64_t)Dy * Hy * Wy * Cout * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.cw_a, (cuuint32_t)(p.bw * sc), (cuuint32_t)(p.bh * sc),
+                         (cuuint32_t)(p.bd * sc), (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, (cuuint32_t)sc, (cuuint32_t)sc, (cuuint32_t)sc, 1};
     CUresult r = encode(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides,
                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.cw_a * 2),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -795,7 +836,9 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
                    cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 256 + 1024;
+  // the M=128 A view of the LAST stage may run past its tile (narrow Cout): keep it inside the window
+  const int a_span_slack = p.rows * 256 > p.stage_bytes ? p.rows * 256 - p.stage_bytes : 0;
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 256 + 1024 + a_span_slack;
   dim3 grid((unsigned)splits, (unsigned)(co_tiles * p.ci_tiles), (unsigned)tap_groups);
   conv_wgrad_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma]");

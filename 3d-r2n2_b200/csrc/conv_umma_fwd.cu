@@ -31,8 +31,41 @@ struct FwdParams {
   int a_bytes, b_bytes, stage_bytes;       // per sub-block A / B bytes (1024-aligned), per stage
   int tmem_cols;
   int flags;
+  int mode;                                // 0 plain, 1 UP2 (zero-stuffed x2 input, 8 parity classes), 2 DOWN2
+  int cls_tiles;                           // tiles per parity class (= m_tiles * n_tiles)
   int* err_word;
 };
+
+// Filter taps that hit non-zero input along one axis.  Plain / DOWN2: all k taps, input offset
+// j - (k-1)/2.  UP2 (input = zero-stuffed x2 upsampling of the small tensor, output position 2i+par):
+// only taps t with (par + t - centre) even touch a stored value, which is small[i + (par+t-centre)/2].
+// Returns count; tap index of entry j is t0 + j*ts, input offset o0 + j.
+static __device__ __forceinline__ int tap_spec(int mode, int k, int par, int& t0, int& ts, int& o0) {
+  const int c = (k - 1) / 2;
+  if (mode != 1) { t0 = 0; ts = 1; o0 = -c; return k; }
+  t0 = (c + par) & 1; ts = 2; o0 = (par + t0 - c) / 2;
+  return (k - t0 + 1) / 2;
+}
+
+struct TileCoord {
+  int nt, tw, th, td, tn, cls;
+};
+static __device__ __forceinline__ TileCoord decode_tile(const FwdParams& p, int tile) {
+  TileCoord c;
+  c.cls = 0;
+  if (p.mode == 1) {                       // heavy classes (8 taps) first: better tail balance
+    const int q = tile / p.cls_tiles;
+    tile -= q * p.cls_tiles;
+    c.cls = 7 - q;
+  }
+  c.nt = tile % p.n_tiles;
+  int t = tile / p.n_tiles;
+  c.tw = t % p.tiles_w; t /= p.tiles_w;
+  c.th = t % p.tiles_h; t /= p.tiles_h;
+  c.td = t % p.tiles_d; t /= p.tiles_d;
+  c.tn = t;
+  return c;
+}
 
 template <typename TOut>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
@@ -92,17 +125,20 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
-      const int th = t % p.tiles_h; t /= p.tiles_h;
-      const int td = t % p.tiles_d; t /= p.tiles_d;
-      const int cx = tw * p.bw - (p.kw - 1) / 2, cy = th * p.bh - (p.kh - 1) / 2,
-                cz = td * p.bd - (p.kd - 1) / 2, n0 = t * p.bn;
-      const int col0 = nt * p.BN;
-      int tz = 0, ty = 0, tx = 0, c0 = 0, kcol = 0;       // current sub-block (tap, channel chunk)
-      for (int q0 = 0; q0 < nq; q0 += p.nsub) {
-        const int ns = (nq - q0 < p.nsub) ? nq - q0 : p.nsub;
+      const TileCoord tc = decode_tile(p, tile);
+      int t0x, tsx, o0x, t0y, tsy, o0y, t0z, tsz, o0z;
+      const int cntx = tap_spec(p.mode, p.kw, tc.cls & 1, t0x, tsx, o0x);
+      const int cnty = tap_spec(p.mode, p.kh, (tc.cls >> 1) & 1, t0y, tsy, o0y);
+      const int cntz = tap_spec(p.mode, p.kd, (tc.cls >> 2) & 1, t0z, tsz, o0z);
+      const int nq_t = cntx * cnty * cntz * p.kchunks;
+      const int sc = (p.mode == 2) ? 2 : 1;              // DOWN2: output i reads input 2i + tap
+      const int cx = sc * tc.tw * p.bw + o0x, cy = sc * tc.th * p.bh + o0y, cz = sc * tc.td * p.bd + o0z;
+      const int n0 = tc.tn * p.bn;
+      const int col0 = tc.nt * p.BN;
+      int jz = 0, jy = 0, jx = 0, c0 = 0;                 // current sub-block (tap, channel chunk)
+      int kcol = (((t0z * p.kh) + t0y) * p.kw + t0x) * p.Cin;
+      for (int q0 = 0; q0 < nq_t; q0 += p.nsub) {
+        const int ns = (nq_t - q0 < p.nsub) ? nq_t - q0 : p.nsub;
         mbar_wait(empty0 + 8u * s, ph ^ 1u, abort_flag, p.err_word);
         const uint32_t bar = full0 + 8u * s;
         const bool leader = elect_one();
@@ -110,14 +146,15 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         uint32_t dst = smem_base + (uint32_t)(s * p.stage_bytes);
         for (int u = 0; u < ns; ++u) {
           if (leader) {
-            tma_load_5d(dst, &map_a, bar, c0, cx + tx, cy + ty, cz + tz, n0);
+            tma_load_5d(dst, &map_a, bar, c0, cx + jx, cy + jy, cz + jz, n0);
             tma_load_2d(dst + (uint32_t)p.a_bytes, &map_b, bar, kcol + c0, col0);
           }
           dst += (uint32_t)sub_bytes;
           c0 += p.kbox;
           if (c0 >= p.Cin) {
-            c0 = 0; kcol += p.Cin;
-            if (++tx == p.kw) { tx = 0; if (++ty == p.kh) { ty = 0; ++tz; } }
+            c0 = 0;
+            if (++jx == cntx) { jx = 0; if (++jy == cnty) { jy = 0; ++jz; } }
+            kcol = ((((t0z + jz * tsz) * p.kh) + (t0y + jy * tsy)) * p.kw + (t0x + jx * tsx)) * p.Cin;
           }
         }
         __syncwarp();
@@ -143,8 +180,15 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn_cols);
       uint32_t acc = 0;
       int cc = 0;                                                          // channel chunk counter
-      for (int q0 = 0; q0 < nq; q0 += p.nsub) {
-        const int ns = (nq - q0 < p.nsub) ? nq - q0 : p.nsub;
+      int nq_t = nq;
+      if (p.mode == 1) {
+        const TileCoord tc = decode_tile(p, tile);
+        int a_, b_, c_;
+        nq_t = tap_spec(1, p.kw, tc.cls & 1, a_, b_, c_) * tap_spec(1, p.kh, (tc.cls >> 1) & 1, a_, b_, c_) *
+               tap_spec(1, p.kd, (tc.cls >> 2) & 1, a_, b_, c_) * p.kchunks;
+      }
+      for (int q0 = 0; q0 < nq_t; q0 += p.nsub) {
+        const int ns = (nq_t - q0 < p.nsub) ? nq_t - q0 : p.nsub;
         mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
@@ -187,15 +231,21 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int nt = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
-      const int th = t % p.tiles_h; t /= p.tiles_h;
-      const int td = t % p.tiles_d; t /= p.tiles_d;
-      const int xx = tw * p.bw + xi, yy = th * p.bh + yi, zz = td * p.bd + zi, nn = t * p.bn + ni;
+      const TileCoord tc = decode_tile(p, tile);
+      const int xx = tc.tw * p.bw + xi, yy = tc.th * p.bh + yi, zz = tc.td * p.bd + zi, nn = tc.tn * p.bn + ni;
       const bool valid = (row < rows) && xx < p.W && yy < p.H && zz < p.D && nn < p.N;
-      const long long pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
-      const int col0 = nt * p.BN;
+      long long pix;
+      bool empty_acc = false;                              // UP2 class without any non-zero tap
+      if (p.mode == 1) {
+        const int px = tc.cls & 1, py = (tc.cls >> 1) & 1, pz = (tc.cls >> 2) & 1;
+        pix = (((long long)nn * (2 * p.D) + 2 * zz + pz) * (2 * p.H) + 2 * yy + py) * (2 * p.W) + 2 * xx + px;
+        int a_, b_, c_;
+        empty_acc = tap_spec(1, p.kw, px, a_, b_, c_) * tap_spec(1, p.kh, py, a_, b_, c_) *
+                        tap_spec(1, p.kd, pz, a_, b_, c_) == 0;
+      } else {
+        pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
+      }
+      const int col0 = tc.nt * p.BN;
       mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
@@ -206,7 +256,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         if (!valid || co >= p.Cout) continue;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) f[j] = empty_acc ? 0.f : __uint_as_float(v[j]);
         if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -283,7 +333,10 @@ int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
                   int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
-  if (getenv("R2N2_UMMA_V1"))          // A/B comparison with the one-tile-per-CTA kernel
+  const int mode = (flags & R2N2_CONV_UP2) ? 1 : ((flags & R2N2_CONV_DOWN2) ? 2 : 0);
+  R2N2_CHECK_ARG(!((flags & R2N2_CONV_UP2) && (flags & R2N2_CONV_DOWN2)), R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd[umma]: UP2 and DOWN2 are exclusive");
+  if (getenv("R2N2_UMMA_V1") && mode == 0)          // A/B comparison with the one-tile-per-CTA kernel
     return conv_fwd_umma_v1(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
                             out_dtype, st);
   R2N2_CHECK_ARG(in_dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: operands must be bf16");
@@ -308,7 +361,9 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.BN = Cout >= 256 ? 256 : Cout;
   if (const char* e = getenv("R2N2_UMMA_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && v <= Cout) p.BN = v; }
   p.n_tiles = (Cout + p.BN - 1) / p.BN;
-  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.mode = mode;
+  p.cls_tiles = p.m_tiles * p.n_tiles;
+  p.total_tiles = p.cls_tiles * (mode == 1 ? 8 : 1);
   p.bn_cols = (p.BN + 31) / 32 * 32;
   p.kbox = Cin >= 64 ? 64 : (Cin >= 32 ? 32 : 16);
   p.kchunks = (Cin + p.kbox - 1) / p.kbox;
@@ -343,19 +398,22 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.stages = stages;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.bn_cols) p.tmem_cols *= 2;
-  p.flags = flags;
+  p.flags = flags & 15;
   p.err_word = get_err_word();
   const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma]: pipeline does not fit smem");
 
   CUtensorMap map_a, map_b;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
-                             (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
-                         (cuuint32_t)p.bn};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    // DOWN2 reads the (2D,2H,2W) input with a traversal stride of 2: a box of 2*b elements lands as b rows
+    const int sc = (mode == 2) ? 2 : 1;
+    const long long Wi = (long long)W * sc, Hi = (long long)H * sc, Di = (long long)D * sc;
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wi * Cin * 2, (cuuint64_t)Hi * Wi * Cin * 2,
+                             (cuuint64_t)Di * Hi * Wi * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)(p.bw * sc), (cuuint32_t)(p.bh * sc),
+                         (cuuint32_t)(p.bd * sc), (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, (cuuint32_t)sc, (cuuint32_t)sc, (cuuint32_t)sc, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -509,9 +509,9 @@ class Engine:
             kk = (1, k, 1) if (k == 7 and self.rowpack) else (1, k, k)
             return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, lrelu, residual)
 
-        def c3(name, inp, lrelu, residual=None, out_dtype=None):
+        def c3(name, inp, lrelu, residual=None, out_dtype=None, up2=False):
             k = 1 if name == 'conv9c' else 3
-            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (k, k, k), lrelu, residual, out_dtype)
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (k, k, k), lrelu, residual, out_dtype, up2)
 
         # ---- encoder over all T*B views (hoisted out of the scan) ----------------------------
         if self.residual:
@@ -540,7 +540,21 @@ class Engine:
         self._marks = (mark_enc, mark_rnn)
 
         # ---- decoder ------------------------------------------------------------------------
-        if self.residual:
+        if self.residual and ctx.zero_skip(HID_C, HID_C):
+            # Unpool3D is never materialised for the convolutions (UP2: 1/8 of the MACs, the data
+            # gradient lands on the small tensor); only the residual adds at 8^3 / 16^3 see a
+            # zero-stuffed tensor (res_gru_net.py:171-178)
+            rect7 = c3('conv7b', c3('conv7a', h, True, up2=True), True)
+            res7 = ctx.add_act(ctx.unpool(h), rect7)
+            rect8 = c3('conv8b', c3('conv8a', res7, True, up2=True), True)
+            res8 = ctx.add_act(ctx.unpool(res7), rect8)
+            rect9 = c3('conv9b', c3('conv9a', res8, True, up2=True), True)
+            res9 = c3('conv9c', res8, False, residual=rect9, up2=True)
+            rect10a = c3('conv10a', res9, True)
+            rect10 = c3('conv10b', rect10a, True)
+            res10 = c3('conv10c', rect10a, False, residual=rect10)
+            logits = c3('conv11', res10, False, out_dtype=torch.float32)
+        elif self.residual:
             unpool7 = ctx.unpool(h)
             rect7 = c3('conv7b', c3('conv7a', unpool7, True), True)
             unpool8 = ctx.unpool(unpool7, rect7)                      # unpool(res7)
@@ -553,9 +567,9 @@ class Engine:
             res10 = c3('conv10c', rect10a, False, residual=rect10)
             logits = c3('conv11', res10, False, out_dtype=torch.float32)
         else:
-            t_ = c3('conv7', ctx.unpool(h), True)
-            t_ = c3('conv8', ctx.unpool(t_), True)
-            t_ = c3('conv9', ctx.unpool(t_), True)
+            t_ = c3('conv7', h, True, up2=True)       # falls back to unpool + conv off the tensor path
+            t_ = c3('conv8', t_, True, up2=True)
+            t_ = c3('conv9', t_, True, up2=True)
             t_ = c3('conv10', t_, True)
             logits = c3('conv11', t_, False, out_dtype=torch.float32)
 

@@ -76,6 +76,7 @@ def _work(flops=0.0, tensors=()):
 
 
 WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
+ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
 
@@ -103,15 +104,19 @@ def umma_error_flag():
 
 # ======================================================================= raw op wrappers
 def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
-    """geom = (N,D,H,W,Cin) of x; k=(kd,kh,kw); y preallocated [N,D,H,W,cout]."""
+    """geom = (N,D,H,W,Cin) of x; k=(kd,kh,kw); y preallocated [N,D,H,W,cout].
+    With L.CONV_UP2 / L.CONV_DOWN2 in flags (N,D,H,W) is the SMALL grid: UP2 writes y (and reads
+    mask/residual) at [N,2D,2H,2W,cout]; DOWN2 reads x at [N,2D,2H,2W,Cin]."""
     N, D, H, W, Cin = geom
     if algo == L.ALGO_UMMA and not (umma_ok(Cin, cout) and x.dtype == torch.bfloat16):
         algo = L.ALGO_SIMT
     for t in (x, w, bias, mask_src, residual, y):
         _check(t)
-    assert x.numel() == N * D * H * W * Cin, (x.shape, geom)
+    xs = 8 if flags & L.CONV_DOWN2 else 1
+    ys = 8 if flags & L.CONV_UP2 else 1
+    assert x.numel() == N * D * H * W * Cin * xs, (x.shape, geom)
     assert w.numel() == cout * k[0] * k[1] * k[2] * Cin, (w.shape, cout, k, Cin)
-    assert y.numel() == N * D * H * W * cout
+    assert y.numel() == N * D * H * W * cout * ys
     assert w.dtype == x.dtype
     global _next_tag
     _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2] * useful_frac,
@@ -123,20 +128,22 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     return y
 
 
-def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate):
+def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate, up2=False):
+    """up2: x is the small [N,D,H,W,Cin] input of an UP2 convolution, dy is [N,2D,2H,2W,cout]."""
     N, D, H, W, Cin = geom
     if algo == L.ALGO_UMMA and not (umma_ok(Cin, cout) and x.dtype == torch.bfloat16 and WGRAD_UMMA):
         algo = L.ALGO_SIMT
     for t in (x, dy, dw):
         _check(t)
     assert dw.dtype == torch.float32 and x.dtype == dy.dtype
-    assert x.numel() == N * D * H * W * Cin and dy.numel() == N * D * H * W * cout
+    assert x.numel() == N * D * H * W * Cin and dy.numel() == N * D * H * W * cout * (8 if up2 else 1)
     assert dw.numel() == cout * k[0] * k[1] * k[2] * Cin
     global _next_tag
     _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2] * useful_frac, (x, dy, dw))
     _next_tag = 'M%dxN%dxK%d' % (cout, k[0] * k[1] * k[2] * Cin, N * D * H * W)
     _call('r2n2_conv_wgrad', _ptr(x), _ptr(dy), _ptr(dw), N, D, H, W, Cin, cout, k[0], k[1], k[2],
-          _DT[x.dtype], algo, 1 if accumulate else 0, _stream())
+          _DT[x.dtype], algo, (L.WGRAD_ACCUMULATE if accumulate else 0) | (L.WGRAD_UP2 if up2 else 0),
+          _stream())
 
 
 def bias_grad(dy, db, C, accumulate):
@@ -385,13 +392,14 @@ class Ctx:
             lrelu_bwd(out.data, out.grad, None, dst)
             out.grad, out.grad_shared, out.grad_preact = dst, False, True
 
-    def dgrad_into(self, x, dy, W, k, extra=None):
+    def dgrad_into(self, x, dy, W, k, extra=None, down2=False):
         """x.grad (+)= conv_T(dy; W), fusing the pending accumulation (RESIDUAL) and, when this is
-        the last contribution to a LeakyReLU output, the LeakyReLU' mask (MASK)."""
+        the last contribution to a LeakyReLU output, the LeakyReLU' mask (MASK).
+        down2: dy lives on the x2 grid of an UP2 convolution; only its even positions reach x."""
         if not x.requires_grad:
             return
         N, D, H, Wd, Cin = x.geom
-        flags = 0
+        flags = L.CONV_DOWN2 if down2 else 0
         res = None
         out_buf = None
         if x.n_recv > 0:
@@ -417,8 +425,8 @@ class Ctx:
         x.grad, x.grad_shared = out_buf, False
         x.n_recv += 1
 
-    def weight_grads(self, x_data, dy, geom, W, b, k):
-        conv_wgrad(x_data, dy, W.grad, geom, W.cout, k, self.wgrad_algo, W.grad_written)
+    def weight_grads(self, x_data, dy, geom, W, b, k, up2=False):
+        conv_wgrad(x_data, dy, W.grad, geom, W.cout, k, self.wgrad_algo, W.grad_written, up2)
         W.grad_written = True
         if b is not None:
             bias_grad(dy, b.grad, W.cout, b.grad_written)
@@ -430,22 +438,34 @@ class Ctx:
         self.tape = []
 
     # ---- differentiable ops --------------------------------------------------------------
-    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None):
-        """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw)."""
+    def zero_skip(self, cin, cout):
+        """Unpool3D+Conv3D can run fused (UP2: only the taps that meet a stored value)."""
+        return (self.algo == L.ALGO_UMMA and umma_ok(cin, cout)
+                and (self.dtype == torch.bfloat16 or ZERO_SKIP_ANY_DTYPE))
+
+    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False):
+        """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw).
+        up2: the convolution runs over Unpool3D(x) (lib/layers.py:375-385) without materialising
+        the 7/8-zero tensor; y lives on the x2 grid and the gradient reaches x directly."""
         N, D, H, Wd, Cin = x.geom
         assert Cin == W.cin and k[0] * k[1] * k[2] == W.taps, (x.geom, W.cin, W.taps, k)
         assert not (lrelu and residual is not None)
         cout = W.cout
-        y = self.empty(N * D * H * Wd * cout, x.data, out_dtype)
+        if up2 and not self.zero_skip(Cin, cout):
+            return self.conv(self.unpool(x), W, b, k, lrelu, residual, out_dtype)
+        og = (N, 2 * D, 2 * H, 2 * Wd, cout) if up2 else (N, D, H, Wd, cout)
+        y = self.empty(og[0] * og[1] * og[2] * og[3] * cout, x.data, out_dtype)
         flags = (L.EPI_BIAS if b is not None else 0) | (L.EPI_LRELU if lrelu else 0)
         if residual is not None:
             flags |= L.EPI_RESIDUAL
+        if up2:
+            flags |= L.CONV_UP2
         global useful_frac
         useful_frac = x.useful
         conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
                  None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
         useful_frac = 1.0
-        out = Act(y, (N, D, H, Wd, cout), requires_grad=self.training, lrelu_out=lrelu)
+        out = Act(y, og, requires_grad=self.training, lrelu_out=lrelu)
         if self.training:
             self.consume(x)
             if residual is not None:
@@ -458,8 +478,8 @@ class Ctx:
                 dy = out.grad
                 global useful_frac
                 useful_frac = x.useful
-                self.weight_grads(x.data, dy, x.geom, W, b, k)
-                self.dgrad_into(x, dy, W, k)
+                self.weight_grads(x.data, dy, x.geom, W, b, k, up2)
+                self.dgrad_into(x, dy, W, k, down2=up2)
                 useful_frac = 1.0
                 if residual is not None:
                     self.accumulate(residual, dy)   # hand the buffer over (we are done with it)

@@ -49,6 +49,18 @@ extern "C" {
 #define R2N2_EPI_LRELU 2
 #define R2N2_EPI_RESIDUAL 4
 #define R2N2_EPI_MASK 8
+/* geometry flags of r2n2_conv_fwd (R2N2_ALGO_UMMA only), N,D,H,W always name the SMALL grid:
+ * UP2  : fused Unpool3DLayer + Conv3DLayer (lib/layers.py:375-385 + 441): x is [N,D,H,W,Cin], the
+ *        convolution runs over its zero-stuffed x2 upsampling and y / residual / mask_src are
+ *        [N,2D,2H,2W,Cout]; only the taps that meet a stored value are computed (1/8 of the MACs).
+ * DOWN2: x is [N,2D,2H,2W,Cin], y[N,D,H,W,Cout] holds the even positions of the 'same' convolution
+ *        (with transposed weights: the gradient of an UP2 convolution w.r.t. its small input). */
+#define R2N2_CONV_UP2 16
+#define R2N2_CONV_DOWN2 32
+/* r2n2_conv_wgrad `accumulate` argument is a bit set: ACCUMULATE adds into dw; UP2: x is the small
+ * [N,D,H,W,Cin] tensor of an UP2 convolution and dy is [N,2D,2H,2W,Cout]. */
+#define R2N2_WGRAD_ACCUMULATE 1
+#define R2N2_WGRAD_UP2 2
 
 /* conv algorithms */
 #define R2N2_ALGO_SIMT 0  /* fp32 FFMA implicit GEMM: the exact-fp32 parity path            */

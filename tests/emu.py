@@ -17,11 +17,29 @@ def _f(t):
     return None if t is None else t.double()
 
 
+CONV_UP2, CONV_DOWN2 = 16, 32
+
+
+def _stuff(x5):
+    """[N,D,H,W,C] -> zero-stuffed [N,2D,2H,2W,C] (value on the even corner, lib/layers.py:375-385)."""
+    N, D, H, W, C = x5.shape
+    o = torch.zeros(N, 2 * D, 2 * H, 2 * W, C, dtype=x5.dtype)
+    o[:, ::2, ::2, ::2] = x5
+    return o
+
+
 def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     N, D, H, W, Cin = geom
-    xi = _f(x).view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+    if flags & CONV_UP2:
+        xi = _stuff(_f(x).view(N, D, H, W, Cin)).permute(0, 4, 1, 2, 3)
+    elif flags & CONV_DOWN2:
+        xi = _f(x).view(N, 2 * D, 2 * H, 2 * W, Cin).permute(0, 4, 1, 2, 3)
+    else:
+        xi = _f(x).view(N, D, H, W, Cin).permute(0, 4, 1, 2, 3)
     wi = _f(w).view(cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3)
     o = F.conv3d(xi, wi, None, padding=((k[0] - 1) // 2, (k[1] - 1) // 2, (k[2] - 1) // 2))
+    if flags & CONV_DOWN2:
+        o = o[:, :, ::2, ::2, ::2]
     o = o.permute(0, 2, 3, 4, 1).reshape(-1, cout)
     if flags & EPI_BIAS:
         o = o + _f(bias).view(1, cout)
@@ -36,11 +54,15 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     return y
 
 
-def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate):
+def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate, up2=False):
     N, D, H, W, Cin = geom
     kd, kh, kw = k
     pd, ph, pw = (kd - 1) // 2, (kh - 1) // 2, (kw - 1) // 2
-    xi = F.pad(_f(x).view(N, D, H, W, Cin), (0, 0, pw, pw, ph, ph, pd, pd))
+    x5 = _f(x).view(N, D, H, W, Cin)
+    if up2:
+        x5 = _stuff(x5)
+        D, H, W = 2 * D, 2 * H, 2 * W
+    xi = F.pad(x5, (0, 0, pw, pw, ph, ph, pd, pd))
     g = _f(dy).view(N, D, H, W, cout)
     out = torch.zeros(cout, kd, kh, kw, Cin, dtype=torch.float64)
     for tz in range(kd):

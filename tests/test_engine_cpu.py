@@ -44,6 +44,30 @@ def test_engine_forward_backward_matches_oracle(monkeypatch, net_name, T):
         assert _rel(g, rg.numpy()) < 2e-4, (name, _rel(g, rg.numpy()))
 
 
+@pytest.mark.parametrize('net_name', ['GRUNet', 'ResidualGRUNet'])
+def test_engine_tensor_path_schedule_matches_oracle(monkeypatch, net_name):
+    """The schedule of the tcgen05 path (row-packed conv1, channel padding, fused Unpool3D+Conv3D
+    with UP2 / DOWN2 / WGRAD_UP2, padded logits) on the emulated ABI, in fp32, against the oracle."""
+    emu.install(monkeypatch, ops)
+    monkeypatch.setattr(ops, 'ZERO_SKIP_ANY_DTYPE', True)
+    B, T = 1, 2
+    params = rt.init_params(net_name, seed=3)
+    x, y = rt.synthetic_batch(T, B)
+    eng = Engine(net_name, B, device='cpu', compute='fp32', conv_algo=1, params_only=True)
+    eng.set_params(params)
+    out = eng.forward(torch.as_tensor(x), torch.as_tensor(y), training=True)
+    eng.backward()
+    grads = eng.get_grads()
+    ref = rt.RefNet(net_name, params, dtype=torch.float64)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    assert np.abs(out['pred'].numpy() - rout['pred'].detach().numpy()).max() < 1e-5
+    assert abs(float(out['loss']) - float(rout['loss'])) < 1e-5
+    for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
+        assert g.shape == tuple(rg.shape), name
+        # fp32 storage between ~40 layers: the first layers' gradients carry the rounding of all of them
+        assert _rel(g, rg.numpy()) < 2e-3, (name, _rel(g, rg.numpy()))
+
+
 def test_solver_adam_steps_match_oracle(monkeypatch):
     """3 Adam steps through Solver (lib/solver.py:20-48,102-109 semantics)."""
     emu.install(monkeypatch, ops)
