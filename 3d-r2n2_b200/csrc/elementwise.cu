@@ -51,31 +51,44 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
 // Cpack channels, so the 7x7x3 first layer (K = 147) runs as 7 tensor-core K blocks of 32 instead of
 // 49 blocks of 16 zero-padded channels.
 template <typename T>
-__global__ void nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C,
-                                       int H, int W, int kw, int Cpack) {
-  // one thread per (pixel, 16-byte group of packed channels): coalesced reads along w for every
-  // (kx, c), 16-byte stores
+__global__ void __launch_bounds__(128)
+nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int H, int W,
+                       int kw, int Cpack) {
+  // one block per image row (n, h): the C channel rows are staged in shared memory with (kw-1)/2
+  // zero columns either side (coalesced fp32 reads, each input element read once), then every
+  // thread assembles 16-byte groups of packed channels from a per-block offset table and stores them
+  // (fully coalesced 16-byte stores: this kernel is bound by the 5x larger packed output).
+  extern __shared__ float rp_smem[];
   constexpr int PN = Pack<T>::N;
-  const int groups = Cpack / PN;
-  long long total = (long long)N * H * W * groups;
   const int pad = (kw - 1) / 2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int gq = (int)(i % groups);
-    long long pix = i / groups;
-    int w = (int)(pix % W);
-    long long t = pix / W;
-    int h = (int)(t % H);
-    int n = (int)(t / H);
-    Pack<T> o;
-#pragma unroll
-    for (int e = 0; e < PN; ++e) {
-      int j = gq * PN + e;
-      int kx = j / C, c = j - kx * C;
-      int sw = w + kx - pad;
-      o.v[e] = (kx < kw && sw >= 0 && sw < W) ? x[(((long long)n * C + c) * H + h) * W + sw] : 0.f;
+  const int pitch = W + 2 * pad;
+  float* row = rp_smem;                                  // [C][pitch]
+  int* lut = reinterpret_cast<int*>(rp_smem + C * pitch);  // [Cpack] offset into row, or -1
+  const int groups = Cpack / PN;
+  for (int j = threadIdx.x; j < Cpack; j += blockDim.x) {
+    const int kx = j / C, c = j - kx * C;
+    lut[j] = (kx < kw) ? c * pitch + kx : -1;
+  }
+  for (long long rh = blockIdx.x; rh < (long long)N * H; rh += gridDim.x) {
+    const int h = (int)(rh % H);
+    const long long n = rh / H;
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * pitch; i += blockDim.x) {
+      const int c = i / pitch, sw = i - c * pitch - pad;
+      row[i] = (sw >= 0 && sw < W) ? x[((n * C + c) * H + h) * W + sw] : 0.f;
     }
-    o.store(y + pix * Cpack + gq * PN);
+    __syncthreads();
+    T* out = y + rh * W * Cpack;
+    for (int i = threadIdx.x; i < W * groups; i += blockDim.x) {
+      const int w = i / groups, gq = i - w * groups;
+      Pack<T> o;
+#pragma unroll
+      for (int e = 0; e < PN; ++e) {
+        const int off = lut[gq * PN + e];
+        o.v[e] = off >= 0 ? row[off + w] : 0.f;
+      }
+      o.store(out + (long long)i * PN);
+    }
   }
 }
 
@@ -506,9 +519,20 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
     if (loss_sum) local += -(y0 * x.x + y1 * x.y) + logf(s);
     if (dlogits) {
       TD* dl = dlogits + v * cstride;
-      dl[0] = from_float<TD>((p0 - y0) * grad_scale);
-      dl[1] = from_float<TD>((p1 - y1) * grad_scale);
-      for (int c = 2; c < cstride; ++c) dl[c] = from_float<TD>(0.f);   // padded logit channels
+      constexpr int PN = Pack<TD>::N;
+      if ((cstride % PN) == 0) {                       // padded logit channels: 16-byte stores
+        Pack<TD> o;
+#pragma unroll
+        for (int e = 0; e < PN; ++e) o.v[e] = 0.f;
+        for (int c = PN; c < cstride; c += PN) o.store(dl + c);
+        o.v[0] = (p0 - y0) * grad_scale;
+        o.v[1] = (p1 - y1) * grad_scale;
+        o.store(dl);
+      } else {
+        dl[0] = from_float<TD>((p0 - y0) * grad_scale);
+        dl[1] = from_float<TD>((p1 - y1) * grad_scale);
+        for (int c = 2; c < cstride; ++c) dl[c] = from_float<TD>(0.f);
+      }
     }
   }
   if (loss_sum) {
@@ -567,6 +591,52 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ d
       for (int k = 0; k < 8; ++k) t += red[k][cx * PN + e];
       atomicAdd(db + c0 + e, t);
     }
+  }
+}
+
+// Flat variant for C a multiple of the vector width with at most 256 vectors per row (every conv
+// layer): the block walks the [rows][C] matrix as ONE contiguous stream -- thread t owns the
+// channel group t % (C/PN) of rows t / (C/PN) + k * rows_per_iter, so a warp always reads 512
+// contiguous bytes whatever C is (the kernel above leaves 28 of 32 lanes idle at C = 32).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_grad_flat_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows, int C,
+                      long long rows_per_block) {
+  constexpr int PN = Pack<T>::N;
+  __shared__ float red[256 * PN];
+  const int CV = C / PN;
+  const int rpi = 256 / CV;                       // rows per block iteration
+  const int tid = threadIdx.x;
+  const int rr = tid / CV, cg = tid - rr * CV;
+  float acc[PN];
+#pragma unroll
+  for (int e = 0; e < PN; ++e) acc[e] = 0.f;
+  if (rr < rpi) {
+    const long long r0 = blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    long long r = r0 + rr;
+    const T* p = dy + r * C + cg * PN;
+    const long long step = (long long)rpi * C;
+    for (; r + 3 * rpi < r1; r += 4 * rpi, p += 4 * step) {
+      Pack<T> v0 = Pack<T>::load(p), v1 = Pack<T>::load(p + step), v2 = Pack<T>::load(p + 2 * step),
+              v3 = Pack<T>::load(p + 3 * step);
+#pragma unroll
+      for (int e = 0; e < PN; ++e) acc[e] += (v0.v[e] + v1.v[e]) + (v2.v[e] + v3.v[e]);
+    }
+    for (; r < r1; r += rpi, p += step) {
+      Pack<T> v = Pack<T>::load(p);
+#pragma unroll
+      for (int e = 0; e < PN; ++e) acc[e] += v.v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < PN; ++e) red[tid * PN + e] = acc[e];   // = red[rr * C + cg * PN + e]
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int k = 0; k < rpi; ++k) t += red[k * C + c];
+    atomicAdd(db + c, t);
   }
 }
 
@@ -709,7 +779,10 @@ int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, in
                  R2N2_ERR_BAD_SHAPE, "nchw_to_rowpack: bad shape");
   long long total = (long long)N * H * W * (Cpack / (out_dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    nchw_to_rowpack_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const size_t smem = sizeof(float) * (size_t)C * (W + kw - 1) + sizeof(int) * (size_t)Cpack;
+    long long blocks = (long long)N * H;
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+    nchw_to_rowpack_kernel<T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
         x, (T*)y, N, C, H, W, kw, Cpack);
   })
   R2N2_CHECK_LAUNCH("nchw_to_rowpack");
@@ -919,6 +992,19 @@ int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, 
   R2N2_CHECK_ARG(rows > 0 && C > 0, R2N2_ERR_BAD_SHAPE, "bias_grad: bad shape");
   if (!accumulate) cudaMemsetAsync(db, 0, sizeof(float) * C, (cudaStream_t)stream);
   const int pn = (dtype == R2N2_BF16) ? 8 : 4;
+  if (C % pn == 0 && C / pn <= 256 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int rpi = 256 / (C / pn);
+    long long blocks = (rows + 8LL * rpi - 1) / (8LL * rpi);       // >= 8 iterations per block
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    if (blocks < 1) blocks = 1;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    blocks = (rows + rpb - 1) / rpb;
+    R2N2_DISPATCH_DTYPE(dtype, T, {
+      bias_grad_flat_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)dy, db, rows, C, rpb);
+    })
+    R2N2_CHECK_LAUNCH("bias_grad");
+    return R2N2_OK;
+  }
   int gx = (C + 32 * pn - 1) / (32 * pn);
   long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
   long long gy = rows / 64;

@@ -175,14 +175,17 @@ def test_pointwise_and_layout():
     emu.weight_transpose(w, want, 10, 27, 12)
     ops.weight_transpose(w.to(DEV), wt, 10, 27, 12)
     _cmp(wt, want, 0.0, 'weight_transpose')
-    for rows, C in [(1000, 96), (77, 2), (3, 1024), (5000, 256)]:
-        dy = _r(rows * C, seed=6)
-        for acc in (False, True):
-            want = _r(C, seed=7)
-            db = want.to(DEV)
-            emu.bias_grad(dy, want, C, acc)
-            ops.bias_grad(dy.to(DEV), db, C, acc)
-            _cmp(db, want, 2e-5, 'bias_grad')
+    # flat kernel (C/vector <= 256 vectors per row), ragged row counts, and the generic kernel
+    for rows, C in [(1000, 96), (77, 2), (3, 1024), (5000, 256), (40003, 32), (12345, 64), (999, 16),
+                    (2, 4096), (70001, 128)]:
+        for dt in (torch.float32, torch.bfloat16):
+            dy = _r(rows * C, seed=6).to(dt)
+            for acc in (False, True):
+                want = _r(C, seed=7)
+                db = want.to(DEV)
+                emu.bias_grad(dy.float(), want, C, acc)
+                ops.bias_grad(dy.to(DEV), db, C, acc)
+                _cmp(db, want, 2e-5, 'bias_grad %d x %d %s' % (rows, C, dt))
 
 
 def test_gate_kernels():
@@ -251,6 +254,18 @@ def test_softmax_ce_adam_voxel():
         _cmp(gp, wp, 2e-6, 'softmax pred')
         _cmp(gd, wd, 2e-6, 'softmax dlogits')
         assert abs(gl.item() - wl.item()) < 2e-5 * abs(wl.item())
+    # padded logits (conv11 on the tensor path: 16 channels per voxel), bf16 gradient rows
+    lp = torch.zeros(B * nv ** 3, 16)
+    lp[:, :2] = logits.view(-1, 2)
+    lp[:, 2:] = 7.0                                   # must be ignored
+    wd16 = torch.empty(lp.numel(), dtype=torch.bfloat16)
+    gd16 = torch.full((lp.numel(),), float('nan'), dtype=torch.bfloat16, device=DEV)
+    wl16, gl16 = torch.zeros(1), torch.zeros(1, device=DEV)
+    emu.softmax_ce3d(lp.reshape(-1), y, wp, wl16, wd16, B, nv, 0.125, 16)
+    ops.softmax_ce3d(lp.reshape(-1).to(DEV), y.to(DEV), gp, gl16, gd16, B, nv, 0.125, 16)
+    _cmp(gp, wp, 2e-6, 'softmax pred (padded)')
+    _cmp(gd16, wd16, 4e-3, 'softmax dlogits (padded, bf16)')
+    assert abs(gl16.item() - wl16.item()) < 2e-5 * abs(wl16.item())
     # prediction-only (inference) call
     gp2 = torch.empty(B, nv, 2, nv, nv, device=DEV)
     ops.softmax_ce3d(logits.to(DEV), None, gp2, None, None, B, nv, 1.0)
