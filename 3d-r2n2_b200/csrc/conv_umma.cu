@@ -720,6 +720,9 @@ static int pow2_chunk(int c) { return c >= 64 ? 64 : (c >= 32 ? 32 : 16); }
 
 int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                      int Cout, int kd, int kh, int kw, int accumulate, cudaStream_t st);
+bool conv_wgrad3_supported(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
+int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin, int Cout,
+                     int accumulate, cudaStream_t st);
 
 int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                     int Cout, int kd, int kh, int kw, int dtype, int wflags, cudaStream_t st) {
@@ -731,6 +734,9 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   if (!up2 && Cout <= 64 && kd * kh * kw == 1 && Cin % 16 == 0 && Cout % 16 == 0 && N > 0 && D > 0 && H > 0 &&
       W > 0 && !getenv("R2N2_UMMA_WGRAD_V1"))
     return conv_wgrad2_umma(x, dy, dw, N, D, H, W, Cin, Cout, kd, kh, kw, accumulate, st);
+  // 3x3x3 with narrow channels: flat halo tiles, shifted descriptor views (conv_umma_wgrad3.cu)
+  if (!up2 && conv_wgrad3_supported(N, D, H, W, Cin, Cout, kd, kh, kw))
+    return conv_wgrad3_umma(x, dy, dw, N, D, H, W, Cin, Cout, accumulate, st);
   R2N2_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, R2N2_ERR_BAD_SHAPE,
                  "conv_wgrad[umma]: non-positive dimension");
   R2N2_CHECK_ARG((kd & 1) && (kh & 1) && (kw & 1), R2N2_ERR_BAD_SHAPE,

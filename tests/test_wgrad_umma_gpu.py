@@ -36,6 +36,12 @@ CASES = [
     (1, 8, 8, 8, 16, 32, (3, 3, 3)),         # conv11 data-gradient operand shapes (TS=8)
     (2, 1, 12, 12, 96, 64, (1, 3, 3)),       # Cin=96: no stacking, 32 idle lanes
     (1, 8, 8, 8, 256, 64, (3, 3, 3)),        # two ci tiles
+    # flat-halo kernel (conv_umma_wgrad3.cu): Cin, Cout in {16,32,64}, 3x3x3
+    (2, 32, 32, 32, 32, 32, (3, 3, 3)),      # conv10b at full spatial size (4 bands of 8 rows)
+    (1, 32, 32, 32, 64, 64, (3, 3, 3)),      # conv9b: two MMAs per dy (2 shifts each)
+    (1, 5, 9, 33, 64, 16, (3, 3, 3)),        # ragged, dy stacked (8 shifts of 16 channels)
+    (3, 4, 4, 4, 16, 16, (3, 3, 3)),
+    (1, 3, 70, 11, 32, 64, (3, 3, 3)),       # many bands, last band partial
 ]
 
 
