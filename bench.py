@@ -35,7 +35,7 @@ UNIT = 'samples/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--compute', default=os.environ.get('R2N2_BENCH_COMPUTE', 'auto'))
@@ -55,6 +55,18 @@ def peaks():
         return dict(tflops=d.get('bf16_tflops_sustained', d.get('bf16_tflops')), hbm=d.get('hbm_gbs'),
                     src='measured (MEASURED_PEAKS.json, bf16 sustained)')
     return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from
+    the committed `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py)."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel_key, {}).get('dram_bytes_per_launch')
+    except Exception:
+        return None
 
 
 def config_dict(args, extra=None):
@@ -265,7 +277,7 @@ def run_ours(args):
             ach = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
             roofline = {'bound': 'tensor', 'kernel': 'r2n2_conv_fwd (implicit-GEMM conv/FC fwd + dgrad)',
                         'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops'],
-                        'traffic': None, 'peak_source': pk['src'],
+                        'traffic': ncu_traffic('r2n2_conv_fwd'), 'peak_source': pk['src'],
                         'launches': conv['calls'], 'avg_launch_ms': conv['ms'] / max(1, conv['calls']),
                         'share_of_step': conv['ms'] / tot_ms if tot_ms else None,
                         'flops_counted': 'algorithmic (useful, zero-skipped unpool), summed over the launches'}
