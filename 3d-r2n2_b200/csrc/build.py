@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, 'libr2n2_b200.so')
-SOURCES = ['elementwise.cu', 'conv_simt.cu', 'conv_umma.cu', 'conv_umma_fwd.cu', 'conv_umma_wgrad2.cu', 'conv_umma_wgrad3.cu']
+SOURCES = ['elementwise.cu', 'conv_simt.cu', 'conv_umma.cu', 'conv_umma_fwd.cu', 'conv_umma_wgrad2.cu', 'conv_umma_wgrad3.cu', 'conv_umma_fwd3.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets']
 if os.environ.get('R2N2_PTXAS_V'):

@@ -1,0 +1,506 @@
+// Flat-halo tcgen05 implicit-GEMM convolution for 3x3 / 3x3x3 filters (forward and data gradient), sm_100a.
+//
+//   y[p, co] = epilogue( sum_{tap, ci} x[p + off(tap), ci] * w[co, tap, ci] )       bf16 x bf16 -> fp32
+//
+// conv_fwd_umma_persistent (conv_umma_fwd.cu) loads one shifted 128-pixel box per filter tap: every
+// input element crosses L2 -> shared memory 9 (27) times, and ncu shows the big 3x3 layers bound by
+// that traffic (lts throughput 66 %, tensor pipe 30 % on conv1b).  Here the input is loaded ONCE:
+//   * a work step is an output block of Yb rows x Xb columns of one (n, z) plane.  TMA loads the
+//     input block with a one-pixel halo, (Yb+2) x (Xb+2) pixels, per 64-channel chunk; in shared
+//     memory a pixel is the flat row  r = y * P + x  (P = Xb + 2), K-major (channels contiguous);
+//   * the outputs of the block are the flat rows 0 .. Yb*P-1 (the two rows-ends x >= Xb are junk and
+//     never stored), cut into T tiles of 128 rows.  For tap (ty, tx) the A operand of tile t is the
+//     SAME shared-memory plane viewed from row 128 t + ty P + tx: a tcgen05 descriptor may start on
+//     any row of a swizzled tile (tools/exp_desc.cu), so a tap costs a descriptor, not a load;
+//   * 3-D: the kd = 3 input planes of output plane z are three ring slots; stepping to z+1 loads only
+//     plane z+2 (rolling ring, `zc` consecutive planes per work item);
+//   * the weights of all taps are streamed through their own small TMA ring once per step and shared
+//     by the T tiles of the step (T accumulators side by side in TMEM, double buffered so that the
+//     epilogue of step i overlaps the MMAs of step i+1).
+// Warp roles: 0 = input-plane TMA, 1 = MMA issuer, 2..5 = epilogue, 6 = weight TMA.
+#include "umma.cuh"
+
+namespace r2n2 {
+
+constexpr int kFwd3Threads = 224;
+
+struct Fwd3Params {
+  int N, D, H, W, Cin, Cout;
+  int kd;                                  // 1 or 3 (kh = kw = 3)
+  int Xb, Yb, P, bx, by;                   // block, row pitch Xb+2, blocks per row / column
+  int R, T;                                // output rows of a block, 128-row tiles
+  int zc, zitems;                          // planes per work item, items along z
+  long long items;
+  int kbox, nchunk, rb, last_nk16, full_nk16;
+  int plane_rows, chunk_bytes, plane_bytes, nring;
+  int BN, bn_cols, w_sub_bytes, wg, wt, wstages, w_off;   // wt taps (wg = wt * chunks sub-tiles) per weight stage
+  int tmem_cols, flags;
+  int* err_word;
+};
+
+struct Item3 {
+  int n, y0, x0, z0, nz;
+};
+static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long long it) {
+  Item3 c;
+  const int xb = (int)(it % p.bx); it /= p.bx;
+  const int yb = (int)(it % p.by); it /= p.by;
+  const int zi = (int)(it % p.zitems); it /= p.zitems;
+  c.n = (int)it;
+  c.x0 = xb * p.Xb;
+  c.y0 = yb * p.Yb;
+  c.z0 = zi * p.zc;
+  c.nz = p.D - c.z0 < p.zc ? p.D - c.z0 : p.zc;
+  return c;
+}
+
+// KB = K16 steps per full channel chunk (row bytes = 32 KB), NCH = channel chunks, LASTK = K16 steps of
+// the last chunk: compile-time so that the MMA issue sequence of one tap is straight-line code with
+// immediate descriptor offsets (a single thread issues every MMA of the SM: each extra instruction per
+// MMA costs more than the MMA itself at N <= 64).
+template <typename TOut, int KB, int NCH, int LASTK>
+__global__ void __launch_bounds__(kFwd3Threads, 1)
+conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
+                      const Fwd3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int ring_bytes = p.nring * p.plane_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.w_off + p.wstages * p.wg * p.w_sub_bytes);
+  uint64_t* pfull = bars;                              // [nring]   plane TMA -> MMA
+  uint64_t* pempty = pfull + p.nring;                  // [nring]   MMA -> plane TMA
+  uint64_t* wfull = pempty + p.nring;                  // [wstages] weight TMA -> MMA
+  uint64_t* wempty = wfull + p.wstages;                // [wstages]
+  uint64_t* tfull = wempty + p.wstages;                // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                        // [2]       epilogue -> MMA
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // rows past the loaded halo block are read by the junk rows of the last tile: keep them finite (zero)
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < ring_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), 1); mbar_init(smem_u32(&pempty[s]), 1); }
+    for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), 1); mbar_init(smem_u32(&wempty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t pfull0 = smem_u32(&pfull[0]), pempty0 = smem_u32(&pempty[0]);
+  const uint32_t wfull0 = smem_u32(&wfull[0]), wempty0 = smem_u32(&wempty[0]);
+  const uint32_t tfull0 = smem_u32(&tfull[0]), tempty0 = smem_u32(&tempty[0]);
+  const int pz = (p.kd - 1) / 2;
+
+  if (warp == 0) {
+    // ================================ input planes (TMA) ====================================
+    int slot = 0;
+    uint32_t ph = 0;
+    const uint32_t tx = (uint32_t)(p.nchunk * p.plane_rows * p.rb);
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item3 c = decode_item(p, it);
+      const int nplanes = c.nz + p.kd - 1;
+      for (int i = 0; i < nplanes; ++i) {
+        mbar_wait(pempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
+        const uint32_t bar = pfull0 + 8u * slot;
+        const uint32_t dst = smem_base + (uint32_t)(slot * p.plane_bytes);
+        if (elect_one()) {
+          mbar_expect_tx(bar, tx);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - 1, c.y0 - 1,
+                        c.z0 + i - pz, c.n);
+        }
+        __syncwarp();
+        if (++slot == p.nring) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 6) {
+    // ================================ weights (TMA): wt filter taps per stage ==================
+    int slot = 0;
+    uint32_t ph = 0;
+    const uint32_t stage_tx = (uint32_t)(p.BN * p.rb * NCH * p.wt);
+    const int ntaps = p.kd * 9;
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item3 c = decode_item(p, it);
+      for (int j = 0; j < c.nz; ++j) {
+        for (int tap = 0; tap < ntaps; tap += p.wt) {
+          mbar_wait(wempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
+          const uint32_t bar = wfull0 + 8u * slot;
+          uint32_t dst = smem_base + (uint32_t)(p.w_off + slot * p.wg * p.w_sub_bytes);
+          if (elect_one()) {
+            mbar_expect_tx(bar, stage_tx);
+            for (int u = 0; u < p.wt; ++u) {
+#pragma unroll
+              for (int ch = 0; ch < NCH; ++ch) {
+                tma_load_2d(dst, &map_b, bar, (tap + u) * p.Cin + ch * p.kbox, 0);
+                dst += (uint32_t)p.w_sub_bytes;
+              }
+            }
+          }
+          __syncwarp();
+          if (++slot == p.wstages) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t kRb = 32u * KB;
+    constexpr uint32_t layout_type = (kRb == 128) ? 2u : (kRb == 64 ? 4u : 6u);
+    const uint64_t desc_hi = make_kmajor_desc(0, 8u * kRb, layout_type);
+    // everything in units of 16 bytes (the descriptor's address granule); smem < 256 KB, so adding
+    // offsets to the 14-bit start-address field never carries into the next field
+    const uint64_t a_ring = desc_hi | (uint64_t)((smem_base & 0x3FFFF) >> 4);
+    const uint64_t b_ring = desc_hi | (uint64_t)(((smem_base + (uint32_t)p.w_off) & 0x3FFFF) >> 4);
+    const uint32_t plane16 = (uint32_t)p.plane_bytes >> 4, chunk16 = (uint32_t)p.chunk_bytes >> 4;
+    const uint32_t wstage16 = (uint32_t)(p.wg * p.w_sub_bytes) >> 4, wsub16 = (uint32_t)p.w_sub_bytes >> 4;
+    constexpr uint32_t tile16 = 128u * kRb / 16u;
+    const uint32_t rowP16 = (uint32_t)p.P * kRb / 16u;      // one image row of the block
+    constexpr uint32_t row16 = kRb / 16u;                   // one pixel
+    int pslot = 0;                 // ring slot of the first plane of the current step
+    uint32_t pph = 0;              // phase of the next plane to wait for
+    int wait_slot = 0;             // next plane slot to wait on
+    int wslot = 0;
+    uint32_t wph = 0;
+    int step = 0;
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item3 c = decode_item(p, it);
+      int waited = 0;              // planes of this item already seen full
+      pslot = wait_slot;
+      for (int j = 0; j < c.nz; ++j, ++step) {
+        const int buf = step & 1;
+        mbar_wait(tempty0 + 8u * buf, ((uint32_t)(step >> 1) & 1u) ^ 1u, abort_flag, p.err_word);
+        while (waited < j + p.kd) {
+          mbar_wait(pfull0 + 8u * wait_slot, pph, abort_flag, p.err_word);
+          if (++wait_slot == p.nring) { wait_slot = 0; pph ^= 1u; }
+          ++waited;
+        }
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * p.T * p.bn_cols);
+        uint32_t acc = 0;
+        const int ntaps = p.kd * 9;
+        for (int tap = 0; tap < ntaps; tap += p.wt) {      // one weight stage = wt taps (1, 3 or 9: never straddles a row / plane)
+          const int tz = tap / 9, r9 = tap - tz * 9;
+          const int ty = r9 / 3, tx = r9 - ty * 3;
+          int ps = pslot + tz;
+          if (ps >= p.nring) ps -= p.nring;
+          mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
+          tc_fence_after();
+          if (elect_one()) {
+            uint64_t a_tap = a_ring + (uint64_t)((uint32_t)ps * plane16 + (uint32_t)ty * rowP16 + (uint32_t)tx * row16);
+            uint64_t b_tap = b_ring + (uint64_t)((uint32_t)wslot * wstage16);
+            int txu = tx;
+            for (int u = 0; u < p.wt; ++u) {
+              uint64_t a_t = a_tap;
+              uint32_t d_t = d0;
+              for (int t = 0; t < p.T; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                  const int nk = (ch == NCH - 1) ? LASTK : KB;
+#pragma unroll
+                  for (int k = 0; k < KB; ++k) {
+                    if (k < nk)
+                      umma_bf16(d_t, a_t + (uint64_t)(ch * chunk16 + 2u * k), b_tap + (uint64_t)(ch * wsub16 + 2u * k),
+                                idesc, (ch == 0 && k == 0) ? acc : 1u);
+                  }
+                }
+              }
+              acc = 1;
+              b_tap += (uint64_t)(NCH * wsub16);
+              a_tap += row16;
+              if (++txu == 3) { txu = 0; a_tap += (uint64_t)(rowP16 - 3u * row16); }
+            }
+            umma_commit(wempty0 + 8u * wslot);
+          }
+          __syncwarp();
+          acc = 1;
+          if (++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
+        }
+        if (elect_one()) {
+          umma_commit(tfull0 + 8u * buf);                 // accumulators of this step complete
+          umma_commit(pempty0 + 8u * pslot);              // plane z-1 is not needed by later steps
+          if (j == c.nz - 1)
+            for (int e = 1; e < p.kd; ++e) {
+              int ps = pslot + e;
+              if (ps >= p.nring) ps -= p.nring;
+              umma_commit(pempty0 + 8u * ps);
+            }
+        }
+        __syncwarp();
+        if (++pslot == p.nring) pslot = 0;
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    // ================================ epilogue ==============================================
+    const int quad = warp & 3;
+    int step = 0;
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item3 c = decode_item(p, it);
+      for (int j = 0; j < c.nz; ++j, ++step) {
+        const int buf = step & 1;
+        const int zz = c.z0 + j;
+        mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+        tc_fence_after();
+        for (int t = 0; t < p.T; ++t) {
+          const int r = t * 128 + quad * 32 + lane;
+          const int yy = r / p.P, xx = r - yy * p.P;
+          const int gy = c.y0 + yy, gx = c.x0 + xx;
+          const bool valid = r < p.R && xx < p.Xb && gx < p.W && gy < p.H;
+          const long long pix = (((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.T + t) * p.bn_cols);
+          for (int cc = 0; cc < p.BN; cc += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)cc, v);
+            if (!valid || cc >= p.Cout) continue;
+            float f[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+            if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc + q));
+                f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
+              }
+            }
+            if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] = lrelu(f[q]);
+            }
+            const long long off = pix * p.Cout + cc;
+            if (p.flags & R2N2_EPI_RESIDUAL) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                float4 r4 = Vec4<TOut>::load(res + off + q);
+                f[q] += r4.x; f[q + 1] += r4.y; f[q + 2] += r4.z; f[q + 3] += r4.w;
+              }
+            }
+            if (p.flags & R2N2_EPI_MASK) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                float4 m4 = Vec4<TOut>::load(mask + off + q);
+                f[q] *= lrelu_slope(m4.x); f[q + 1] *= lrelu_slope(m4.y);
+                f[q + 2] *= lrelu_slope(m4.z); f[q + 3] *= lrelu_slope(m4.w);
+              }
+            }
+            store16(y + off, f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+static inline int ru(int v, int m) { return (v + m - 1) / m * m; }
+
+// Choose the block (Xb, Yb), ring depth and weight staging.  Returns false when the layer does not fit
+// (caller falls back to the per-tap kernel).
+static bool plan_fwd3(Fwd3Params& p) {
+  const int budget = 222 * 1024;
+  p.kbox = p.Cin >= 64 ? 64 : (p.Cin >= 32 ? 32 : 16);
+  p.nchunk = (p.Cin + p.kbox - 1) / p.kbox;
+  p.rb = p.kbox * 2;
+  p.full_nk16 = p.kbox >> 4;
+  p.last_nk16 = (p.Cin - (p.nchunk - 1) * p.kbox) >> 4;
+  p.BN = p.Cout;
+  p.bn_cols = ru(p.BN, 32);
+  const int Tmax = 256 / p.bn_cols;                       // two accumulator sets in 512 TMEM columns
+  if (Tmax < 1) return false;
+  p.w_sub_bytes = ru(p.BN * p.rb, 1024);
+  // weight ring: one filter tap (all channel chunks) per stage; depth fixed after the block is chosen
+  // (9, 3 or 1 taps: each barrier round costs the issuing thread ~300 cycles, so small taps are grouped)
+  p.wt = 9;
+  while (p.wt > 1 && p.wt * p.nchunk * p.w_sub_bytes > 24 * 1024) p.wt /= 3;
+  if (const char* e = getenv("R2N2_FWD3_WT")) { int v = atoi(e); if (v == 1 || v == 3 || v == 9) p.wt = v; }
+  p.wg = p.wt * p.nchunk;
+  const int wstage_bytes = p.wg * p.w_sub_bytes;
+  p.wstages = 2;
+  const int w_bytes = p.wstages * wstage_bytes;
+  p.nring = p.kd == 1 ? 2 : 4;
+  double best = -1.0;
+  int bX = 0, bY = 0;
+  for (int Xb = (p.W < 8 ? p.W : 8); Xb <= 126 && Xb <= p.W; ++Xb) {
+    const int bx = (p.W + Xb - 1) / Xb;
+    const int P = Xb + 2;
+    for (int Yb = 1; Yb <= p.H && Yb <= 64; ++Yb) {
+      const int R = Yb * P;
+      const int T = (R + 127) / 128;
+      if (T > Tmax) break;
+      const int reach = T * 128 + 2 * P + 2;
+      const int rows = (Yb + 2) * P;
+      const int chunk_bytes = ru((reach > rows ? reach : rows) * p.rb, 1024);
+      if ((long long)p.nring * p.nchunk * chunk_bytes + w_bytes + 256 > budget) break;
+      const int by = (p.H + Yb - 1) / Yb;
+      // useful MMA rows / issued rows, and (weakly) the halo overhead of the loads
+      const double eff = ((double)p.W / (bx * Xb)) * ((double)Xb * Yb / (T * 128)) * ((double)p.H / (by * Yb)) *
+                         (0.8 + 0.2 * ((double)Xb * Yb / rows));
+      if (eff > best + 1e-9) { best = eff; bX = Xb; bY = Yb; }
+    }
+  }
+  if (bX == 0 || best < 0.6) return false;
+  if (const char* e = getenv("R2N2_FWD3_BLOCK")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2) { bX = a; bY = b; } }
+  p.Xb = bX; p.Yb = bY; p.P = bX + 2;
+  p.bx = (p.W + bX - 1) / bX; p.by = (p.H + bY - 1) / bY;
+  p.R = bY * p.P;
+  p.T = (p.R + 127) / 128;
+  p.plane_rows = (bY + 2) * p.P;
+  const int reach = p.T * 128 + 2 * p.P + 2;
+  p.chunk_bytes = ru((reach > p.plane_rows ? reach : p.plane_rows) * p.rb, 1024);
+  p.plane_bytes = p.nchunk * p.chunk_bytes;
+  p.w_off = p.nring * p.plane_bytes;
+  // as many weight stages as fit (the taps of a step stream through them back to back)
+  p.wstages = (budget - 256 - p.w_off) / wstage_bytes;
+  if (p.wstages > 9) p.wstages = 9;
+  if (p.wstages < 2) return false;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.T * p.bn_cols) p.tmem_cols *= 2;
+  if (p.kd == 1) { p.zc = 1; }
+  else {
+    // planes per item: amortise the 2 halo planes, keep enough items to balance the SMs
+    p.zc = p.D < 8 ? p.D : 8;
+    if (const char* e = getenv("R2N2_FWD3_ZC")) { int v = atoi(e); if (v >= 1 && v <= p.D) p.zc = v; }
+  }
+  p.zitems = (p.D + p.zc - 1) / p.zc;
+  p.items = (long long)p.N * p.zitems * p.by * p.bx;
+  return p.T >= 1 && p.T <= Tmax;
+}
+
+bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
+  if (getenv("R2N2_UMMA_NO_FWD3")) return false;
+  if (kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
+  if (kd == 1 && D != 1) return false;
+  if (Cout % 16 || Cout > 128) return false;
+  if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 96 && Cin != 128) return false;   // instantiated chunk patterns
+  if (!getenv("R2N2_FWD3_FORCE")) {
+    if ((long long)N * D * H * W < 128 * 148) return false;   // small layers: the per-tap kernel is fine
+    // Measured (tools/bench_conv.py, B200): the win needs the streamed weights of a step to be small next to
+    // its MMA time.  3-D layers with Cin <= 32 (conv10b/c, conv11 and their data gradients) run 1.6-2.3x
+    // faster, conv1b (96 -> 96, 127^2) 1.25x; at Cin >= 64 only two weight stages fit beside the plane ring
+    // and the weight TMA latency is exposed (conv9b, conv10a, conv2a/b: 0.9-1.0x) -> per-tap kernel.
+    const bool small3d = kd == 3 && Cin <= 32;
+    const bool conv1b_like = kd == 1 && Cin == 96 && Cout == 96;
+    if (!small3d && !conv1b_like) return false;
+  }
+  Fwd3Params p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd;
+  return plan_fwd3(p);
+}
+
+struct Fwd3Launch {
+  const CUtensorMap& map_a;
+  const CUtensorMap& map_b;
+  const float* bias;
+  const void* mask;
+  const void* res;
+  void* y;
+  const Fwd3Params& p;
+  unsigned grid;
+  size_t smem;
+  cudaStream_t st;
+};
+
+template <typename TOut, int KB, int NCH, int LASTK>
+static int launch_fwd3(const Fwd3Launch& L) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
+      L.map_a, L.map_b, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+  return R2N2_OK;
+}
+template <int KB, int NCH, int LASTK>
+static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
+  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK>(L) : launch_fwd3<float, KB, NCH, LASTK>(L);
+}
+
+int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
+                   int N, int D, int H, int W, int Cin, int Cout, int kd, int flags, int out_dtype,
+                   cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled unavailable");
+  Fwd3Params p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd;
+  R2N2_CHECK_ARG(plan_fwd3(p), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
+  p.flags = flags & 15;
+  p.err_word = get_err_word();
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                             (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.P, (cuuint32_t)(p.Yb + 2), 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.rb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
+  }
+  {
+    const long long K = (long long)kd * 9 * Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.rb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
+  }
+  const size_t smem_bytes = (size_t)p.w_off + (size_t)p.wstages * p.wg * p.w_sub_bytes +
+                            (2 * p.nring + 2 * p.wstages + 4) * 8 + 16 + 1024;
+  R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: smem %zu too large", smem_bytes);
+  long long grid = num_sms();
+  if (grid > p.items) grid = p.items;
+  if (getenv("R2N2_UMMA_DBG"))
+    fprintf(stderr, "[umma fwd3] %dx%dx%dx%d Cin %d Cout %d kd %d block %dx%d P %d R %d T %d bands %dx%d zc %d items %lld "
+            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
+            p.Xb, p.Yb, p.P, p.R, p.T, p.bx, p.by, p.zc, p.items, p.kbox, p.nchunk, p.plane_bytes, p.nring,
+            p.w_sub_bytes, p.wt, p.wstages, p.tmem_cols, smem_bytes);
+  R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE,
+                 "conv_fwd[umma3]: bad out dtype %d", out_dtype);
+  const Fwd3Launch L{map_a, map_b, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
+  int rc;
+  if (Cin == 16) rc = launch_fwd3_dt<1, 1, 1>(L, out_dtype);
+  else if (Cin == 32) rc = launch_fwd3_dt<2, 1, 2>(L, out_dtype);
+  else if (Cin == 64) rc = launch_fwd3_dt<4, 1, 4>(L, out_dtype);
+  else if (Cin == 96) rc = launch_fwd3_dt<4, 2, 2>(L, out_dtype);
+  else rc = launch_fwd3_dt<4, 2, 4>(L, out_dtype);
+  if (rc != R2N2_OK) return rc;
+  R2N2_CHECK_LAUNCH("conv_fwd[umma3]");
+  return R2N2_OK;
+}
+
+}  // namespace r2n2

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(192) exp_kernel(const __nv_bfloat16* ga, const
     // issue-rate test without any per-iteration ALU work: whole warp runs the loop, one elected lane issues
     uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | (((uint32_t)p.M >> 4) << 24);
     uint64_t hi = ((uint64_t)1 << 16) | ((uint64_t)((8u * p.rb) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)lt << 61);
-    uint64_t da = hi | (uint64_t)((a0 & 0x3FFFF) >> 4);
+    uint64_t da = hi | (uint64_t)(((a0 + p.r0 * p.rb) & 0x3FFFF) >> 4);
     uint64_t db = hi | (uint64_t)((b0 & 0x3FFFF) >> 4);
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -275,6 +275,18 @@ int main() {
         printf("issue rate rb %3d N %3d reps %4d : %lld cycles = %.1f / MMA\n", rb, N, reps, h, (double)h / reps);
       }
     }
+  for (int rbb : {128, 64, 32})
+    for (int r0 : {0, 1, 3, 4, 8})
+      for (int N : {32, 64, 128}) {
+        Params p;
+        p.mode = 4; p.rb = rbb; p.r0 = r0; p.base_off = 0; p.lbo_rows = 1; p.N = N; p.reps = 1024; p.M = 128;
+        exp_kernel<<<1, 192, smem_bytes>>>(ga, gb, out, cyc, p);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+        long long h;
+        cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("K-major A start row %d rb %3d N %3d : %.1f cycles / MMA\n", r0, rbb, N, (double)h / p.reps);
+      }
   for (int M : {128, 64})
     for (int N : {16, 32, 64, 128, 256}) {
       Params p;
