@@ -661,6 +661,36 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, T* __restri
   }
 }
 
+// All weight tensors of a network in ONE launch: table[e] = {src offset (floats), dst offset
+// (elements), Cout, taps, Cin, first tile}; a block finds its entry by scanning the (<= 64-entry) table.
+template <typename T>
+__global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T* __restrict__ wt_base,
+                                              const long long* __restrict__ table, int n) {
+  __shared__ float tile[32][33];
+  const long long bid = blockIdx.x;
+  int e = 0;
+  while (e + 1 < n && __ldg(table + (e + 1) * 6 + 5) <= bid) ++e;
+  const long long* row = table + e * 6;
+  const float* w = base + __ldg(row + 0);
+  T* wt = wt_base + __ldg(row + 1);
+  const int Cout = (int)__ldg(row + 2), taps = (int)__ldg(row + 3), Cin = (int)__ldg(row + 4);
+  long long local = bid - __ldg(row + 5);
+  const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 31) / 32;
+  const int ci0 = (int)(local % tiles_ci) * 32; local /= tiles_ci;
+  const int co0 = (int)(local % tiles_co) * 32; local /= tiles_co;
+  const int t = (int)local;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int co = co0 + j, ci = ci0 + threadIdx.x;
+    tile[j][threadIdx.x] = (co < Cout && ci < Cin) ? w[((long long)co * taps + t) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int ci = ci0 + j, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout)
+      wt[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = from_float<T>(tile[threadIdx.x][j]);
+  }
+}
+
 // ------------------------------------------------------------------ optimisers
 template <typename TM, bool kMirror>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -1031,6 +1061,18 @@ int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin,
                                                                                 taps, Cin);
   })
   R2N2_CHECK_LAUNCH("weight_transpose");
+  return R2N2_OK;
+}
+
+int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long long* table, int n_entries,
+                                long long total_tiles, int out_dtype, void* stream) {
+  R2N2_CHECK_ARG(base && wt_base && table && n_entries > 0 && total_tiles > 0 && total_tiles < (1LL << 31),
+                 R2N2_ERR_BAD_SHAPE, "weight_transpose_batch: bad arguments");
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    weight_transpose_batch_kernel<T><<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        base, (T*)wt_base, table, n_entries);
+  })
+  R2N2_CHECK_LAUNCH("weight_transpose_batch");
   return R2N2_OK;
 }
 

@@ -283,6 +283,11 @@ class Engine:
                     self.weights.append(RefWeight(lname + '.b', (HID_C,), True, bb,
                                                   lambda t: t, lambda v: v))
 
+        if st.p.is_cuda:
+            # conv1's input has no gradient: its transposed operand is never used
+            self.tbatch = ops.TransposeBatch(
+                [p for n, p in self.P.items() if p.taps * p.cin > 1 and not n.startswith(('conv1a.', 'conv1.'))], st)
+
     # ------------------------------------------------------------------ parameter I/O
     def set_params(self, arrays):
         """arrays: list in the reference's weights.npy order (models/net.py:60-86)."""

@@ -159,6 +159,36 @@ def weight_transpose(w, wt, cout, taps, cin):
     _call('r2n2_weight_transpose', _ptr(w), _ptr(wt), cout, taps, cin, _DT[wt.dtype], _stream())
 
 
+class TransposeBatch:
+    """Transposed (data-gradient) operands of ALL weight tensors of a flat store, refreshed by one
+    launch per parameter version instead of one launch per layer."""
+
+    def __init__(self, params, store):
+        self.store = store
+        self.params = params
+        dt = store.mirror.dtype if store.mirror is not None else torch.float32
+        rows, dst, tiles = [], 0, 0
+        for p in params:
+            rows.append([p.data.storage_offset(), dst, p.cout, p.taps, p.cin, tiles])
+            dst += (p.data.numel() + 63) // 64 * 64
+            tiles += ((p.cin + 31) // 32) * ((p.cout + 31) // 32) * p.taps
+        self.total_tiles = tiles
+        self.table = torch.tensor(rows, dtype=torch.int64, device=store.p.device)
+        self.wt_all = torch.empty(dst, dtype=dt, device=store.p.device)
+        for p, r in zip(params, rows):
+            p.wt = self.wt_all[r[1]:r[1] + p.data.numel()]
+            p.tbatch = self
+        self.version = -1
+
+    def ensure(self):
+        if self.version != self.store.version:
+            _check(self.store.p, torch.float32)
+            _work(0.0, (self.store.p, self.wt_all))
+            _call('r2n2_weight_transpose_batch', _ptr(self.store.p), _ptr(self.wt_all), _ptr(self.table),
+                  len(self.params), self.total_tiles, _DT[self.wt_all.dtype], _stream())
+            self.version = self.store.version
+
+
 def cast(src, dst):
     _check(src, torch.float32), _check(dst)
     _work(0.0, (src, dst))
@@ -336,12 +366,16 @@ class Param:
         self.store = store
         self.wt = None
         self.wt_version = -1
+        self.tbatch = None       # TransposeBatch: all transposed operands refreshed by one launch
         self.grad_written = False
 
     def operand(self):
         return self.mirror if self.mirror is not None else self.data
 
     def operand_t(self):
+        if self.tbatch is not None:
+            self.tbatch.ensure()
+            return self.wt
         ver = self.store.version if self.store is not None else 0
         if self.wt is None or self.wt_version != ver:
             dt = self.mirror.dtype if self.mirror is not None else torch.float32

@@ -97,6 +97,13 @@ int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, 
 int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin, int out_dtype,
                           void* stream);
 
+/* the same for every weight tensor of a network in one launch (after each optimiser step): `table`
+ * is a DEVICE array of n_entries rows of 6 int64 {src offset in floats from base, dst offset in
+ * elements from wt_base, Cout, taps, Cin, index of the entry's first 32x32 tile}; total_tiles =
+ * sum over entries of ceil(Cin/32) * ceil(Cout/32) * taps. */
+int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long long* table, int n_entries,
+                                long long total_tiles, int out_dtype, void* stream);
+
 /* fp32 -> out_dtype copy (bf16 operand mirrors of the fp32 master weights). */
 int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream);
 

@@ -175,6 +175,25 @@ def test_pointwise_and_layout():
     emu.weight_transpose(w, want, 10, 27, 12)
     ops.weight_transpose(w.to(DEV), wt, 10, 27, 12)
     _cmp(wt, want, 0.0, 'weight_transpose')
+    # every weight tensor of a store in one launch
+    shapes = [(10, 27, 12), (96, 9, 96), (33, 1, 70), (128, 27, 16)]
+    flat, rows, dst, tiles = [], [], 0, 0
+    for i, (co, tp, ci) in enumerate(shapes):
+        t_ = _r(co * tp * ci, seed=20 + i)
+        rows.append([sum(x.numel() for x in flat), dst, co, tp, ci, tiles])
+        flat.append(t_)
+        dst += co * tp * ci
+        tiles += ((ci + 31) // 32) * ((co + 31) // 32) * tp
+    base = torch.cat(flat).to(DEV)
+    for dt in (torch.float32, torch.bfloat16):
+        out = torch.full((dst,), float('nan'), dtype=dt, device=DEV)
+        table = torch.tensor(rows, dtype=torch.int64, device=DEV)
+        L.call('r2n2_weight_transpose_batch', base.data_ptr(), out.data_ptr(), table.data_ptr(), len(rows), tiles,
+               L.F32 if dt == torch.float32 else L.BF16, None)
+        for (co, tp, ci), r_, t_ in zip(shapes, rows, flat):
+            want = torch.empty(t_.numel())
+            emu.weight_transpose(t_, want, co, tp, ci)
+            _cmp(out[r_[1]:r_[1] + t_.numel()], want.to(dt), 0.0, 'weight_transpose_batch')
     # flat kernel (C/vector <= 256 vectors per row), ragged row counts, and the generic kernel
     for rows, C in [(1000, 96), (77, 2), (3, 1024), (5000, 256), (40003, 32), (12345, 64), (999, 16),
                     (2, 4096), (70001, 128)]:
