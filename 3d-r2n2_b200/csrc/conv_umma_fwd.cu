@@ -12,7 +12,7 @@
 //   * TWO accumulators live in TMEM (2 x BN columns): the epilogue warps drain tile i
 //     (tcgen05.ld -> bias / LeakyReLU / residual / LeakyReLU' -> 16-byte global stores) while the
 //     MMA warp already accumulates tile i+1 and the TMA warp prefetches further ahead.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.  All role loops are executed by
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two warps per TMEM lane quadrant).  All role loops are executed by
 // the whole warp (elect.sync around the issuing instructions) so operands stay in uniform registers.
 #include "umma.cuh"
 
@@ -67,8 +67,10 @@ static __device__ __forceinline__ TileCoord decode_tile(const FwdParams& p, int 
   return c;
 }
 
+constexpr int kFwdThreads = 64 + 32 * kEpiWarps;
+
 template <typename TOut>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 2)
 conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
                          const FwdParams p) {
@@ -93,7 +95,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
-      mbar_init(smem_u32(&tempty_bar[b]), 4);      // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[b]), kEpiWarps);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -219,7 +221,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
       __syncwarp();
     }
   } else {
-    // ================================ epilogue (warps 2..5) =================================
+    // ================================ epilogue (warps 2..9) =================================
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
     int r = row;
@@ -227,6 +229,9 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     const int yi = r % p.bh; r /= p.bh;
     const int zi = r % p.bd; r /= p.bd;
     const int ni = r;
+    // two warps per lane quadrant: each takes half of the tile's 16-column chunks
+    const int nch = p.BN >> 4, half = (warp - 2) >> 2;
+    const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -246,46 +251,13 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         pix = (((long long)nn * p.D + zz) * p.H + yy) * p.W + xx;
       }
       const int col0 = tc.nt * p.BN;
+      const long long off = pix * p.Cout;
+      EpiPrefetch<TOut> pf;
+      epi_prefetch(pf, p.flags, valid, res + off, mask + off, col0 + c_begin, p.Cout);
       mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
-        const int co = col0 + c;
-        if (!valid || co >= p.Cout) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = empty_acc ? 0.f : __uint_as_float(v[j]);
-        if (p.flags & R2N2_EPI_BIAS) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
-        }
-        if (p.flags & R2N2_EPI_LRELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
-        }
-        const long long off = pix * p.Cout + co;
-        if (p.flags & R2N2_EPI_RESIDUAL) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 r4 = Vec4<TOut>::load(res + off + j);
-            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-          }
-        }
-        if (p.flags & R2N2_EPI_MASK) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 m4 = Vec4<TOut>::load(mask + off + j);
-            f[j] *= lrelu_slope(m4.x); f[j + 1] *= lrelu_slope(m4.y);
-            f[j + 2] *= lrelu_slope(m4.z); f[j + 3] *= lrelu_slope(m4.w);
-          }
-        }
-        store16(y + off, f);
-      }
+      epi_row(pf, taddr, c_begin, c_end, col0, p.Cout, valid, empty_acc, p.flags, bias, res + off, mask + off, y + off);
       // this warp has finished reading the accumulator: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -457,7 +429,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
       R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
       attr_set = true;
     }
-    conv_fwd_umma_persistent<__nv_bfloat16><<<grid, kUmmaThreads, smem_bytes, st>>>(
+    conv_fwd_umma_persistent<__nv_bfloat16><<<grid, kFwdThreads, smem_bytes, st>>>(
         map_a, map_b, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
   } else if (out_dtype == R2N2_F32) {
     static bool attr_set = false;
@@ -467,7 +439,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
       R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
       attr_set = true;
     }
-    conv_fwd_umma_persistent<float><<<grid, kUmmaThreads, smem_bytes, st>>>(
+    conv_fwd_umma_persistent<float><<<grid, kFwdThreads, smem_bytes, st>>>(
         map_a, map_b, bias, (const float*)mask, (const float*)res, (float*)y, p);
   } else {
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);

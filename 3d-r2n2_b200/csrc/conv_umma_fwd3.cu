@@ -17,12 +17,12 @@
 //   * the weights of all taps are streamed through their own small TMA ring once per step and shared
 //     by the T tiles of the step (T accumulators side by side in TMEM, double buffered so that the
 //     epilogue of step i overlaps the MMAs of step i+1).
-// Warp roles: 0 = input-plane TMA, 1 = MMA issuer, 2..5 = epilogue, 6 = weight TMA.
+// Warp roles: 0 = input-plane TMA, 1 = MMA issuer, 2..9 = epilogue, 10 = weight TMA.
 #include "umma.cuh"
 
 namespace r2n2 {
 
-constexpr int kFwd3Threads = 224;
+constexpr int kFwd3Threads = 96 + 32 * kEpiWarps;   // planes, MMA, 8 epilogue warps, weights
 
 struct Fwd3Params {
   int N, D, H, W, Cin, Cout;
@@ -88,7 +88,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     *abort_flag = 0;
     for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), 1); mbar_init(smem_u32(&pempty[s]), 1); }
     for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), 1); mbar_init(smem_u32(&wempty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -132,7 +132,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (++slot == p.nring) { slot = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2 + kEpiWarps) {
     // ================================ weights (TMA): wt filter taps per stage ==================
     int slot = 0;
     uint32_t ph = 0;
@@ -249,60 +249,33 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (++pslot == p.nring) pslot = 0;
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
+  } else if (warp >= 2 && warp < 2 + kEpiWarps) {
     // ================================ epilogue ==============================================
     const int quad = warp & 3;
+    const int nch = p.BN >> 4, half = (warp - 2) >> 2;     // two warps per lane quadrant, half the columns each
+    const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
     int step = 0;
     for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const Item3 c = decode_item(p, it);
       for (int j = 0; j < c.nz; ++j, ++step) {
         const int buf = step & 1;
         const int zz = c.z0 + j;
-        mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
-        tc_fence_after();
+        bool first = true;
         for (int t = 0; t < p.T; ++t) {
           const int r = t * 128 + quad * 32 + lane;
           const int yy = r / p.P, xx = r - yy * p.P;
           const int gy = c.y0 + yy, gx = c.x0 + xx;
           const bool valid = r < p.R && xx < p.Xb && gx < p.W && gy < p.H;
-          const long long pix = (((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.T + t) * p.bn_cols);
-          for (int cc = 0; cc < p.BN; cc += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + (uint32_t)cc, v);
-            if (!valid || cc >= p.Cout) continue;
-            float f[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
-            if (p.flags & R2N2_EPI_BIAS) {
-#pragma unroll
-              for (int q = 0; q < 16; q += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc + q));
-                f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
-              }
-            }
-            if (p.flags & R2N2_EPI_LRELU) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) f[q] = lrelu(f[q]);
-            }
-            const long long off = pix * p.Cout + cc;
-            if (p.flags & R2N2_EPI_RESIDUAL) {
-#pragma unroll
-              for (int q = 0; q < 16; q += 4) {
-                float4 r4 = Vec4<TOut>::load(res + off + q);
-                f[q] += r4.x; f[q + 1] += r4.y; f[q + 2] += r4.z; f[q + 3] += r4.w;
-              }
-            }
-            if (p.flags & R2N2_EPI_MASK) {
-#pragma unroll
-              for (int q = 0; q < 16; q += 4) {
-                float4 m4 = Vec4<TOut>::load(mask + off + q);
-                f[q] *= lrelu_slope(m4.x); f[q + 1] *= lrelu_slope(m4.y);
-                f[q + 2] *= lrelu_slope(m4.z); f[q + 3] *= lrelu_slope(m4.w);
-              }
-            }
-            store16(y + off, f);
+          const long long off = ((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * p.Cout;
+          EpiPrefetch<TOut> pf;
+          epi_prefetch(pf, p.flags, valid, res + off, mask + off, c_begin, p.Cout);
+          if (first) {
+            mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+            tc_fence_after();
+            first = false;
           }
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.T + t) * p.bn_cols);
+          epi_row(pf, taddr, c_begin, c_end, 0, p.Cout, valid, false, p.flags, bias, res + off, mask + off, y + off);
         }
         tc_fence_before();
         __syncwarp();

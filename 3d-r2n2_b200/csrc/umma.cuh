@@ -133,6 +133,98 @@ static __device__ __forceinline__ void store16(float* dst, const float (&f)[16])
 }
 
 
+// 16 consecutive channels of one pixel as stored in memory (raw 16-byte loads; converted on use)
+template <typename T>
+struct Row16;
+template <>
+struct Row16<__nv_bfloat16> {
+  uint4 a, b;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    a = reinterpret_cast<const uint4*>(p)[0];
+    b = reinterpret_cast<const uint4*>(p)[1];
+  }
+  __device__ __forceinline__ void unpack(float (&f)[16]) const {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      float2 t = __bfloat1622float2(h);
+      f[2 * j] = t.x; f[2 * j + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Row16<float> {
+  float4 q[4];
+  __device__ __forceinline__ void load(const float* p) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = reinterpret_cast<const float4*>(p)[j];
+  }
+  __device__ __forceinline__ void unpack(float (&f)[16]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[4 * j] = q[j].x; f[4 * j + 1] = q[j].y; f[4 * j + 2] = q[j].z; f[4 * j + 3] = q[j].w; }
+  }
+};
+
+// Epilogue of one accumulator row (one pixel) over the 16-column chunks [c_begin, c_end) of a tile:
+// TMEM -> bias -> LeakyReLU -> + residual -> x LeakyReLU'(mask) -> 16-byte stores.  The residual / mask
+// rows of chunk c+1 are fetched while chunk c is processed, and those of the first chunk are issued
+// by epi_prefetch() BEFORE the accumulator-ready wait, so the global-load latency overlaps the MMAs.
+// res / mask / y point at channel 0 of this pixel; `ok` = pixel in bounds; co0 = first channel of the tile.
+template <typename TOut>
+struct EpiPrefetch {
+  Row16<TOut> r, m;
+};
+template <typename TOut>
+static __device__ __forceinline__ void epi_prefetch(EpiPrefetch<TOut>& pf, int flags, bool ok, const TOut* res,
+                                                     const TOut* mask, int co, int Cout) {
+  if (ok && co < Cout) {
+    if (flags & R2N2_EPI_RESIDUAL) pf.r.load(res + co);
+    if (flags & R2N2_EPI_MASK) pf.m.load(mask + co);
+  }
+}
+template <typename TOut>
+static __device__ __forceinline__ void epi_row(EpiPrefetch<TOut>& pf, uint32_t taddr, int c_begin, int c_end, int co0,
+                                                int Cout, bool ok, bool empty_acc, int flags,
+                                                const float* __restrict__ bias, const TOut* res, const TOut* mask,
+                                                TOut* y) {
+  for (int c = c_begin; c < c_end; c += 16) {
+    const EpiPrefetch<TOut> cur = pf;
+    if (c + 16 < c_end) epi_prefetch(pf, flags, ok, res, mask, co0 + c + 16, Cout);
+    uint32_t v[16];
+    tmem_ld16(taddr + (uint32_t)c, v);
+    const int co = co0 + c;
+    if (!ok || co >= Cout) continue;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = empty_acc ? 0.f : __uint_as_float(v[j]);
+    if (flags & R2N2_EPI_BIAS) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    }
+    if (flags & R2N2_EPI_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
+    }
+    if (flags & R2N2_EPI_RESIDUAL) {
+      float r[16];
+      cur.r.unpack(r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] += r[j];
+    }
+    if (flags & R2N2_EPI_MASK) {
+      float m[16];
+      cur.m.unpack(m);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] *= lrelu_slope(m[j]);
+    }
+    store16(y + co, f);
+  }
+}
+
 static __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes,
                                                       uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
@@ -152,6 +244,7 @@ static __device__ __forceinline__ void red_add_v4(float* addr, float a, float b,
 
 
 constexpr int kUmmaThreads = 192;
+constexpr int kEpiWarps = 8;                 // conv_umma_fwd.cu / conv_umma_fwd3.cu: two epilogue warps per TMEM lane quadrant
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
