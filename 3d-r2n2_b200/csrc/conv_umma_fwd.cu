@@ -304,7 +304,7 @@ int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void
 
 bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw);
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
-                   int N, int D, int H, int W, int Cin, int Cout, int kd, int flags, int out_dtype,
+                   int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int flags, int out_dtype,
                    cudaStream_t st);
 
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
@@ -327,7 +327,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
                  R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
   // 3x3 / 3x3x3 layers with <= 128 output channels: input loaded once, taps as descriptor views
   if (mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw))
-    return conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, flags, out_dtype, st);
+    return conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, out_dtype, st);
   EncodeTiledFn encode = get_encode();
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled unavailable");
 

@@ -26,7 +26,9 @@ constexpr int kFwd3Threads = 96 + 32 * kEpiWarps;   // planes, MMA, 8 epilogue w
 
 struct Fwd3Params {
   int N, D, H, W, Cin, Cout;
-  int kd;                                  // 1 or 3 (kh = kw = 3)
+  int kd, kh, kw;                          // kd 1 or 3; (kh, kw) = (3, 3) or (7, 1)
+  int w_bytes;                             // bytes of the weight region (ring or resident filter)
+  int w_res;                               // all filter taps stay resident in shared memory (loaded once per CTA)
   int Xb, Yb, P, bx, by;                   // block, row pitch Xb+2, blocks per row / column
   int R, T;                                // output rows of a block, 128-row tiles
   int zc, zitems;                          // planes per work item, items along z
@@ -66,7 +68,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int ring_bytes = p.nring * p.plane_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.w_off + p.wstages * p.wg * p.w_sub_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.w_off + p.w_bytes);
   uint64_t* pfull = bars;                              // [nring]   plane TMA -> MMA
   uint64_t* pempty = pfull + p.nring;                  // [nring]   MMA -> plane TMA
   uint64_t* wfull = pempty + p.nring;                  // [wstages] weight TMA -> MMA
@@ -125,7 +127,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_expect_tx(bar, tx);
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - 1, c.y0 - 1,
+            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (p.kw - 1) / 2, c.y0 - (p.kh - 1) / 2,
                         c.z0 + i - pz, c.n);
         }
         __syncwarp();
@@ -137,7 +139,22 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int slot = 0;
     uint32_t ph = 0;
     const uint32_t stage_tx = (uint32_t)(p.BN * p.rb * NCH * p.wt);
-    const int ntaps = p.kd * 9;
+    const int ntaps = p.kd * p.kh * p.kw;
+    if (p.w_res) {
+      // small filters: every tap is loaded once and stays in shared memory for the whole kernel
+      uint32_t dst = smem_base + (uint32_t)p.w_off;
+      if (elect_one()) {
+        mbar_expect_tx(wfull0, (uint32_t)(p.BN * p.rb * NCH * ntaps));
+        for (int tap = 0; tap < ntaps; ++tap) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            tma_load_2d(dst, &map_b, wfull0, tap * p.Cin + ch * p.kbox, 0);
+            dst += (uint32_t)p.w_sub_bytes;
+          }
+        }
+      }
+      __syncwarp();
+    } else
     for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const Item3 c = decode_item(p, it);
       for (int j = 0; j < c.nz; ++j) {
@@ -197,17 +214,24 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * p.T * p.bn_cols);
         uint32_t acc = 0;
-        const int ntaps = p.kd * 9;
-        for (int tap = 0; tap < ntaps; tap += p.wt) {      // one weight stage = wt taps (1, 3 or 9: never straddles a row / plane)
-          const int tz = tap / 9, r9 = tap - tz * 9;
-          const int ty = r9 / 3, tx = r9 - ty * 3;
+        const int tpp = p.kh * p.kw;                        // taps per plane
+        const int ntaps = p.kd * tpp;
+        if (p.w_res && step == 0) {
+          mbar_wait(wfull0, 0u, abort_flag, p.err_word);
+          tc_fence_after();
+        }
+        for (int tap = 0; tap < ntaps; tap += p.wt) {      // one weight stage = wt taps of ONE plane
+          const int tz = tap / tpp, rp = tap - tz * tpp;
+          const int ty = rp / p.kw, tx = rp - ty * p.kw;
           int ps = pslot + tz;
           if (ps >= p.nring) ps -= p.nring;
-          mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
-          tc_fence_after();
+          if (!p.w_res) {
+            mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
+            tc_fence_after();
+          }
           if (elect_one()) {
             uint64_t a_tap = a_ring + (uint64_t)((uint32_t)ps * plane16 + (uint32_t)ty * rowP16 + (uint32_t)tx * row16);
-            uint64_t b_tap = b_ring + (uint64_t)((uint32_t)wslot * wstage16);
+            uint64_t b_tap = b_ring + (uint64_t)(p.w_res ? (uint32_t)tap * (NCH * wsub16) : (uint32_t)wslot * wstage16);
             int txu = tx;
             for (int u = 0; u < p.wt; ++u) {
               uint64_t a_t = a_tap;
@@ -227,13 +251,13 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               acc = 1;
               b_tap += (uint64_t)(NCH * wsub16);
               a_tap += row16;
-              if (++txu == 3) { txu = 0; a_tap += (uint64_t)(rowP16 - 3u * row16); }
+              if (++txu == p.kw) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)p.kw * row16); }
             }
-            umma_commit(wempty0 + 8u * wslot);
+            if (!p.w_res) umma_commit(wempty0 + 8u * wslot);
           }
           __syncwarp();
           acc = 1;
-          if (++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
+          if (!p.w_res && ++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
         }
         if (elect_one()) {
           umma_commit(tfull0 + 8u * buf);                 // accumulators of this step complete
@@ -311,49 +335,68 @@ static bool plan_fwd3(Fwd3Params& p) {
   p.w_sub_bytes = ru(p.BN * p.rb, 1024);
   // weight ring: one filter tap (all channel chunks) per stage; depth fixed after the block is chosen
   // (9, 3 or 1 taps: each barrier round costs the issuing thread ~300 cycles, so small taps are grouped)
-  p.wt = 9;
-  while (p.wt > 1 && p.wt * p.nchunk * p.w_sub_bytes > 24 * 1024) p.wt /= 3;
-  if (const char* e = getenv("R2N2_FWD3_WT")) { int v = atoi(e); if (v == 1 || v == 3 || v == 9) p.wt = v; }
+  const int tpp = p.kh * p.kw, ntaps = p.kd * tpp;
+  const int all_w = ntaps * p.nchunk * p.w_sub_bytes;
+  p.w_res = (all_w <= 64 * 1024 && !getenv("R2N2_FWD3_NO_RES")) ? 1 : 0;
+  p.wt = tpp;                                            // a stage never straddles two planes
+  if (!p.w_res) {
+    while (p.wt > 1 && p.wt * p.nchunk * p.w_sub_bytes > 24 * 1024) p.wt = (p.wt % 3 == 0) ? p.wt / 3 : 1;
+    if (const char* e = getenv("R2N2_FWD3_WT")) { int v = atoi(e); if (v >= 1 && tpp % v == 0) p.wt = v; }
+  }
   p.wg = p.wt * p.nchunk;
   const int wstage_bytes = p.wg * p.w_sub_bytes;
-  p.wstages = 2;
-  const int w_bytes = p.wstages * wstage_bytes;
+  p.wstages = p.w_res ? 1 : 2;
+  const int w_bytes = p.w_res ? all_w : p.wstages * wstage_bytes;
   p.nring = p.kd == 1 ? 2 : 4;
   double best = -1.0;
   int bX = 0, bY = 0;
-  for (int Xb = (p.W < 8 ? p.W : 8); Xb <= 126 && Xb <= p.W; ++Xb) {
+  for (int Xb = (p.W < 8 ? p.W : 8); Xb + p.kw - 1 <= 256 && Xb <= p.W; ++Xb) {
     const int bx = (p.W + Xb - 1) / Xb;
-    const int P = Xb + 2;
+    const int P = Xb + p.kw - 1;
     for (int Yb = 1; Yb <= p.H && Yb <= 64; ++Yb) {
       const int R = Yb * P;
       const int T = (R + 127) / 128;
       if (T > Tmax) break;
-      const int reach = T * 128 + 2 * P + 2;
-      const int rows = (Yb + 2) * P;
+      const int reach = T * 128 + (p.kh - 1) * P + p.kw - 1;
+      const int rows = (Yb + p.kh - 1) * P;
+      if (Yb + p.kh - 1 > 256) break;
       const int chunk_bytes = ru((reach > rows ? reach : rows) * p.rb, 1024);
       if ((long long)p.nring * p.nchunk * chunk_bytes + w_bytes + 256 > budget) break;
       const int by = (p.H + Yb - 1) / Yb;
       // useful MMA rows / issued rows, and (weakly) the halo overhead of the loads
       const double eff = ((double)p.W / (bx * Xb)) * ((double)Xb * Yb / (T * 128)) * ((double)p.H / (by * Yb)) *
-                         (0.8 + 0.2 * ((double)Xb * Yb / rows));
+                         (0.7 + 0.3 * ((double)Xb * Yb / rows));
       if (eff > best + 1e-9) { best = eff; bX = Xb; bY = Yb; }
     }
   }
   if (bX == 0 || best < 0.6) return false;
   if (const char* e = getenv("R2N2_FWD3_BLOCK")) { int a, b; if (sscanf(e, "%d,%d", &a, &b) == 2) { bX = a; bY = b; } }
-  p.Xb = bX; p.Yb = bY; p.P = bX + 2;
+  p.Xb = bX; p.Yb = bY; p.P = bX + p.kw - 1;
   p.bx = (p.W + bX - 1) / bX; p.by = (p.H + bY - 1) / bY;
   p.R = bY * p.P;
   p.T = (p.R + 127) / 128;
-  p.plane_rows = (bY + 2) * p.P;
-  const int reach = p.T * 128 + 2 * p.P + 2;
+  p.plane_rows = (bY + p.kh - 1) * p.P;
+  const int reach = p.T * 128 + (p.kh - 1) * p.P + p.kw - 1;
   p.chunk_bytes = ru((reach > p.plane_rows ? reach : p.plane_rows) * p.rb, 1024);
   p.plane_bytes = p.nchunk * p.chunk_bytes;
+  // deeper input ring when shared memory allows: a plane load is ~3-4K cycles of latency, a small step
+  // only ~1.5K cycles of MMA, so one plane of prefetch is not enough to keep the tensor pipe fed
+  {
+    const int w_need = p.w_res ? all_w : 3 * wstage_bytes;
+    int extra = (budget - 256 - w_need) / p.plane_bytes - p.nring;
+    const int max_extra = p.kd == 1 ? 6 : 2;
+    if (extra > max_extra) extra = max_extra;
+    if (extra > 0) p.nring += extra;
+    if (const char* e = getenv("R2N2_FWD3_RING")) { int v = atoi(e); if (v >= p.kd + 1 && v <= 12) p.nring = v; }
+  }
   p.w_off = p.nring * p.plane_bytes;
   // as many weight stages as fit (the taps of a step stream through them back to back)
-  p.wstages = (budget - 256 - p.w_off) / wstage_bytes;
-  if (p.wstages > 9) p.wstages = 9;
-  if (p.wstages < 2) return false;
+  if (!p.w_res) {
+    p.wstages = (budget - 256 - p.w_off) / wstage_bytes;
+    if (p.wstages > 9) p.wstages = 9;
+    if (p.wstages < 2) return false;
+  }
+  p.w_bytes = p.w_res ? all_w : p.wstages * wstage_bytes;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.T * p.bn_cols) p.tmem_cols *= 2;
   if (p.kd == 1) { p.zc = 1; }
@@ -369,7 +412,9 @@ static bool plan_fwd3(Fwd3Params& p) {
 
 bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw) {
   if (getenv("R2N2_UMMA_NO_FWD3")) return false;
-  if (kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
+  const bool k33 = kh == 3 && kw == 3 && (kd == 1 || kd == 3);
+  const bool k71 = kd == 1 && kh == 7 && kw == 1;           // row-packed first layer
+  if (!k33 && !k71) return false;
   if (kd == 1 && D != 1) return false;
   if (Cout % 16 || Cout > 128) return false;
   if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 96 && Cin != 128) return false;   // instantiated chunk patterns
@@ -381,10 +426,10 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
     // and the weight TMA latency is exposed (conv9b, conv10a, conv2a/b: 0.9-1.0x) -> per-tap kernel.
     const bool small3d = kd == 3 && Cin <= 32;
     const bool conv1b_like = kd == 1 && Cin == 96 && Cout == 96;
-    if (!small3d && !conv1b_like) return false;
+    if (!small3d && !conv1b_like && !(k71 && Cin <= 32)) return false;
   }
   Fwd3Params p;
-  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   return plan_fwd3(p);
 }
 
@@ -420,12 +465,12 @@ static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
 }
 
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
-                   int N, int D, int H, int W, int Cin, int Cout, int kd, int flags, int out_dtype,
+                   int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int flags, int out_dtype,
                    cudaStream_t st) {
   EncodeTiledFn encode = get_encode();
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled unavailable");
   Fwd3Params p;
-  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   R2N2_CHECK_ARG(plan_fwd3(p), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
   p.flags = flags & 15;
   p.err_word = get_err_word();
@@ -434,7 +479,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
                              (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.P, (cuuint32_t)(p.Yb + 2), 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)p.P, (cuuint32_t)(p.Yb + kh - 1), 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.rb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -442,7 +487,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
   }
   {
-    const long long K = (long long)kd * 9 * Cin;
+    const long long K = (long long)kd * kh * kw * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)p.BN};
@@ -452,16 +497,16 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
   }
-  const size_t smem_bytes = (size_t)p.w_off + (size_t)p.wstages * p.wg * p.w_sub_bytes +
+  const size_t smem_bytes = (size_t)p.w_off + (size_t)p.w_bytes +
                             (2 * p.nring + 2 * p.wstages + 4) * 8 + 16 + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: smem %zu too large", smem_bytes);
   long long grid = num_sms();
   if (grid > p.items) grid = p.items;
   if (getenv("R2N2_UMMA_DBG"))
     fprintf(stderr, "[umma fwd3] %dx%dx%dx%d Cin %d Cout %d kd %d block %dx%d P %d R %d T %d bands %dx%d zc %d items %lld "
-            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
+            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
             p.Xb, p.Yb, p.P, p.R, p.T, p.bx, p.by, p.zc, p.items, p.kbox, p.nchunk, p.plane_bytes, p.nring,
-            p.w_sub_bytes, p.wt, p.wstages, p.tmem_cols, smem_bytes);
+            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tmem_cols, smem_bytes);
   R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE,
                  "conv_fwd[umma3]: bad out dtype %d", out_dtype);
   const Fwd3Launch L{map_a, map_b, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};

@@ -31,6 +31,8 @@ CASES = [
     (1, 8, 8, 8, 16, 32, (3, 3, 3)),         # conv11 data gradient: Cin = 16 (SW32)
     (1, 5, 32, 32, 128, 128, (3, 3, 3)),     # two chunks, N = 128, 3-D
     (2, 3, 6, 5, 64, 64, (3, 3, 3)),         # tiny planes (one partial tile)
+    (3, 1, 40, 45, 32, 96, (1, 7, 1)),       # row-packed first layer: 7x1 taps, resident weights
+    (2, 1, 127, 127, 32, 96, (1, 7, 1)),
 ]
 
 
