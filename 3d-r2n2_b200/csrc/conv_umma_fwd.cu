@@ -31,6 +31,8 @@ struct FwdParams {
   int a_bytes, b_bytes, stage_bytes;       // per sub-block A / B bytes (1024-aligned), per stage
   int tmem_cols;
   int flags;
+  int tma_epi;                             // epilogue through shared memory + TMA loads/stores (bf16 out, mode != UP2)
+  int SC, slab_bytes, epi_off;             // slab = 128 rows x SC output channels; smem offset of the staging buffers
   int mode;                                // 0 plain, 1 UP2 (zero-stuffed x2 input, 8 parity classes), 2 DOWN2
   int cls_tiles;                           // tiles per parity class (= m_tiles * n_tiles)
   int* err_word;
@@ -72,6 +74,8 @@ constexpr int kFwdThreads = 64 + 32 * kEpiWarps;
 template <typename TOut>
 __global__ void __launch_bounds__(kFwdThreads, 2)
 conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
+                         const __grid_constant__ CUtensorMap map_mask,
                          const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
                          const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -81,7 +85,8 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
   uint64_t* empty_bar = bars + p.stages;           // [stages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]       MMA -> epilogue (accumulator ready)
   uint64_t* tempty_bar = bars + 2 * p.stages + 2;  // [2]       epilogue -> MMA (accumulator drained)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  uint64_t* efull_bar = bars + 2 * p.stages + 4;   // [2]       residual / mask slab landed (one per epilogue team)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 6);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -95,7 +100,9 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
-      mbar_init(smem_u32(&tempty_bar[b]), kEpiWarps);   // one arrive per epilogue warp
+      // one arrive per epilogue warp that drains the buffer (TMA epilogue: the 4 warps of one team)
+      mbar_init(smem_u32(&tempty_bar[b]), p.tma_epi ? kEpiWarps / 2 : kEpiWarps);
+      mbar_init(smem_u32(&efull_bar[b]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -224,6 +231,114 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     // ================================ epilogue (warps 2..9) =================================
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
+    if (p.tma_epi) {
+      // Two teams of 4 warps; team t drains accumulator buffer t (every other tile).  A thread-per-pixel
+      // global access touches 32 different 128-byte lines per instruction (32 L1 wavefronts): on layers
+      // with K <= ~1000 that, not the MMAs, bounded the tile time.  Here the tile goes through a swizzled
+      // shared-memory slab (128 pixels x SC channels): residual / mask slabs arrive by TMA load, the result
+      // leaves by ONE TMA tensor store (clipped at the tensor bounds), the threads only touch TMEM + smem.
+      if constexpr (sizeof(TOut) == 2) {
+        const int team = (warp - 2) >> 2;
+        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;     // always the same thread: it owns the bulk groups
+        const uint32_t bufY = smem_base + (uint32_t)(p.epi_off + team * p.slab_bytes);
+        const uint32_t bufM = smem_base + (uint32_t)(p.epi_off + (2 + team) * p.slab_bytes);
+        const uint32_t efull = smem_u32(&efull_bar[team]);
+        const uint32_t rb = (uint32_t)p.SC * 2u;
+        const uint32_t smask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
+        const bool has_in = (p.flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_MASK)) != 0;
+        const uint32_t in_tx = (uint32_t)(rows * p.SC * 2) *
+                               (((p.flags & R2N2_EPI_RESIDUAL) ? 1u : 0u) + ((p.flags & R2N2_EPI_MASK) ? 1u : 0u));
+        uint32_t eph = 0;
+        bool pending = false;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+          if ((it & 1) != team) continue;
+          const int buf = team;
+          const uint32_t use = (uint32_t)(it >> 1);
+          const TileCoord tc = decode_tile(p, tile);
+          const int x0 = tc.tw * p.bw, y0 = tc.th * p.bh, z0 = tc.td * p.bd, n0 = tc.tn * p.bn;
+          const int col0 = tc.nt * p.BN;
+          int ncol = p.Cout - col0;
+          if (ncol > p.BN) ncol = p.BN;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
+          for (int sc = 0; sc < ncol; sc += p.SC) {
+            if (leader && pending) tma_store_wait_read();          // previous store has read its slab
+            named_bar_sync(1 + team, 128);
+            if (has_in && leader) {
+              mbar_expect_tx(efull, in_tx);
+              if (p.flags & R2N2_EPI_RESIDUAL) tma_load_5d(bufY, &map_res, efull, col0 + sc, x0, y0, z0, n0);
+              if (p.flags & R2N2_EPI_MASK) tma_load_5d(bufM, &map_mask, efull, col0 + sc, x0, y0, z0, n0);
+            }
+            if (sc == 0) {
+              mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
+              tc_fence_after();
+            }
+            if (has_in) {
+              mbar_wait(efull, eph, abort_flag, p.err_word);
+              eph ^= 1u;
+            }
+            for (int c = 0; c < p.SC; c += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + (uint32_t)(sc + c), v);
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+              const int co = col0 + sc + c;
+              if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+                  f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
+              }
+              if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
+              }
+              const uint32_t o0 = swz_off((uint32_t)row * rb + (uint32_t)c * 2u, smask);
+              const uint32_t o1 = swz_off((uint32_t)row * rb + (uint32_t)c * 2u + 16u, smask);
+              if (p.flags & R2N2_EPI_RESIDUAL) {
+                Row16<__nv_bfloat16> r16;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r16.a.x), "=r"(r16.a.y), "=r"(r16.a.z), "=r"(r16.a.w) : "r"(bufY + o0));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r16.b.x), "=r"(r16.b.y), "=r"(r16.b.z), "=r"(r16.b.w) : "r"(bufY + o1));
+                float r[16];
+                r16.unpack(r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] += r[j];
+              }
+              if (p.flags & R2N2_EPI_MASK) {
+                Row16<__nv_bfloat16> m16;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m16.a.x), "=r"(m16.a.y), "=r"(m16.a.z), "=r"(m16.a.w) : "r"(bufM + o0));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m16.b.x), "=r"(m16.b.y), "=r"(m16.b.z), "=r"(m16.b.w) : "r"(bufM + o1));
+                float m[16];
+                m16.unpack(m);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] *= lrelu_slope(m[j]);
+              }
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1 + team, 128);
+            if (leader) {
+              tma_store_5d(&map_y, bufY, col0 + sc, x0, y0, z0, n0);
+              pending = true;
+            }
+          }
+          // this team has finished reading the accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        }
+        if (leader && pending) tma_store_wait_all();               // smem must outlive the last store
+      }
+    } else {
     int r = row;
     const int xi = r % p.bw; r /= p.bw;
     const int yi = r % p.bh; r /= p.bh;
@@ -262,6 +377,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+    }
     }
   }
   tc_fence_before();
@@ -346,6 +462,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.total_tiles = p.cls_tiles * (mode == 1 ? 8 : 1);
   p.bn_cols = (p.BN + 31) / 32 * 32;
   p.kbox = Cin >= 64 ? 64 : (Cin >= 32 ? 32 : 16);
+  if (Cin > 64 && Cin % 64 == 32 && Cin <= 160) p.kbox = 32;   // 96 = 3 x 32: no zero-filled half K block
   p.kchunks = (Cin + p.kbox - 1) / p.kbox;
   const int row_bytes = p.kbox * 2;
   p.a_bytes = (128 * row_bytes + 1023) / 1024 * 1024;
@@ -360,8 +477,22 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   int ctas = (p.BN <= 64 || (p.BN <= 128 && sub_cycles >= 256)) ? 2 : 1;
   if (const char* e = getenv("R2N2_UMMA_CTAS")) { int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
   if (2 * p.bn_cols * ctas > 512) ctas = 1;
-  const int smem_budget = (ctas == 2 ? 100 : 200) * 1024;
-  const int stage_cap = (ctas == 2 ? 48 : 64) * 1024;
+  // epilogue through shared memory + TMA (bf16 outputs; UP2 writes strided positions and keeps the register path)
+  // Worth its shared memory only where the register epilogue would be the critical path: thread-per-pixel
+  // accesses cost ~66 L1 wavefront cycles per 16-byte instruction (2 stores + 2 loads per input tensor per
+  // 16-column chunk per warp), to be compared with the MMA time of a tile.
+  {
+    const int nin = ((flags & R2N2_EPI_RESIDUAL) ? 1 : 0) + ((flags & R2N2_EPI_MASK) ? 1 : 0);
+    const double epi_cycles = 4.0 * (p.BN / 16) * (2 + 2 * nin) * 66.0;
+    const double mma_cycles = (double)nq * (p.kbox / 16) * (p.BN >= 128 ? p.BN / 2 : 32 + p.BN / 4);
+    p.tma_epi = (out_dtype == R2N2_BF16 && mode != 1 && epi_cycles > 0.5 * mma_cycles) ? 1 : 0;
+    if (const char* e = getenv("R2N2_TMA_EPI")) p.tma_epi = (atoi(e) != 0 && out_dtype == R2N2_BF16 && mode != 1) ? 1 : 0;
+  }
+  p.SC = (p.BN % 64 == 0 && ctas == 1) ? 64 : (p.BN % 32 == 0 ? 32 : 16);
+  p.slab_bytes = 128 * p.SC * 2;
+  const int epi_bytes = p.tma_epi ? ((flags & R2N2_EPI_MASK) ? 4 : 2) * p.slab_bytes : 0;
+  const int smem_budget = (ctas == 2 ? 104 : 208) * 1024 - epi_bytes;
+  const int stage_cap = ctas == 2 ? (smem_budget / 2 < 48 * 1024 ? smem_budget / 2 : 48 * 1024) : 64 * 1024;
   // sub-blocks per stage: aim at >= 512 cycles of MMA per barrier round, stage <= stage_cap
   const int mma_cycles_per_sub = (p.kbox / 16) * (p.BN / 2);
   int nsub = (512 + mma_cycles_per_sub - 1) / mma_cycles_per_sub;
@@ -380,7 +511,9 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   while (p.tmem_cols < 2 * p.bn_cols) p.tmem_cols *= 2;
   p.flags = flags & 15;
   p.err_word = get_err_word();
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+  // [stages][barriers ...][1024-aligned epilogue slabs]
+  p.epi_off = (int)(((size_t)p.stages * p.stage_bytes + (2 * p.stages + 6) * 8 + 16 + 1023) / 1024 * 1024);
+  const size_t smem_bytes = (size_t)p.epi_off + epi_bytes + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma]: pipeline does not fit smem");
 
   CUtensorMap map_a, map_b;
@@ -414,12 +547,31 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
                    "conv_fwd[umma]: cuTensorMapEncodeTiled(B) failed (%d) K %lld Cout %d box %d,%d", (int)r,
                    K, Cout, p.kbox, p.BN);
   }
+  CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
+  if (p.tma_epi) {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2,
+                             (cuuint64_t)D * H * W * Cout * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.SC, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, (cuuint32_t)p.bn};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const void* ptrs[3] = {y, (flags & R2N2_EPI_RESIDUAL) ? res : y, (flags & R2N2_EPI_MASK) ? mask : y};
+    CUtensorMap* maps[3] = {&map_y, &map_res, &map_mask};
+    for (int i = 0; i < 3; ++i) {
+      R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, R2N2_ERR_BAD_ALIGN,
+                     "conv_fwd[umma]: y / residual / mask must be 16-byte aligned");
+      CUresult r = encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptrs[i]), dims, strides, box,
+                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.SC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled(epilogue %d) failed (%d)",
+                     i, (int)r);
+    }
+  }
   int grid = num_sms() * ctas;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (getenv("R2N2_UMMA_DBG"))
-    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d smem %zu\n",
+    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d tma_epi %d SC %d smem %zu\n",
             p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages, ctas,
-            smem_bytes);
+            p.tma_epi, p.SC, smem_bytes);
   cudaError_t e;
   if (out_dtype == R2N2_BF16) {
     static bool attr_set = false;
@@ -430,7 +582,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
       attr_set = true;
     }
     conv_fwd_umma_persistent<__nv_bfloat16><<<grid, kFwdThreads, smem_bytes, st>>>(
-        map_a, map_b, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
+        map_a, map_b, map_y, map_res, map_mask, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
   } else if (out_dtype == R2N2_F32) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -440,7 +592,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
       attr_set = true;
     }
     conv_fwd_umma_persistent<float><<<grid, kFwdThreads, smem_bytes, st>>>(
-        map_a, map_b, bias, (const float*)mask, (const float*)res, (float*)y, p);
+        map_a, map_b, map_y, map_res, map_mask, bias, (const float*)mask, (const float*)res, (float*)y, p);
   } else {
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
   }
