@@ -455,6 +455,10 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
   p.BN = Cout >= 256 ? 256 : Cout;
+  // few M tiles (recurrent unit: 18, FC layers: 2): split N further so that the tiles cover the SMs; the
+  // narrower MMAs are less efficient but the layer is latency-bound by its longest CTA, not throughput-bound
+  while (p.BN >= 64 && p.BN % 32 == 0 && (long long)p.m_tiles * ((Cout + p.BN - 1) / p.BN) * 2 <= num_sms())
+    p.BN /= 2;
   if (const char* e = getenv("R2N2_UMMA_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && v <= Cout) p.BN = v; }
   p.n_tiles = (Cout + p.BN - 1) / p.BN;
   p.mode = mode;
