@@ -133,10 +133,36 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict_
   }
 }
 
+// raw 16-byte vector -> floats (4 x fp32 / 8 x bf16): lets a kernel keep many loads in flight in 4
+// registers each and widen them only when they are consumed
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
-                                   const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
-                                   int W, int C, int Ho, int Wo, int lrelu_mask) {
+__device__ __forceinline__ Pack<T> unpack16(const uint4& raw);
+template <>
+__device__ __forceinline__ Pack<float> unpack16<float>(const uint4& raw) {
+  Pack<float> r;
+  r.v[0] = __uint_as_float(raw.x); r.v[1] = __uint_as_float(raw.y);
+  r.v[2] = __uint_as_float(raw.z); r.v[3] = __uint_as_float(raw.w);
+  return r;
+}
+template <>
+__device__ __forceinline__ Pack<__nv_bfloat16> unpack16<__nv_bfloat16>(const uint4& raw) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  Pack<__nv_bfloat16> r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    r.v[2 * j] = f.x; r.v[2 * j + 1] = f.y;
+  }
+  return r;
+}
+
+template <typename T, bool HAS_B>
+__global__ void __launch_bounds__(256, 3)
+maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ dy,
+                   T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask) {
+  // one thread per (output pixel, 16-byte channel group): the up to 8 input vectors of the window stay
+  // RAW in registers (all loads issued before the first use), the window maximum is formed first, then
+  // each position is re-widened, compared and stored (HBM-bound: registers buy loads in flight)
   constexpr int PN = Pack<T>::N;
   int CG = C / PN;
   long long total = (long long)N * Ho * Wo * CG;
@@ -148,40 +174,55 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict_
     t /= Wo;
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
-    Pack<T> s[4], av[4], m;
+    uint4 ra[4], rb[4];
+    long long off[4];
     bool valid[4];
-#pragma unroll
-    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
       valid[k] = (h >= 0 && h < H && w >= 0 && w < W);
-      if (!valid[k]) continue;
-      long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
-      Pack<T> v = Pack<T>::load(a + off);
-      av[k] = v;
-      if (b) {
-        Pack<T> u = Pack<T>::load(b + off);
-#pragma unroll
-        for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];      // same fp32 sums the forward compared
+      off[k] = (((long long)n * H + h) * W + w) * C + cg * PN;
+      ra[k] = make_uint4(0, 0, 0, 0);
+      rb[k] = make_uint4(0, 0, 0, 0);
+      if (valid[k]) {
+        ra[k] = *reinterpret_cast<const uint4*>(a + off[k]);
+        if (HAS_B) rb[k] = *reinterpret_cast<const uint4*>(b + off[k]);
       }
-      s[k] = v;
-#pragma unroll
-      for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
     }
-    Pack<T> g = Pack<T>::load(dy + i * PN);
+    const uint4 rg = *reinterpret_cast<const uint4*>(dy + i * PN);
+    Pack<T> m;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!valid[k]) continue;
-      int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
-      long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+      Pack<T> s = unpack16<T>(ra[k]);
+      if (HAS_B) {
+        Pack<T> u = unpack16<T>(rb[k]);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) s.v[e] += u.v[e];      // same fp32 sums the forward compared
+      }
+#pragma unroll
+      for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], s.v[e]);
+    }
+    const Pack<T> g = unpack16<T>(rg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      Pack<T> av = unpack16<T>(ra[k]);
+      Pack<T> s = av;
+      if (HAS_B) {
+        Pack<T> u = unpack16<T>(rb[k]);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) s.v[e] += u.v[e];
+      }
       Pack<T> o;
 #pragma unroll
       for (int e = 0; e < PN; ++e) {
-        o.v[e] = (s[k].v[e] == m.v[e]) ? g.v[e] : 0.f;
-        if (lrelu_mask) o.v[e] *= lrelu_slope(av[k].v[e]);
+        o.v[e] = (s.v[e] == m.v[e]) ? g.v[e] : 0.f;
+        if (lrelu_mask) o.v[e] *= lrelu_slope(av.v[e]);
       }
-      o.store(dx + off);
+      o.store(dx + off[k]);
     }
   }
 }
@@ -840,8 +881,13 @@ int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, i
   int Ho = H / 2 + 1, Wo = W / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    if (b) {
+      maxpool_bwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
+    } else {
+      maxpool_bwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
+    }
   })
   R2N2_CHECK_LAUNCH("maxpool2d_bwd");
   return R2N2_OK;
