@@ -479,6 +479,8 @@ struct UmmaWgradParams {
   int stages, tmem_cols;
   int up2;                                 // x is the small tensor of an UP2 conv: dy is read with stride 2,
   int a_tap_bytes, b_off;                  //   one dy tile PER TAP (A side), one shared x tile (B side)
+  int dxh;                                 // dx-halo mode: the CTA owns the kw=3 taps of ONE (dz,dy) filter row and loads
+  int P, segs, chunk_bx;                   //   ONE x box that is 2 pixels wider (pitch P = bw+2); tap dx = view shifted by dx rows
   int* err_word;
 };
 
@@ -553,8 +555,9 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (warp == 0) {
     if (nkb > 0) {
       // warp-uniform loop: incremental box coordinates, tap offsets precomputed in smem
-      const uint32_t tx_bytes = p.up2 ? (uint32_t)(ntap * na * chunk_a + nb * chunk_b)
-                                      : (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
+      const uint32_t tx_bytes = p.dxh ? (uint32_t)(na * chunk_a + nb * p.chunk_bx)
+                                : p.up2 ? (uint32_t)(ntap * na * chunk_a + nb * chunk_b)
+                                        : (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       long long b = box_begin;
@@ -571,7 +574,15 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const uint32_t bar = full0 + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(bar, tx_bytes);
-          if (!p.up2) {
+          if (p.dxh) {
+            for (int c = 0; c < na; ++c)
+              tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+            const int o = tap_off[0];
+            const int oy = ((o >> 8) & 0xff) - 8, oz = ((o >> 16) & 0xff) - 8;
+            const uint32_t bdst = stage + p.b_off;
+            for (int c = 0; c < nb; ++c)
+              tma_load_5d(bdst + c * p.chunk_bx, &map_x, bar, ci0 + c * p.cw_b, x0 - 1, y0 + oy, z0 + oz, n0);
+          } else if (!p.up2) {
             for (int c = 0; c < na; ++c)
               tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
             uint32_t bdst = stage + p.b_off;
@@ -619,13 +630,13 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       const uint32_t lt_a = (rb_a == 128) ? 2u : (rb_a == 64 ? 4u : 6u);
       const uint32_t lt_b = (rb_b == 128) ? 2u : (rb_b == 64 ? 4u : 6u);
       const uint64_t da_hi = make_mnmajor_desc(0, chunk_a, 8 * rb_a, lt_a);
-      const uint64_t db_hi = make_mnmajor_desc(0, chunk_b, 8 * rb_b, lt_b);
+      const uint64_t db_hi = make_mnmajor_desc(0, p.dxh ? p.chunk_bx : chunk_b, 8 * rb_b, lt_b);
       const uint32_t ka = (uint32_t)(16 * rb_a) >> 4, kbs = (uint32_t)(16 * rb_b) >> 4;  // desc step / K16
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       const int nk = p.rows >> 4;
       const uint32_t a_step = p.up2 ? (uint32_t)p.a_tap_bytes : 0u;       // the operand that changes per tap
-      const uint32_t b_step = p.up2 ? 0u : (uint32_t)p.b_tap_bytes;
+      const uint32_t b_step = (p.up2 || p.dxh) ? 0u : (uint32_t)p.b_tap_bytes;
       int s = 0;
       uint32_t ph = 0;
       uint32_t acc = 0;
@@ -640,9 +651,23 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
             const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
             const uint64_t db0 = db_hi | (uint64_t)((b_addr & 0x3FFFF) >> 4);
             uint32_t a2 = acc;
-            for (int k = 0; k < nk; ++k) {
-              umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
-              a2 = 1;
+            if (p.dxh) {
+              // K16 step = 16 consecutive pixels of ONE image row (bw % 16 == 0): in the wider x tile the same
+              // pixels start 2 rows further per image row, and tap g looks g pixels to the right
+              uint32_t koff = 0;
+              int seg = 0;
+              for (int k = 0; k < nk; ++k) {
+                umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)koff, idesc, a2);
+                a2 = 1;
+                koff += kbs;
+                if (++seg == p.segs) { seg = 0; koff += (uint32_t)(2 * rb_b) >> 4; }
+              }
+              b_addr += (uint32_t)rb_b;                      // next dx tap: one pixel to the right
+            } else {
+              for (int k = 0; k < nk; ++k) {
+                umma_bf16(d_tmem, da0 + (uint64_t)(ka * k), db0 + (uint64_t)(kbs * k), idesc, a2);
+                a2 = 1;
+              }
             }
             a_addr += a_step;
             b_addr += b_step;
@@ -716,6 +741,28 @@ static void choose_kbox(int N, int D, int H, int W, int max_rows, int& bw, int& 
         }
 }
 
+// dx-halo variant: box width a multiple of 16 (may overhang the image: TMA zero-fills), so that every K16
+// step lies inside one image row
+static void choose_kbox_dx(int N, int D, int H, int W, int max_rows, int& bw, int& bh, int& bd, int& bn) {
+  double best_eff = -1.0;
+  int best_rows = 0;
+  bw = 0;
+  for (int w = 16; w <= 240 && w <= (W + 15) / 16 * 16 && w <= max_rows; w += 16)
+    for (int h = 1; h <= H && w * h <= max_rows; ++h)
+      for (int d = 1; d <= D && w * h * d <= max_rows; ++d)
+        for (int n = 1; n <= N && w * h * d * n <= max_rows; ++n) {
+          int rows = w * h * d * n;
+          double cover = (double)((W + w - 1) / w * w) * ((H + h - 1) / h * h) * ((D + d - 1) / d * d) *
+                         ((N + n - 1) / n * n);
+          double eff = ((double)W * H * D * N) / cover;
+          const bool better = eff > best_eff + 1e-9 ||
+                              (eff > best_eff - 1e-9 &&
+                               (rows > best_rows || (rows == best_rows && (w > bw || (w == bw && h > bh)))));
+          if (better) { best_eff = eff; best_rows = rows; bw = w; bh = h; bd = d; bn = n; }
+        }
+  if (best_eff < 0.8) bw = 0;                // too much overhang (e.g. W = 33): keep the per-tap loads
+}
+
 static int pow2_chunk(int c) { return c >= 64 ? 64 : (c >= 32 ? 32 : 16); }
 
 int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
@@ -757,21 +804,36 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   p.G = 512 / p.ci_cols;
   if (p.G > p.taps) p.G = p.taps;
   const int co_tiles = (Cout + 127) / 128;
-  const int tap_groups = (p.taps + p.G - 1) / p.G;
   // bytes per K row (pixel) in one stage
   const int a_row = ((Cout < 128 ? Cout : 128) + p.cw_a - 1) / p.cw_a * p.cw_a * 2;
   const int b_row = (p.ci_tile + p.cw_b - 1) / p.cw_b * p.cw_b * 2;
   p.up2 = up2;
-  const int per_row = up2 ? p.G * a_row + (b_row > 256 - a_row ? b_row : 256 - a_row) : a_row + p.G * b_row;
+  // dx-halo mode: 3x3(x3) filters whose rows can be cut into 16-pixel segments; the CTA takes the 3 dx taps
+  // of one filter row from ONE x box (3x less L2 -> SM traffic for x, the operand that bounded these layers)
+  p.dxh = 0;
   p.stages = 3;
-  int max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
-  if (max_rows > 128) max_rows = 128;
-  if (max_rows < 16) {
-    p.stages = 2;
-    max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
+  int max_rows = 0;
+  if (!up2 && kw == 3 && p.ci_tile <= 160 && !getenv("R2N2_WGRAD_NO_DXH")) {
+    const int per_row_dx = a_row + b_row * 5 / 4;
+    int mr = (180 * 1024 / p.stages) / per_row_dx / 16 * 16;
+    if (mr > 256) mr = 256;
+    if (mr >= 64) {
+      choose_kbox_dx(N, D, H, W, mr, p.bw, p.bh, p.bd, p.bn);
+      if (p.bw > 0 && p.bw * p.bh * p.bd * p.bn >= 64) { p.dxh = 1; p.G = 3; max_rows = mr; }
+    }
   }
-  R2N2_CHECK_ARG(max_rows >= 16, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: tile does not fit shared memory");
-  choose_kbox(N, D, H, W, max_rows, p.bw, p.bh, p.bd, p.bn);
+  if (!p.dxh) {
+    const int per_row = up2 ? p.G * a_row + (b_row > 256 - a_row ? b_row : 256 - a_row) : a_row + p.G * b_row;
+    max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
+    if (max_rows > 128) max_rows = 128;
+    if (max_rows < 16) {
+      p.stages = 2;
+      max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
+    }
+    R2N2_CHECK_ARG(max_rows >= 16, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: tile does not fit shared memory");
+    choose_kbox(N, D, H, W, max_rows, p.bw, p.bh, p.bd, p.bn);
+  }
+  const int tap_groups = (p.taps + p.G - 1) / p.G;
   p.rows = p.bw * p.bh * p.bd * p.bn;
   p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
   p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
@@ -787,6 +849,13 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     const int span = p.rows * 256 - p.a_tap_bytes;
     const int xb = p.rows * b_row > span ? p.rows * b_row : span;
     p.stage_bytes = (p.b_off + xb + 1023) / 1024 * 1024;
+  } else if (p.dxh) {
+    p.P = p.bw + 2;
+    p.segs = p.bw / 16;
+    p.chunk_bx = p.P * p.bh * p.bd * p.bn * p.cw_b * 2;                 // one channel chunk of the wider x tile
+    p.b_off = p.a_bytes;
+    // (+2 rows: the dx = 2 view of the last K16 step runs two pixels past the tile)
+    p.stage_bytes = (p.a_bytes + ((p.ci_tile + p.cw_b - 1) / p.cw_b) * p.chunk_bx + 2 * p.cw_b * 2 + 1023) / 1024 * 1024;
   } else {
     p.b_off = p.a_bytes;
     p.stage_bytes = (p.a_bytes + p.G * p.b_tap_bytes + 1023) / 1024 * 1024;
@@ -823,7 +892,7 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
                              (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.cw_b, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd,
+    cuuint32_t box[5] = {(cuuint32_t)p.cw_b, (cuuint32_t)(p.dxh ? p.bw + 2 : p.bw), (cuuint32_t)p.bh, (cuuint32_t)p.bd,
                          (cuuint32_t)p.bn};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,

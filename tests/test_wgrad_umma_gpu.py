@@ -42,6 +42,12 @@ CASES = [
     (1, 5, 9, 33, 64, 16, (3, 3, 3)),        # ragged, dy stacked (8 shifts of 16 channels)
     (3, 4, 4, 4, 16, 16, (3, 3, 3)),
     (1, 3, 70, 11, 32, 64, (3, 3, 3)),       # many bands, last band partial
+    # dx-halo mode of the per-tap kernel (box width multiple of 16, one 2-pixel-wider x box per filter row)
+    (2, 1, 64, 64, 96, 128, (1, 3, 3)),      # conv2a
+    (1, 1, 127, 127, 96, 96, (1, 3, 3)),     # conv1b: box overhangs the image by one column
+    (1, 16, 16, 16, 128, 128, (3, 3, 3)),    # conv8b: 9 filter rows
+    (2, 1, 30, 40, 128, 128, (1, 3, 3)),     # W = 40 -> 48-wide boxes (17 % overhang)
+    (3, 1, 16, 32, 160, 256, (1, 3, 3)),     # two co tiles, ci tile 160
 ]
 
 
