@@ -481,6 +481,8 @@ struct UmmaWgradParams {
   int a_tap_bytes, b_off;                  //   one dy tile PER TAP (A side), one shared x tile (B side)
   int dxh;                                 // dx-halo mode: the CTA owns the kw=3 taps of ONE (dz,dy) filter row and loads
   int P, segs, chunk_bx;                   //   ONE x box that is 2 pixels wider (pitch P = bw+2); tap dx = view shifted by dx rows
+  int ystack;                              // kh x 1 filter over one channel chunk (row-packed conv1a): ONE x box with kh-1 halo
+                                           //   rows; the kh taps are stacked along N (B chunk stride = one image row): 1 MMA per K16
   int* err_word;
 };
 
@@ -509,6 +511,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (ntap > p.G) ntap = p.G;
   int nci = p.Cin - ci0;                       // valid ci in this tile (multiple of 16)
   if (nci > p.ci_tile) nci = p.ci_tile;
+  if (p.ystack) { ntap = 1; nci = p.taps * p.Cin; }   // all taps live in ONE accumulator of taps*Cin columns
   int nco = p.Cout - co0;
   if (nco > 128) nco = 128;
   const int na = (nco + p.cw_a - 1) / p.cw_a;  // dy chunks to load
@@ -555,7 +558,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (warp == 0) {
     if (nkb > 0) {
       // warp-uniform loop: incremental box coordinates, tap offsets precomputed in smem
-      const uint32_t tx_bytes = p.dxh ? (uint32_t)(na * chunk_a + nb * p.chunk_bx)
+      const uint32_t tx_bytes = p.ystack ? (uint32_t)(na * chunk_a + p.chunk_bx)
+                                : p.dxh ? (uint32_t)(na * chunk_a + nb * p.chunk_bx)
                                 : p.up2 ? (uint32_t)(ntap * na * chunk_a + nb * chunk_b)
                                         : (uint32_t)(na * chunk_a + ntap * nb * chunk_b);
       const uint32_t smem_base = smem_u32(smem);
@@ -574,7 +578,11 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         const uint32_t bar = full0 + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(bar, tx_bytes);
-          if (p.dxh) {
+          if (p.ystack) {
+            for (int c = 0; c < na; ++c)
+              tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
+            tma_load_5d(stage + p.b_off, &map_x, bar, 0, x0, y0 - (p.kh - 1) / 2, z0, n0);
+          } else if (p.dxh) {
             for (int c = 0; c < na; ++c)
               tma_load_5d(stage + c * chunk_a, &map_dy, bar, co0 + c * p.cw_a, x0, y0, z0, n0);
             const int o = tap_off[0];
@@ -630,7 +638,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       const uint32_t lt_a = (rb_a == 128) ? 2u : (rb_a == 64 ? 4u : 6u);
       const uint32_t lt_b = (rb_b == 128) ? 2u : (rb_b == 64 ? 4u : 6u);
       const uint64_t da_hi = make_mnmajor_desc(0, chunk_a, 8 * rb_a, lt_a);
-      const uint64_t db_hi = make_mnmajor_desc(0, p.dxh ? p.chunk_bx : chunk_b, 8 * rb_b, lt_b);
+      // ystack: chunk j of the N side = the x tile shifted by j image rows (bw pixels) = filter tap j
+      const uint64_t db_hi = make_mnmajor_desc(0, p.ystack ? p.bw * rb_b : (p.dxh ? p.chunk_bx : chunk_b), 8 * rb_b, lt_b);
       const uint32_t ka = (uint32_t)(16 * rb_a) >> 4, kbs = (uint32_t)(16 * rb_b) >> 4;  // desc step / K16
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
@@ -822,7 +831,28 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
       if (p.bw > 0 && p.bw * p.bh * p.bd * p.bn >= 64) { p.dxh = 1; p.G = 3; max_rows = mr; }
     }
   }
-  if (!p.dxh) {
+  p.ystack = 0;
+  if (!up2 && !p.dxh && kd == 1 && kw == 1 && kh > 1 && Cin == p.cw_b && kh * Cin <= 256 && Cout <= 128 &&
+      !getenv("R2N2_WGRAD_NO_YSTACK")) {
+    // box (bw multiple of 16) x bh image rows of one sample; the x tile carries kh-1 halo rows: pick the box
+    // with the least overhang, then the least halo traffic per pixel, within a 60 KB stage
+    double best = -1.0;
+    int bw_ = 0, bh_ = 0;
+    for (int w = 16; w <= 240 && w <= (W + 15) / 16 * 16; w += 16)
+      for (int h = 1; h <= H && w * h <= 256; ++h) {
+        const int stage = w * h * a_row + w * (h + kh - 1) * b_row;
+        if (stage > 60 * 1024 || w * h < 64) continue;
+        const double cover = (double)((W + w - 1) / w * w) * ((H + h - 1) / h * h);
+        const double score = ((double)W * H / cover) * ((double)h / (h + kh - 1) * 0.5 + 0.5);
+        if (score > best + 1e-9) { best = score; bw_ = w; bh_ = h; }
+      }
+    if (bw_ > 0 && (double)W / ((W + bw_ - 1) / bw_ * bw_) >= 0.8) {
+      p.ystack = 1; p.G = 1; max_rows = 256;
+      p.bw = bw_; p.bh = bh_; p.bd = 1; p.bn = 1;
+      p.ci_cols = (kh * Cin + 31) / 32 * 32;
+    }
+  }
+  if (!p.dxh && !p.ystack) {
     const int per_row = up2 ? p.G * a_row + (b_row > 256 - a_row ? b_row : 256 - a_row) : a_row + p.G * b_row;
     max_rows = (180 * 1024 / p.stages) / per_row / 16 * 16;
     if (max_rows > 128) max_rows = 128;
@@ -833,7 +863,7 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     R2N2_CHECK_ARG(max_rows >= 16, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: tile does not fit shared memory");
     choose_kbox(N, D, H, W, max_rows, p.bw, p.bh, p.bd, p.bn);
   }
-  const int tap_groups = (p.taps + p.G - 1) / p.G;
+  const int tap_groups = p.ystack ? 1 : (p.taps + p.G - 1) / p.G;
   p.rows = p.bw * p.bh * p.bd * p.bn;
   p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh;
   p.tiles_d = (D + p.bd - 1) / p.bd; p.tiles_n = (N + p.bn - 1) / p.bn;
@@ -849,6 +879,10 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     const int span = p.rows * 256 - p.a_tap_bytes;
     const int xb = p.rows * b_row > span ? p.rows * b_row : span;
     p.stage_bytes = (p.b_off + xb + 1023) / 1024 * 1024;
+  } else if (p.ystack) {
+    p.chunk_bx = p.bw * (p.bh + kh - 1) * p.cw_b * 2;
+    p.b_off = p.a_bytes;
+    p.stage_bytes = (p.a_bytes + p.chunk_bx + 1023) / 1024 * 1024;
   } else if (p.dxh) {
     p.P = p.bw + 2;
     p.segs = p.bw / 16;
@@ -892,8 +926,8 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
                              (cuuint64_t)D * H * W * Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.cw_b, (cuuint32_t)(p.dxh ? p.bw + 2 : p.bw), (cuuint32_t)p.bh, (cuuint32_t)p.bd,
-                         (cuuint32_t)p.bn};
+    cuuint32_t box[5] = {(cuuint32_t)p.cw_b, (cuuint32_t)(p.dxh ? p.bw + 2 : p.bw),
+                         (cuuint32_t)(p.ystack ? p.bh + kh - 1 : p.bh), (cuuint32_t)p.bd, (cuuint32_t)p.bn};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.cw_b * 2),
@@ -915,6 +949,11 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   const int a_span_slack = p.rows * 256 > p.stage_bytes ? p.rows * 256 - p.stage_bytes : 0;
   const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 256 + 1024 + a_span_slack;
   dim3 grid((unsigned)splits, (unsigned)(co_tiles * p.ci_tiles), (unsigned)tap_groups);
+  if (getenv("R2N2_UMMA_DBG"))
+    fprintf(stderr, "[umma wgrad] Cin %d Cout %d taps %d G %d box %dx%dx%dx%d rows %d dxh %d ystack %d up2 %d stage %d x %d "
+            "smem %zu grid %ux%ux%u tmem %d ci_cols %d\n", Cin, Cout, p.taps, p.G, p.bw, p.bh, p.bd, p.bn, p.rows, p.dxh,
+            p.ystack, p.up2, p.stage_bytes, p.stages, smem_bytes, grid.x, grid.y, grid.z, p.tmem_cols, p.ci_cols);
+  R2N2_CHECK_ARG(smem_bytes <= 200 * 1024, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: smem %zu too large", smem_bytes);
   conv_wgrad_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma]");
   return R2N2_OK;

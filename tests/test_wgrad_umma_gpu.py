@@ -48,6 +48,10 @@ CASES = [
     (1, 16, 16, 16, 128, 128, (3, 3, 3)),    # conv8b: 9 filter rows
     (2, 1, 30, 40, 128, 128, (1, 3, 3)),     # W = 40 -> 48-wide boxes (17 % overhang)
     (3, 1, 16, 32, 160, 256, (1, 3, 3)),     # two co tiles, ci tile 160
+    # kh x 1 filter over one channel chunk (row-packed conv1a): taps stacked along N, one MMA per K16
+    (2, 1, 40, 64, 32, 96, (1, 7, 1)),
+    (1, 1, 127, 127, 32, 96, (1, 7, 1)),
+    (2, 1, 33, 50, 16, 64, (1, 5, 1)),
 ]
 
 
