@@ -20,6 +20,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argtypes (must mirror include/r2n2_b200.h exactly; tests/test_abi.py checks the list)
 PROTOTYPES = {
     'r2n2_conv_fwd': [_p, _p, _p, _p, _p, _p] + [_i] * 9 + [_i, _i, _i, _i, _p],
+    'r2n2_conv_fwd_colsum': [_p, _p, _p, _p, _p, _p] + [_i] * 9 + [_i, _i, _i, _i, _p, _p],
     'r2n2_conv_wgrad': [_p, _p, _p] + [_i] * 9 + [_i, _i, _i, _p],
     'r2n2_bias_grad': [_p, _p, _ll, _i, _i, _i, _p],
     'r2n2_weight_transpose': [_p, _p, _i, _i, _i, _i, _p],

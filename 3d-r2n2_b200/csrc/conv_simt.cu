@@ -397,7 +397,7 @@ int conv_wgrad_simt(const void* x, const void* dy, float* dw, int N, int D, int 
 // implemented in conv_umma.cu
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
-                  int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st);
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st);
 int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                     int Cout, int kd, int kh, int kw, int dtype, int accumulate, cudaStream_t st);
 
@@ -405,10 +405,10 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
 
 extern "C" {
 
-int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* mask_src,
-                  const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
-                  int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
-                  void* stream) {
+static int conv_fwd_dispatch(const void* x, const void* w, const float* bias, const void* mask_src,
+                             const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                             int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
+                             float* colsum, void* stream) {
   using namespace r2n2;
   R2N2_CHECK_ARG(x && w && y, R2N2_ERR_BAD_SHAPE, "conv_fwd: null pointer");
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_BIAS) || bias, R2N2_ERR_BAD_SHAPE, "conv_fwd: BIAS flag without bias");
@@ -416,13 +416,34 @@ int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* m
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_MASK) || mask_src, R2N2_ERR_BAD_SHAPE, "conv_fwd: MASK flag without mask_src");
   R2N2_CHECK_ARG(algo == R2N2_ALGO_UMMA || !(flags & (R2N2_CONV_UP2 | R2N2_CONV_DOWN2)), R2N2_ERR_UNSUPPORTED,
                  "conv_fwd: UP2 / DOWN2 need R2N2_ALGO_UMMA (materialise the unpooled tensor for ALGO_SIMT)");
-  if (algo == R2N2_ALGO_SIMT)
-    return conv_fwd_simt(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags,
-                         in_dtype, out_dtype, (cudaStream_t)stream);
+  if (algo == R2N2_ALGO_SIMT) {
+    int rc = conv_fwd_simt(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags,
+                           in_dtype, out_dtype, (cudaStream_t)stream);
+    if (rc == R2N2_OK && colsum)
+      rc = r2n2_bias_grad(y, colsum, (long long)N * D * H * W, Cout, out_dtype, 1, stream);
+    return rc;
+  }
   if (algo == R2N2_ALGO_UMMA)
     return conv_fwd_umma(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags,
-                         in_dtype, out_dtype, (cudaStream_t)stream);
+                         in_dtype, out_dtype, colsum, (cudaStream_t)stream);
   R2N2_CHECK_ARG(false, R2N2_ERR_UNSUPPORTED, "conv_fwd: unknown algo %d", algo);
+}
+
+int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* mask_src,
+                  const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                  int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
+                  void* stream) {
+  return conv_fwd_dispatch(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
+                           out_dtype, algo, nullptr, stream);
+}
+
+int r2n2_conv_fwd_colsum(const void* x, const void* w, const float* bias, const void* mask_src,
+                         const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                         int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
+                         float* colsum, void* stream) {
+  R2N2_CHECK_ARG(colsum != nullptr, R2N2_ERR_BAD_SHAPE, "conv_fwd_colsum: null colsum");
+  return conv_fwd_dispatch(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
+                           out_dtype, algo, colsum, stream);
 }
 
 int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,

@@ -33,6 +33,8 @@ struct FwdParams {
   int flags;
   int tma_epi;                             // epilogue through shared memory + TMA loads/stores (bf16 out, mode != UP2)
   int SC, slab_bytes, epi_off;             // slab = 128 rows x SC output channels; smem offset of the staging buffers
+  float* colsum;                           // TMA epilogue, one N tile: colsum[c] += sum over pixels of y[p, c] (fp32), or NULL
+  int csum_off;                            //   smem offset of the per-team partial sums (2 x BN floats)
   int mode;                                // 0 plain, 1 UP2 (zero-stuffed x2 input, 8 parity classes), 2 DOWN2
   int cls_tiles;                           // tiles per parity class (= m_tiles * n_tiles)
   int* err_word;
@@ -106,6 +108,10 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (p.colsum) {
+    float* cs = reinterpret_cast<float*>(smem + p.csum_off);
+    for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) cs[i] = 0.f;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -251,12 +257,23 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         uint32_t eph = 0;
         bool pending = false;
         int it = 0;
+        // this thread's pixel inside the box (for the column sums: out-of-bounds rows must hold zeros)
+        int rr = row;
+        const int xi = rr % p.bw; rr /= p.bw;
+        const int yi = rr % p.bh; rr /= p.bh;
+        const int zi = rr % p.bd; rr /= p.bd;
+        const int ni = rr;
+        float* csum = reinterpret_cast<float*>(smem + p.csum_off) + team * p.BN;
+        const int tt = ((warp - 2) & 3) * 32 + lane;          // thread index inside the team
+        const int ncp = p.SC >> 1;                            // column pairs of a slab
+        const int cp = tt % ncp, rg = tt / ncp, rows_per_rg = 128 / (128 / ncp);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
           if ((it & 1) != team) continue;
           const int buf = team;
           const uint32_t use = (uint32_t)(it >> 1);
           const TileCoord tc = decode_tile(p, tile);
           const int x0 = tc.tw * p.bw, y0 = tc.th * p.bh, z0 = tc.td * p.bd, n0 = tc.tn * p.bn;
+          const bool inb = (row < rows) && x0 + xi < p.W && y0 + yi < p.H && z0 + zi < p.D && n0 + ni < p.N;
           const int col0 = tc.nt * p.BN;
           int ncol = p.Cout - col0;
           if (ncol > p.BN) ncol = p.BN;
@@ -319,7 +336,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&h);
+                w[j] = (p.colsum && !inb) ? 0u : *reinterpret_cast<uint32_t*>(&h);
               }
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
@@ -330,6 +347,21 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
               tma_store_5d(&map_y, bufY, col0 + sc, x0, y0, z0, n0);
               pending = true;
             }
+            if (p.colsum) {
+              // column sums of the finished slab (the bf16 values that were stored): thread (rg, cp) adds the
+              // rows of its group for one column pair; per-CTA partial sums live in shared memory
+              float s0 = 0.f, s1 = 0.f;
+              const int r0 = rg * rows_per_rg;
+              for (int r = r0; r < r0 + rows_per_rg; ++r) {
+                const uint32_t o = swz_off((uint32_t)r * rb + ((uint32_t)(cp * 4) & ~15u), smask) + ((uint32_t)(cp * 4) & 15u);
+                uint32_t wv;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(bufY + o));
+                float2 fv = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wv));
+                s0 += fv.x; s1 += fv.y;
+              }
+              atomicAdd(csum + sc + 2 * cp, s0);
+              atomicAdd(csum + sc + 2 * cp + 1, s1);
+            }
           }
           // this team has finished reading the accumulator: hand it back to the MMA warp
           tc_fence_before();
@@ -337,6 +369,10 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
         }
         if (leader && pending) tma_store_wait_all();               // smem must outlive the last store
+        if (p.colsum) {
+          named_bar_sync(1 + team, 128);
+          for (int c = tt; c < p.Cout; c += 128) atomicAdd(p.colsum + c, csum[c]);
+        }
       }
     } else {
     int r = row;
@@ -423,13 +459,16 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
                    int N, int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int flags, int out_dtype,
                    cudaStream_t st);
 
+// colsum (may be NULL): colsum[c] += sum over output pixels of y[p, c] -- the bias gradient of the layer
+// whose output gradient this call produces; fused into the TMA epilogue where possible, else a second pass
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
-                  int kh, int kw, int flags, int in_dtype, int out_dtype, cudaStream_t st) {
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st) {
   const int mode = (flags & R2N2_CONV_UP2) ? 1 : ((flags & R2N2_CONV_DOWN2) ? 2 : 0);
   R2N2_CHECK_ARG(!((flags & R2N2_CONV_UP2) && (flags & R2N2_CONV_DOWN2)), R2N2_ERR_BAD_SHAPE,
                  "conv_fwd[umma]: UP2 and DOWN2 are exclusive");
-  if (getenv("R2N2_UMMA_V1") && mode == 0)          // A/B comparison with the one-tile-per-CTA kernel
+  const long long out_rows = (long long)N * D * H * W * (mode == 1 ? 8 : 1);
+  if (getenv("R2N2_UMMA_V1") && mode == 0 && !colsum)   // A/B comparison with the one-tile-per-CTA kernel
     return conv_fwd_umma_v1(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
                             out_dtype, st);
   R2N2_CHECK_ARG(in_dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: operands must be bf16");
@@ -442,8 +481,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
   // 3x3 / 3x3x3 layers with <= 128 output channels: input loaded once, taps as descriptor views
-  if (mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw))
-    return conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, out_dtype, st);
+  if (mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw)) {
+    int rc = conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, out_dtype, st);
+    if (rc == R2N2_OK && colsum) rc = r2n2_bias_grad(y, colsum, out_rows, Cout, out_dtype, 1, (void*)st);
+    return rc;
+  }
   EncodeTiledFn encode = get_encode();
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled unavailable");
 
@@ -491,10 +533,17 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     const double mma_cycles = (double)nq * (p.kbox / 16) * (p.BN >= 128 ? p.BN / 2 : 32 + p.BN / 4);
     p.tma_epi = (out_dtype == R2N2_BF16 && mode != 1 && epi_cycles > 0.5 * mma_cycles) ? 1 : 0;
     if (const char* e = getenv("R2N2_TMA_EPI")) p.tma_epi = (atoi(e) != 0 && out_dtype == R2N2_BF16 && mode != 1) ? 1 : 0;
+    // (measured: forcing the TMA epilogue just to fuse a column sum costs more than the separate bias-gradient
+    // pass it saves -- conv1b dgrad 0.68 + 0.20 -> 0.97 ms, conv3b dgrad 0.19 + 0.03 -> 0.26 ms -- so the sum
+    // is fused only where the TMA epilogue is chosen anyway)
+    if (getenv("R2N2_FORCE_COLSUM_FUSE") && colsum && out_dtype == R2N2_BF16 && mode != 1 && Cout <= p.BN) p.tma_epi = 1;
   }
+  const bool fuse_colsum = colsum && p.tma_epi && Cout <= p.BN && !getenv("R2N2_NO_COLSUM_FUSE");
   p.SC = (p.BN % 64 == 0 && ctas == 1) ? 64 : (p.BN % 32 == 0 ? 32 : 16);
   p.slab_bytes = 128 * p.SC * 2;
-  const int epi_bytes = p.tma_epi ? ((flags & R2N2_EPI_MASK) ? 4 : 2) * p.slab_bytes : 0;
+  const int slab_region = p.tma_epi ? ((flags & R2N2_EPI_MASK) ? 4 : 2) * p.slab_bytes : 0;
+  const int epi_bytes = slab_region + (fuse_colsum ? 2 * p.BN * 4 : 0);
+  p.colsum = fuse_colsum ? colsum : nullptr;
   const int smem_budget = (ctas == 2 ? 104 : 208) * 1024 - epi_bytes;
   const int stage_cap = ctas == 2 ? (smem_budget / 2 < 48 * 1024 ? smem_budget / 2 : 48 * 1024) : 64 * 1024;
   // sub-blocks per stage: aim at >= 512 cycles of MMA per barrier round, stage <= stage_cap
@@ -517,6 +566,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.err_word = get_err_word();
   // [stages][barriers ...][1024-aligned epilogue slabs]
   p.epi_off = (int)(((size_t)p.stages * p.stage_bytes + (2 * p.stages + 6) * 8 + 16 + 1023) / 1024 * 1024);
+  p.csum_off = p.epi_off + slab_region;
   const size_t smem_bytes = (size_t)p.epi_off + epi_bytes + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma]: pipeline does not fit smem");
 
@@ -601,6 +651,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
   }
   R2N2_CHECK_LAUNCH("conv_fwd[umma]");
+  if (colsum && !fuse_colsum) return r2n2_bias_grad(y, colsum, out_rows, Cout, out_dtype, 1, (void*)st);
   return R2N2_OK;
 }
 

@@ -496,6 +496,14 @@ class Engine:
         if training:
             for p in self.P.values():
                 p.grad_written = False
+            # bias gradients accumulate (several of them are formed inside data-gradient epilogues):
+            # the biases sit together at the end of the flat store, one memset clears them all
+            st = self.store
+            if st.n > st.n_decay:
+                ops.fill_zero(st.g[st.n_decay:])
+                for n, p in self.P.items():
+                    if n.endswith('.b') or '.b_' in n:
+                        p.grad_written = True
         P = self.P
         x = x.contiguous()
         if self.rowpack:

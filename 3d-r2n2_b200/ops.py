@@ -76,6 +76,7 @@ def _work(flops=0.0, tensors=()):
 
 
 WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
+FUSE_BIAS_GRAD = True     # bias gradients as column sums of the data-gradient epilogue that produces dy
 ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
@@ -103,10 +104,11 @@ def umma_error_flag():
 
 
 # ======================================================================= raw op wrappers
-def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
+def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo, colsum=None):
     """geom = (N,D,H,W,Cin) of x; k=(kd,kh,kw); y preallocated [N,D,H,W,cout].
     With L.CONV_UP2 / L.CONV_DOWN2 in flags (N,D,H,W) is the SMALL grid: UP2 writes y (and reads
-    mask/residual) at [N,2D,2H,2W,cout]; DOWN2 reads x at [N,2D,2H,2W,Cin]."""
+    mask/residual) at [N,2D,2H,2W,cout]; DOWN2 reads x at [N,2D,2H,2W,Cin].
+    colsum (fp32 [cout]): additionally colsum[c] += sum_p y[p,c] (bias gradient of the producing layer)."""
     N, D, H, W, Cin = geom
     if algo == L.ALGO_UMMA and not (umma_ok(Cin, cout) and x.dtype == torch.bfloat16):
         algo = L.ALGO_SIMT
@@ -122,6 +124,13 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
     _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2] * useful_frac,
           (x, w, bias, mask_src, residual, y))
     _next_tag = 'M%dxN%dxK%d' % (N * D * H * W, cout, k[0] * k[1] * k[2] * Cin)
+    if colsum is not None:
+        _check(colsum, torch.float32)
+        assert colsum.numel() == cout
+        _call('r2n2_conv_fwd_colsum', _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(residual), _ptr(y),
+              N, D, H, W, Cin, cout, k[0], k[1], k[2], flags, _DT[x.dtype], _DT[y.dtype], algo,
+              _ptr(colsum), _stream())
+        return y
     _call('r2n2_conv_fwd', _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(residual), _ptr(y),
           N, D, H, W, Cin, cout, k[0], k[1], k[2], flags, _DT[x.dtype], _DT[y.dtype], algo,
           _stream())
@@ -187,6 +196,11 @@ class TransposeBatch:
             _call('r2n2_weight_transpose_batch', _ptr(self.store.p), _ptr(self.wt_all), _ptr(self.table),
                   len(self.params), self.total_tiles, _DT[self.wt_all.dtype], _stream())
             self.version = self.store.version
+
+
+def fill_zero(t):
+    _check(t)
+    _call('r2n2_fill_zero', _ptr(t), t.numel() * t.element_size(), _stream())
 
 
 def cast(src, dst):
@@ -339,7 +353,7 @@ def voxel_eval(pred, gt, thresh):
 class Act:
     """An activation on the tape: channels-last data + gradient bookkeeping."""
     __slots__ = ('data', 'geom', 'grad', 'n_cons', 'n_recv', 'lrelu_out', 'grad_preact',
-                 'grad_shared', 'requires_grad', 'useful')
+                 'grad_shared', 'requires_grad', 'useful', 'bias', 'bias_done')
 
     def __init__(self, data, geom, requires_grad=False, lrelu_out=False):
         self.data = data
@@ -352,6 +366,8 @@ class Act:
         self.grad_shared = False        # grad buffer aliased by another Act: no in-place edits
         self.requires_grad = requires_grad
         self.useful = 1.0               # non-structural-zero fraction (1/8 after Unpool3D)
+        self.bias = None                # bias Param of the conv that produced this activation
+        self.bias_done = False          # its gradient was already formed by the epilogue that wrote .grad
 
 
 class Param:
@@ -454,8 +470,14 @@ class Ctx:
             flags |= L.EPI_MASK
             mask = x.data
             x.grad_preact = True
+        # last contribution: out_buf is the final gradient of x's pre-activation, so its column sums are the
+        # bias gradient of the convolution that produced x (fused into the epilogue: no second pass)
+        colsum = None
+        if last and x.bias is not None and not x.bias_done and FUSE_BIAS_GRAD and x.bias.grad_written:
+            colsum = x.bias.grad
+            x.bias_done = True
         conv_fwd(dy, W.operand_t(), None, mask, res, out_buf, (N, D, H, Wd, W.cout), Cin, k,
-                 flags, self.algo)
+                 flags, self.algo, colsum)
         x.grad, x.grad_shared = out_buf, False
         x.n_recv += 1
 
@@ -500,6 +522,7 @@ class Ctx:
                  None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
         useful_frac = 1.0
         out = Act(y, og, requires_grad=self.training, lrelu_out=lrelu)
+        out.bias = b
         if self.training:
             self.consume(x)
             if residual is not None:
@@ -512,7 +535,7 @@ class Ctx:
                 dy = out.grad
                 global useful_frac
                 useful_frac = x.useful
-                self.weight_grads(x.data, dy, x.geom, W, b, k, up2)
+                self.weight_grads(x.data, dy, x.geom, W, None if out.bias_done else b, k, up2)
                 self.dgrad_into(x, dy, W, k, down2=up2)
                 useful_frac = 1.0
                 if residual is not None:

@@ -81,6 +81,15 @@ int r2n2_conv_fwd(const void* x, const void* w, const float* bias, const void* m
                   int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
                   void* stream);
 
+/* r2n2_conv_fwd_colsum: r2n2_conv_fwd plus colsum[c] += sum over output pixels of y[p,c] (fp32, always
+ * accumulates).  Used for data gradients: y is then the gradient of the producing layer's output and
+ * colsum its bias gradient (`+ b.dimshuffle(...)`, lib/layers.py:333,442) -- fused into the TMA epilogue
+ * where the tile is in shared memory anyway, otherwise one r2n2_bias_grad pass over y. */
+int r2n2_conv_fwd_colsum(const void* x, const void* w, const float* bias, const void* mask_src,
+                         const void* residual, void* y, int N, int D, int H, int W, int Cin, int Cout,
+                         int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
+                         float* colsum, void* stream);
+
 /* r2n2_conv_wgrad: dw[co][tap][ci] (+)= sum_p dy[p,co] * x[p+tap-centre,ci]  (fp32 output in
  * packed layout).  tensor.grad of the call sites above w.r.t. W / Wh / Wx. */
 int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,

@@ -28,7 +28,7 @@ def _stuff(x5):
     return o
 
 
-def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
+def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo, colsum=None):
     N, D, H, W, Cin = geom
     if flags & CONV_UP2:
         xi = _stuff(_f(x).view(N, D, H, W, Cin)).permute(0, 4, 1, 2, 3)
@@ -51,6 +51,8 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo):
         m = _f(mask_src).view(-1, cout)
         o = o * torch.where(m > 0, torch.ones_like(m), torch.full_like(m, LEAK))
     y.copy_(o.reshape(-1).to(y.dtype))
+    if colsum is not None:
+        colsum.add_(y.view(-1, cout).double().sum(0).to(colsum.dtype))
     return y
 
 
@@ -87,6 +89,10 @@ def bias_grad(dy, db, C, accumulate):
 
 def weight_transpose(w, wt, cout, taps, cin):
     wt.copy_(w.view(cout, taps, cin).flip(1).permute(2, 1, 0).reshape(-1).to(wt.dtype))
+
+
+def fill_zero(t):
+    t.zero_()
 
 
 def cast(src, dst):
@@ -278,7 +284,7 @@ def voxel_eval(pred, gt, thresh):
     return torch.stack([f(occ ^ g1), f(occ & g1), f(occ | g1), f(occ & g0), f(~occ & g1)], 1)
 
 
-ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'nchw_to_nhwc', 'nchw_to_rowpack',
+ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
        'maxpool_fwd', 'maxpool_bwd', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
        'eltwise', 'gru_ur_fwd', 'gru_out_fwd', 'gru_out_bwd', 'gru_r_bwd', 'lstm_fwd', 'lstm_bwd',
        'softmax_ce3d', 'adam', 'sgd', 'voxel_eval']

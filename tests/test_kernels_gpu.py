@@ -379,3 +379,36 @@ def test_conv_fwd_umma_bf16(case, flags, out_dtype):
         cols = torch.unique(bad % Cout)[:12].tolist()
         raise AssertionError('umma %s flags %d: max err %.3e (ref %.3e), %d bad; rows %s cols %s'
                              % (case, flags, err, ref, bad.numel(), rows, cols))
+
+
+@pytest.mark.parametrize('case', [(2, 1, 16, 16, 64, 128, (1, 3, 3)), (3, 1, 17, 17, 96, 96, (1, 3, 3)),
+                                  (2, 6, 5, 7, 64, 64, (3, 3, 3)), (1, 16, 16, 16, 32, 32, (3, 3, 3)),
+                                  (2, 1, 5, 5, 256, 256, (1, 1, 1)), (2, 1, 9, 9, 64, 384, (1, 3, 3))])
+@pytest.mark.parametrize('flags', [0, L.EPI_RESIDUAL | L.EPI_MASK])
+def test_conv_fwd_colsum(case, flags):
+    """r2n2_conv_fwd_colsum: column sums of the stored (bf16) output accumulate into an fp32 vector -- fused
+    in the TMA epilogue, or a second pass (flat-halo kernel, several N tiles)."""
+    N, D, H, W, Cin, Cout, k = case
+    taps = k[0] * k[1] * k[2]
+    P = N * D * H * W
+    bf = torch.bfloat16
+    x = _r(P * Cin, seed=1).to(bf)
+    w = _r(Cout * taps * Cin, seed=2, scale=(2.0 / (taps * Cin)) ** 0.5).to(bf)
+    res = _r(P * Cout, seed=4).to(bf)
+    mask = _r(P * Cout, seed=5).to(bf)
+    want = torch.empty(P * Cout, dtype=bf)
+    cs0 = _r(Cout, seed=6)
+    want_cs = cs0.clone()
+    emu.conv_fwd(x.float(), w.float(), None, mask.float(), res.float(), want, (N, D, H, W, Cin), Cout, k, flags, 0,
+                 colsum=want_cs)
+    y = torch.full((P * Cout,), float('nan'), dtype=bf, device=DEV)
+    cs = cs0.to(DEV)
+    ops.conv_fwd(x.to(DEV), w.to(DEV), None, mask.to(DEV), res.to(DEV), y, (N, D, H, W, Cin), Cout, k, flags,
+                 L.ALGO_UMMA, colsum=cs)
+    torch.cuda.synchronize()
+    assert ops.umma_error_flag() == 0
+    _cmp(y, want, 1.2e-2, 'conv_fwd_colsum y')
+    # the sums are over the bf16 values actually stored: compare with the sums of OUR output, tightly
+    own = cs0 + y.float().cpu().view(-1, Cout).double().sum(0).float()
+    assert (cs.cpu() - own).abs().max().item() <= 2e-3 * max(1.0, own.abs().max().item())
+    assert (cs.cpu() - want_cs).abs().max().item() <= 5e-2 * max(1.0, want_cs.abs().max().item())
