@@ -772,7 +772,11 @@ static void choose_kbox_dx(int N, int D, int H, int W, int max_rows, int& bw, in
   if (best_eff < 0.8) bw = 0;                // too much overhang (e.g. W = 33): keep the per-tap loads
 }
 
-static int pow2_chunk(int c) { return c >= 64 ? 64 : (c >= 32 ? 32 : 16); }
+// channels per TMA box / swizzle span; 96 (160) = 3 (5) x 32: no zero-filled half chunk -> 25 % less smem + traffic
+static int pow2_chunk(int c) {
+  if (c > 64 && c % 64 == 32 && !getenv("R2N2_WGRAD_CHUNK64")) return 32;
+  return c >= 64 ? 64 : (c >= 32 ? 32 : 16);
+}
 
 int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                      int Cout, int kd, int kh, int kw, int accumulate, cudaStream_t st);
@@ -899,7 +903,14 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   p.err_word = get_err_word();
   // pixel splits: enough CTAs to fill the machine, but at least ~4 K blocks each
   const long long units = (long long)co_tiles * p.ci_tiles * tap_groups;
-  long long splits = ((long long)num_sms() * 2 + units - 1) / units;
+  // resident CTAs per SM (shared memory and the 512 TMEM columns): the grid should be ONE wave of them --
+  // 297 CTAs at one CTA per SM is three waves with a single CTA in the last
+  const size_t smem_est = (size_t)p.stages * p.stage_bytes + 2048 + (p.rows * 256 > p.stage_bytes ? p.rows * 256 - p.stage_bytes : 0);
+  int occ = (int)((size_t)227 * 1024 / smem_est);
+  if (occ > 512 / p.tmem_cols) occ = 512 / p.tmem_cols;
+  if (occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  long long splits = ((long long)num_sms() * occ) / units;
   if (splits > p.nbox / 4) splits = p.nbox / 4;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
