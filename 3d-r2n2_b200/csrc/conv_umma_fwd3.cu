@@ -60,7 +60,11 @@ static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long lo
 // the last chunk: compile-time so that the MMA issue sequence of one tap is straight-line code with
 // immediate descriptor offsets (a single thread issues every MMA of the SM: each extra instruction per
 // MMA costs more than the MMA itself at N <= 64).
-template <typename TOut, int KB, int NCH, int LASTK>
+// TT / WTT / RESS / KDD > 0 (RESS >= 0): tiles per step, taps per weight stage, resident filter and kd are
+// compile-time too (3x3 taps) -- the hot configurations get a fully unrolled, branch-free issue sequence
+// (ncu: the generic loop spent 158 instructions per tap for 12 MMAs and the issuing thread, not the tensor
+// pipe, set the pace of conv1b); 0 / -1 = read from the parameter block.
+template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD>
 __global__ void __launch_bounds__(kFwd3Threads, 1)
 conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
@@ -80,6 +84,11 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int T_ = TT > 0 ? TT : p.T;
+  const int WT_ = WTT > 0 ? WTT : p.wt;
+  const bool RES_ = RESS >= 0 ? (RESS != 0) : (p.w_res != 0);
+  const int KD_ = KDD > 0 ? KDD : p.kd;
+  const int KH_ = KDD > 0 ? 3 : p.kh, KW_ = KDD > 0 ? 3 : p.kw;
 
   // rows past the loaded halo block are read by the junk rows of the last tile: keep them finite (zero)
   {
@@ -109,7 +118,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t pfull0 = smem_u32(&pfull[0]), pempty0 = smem_u32(&pempty[0]);
   const uint32_t wfull0 = smem_u32(&wfull[0]), wempty0 = smem_u32(&wempty[0]);
   const uint32_t tfull0 = smem_u32(&tfull[0]), tempty0 = smem_u32(&tempty[0]);
-  const int pz = (p.kd - 1) / 2;
+  const int pz = (KD_ - 1) / 2;
 
   if (warp == 0) {
     // ================================ input planes (TMA) ====================================
@@ -118,7 +127,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t tx = (uint32_t)(p.nchunk * p.plane_rows * p.rb);
     for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const Item3 c = decode_item(p, it);
-      const int nplanes = c.nz + p.kd - 1;
+      const int nplanes = c.nz + KD_ - 1;
       for (int i = 0; i < nplanes; ++i) {
         mbar_wait(pempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
         const uint32_t bar = pfull0 + 8u * slot;
@@ -127,7 +136,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_expect_tx(bar, tx);
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (p.kw - 1) / 2, c.y0 - (p.kh - 1) / 2,
+            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (KW_ - 1) / 2, c.y0 - (KH_ - 1) / 2,
                         c.z0 + i - pz, c.n);
         }
         __syncwarp();
@@ -138,9 +147,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ================================ weights (TMA): wt filter taps per stage ==================
     int slot = 0;
     uint32_t ph = 0;
-    const uint32_t stage_tx = (uint32_t)(p.BN * p.rb * NCH * p.wt);
-    const int ntaps = p.kd * p.kh * p.kw;
-    if (p.w_res) {
+    const uint32_t stage_tx = (uint32_t)(p.BN * p.rb * NCH * WT_);
+    const int ntaps = KD_ * KH_ * KW_;
+    if (RES_) {
       // small filters: every tap is loaded once and stays in shared memory for the whole kernel
       uint32_t dst = smem_base + (uint32_t)p.w_off;
       if (elect_one()) {
@@ -158,13 +167,13 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const Item3 c = decode_item(p, it);
       for (int j = 0; j < c.nz; ++j) {
-        for (int tap = 0; tap < ntaps; tap += p.wt) {
+        for (int tap = 0; tap < ntaps; tap += WT_) {
           mbar_wait(wempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
           const uint32_t bar = wfull0 + 8u * slot;
           uint32_t dst = smem_base + (uint32_t)(p.w_off + slot * p.wg * p.w_sub_bytes);
           if (elect_one()) {
             mbar_expect_tx(bar, stage_tx);
-            for (int u = 0; u < p.wt; ++u) {
+            for (int u = 0; u < WT_; ++u) {
 #pragma unroll
               for (int ch = 0; ch < NCH; ++ch) {
                 tma_load_2d(dst, &map_b, bar, (tap + u) * p.Cin + ch * p.kbox, 0);
@@ -206,35 +215,35 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int j = 0; j < c.nz; ++j, ++step) {
         const int buf = step & 1;
         mbar_wait(tempty0 + 8u * buf, ((uint32_t)(step >> 1) & 1u) ^ 1u, abort_flag, p.err_word);
-        while (waited < j + p.kd) {
+        while (waited < j + KD_) {
           mbar_wait(pfull0 + 8u * wait_slot, pph, abort_flag, p.err_word);
           if (++wait_slot == p.nring) { wait_slot = 0; pph ^= 1u; }
           ++waited;
         }
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(buf * p.T * p.bn_cols);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * T_ * p.bn_cols);
         uint32_t acc = 0;
-        const int ntaps = p.kd * p.kh * p.kw;
-        if (p.w_res && step == 0) {
+        const int ntaps = KD_ * KH_ * KW_;
+        if (RES_ && step == 0) {
           mbar_wait(wfull0, 0u, abort_flag, p.err_word);
           tc_fence_after();
         }
         int tz = 0, ty = 0, tx = 0;                        // first tap of the group (no divisions in this loop)
-        for (int tap = 0; tap < ntaps; tap += p.wt) {      // one weight stage = wt taps of ONE plane
+        for (int tap = 0; tap < ntaps; tap += WT_) {      // one weight stage = wt taps of ONE plane
           int ps = pslot + tz;
           if (ps >= p.nring) ps -= p.nring;
-          if (!p.w_res) {
+          if (!RES_) {
             mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
             tc_fence_after();
           }
           if (elect_one()) {
             uint64_t a_tap = a_ring + (uint64_t)((uint32_t)ps * plane16 + (uint32_t)ty * rowP16 + (uint32_t)tx * row16);
-            uint64_t b_tap = b_ring + (uint64_t)(p.w_res ? (uint32_t)tap * (NCH * wsub16) : (uint32_t)wslot * wstage16);
+            uint64_t b_tap = b_ring + (uint64_t)(RES_ ? (uint32_t)tap * (NCH * wsub16) : (uint32_t)wslot * wstage16);
             int txu = tx;
-            for (int u = 0; u < p.wt; ++u) {
+            for (int u = 0; u < WT_; ++u) {
               uint64_t a_t = a_tap;
               uint32_t d_t = d0;
-              for (int t = 0; t < p.T; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
+              for (int t = 0; t < T_; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                   const int nk = (ch == NCH - 1) ? LASTK : KB;
@@ -249,22 +258,22 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               acc = 1;
               b_tap += (uint64_t)(NCH * wsub16);
               a_tap += row16;
-              if (++txu == p.kw) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)p.kw * row16); }
+              if (++txu == KW_) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)KW_ * row16); }
             }
-            if (!p.w_res) umma_commit(wempty0 + 8u * wslot);
+            if (!RES_) umma_commit(wempty0 + 8u * wslot);
           }
           __syncwarp();
           acc = 1;
-          if (!p.w_res && ++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
-          tx += p.wt;
-          while (tx >= p.kw) { tx -= p.kw; ++ty; }
-          if (ty >= p.kh) { ty = 0; ++tz; }
+          if (!RES_ && ++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
+          tx += WT_;
+          while (tx >= KW_) { tx -= KW_; ++ty; }
+          if (ty >= KH_) { ty = 0; ++tz; }
         }
         if (elect_one()) {
           umma_commit(tfull0 + 8u * buf);                 // accumulators of this step complete
           umma_commit(pempty0 + 8u * pslot);              // plane z-1 is not needed by later steps
           if (j == c.nz - 1)
-            for (int e = 1; e < p.kd; ++e) {
+            for (int e = 1; e < KD_; ++e) {
               int ps = pslot + e;
               if (ps >= p.nring) ps -= p.nring;
               umma_commit(pempty0 + 8u * ps);
@@ -286,7 +295,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int buf = step & 1;
         const int zz = c.z0 + j;
         bool first = true;
-        for (int t = 0; t < p.T; ++t) {
+        for (int t = 0; t < T_; ++t) {
           const int r = t * 128 + quad * 32 + lane;
           const int yy = r / p.P, xx = r - yy * p.P;
           const int gy = c.y0 + yy, gx = c.x0 + xx;
@@ -299,7 +308,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             tc_fence_after();
             first = false;
           }
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * p.T + t) * p.bn_cols);
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols);
           epi_row(pf, taddr, c_begin, c_end, 0, p.Cout, valid, false, p.flags, bias, res + off, mask + off, y + off);
         }
         tc_fence_before();
@@ -426,7 +435,7 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
     // its MMA time.  3-D layers with Cin <= 32 (conv10b/c, conv11 and their data gradients) run 1.6-2.3x
     // faster, conv1b (96 -> 96, 127^2) 1.25x; at Cin >= 64 only two weight stages fit beside the plane ring
     // and the weight TMA latency is exposed (conv9b, conv10a, conv2a/b: 0.9-1.0x) -> per-tap kernel.
-    const bool small3d = kd == 3 && Cin <= 32;
+    const bool small3d = kd == 3 && (Cin <= 32 || (Cin == 64 && getenv("R2N2_FWD3_C64")));
     const bool conv1b_like = kd == 1 && Cin == 96 && Cout == 96;
     // (the row-packed 7x1 first layer is 10 % faster on the per-tap kernel with the TMA epilogue: 0.34 vs 0.38 ms)
     if (!small3d && !conv1b_like && !(k71 && Cin <= 32 && getenv("R2N2_FWD3_K71"))) return false;
@@ -449,22 +458,23 @@ struct Fwd3Launch {
   cudaStream_t st;
 };
 
-template <typename TOut, int KB, int NCH, int LASTK>
+template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0>
 static int launch_fwd3(const Fwd3Launch& L) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK>,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
+  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
       L.map_a, L.map_b, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
 }
-template <int KB, int NCH, int LASTK>
+template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0>
 static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
-  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK>(L) : launch_fwd3<float, KB, NCH, LASTK>(L);
+  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD>(L)
+                                : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD>(L);
 }
 
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
@@ -514,7 +524,15 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
                  "conv_fwd[umma3]: bad out dtype %d", out_dtype);
   const Fwd3Launch L{map_a, map_b, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
   int rc;
-  if (Cin == 16) rc = launch_fwd3_dt<1, 1, 1>(L, out_dtype);
+  const bool k33 = kh == 3 && kw == 3 && !getenv("R2N2_FWD3_GENERIC");
+  // specialised (compile-time issue sequence) configurations of the training step
+  if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 1 && !p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 1, 0, 1>(L, out_dtype);
+  else if (k33 && Cin == 32 && kd == 3 && p.T == 3 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 3, 9, 1, 3>(L, out_dtype);
+  else if (k33 && Cin == 16 && kd == 3 && p.T == 3 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<1, 1, 1, 3, 9, 1, 3>(L, out_dtype);
+  else if (k33 && Cin == 64 && kd == 3 && p.T == 2 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<4, 1, 4, 2, 3, 0, 3>(L, out_dtype);
+  else if (k33 && Cin == 32 && kd == 3 && p.T == 2 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<2, 1, 2, 2, 3, 0, 3>(L, out_dtype);
+  else if (k33 && Cin == 32 && kd == 3 && p.T == 3 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<2, 1, 2, 3, 3, 0, 3>(L, out_dtype);
+  else if (Cin == 16) rc = launch_fwd3_dt<1, 1, 1>(L, out_dtype);
   else if (Cin == 32) rc = launch_fwd3_dt<2, 1, 2>(L, out_dtype);
   else if (Cin == 64) rc = launch_fwd3_dt<4, 1, 4>(L, out_dtype);
   else if (Cin == 96) rc = launch_fwd3_dt<2, 3, 2>(L, out_dtype);
