@@ -73,7 +73,10 @@ static __device__ __forceinline__ TileCoord decode_tile(const FwdParams& p, int 
 
 constexpr int kFwdThreads = 64 + 32 * kEpiWarps;
 
-template <typename TOut>
+// NK16 / NSUB > 0: K16 steps per sub-block and sub-blocks per stage are compile-time (every stage full, every
+// channel chunk full): the MMA issue sequence of a stage is straight-line code with immediate descriptor
+// offsets -- the issuing thread, not the tensor pipe, sets the pace when it spends ~17 instructions per MMA.
+template <typename TOut, int NK16, int NSUB>
 __global__ void __launch_bounds__(kFwdThreads, 2)
 conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -207,7 +210,21 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
-        if (elect_one()) {
+        if (NK16 > 0) {
+          if (elect_one()) {
+            const uint64_t da0 = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+            const uint64_t db0 = da0 + (uint64_t)((uint32_t)p.a_bytes >> 4);
+            const uint32_t sub16 = (uint32_t)sub_bytes >> 4;
+#pragma unroll
+            for (int u = 0; u < (NSUB > 0 ? NSUB : 1); ++u) {
+#pragma unroll
+              for (int k = 0; k < (NK16 > 0 ? NK16 : 1); ++k)
+                umma_bf16(d_tmem, da0 + (uint64_t)(u * sub16 + 2u * k), db0 + (uint64_t)(u * sub16 + 2u * k), idesc,
+                          (u == 0 && k == 0) ? acc : 1u);
+            }
+            umma_commit(empty0 + 8u * s);
+          }
+        } else if (elect_one()) {
           uint32_t addr = a_addr;
           int c = cc;
           uint32_t a2 = acc;
@@ -426,6 +443,31 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
   }
 }
 
+struct FwdLaunch {
+  const CUtensorMap& map_a; const CUtensorMap& map_b; const CUtensorMap& map_y; const CUtensorMap& map_res;
+  const CUtensorMap& map_mask;
+  const float* bias; const void* mask; const void* res; void* y;
+  const FwdParams& p;
+  int grid; size_t smem; cudaStream_t st;
+};
+template <typename TOut, int NK16, int NSUB>
+static int launch_fwd(const FwdLaunch& L) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_umma_persistent<TOut, NK16, NSUB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_fwd_umma_persistent<TOut, NK16, NSUB><<<L.grid, kFwdThreads, L.smem, L.st>>>(
+      L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+  return R2N2_OK;
+}
+template <int NK16, int NSUB>
+static int launch_fwd_dt(const FwdLaunch& L, int out_dtype) {
+  return out_dtype == R2N2_BF16 ? launch_fwd<__nv_bfloat16, NK16, NSUB>(L) : launch_fwd<float, NK16, NSUB>(L);
+}
+
 // choose the spatial box (bw,bh,bd,bn), product <= 128, minimising the number of M tiles
 static void choose_box_fwd(int N, int D, int H, int W, int& bw, int& bh, int& bd, int& bn) {
   long long best = -1;
@@ -626,30 +668,19 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d tma_epi %d SC %d smem %zu\n",
             p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages, ctas,
             p.tma_epi, p.SC, smem_bytes);
-  cudaError_t e;
-  if (out_dtype == R2N2_BF16) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      e = cudaFuncSetAttribute(conv_fwd_umma_persistent<__nv_bfloat16>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    conv_fwd_umma_persistent<__nv_bfloat16><<<grid, kFwdThreads, smem_bytes, st>>>(
-        map_a, map_b, map_y, map_res, map_mask, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
-  } else if (out_dtype == R2N2_F32) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      e = cudaFuncSetAttribute(conv_fwd_umma_persistent<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024);
-      R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    conv_fwd_umma_persistent<float><<<grid, kFwdThreads, smem_bytes, st>>>(
-        map_a, map_b, map_y, map_res, map_mask, bias, (const float*)mask, (const float*)res, (float*)y, p);
-  } else {
-    R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
-  }
+  R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d",
+                 out_dtype);
+  const FwdLaunch L{map_a, map_b, map_y, map_res, map_mask, bias, mask, res, y, p, grid, smem_bytes, st};
+  // compile-time issue sequence when every stage holds nsub full sub-blocks (not for UP2: taps vary per class)
+  const bool spec = mode != 1 && Cin % p.kbox == 0 && nq % p.nsub == 0 && !getenv("R2N2_UMMA_GENERIC");
+  const int nk16 = p.kbox / 16;
+  int rc;
+  if (spec && nk16 == 4 && p.nsub == 1) rc = launch_fwd_dt<4, 1>(L, out_dtype);
+  else if (spec && nk16 == 4 && p.nsub == 2) rc = launch_fwd_dt<4, 2>(L, out_dtype);
+  else if (spec && nk16 == 2 && p.nsub == 3) rc = launch_fwd_dt<2, 3>(L, out_dtype);
+  else if (spec && nk16 == 2 && p.nsub == 4) rc = launch_fwd_dt<2, 4>(L, out_dtype);
+  else rc = launch_fwd_dt<0, 0>(L, out_dtype);
+  if (rc != R2N2_OK) return rc;
   R2N2_CHECK_LAUNCH("conv_fwd[umma]");
   if (colsum && !fuse_colsum) return r2n2_bias_grad(y, colsum, out_rows, Cout, out_dtype, 1, (void*)st);
   return R2N2_OK;
