@@ -562,7 +562,9 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   // (measured, profiles/r01_umma_ctas_nsub_sweep.txt: N<=64 +40%, N=128 +5..18%; N=96 prefers one
   // CTA with two sub-blocks per stage because a single 28 KB sub-block is < 256 MMA cycles)
   const int sub_cycles = (p.kbox / 16) * (p.BN / 2);
-  int ctas = (p.BN <= 64 || (p.BN <= 128 && sub_cycles >= 256)) ? 2 : 1;
+  // (re-measured after the issue-sequence work: two CTAs are never slower up to BN = 128 -- conv2a 0.25 -> 0.23 ms)
+  int ctas = p.BN <= 128 ? 2 : 1;
+  (void)sub_cycles;
   if (const char* e = getenv("R2N2_UMMA_CTAS")) { int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
   if (2 * p.bn_cols * ctas > 512) ctas = 1;
   // epilogue through shared memory + TMA (bf16 outputs; UP2 writes strided positions and keeps the register path)
