@@ -107,7 +107,11 @@ class Net(object):
     def forward(self, x, y=None):
         """(prediction, loss, activations) as CUDA tensors; the compiled test function of
         lib/solver.py:215-218."""
-        out = self.engine.forward(self._to_dev(x), self._to_dev(y), training=False)
+        xd, yd = self._to_dev(x), self._to_dev(y)
+        if cfg.CONST.INFER_GRAPH and xd.is_cuda:
+            out = self.engine.forward_graph(xd.contiguous(), None if yd is None else yd.contiguous())
+        else:
+            out = self.engine.forward(xd, yd, training=False)
         self.output, self.loss, self.activations = out['pred'], out['loss'], [out['update_gates']]
         return out
 

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--views', type=int, default=5)
     ap.add_argument('--cpu-sample-batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-infer', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel event table here')
     return ap.parse_args()
 
@@ -305,6 +306,29 @@ def run_ours(args):
                'sample': 'oracle torch-CPU fp32 restatement of the reference graph: 1 warm-up + 1 timed '
                          'training step at batch %d, %d views (batch reduced from %d)' % (Bc, T, B)}
 
+    # ---- 1-view inference latency (second half of BASELINE.json's metric; rank 0, N=1 only) ---------
+    infer = None
+    if rank == 0 and world == 1 and not args.no_infer:
+        infer = {}
+        for name, net_name, Bi in (('GRUNet_b36_1view_ms', 'GRUNet', 36), ('ResidualGRUNet_b1_1view_ms', 'ResidualGRUNet', 1),
+                                   ('ResidualGRUNet_b36_1view_ms', 'ResidualGRUNet', 36)):
+            cfg.CONST.BATCH_SIZE = Bi
+            neti = load_model(net_name)(random_seed=0, compute_grad=False)
+            xi = torch.rand(1, Bi, 3, 127, 127, device='cuda')
+            for _ in range(3):
+                neti.engine.forward_graph(xi, None)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                neti.engine.forward_graph(xi, None)
+            b.record()
+            torch.cuda.synchronize()
+            infer[name] = round(a.elapsed_time(b) / 20, 4)
+            del neti
+        cfg.CONST.BATCH_SIZE = B
+        infer['note'] = 'bf16/tcgen05 forward replayed as one CUDA graph, input resident in HBM, CUDA events'
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -317,6 +341,7 @@ def run_ours(args):
                         'h2d_bytes_per_step': int(x_pin.numel() * 4 + y_pin.numel() * 4),
                         'd2h_bytes_per_step': 4, 'steps': e2e_steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+                'infer': infer,
                 'per_kernel': {k: {'ms': round(v['ms'], 4), 'calls': v['calls'], 'share': round(v['share'], 4),
                                    'tflops': round(v['tflops'], 2), 'gbs': round(v['gbs'], 1)}
                                for k, v in (table_out or {}).items()}}

@@ -173,3 +173,26 @@ def test_gradients_bf16_umma():
         worst = min(worst, cos) if worst else cos
         assert cos > 0.9, (name, cos)
     print('bf16 grads: worst cosine %.4f' % worst)
+
+
+def test_long_recurrence_config5():
+    """BASELINE config 5 (24-view sequence inference, long recurrence of the fused GRU kernels), reduced
+    batch: fp32 path against the oracle at T=8, then the bf16/tcgen05 path against our own fp32 path at
+    T=24 (the oracle's 24 CPU encoders would dominate the test time)."""
+    net, params = _build('ResidualGRUNet', 1)
+    x, y = rt.synthetic_batch(8, 1, seed_x=11)
+    pred, loss, acts = Solver(net).test_output(x, y)
+    ref = rt.RefNet('ResidualGRUNet', params)
+    with torch.no_grad():
+        out = ref.forward(x, y)
+    err = np.abs(pred - out['pred'].numpy()).max()
+    print('T=8 fp32: max|dp| %.3e' % err)
+    assert err < 1e-4 and acts[0].shape == (8, 1, 4, 128, 4, 4)
+    x24, y24 = rt.synthetic_batch(24, 1, seed_x=12)
+    p32, _, a32 = Solver(net).test_output(x24, y24)
+    net16, _ = _build('ResidualGRUNet', 1, compute='bf16')
+    p16, _, a16 = Solver(net16).test_output(x24, y24)
+    e16 = np.abs(p16 - p32).max()
+    print('T=24 bf16 vs fp32: max|dp| %.3e, update gates %.3e' % (e16, np.abs(a16[0] - a32[0]).max()))
+    assert np.isfinite(p16).all() and e16 < 3e-2
+    assert abs(rt.iou(p16, y24, 0.4) - rt.iou(p32, y24, 0.4)) < 5e-3
