@@ -480,7 +480,7 @@ class Engine:
         return h_last, gates_i
 
     # ------------------------------------------------------------------ whole network
-    def forward(self, x, y=None, training=False, want_pred=True):
+    def forward(self, x, y=None, training=False, want_pred=True, x_events=None, y_event=None):
         """x: CUDA fp32 (T,B,3,H,W); y: CUDA fp32 (B,nv,2,nv,nv) or None.
         Returns dict(pred (B,nv,2,nv,nv), loss (0-d CUDA tensor or None), update_gates)."""
         T, B = int(x.shape[0]), int(x.shape[1])
@@ -507,7 +507,39 @@ class Engine:
                         p.grad_written = True
         P = self.P
         x = x.contiguous()
-        if self.rowpack:
+        head = None
+        if self.rowpack and x_events is not None:
+            # x is still arriving from the host, one view per event (Net._stage_inputs): run the first
+            # layers view by view so that they overlap the remaining copies (the views are the outermost
+            # axis of every channels-last tensor, so a view is a contiguous slice); the tape entries are
+            # made below on the full tensors
+            cur = torch.cuda.current_stream()
+            img, rp = self.img, self.rowpack
+            names = ['conv1a', 'conv1b'] if self.residual else ['conv1']
+            po = img // 2 + 1
+            xin = ctx.empty(TB * img * img * rp, x)
+            ys = [ctx.empty(TB * img * img * P[n + '.W'].cout, x) for n in names]
+            pooled = ctx.empty(TB * po * po * P[names[-1] + '.W'].cout, x)
+            for t in range(T):
+                cur.wait_event(x_events[t])
+                sl = lambda buf, per: buf[t * B * per:(t + 1) * B * per]
+                ops.nchw_to_rowpack(x[t], sl(xin, img * img * rp), 7, rp)
+                src, cin = sl(xin, img * img * rp), rp
+                for i, n in enumerate(names):
+                    W_, b_ = P[n + '.W'], P[n + '.b']
+                    kk = (1, 7, 1) if i == 0 else (1, 3, 3)
+                    ops.useful_frac = 21.0 / rp if i == 0 else 1.0
+                    dst = sl(ys[i], img * img * W_.cout)
+                    ops.conv_fwd(src, W_.operand(), b_.data, None, None, dst, (B, 1, img, img, cin), W_.cout, kk,
+                                 L.EPI_BIAS | L.EPI_LRELU, ctx.algo)
+                    ops.useful_frac = 1.0
+                    src, cin = dst, W_.cout
+                ops.maxpool_fwd(src, None, sl(pooled, po * po * cin), B, img, img, cin)
+            head = (xin, ys, pooled)
+        if head is not None:
+            a = Act(head[0], (TB, 1, self.img, self.img, self.rowpack))
+            a.useful = 21.0 / self.rowpack
+        elif self.rowpack:
             xin = ctx.empty(TB * self.img * self.img * self.rowpack, x)
             ops.nchw_to_rowpack(x.view(TB, 3, self.img, self.img), xin, 7, self.rowpack)
             a = Act(xin, (TB, 1, self.img, self.img, self.rowpack))
@@ -528,8 +560,15 @@ class Engine:
             return ctx.conv(inp, P[name + '.W'], P[name + '.b'], (k, k, k), lrelu, residual, out_dtype, up2)
 
         # ---- encoder over all T*B views (hoisted out of the scan) ----------------------------
+        def c2h(name, inp, i):          # chunked head: outputs exist already
+            kk = (1, 7, 1) if i == 0 else (1, 3, 3)
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, True, out_data=head[1][i])
+
         if self.residual:
-            pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
+            if head is not None:
+                pool1 = ctx.pool(c2h('conv1b', c2h('conv1a', a, 0), 1), out_data=head[2])
+            else:
+                pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
             pool2 = ctx.pool(c2('conv2c', pool1, False), c2('conv2b', c2('conv2a', pool1, True), True))
             pool3 = ctx.pool(c2('conv3c', pool2, False), c2('conv3b', c2('conv3a', pool2, True), True))
             pool4 = ctx.pool(c2('conv4b', c2('conv4a', pool3, True), True))
@@ -538,7 +577,10 @@ class Engine:
         else:
             t_ = a
             for i in range(6):       # conv -> pool -> lrelu == conv -> lrelu -> pool (monotone)
-                t_ = ctx.pool(c2('conv%d' % (i + 1), t_, True))
+                if i == 0 and head is not None:
+                    t_ = ctx.pool(c2h('conv1', t_, 0), out_data=head[2])
+                else:
+                    t_ = ctx.pool(c2('conv%d' % (i + 1), t_, True))
             pool6 = t_
         flat = ctx.reshape(pool6, (TB, 1, 1, 1, N_CONVFILTER[5] * 9))
         f = ctx.conv(flat, P['fc7.W'], P['fc7.b'], (1, 1, 1), True)
@@ -594,6 +636,8 @@ class Engine:
         dlogits = None
         if training:
             dlogits = ctx.empty(B * nv ** 3 * self.logit_c, x)
+        if y_event is not None:
+            torch.cuda.current_stream().wait_event(y_event)
         ops.softmax_ce3d(logits.data, None if y is None else y.contiguous(), pred, loss_sum, dlogits,
                          B, nv, 1.0 / (B * nv ** 3), self.logit_c)
         if training:

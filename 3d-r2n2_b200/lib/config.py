@@ -33,6 +33,7 @@ __C.CONST.WEIGHTS = ''
 # not in the reference: arithmetic of the dense contractions.
 #   'fp32' -> exact fp32 FFMA kernels (parity path); 'bf16' -> tcgen05 bf16 operands, fp32 accumulate
 __C.CONST.COMPUTE = 'fp32'
+__C.CONST.OVERLAP_H2D = True   # new key: training inputs are copied view by view on a side stream, behind the first layers
 __C.CONST.INFER_GRAPH = True   # new key: replay inference (Solver.test_output) as one CUDA graph per (views, has-y)
 
 __C.DIR = _AttrDict()

@@ -499,10 +499,12 @@ class Ctx:
         return (self.algo == L.ALGO_UMMA and umma_ok(cin, cout)
                 and (self.dtype == torch.bfloat16 or ZERO_SKIP_ANY_DTYPE))
 
-    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False):
+    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False, out_data=None):
         """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw).
         up2: the convolution runs over Unpool3D(x) (lib/layers.py:375-385) without materialising
-        the 7/8-zero tensor; y lives on the x2 grid and the gradient reaches x directly."""
+        the 7/8-zero tensor; y lives on the x2 grid and the gradient reaches x directly.
+        out_data: the output was already computed into this buffer (chunked head of the step, overlapped
+        with the host-to-device copy): only the tape entry is made."""
         N, D, H, Wd, Cin = x.geom
         assert Cin == W.cin and k[0] * k[1] * k[2] == W.taps, (x.geom, W.cin, W.taps, k)
         assert not (lrelu and residual is not None)
@@ -510,17 +512,20 @@ class Ctx:
         if up2 and not self.zero_skip(Cin, cout):
             return self.conv(self.unpool(x), W, b, k, lrelu, residual, out_dtype)
         og = (N, 2 * D, 2 * H, 2 * Wd, cout) if up2 else (N, D, H, Wd, cout)
-        y = self.empty(og[0] * og[1] * og[2] * og[3] * cout, x.data, out_dtype)
-        flags = (L.EPI_BIAS if b is not None else 0) | (L.EPI_LRELU if lrelu else 0)
-        if residual is not None:
-            flags |= L.EPI_RESIDUAL
-        if up2:
-            flags |= L.CONV_UP2
         global useful_frac
-        useful_frac = x.useful
-        conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
-                 None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
-        useful_frac = 1.0
+        if out_data is not None:
+            y = out_data
+        else:
+            y = self.empty(og[0] * og[1] * og[2] * og[3] * cout, x.data, out_dtype)
+            flags = (L.EPI_BIAS if b is not None else 0) | (L.EPI_LRELU if lrelu else 0)
+            if residual is not None:
+                flags |= L.EPI_RESIDUAL
+            if up2:
+                flags |= L.CONV_UP2
+            useful_frac = x.useful
+            conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
+                     None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
+            useful_frac = 1.0
         out = Act(y, og, requires_grad=self.training, lrelu_out=lrelu)
         out.bias = b
         if self.training:
@@ -544,13 +549,16 @@ class Ctx:
             self.tape.append(bwd)
         return out
 
-    def pool(self, a, b=None):
-        """2x2/2 max-pool (pad 1) of a (+ b)."""
+    def pool(self, a, b=None, out_data=None):
+        """2x2/2 max-pool (pad 1) of a (+ b).  out_data: already computed (chunked head)."""
         N, D, H, W, C = a.geom
         assert D == 1
         Ho, Wo = H // 2 + 1, W // 2 + 1
-        y = self.empty(N * Ho * Wo * C, a.data)
-        maxpool_fwd(a.data, None if b is None else b.data, y, N, H, W, C)
+        if out_data is not None:
+            y = out_data
+        else:
+            y = self.empty(N * Ho * Wo * C, a.data)
+            maxpool_fwd(a.data, None if b is None else b.data, y, N, H, W, C)
         out = Act(y, (N, 1, Ho, Wo, C), requires_grad=self.training,
                   lrelu_out=(b is None and a.lrelu_out))
         if self.training:
