@@ -37,6 +37,7 @@ struct Fwd3Params {
   int plane_rows, chunk_bytes, plane_bytes, nring;
   int BN, bn_cols, w_sub_bytes, wg, wt, wstages, w_off;   // wt taps (wg = wt * chunks sub-tiles) per weight stage
   int tmem_cols, flags;
+  int tma_epi, SC, slab_bytes, epi_off;    // epilogue through a dense (Yb x Xb pixels) x SC channels smem slab + TMA
   int* err_word;
 };
 
@@ -67,6 +68,8 @@ static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long lo
 template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD>
 __global__ void __launch_bounds__(kFwd3Threads, 1)
 conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
+                      const __grid_constant__ CUtensorMap map_mask,
                       const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
                       const Fwd3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -79,7 +82,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* wempty = wfull + p.wstages;                // [wstages]
   uint64_t* tfull = wempty + p.wstages;                // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;                        // [2]       epilogue -> MMA
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* efull = tempty + 2;                        // [1]       residual / mask slab landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(efull + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -100,6 +104,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), 1); mbar_init(smem_u32(&pempty[s]), 1); }
     for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), 1); mbar_init(smem_u32(&wempty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), kEpiWarps); }
+    mbar_init(smem_u32(efull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -286,6 +291,114 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp >= 2 && warp < 2 + kEpiWarps) {
     // ================================ epilogue ==============================================
     const int quad = warp & 3;
+    if (p.tma_epi) {
+      // TMA epilogue (see conv_umma_fwd.cu): the block's outputs are gathered DENSELY (junk columns dropped)
+      // into a swizzled smem slab of Yb x Xb pixels x SC channels; residual / mask slabs arrive by TMA load,
+      // the result leaves by one TMA store.  Warp (quadrant, half) takes the tiles t = half, half+2, ...
+      if constexpr (sizeof(TOut) == 2) {
+        const int half = (warp - 2) >> 2;
+        const bool leader = warp == 2 && lane == 0;
+        const uint32_t bufY = smem_base + (uint32_t)p.epi_off;
+        const uint32_t bufM = bufY + (uint32_t)p.slab_bytes;
+        const uint32_t ef = smem_u32(efull);
+        const uint32_t rb = (uint32_t)p.SC * 2u;
+        const uint32_t smask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
+        const bool has_in = (p.flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_MASK)) != 0;
+        const uint32_t in_tx = (uint32_t)(p.Xb * p.Yb * p.SC * 2) *
+                               (((p.flags & R2N2_EPI_RESIDUAL) ? 1u : 0u) + ((p.flags & R2N2_EPI_MASK) ? 1u : 0u));
+        uint32_t eph = 0;
+        bool pending = false;
+        int step = 0;
+        for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+          const Item3 c = decode_item(p, it);
+          for (int j = 0; j < c.nz; ++j, ++step) {
+            const int buf = step & 1;
+            const int zz = c.z0 + j;
+            for (int sc = 0; sc < p.BN; sc += p.SC) {
+              if (leader && pending) tma_store_wait_read();
+              named_bar_sync(1, 32 * kEpiWarps);
+              if (has_in && leader) {
+                mbar_expect_tx(ef, in_tx);
+                if (p.flags & R2N2_EPI_RESIDUAL) tma_load_5d(bufY, &map_res, ef, sc, c.x0, c.y0, zz, c.n);
+                if (p.flags & R2N2_EPI_MASK) tma_load_5d(bufM, &map_mask, ef, sc, c.x0, c.y0, zz, c.n);
+              }
+              if (sc == 0) {
+                mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+                tc_fence_after();
+              }
+              if (has_in) {
+                mbar_wait(ef, eph, abort_flag, p.err_word);
+                eph ^= 1u;
+              }
+              for (int t = half; t < T_; t += 2) {
+                const int r = t * 128 + quad * 32 + lane;
+                const int yy = r / p.P, xx = r - yy * p.P;
+                const bool valid = r < p.R && xx < p.Xb;
+                const uint32_t drow = (uint32_t)(yy * p.Xb + xx) * rb;       // dense row in the slab
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols);
+                for (int cc = 0; cc < p.SC; cc += 16) {
+                  uint32_t v[16];
+                  tmem_ld16(taddr + (uint32_t)(sc + cc), v);
+                  if (!valid) continue;
+                  float f[16];
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+                  if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                      float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + sc + cc + q));
+                      f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
+                    }
+                  }
+                  if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] = lrelu(f[q]);
+                  }
+                  const uint32_t o0 = swz_off(drow + (uint32_t)cc * 2u, smask);
+                  const uint32_t o1 = swz_off(drow + (uint32_t)cc * 2u + 16u, smask);
+                  if (p.flags & R2N2_EPI_RESIDUAL) {
+                    Row16<__nv_bfloat16> r16;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r16.a.x), "=r"(r16.a.y), "=r"(r16.a.z), "=r"(r16.a.w) : "r"(bufY + o0));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r16.b.x), "=r"(r16.b.y), "=r"(r16.b.z), "=r"(r16.b.w) : "r"(bufY + o1));
+                    float rr[16];
+                    r16.unpack(rr);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] += rr[q];
+                  }
+                  if (p.flags & R2N2_EPI_MASK) {
+                    Row16<__nv_bfloat16> m16;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m16.a.x), "=r"(m16.a.y), "=r"(m16.a.z), "=r"(m16.a.w) : "r"(bufM + o0));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m16.b.x), "=r"(m16.b.y), "=r"(m16.b.z), "=r"(m16.b.w) : "r"(bufM + o1));
+                    float mm[16];
+                    m16.unpack(mm);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] *= lrelu_slope(mm[q]);
+                  }
+                  uint32_t w[8];
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                    w[q] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(bufY + o1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                }
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              named_bar_sync(1, 32 * kEpiWarps);
+              if (leader) {
+                tma_store_5d(&map_y, bufY, sc, c.x0, c.y0, zz, c.n);
+                pending = true;
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+          }
+        }
+        if (leader && pending) tma_store_wait_all();
+      }
+    } else {
     const int nch = p.BN >> 4, half = (warp - 2) >> 2;     // two warps per lane quadrant, half the columns each
     const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
     int step = 0;
@@ -316,6 +429,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -331,8 +445,10 @@ static inline int ru(int v, int m) { return (v + m - 1) / m * m; }
 
 // Choose the block (Xb, Yb), ring depth and weight staging.  Returns false when the layer does not fit
 // (caller falls back to the per-tap kernel).
-static bool plan_fwd3(Fwd3Params& p) {
-  const int budget = 222 * 1024;
+// want_tma_epi: 0 never, 1 if it pays (heuristic), 2 always (bf16 outputs only; decided by the caller)
+static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
+  int budget = 222 * 1024;
+  p.tma_epi = 0; p.SC = 32; p.slab_bytes = 0; p.epi_off = 0;
   // channel chunk = TMA box / swizzle width; 96 = 3 x 32 (no zero-filled half chunk: 25 % less smem + traffic)
   p.kbox = p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16);
   p.nchunk = (p.Cin + p.kbox - 1) / p.kbox;
@@ -390,6 +506,25 @@ static bool plan_fwd3(Fwd3Params& p) {
   const int reach = p.T * 128 + (p.kh - 1) * p.P + p.kw - 1;
   p.chunk_bytes = ru((reach > p.plane_rows ? reach : p.plane_rows) * p.rb, 1024);
   p.plane_bytes = p.nchunk * p.chunk_bytes;
+  // TMA epilogue: worth its shared memory where thread-per-pixel global accesses (~66 L1 wavefront cycles per
+  // 16-byte instruction: 2 stores + 2 loads per input tensor per 16-column chunk per warp and tile) would take
+  // more than half of the step's MMA time
+  if (want_tma_epi) {
+    const int nin = ((p.flags & R2N2_EPI_RESIDUAL) ? 1 : 0) + ((p.flags & R2N2_EPI_MASK) ? 1 : 0);
+    const double epi_cycles = (double)p.T * 4.0 * (p.BN / 16) * (2 + 2 * nin) * 66.0;
+    const double mma_cycles = (double)p.T * ntaps * (p.Cin / 16) * (p.BN >= 128 ? p.BN / 2 : 32 + p.BN / 4);
+    if (want_tma_epi == 2 || epi_cycles > 0.5 * mma_cycles) {
+      p.SC = p.BN % 32 == 0 ? 32 : 16;
+      p.slab_bytes = ru(p.Xb * p.Yb * p.SC * 2, 1024);
+      const int need = ((p.flags & R2N2_EPI_MASK) ? 2 : 1) * p.slab_bytes;
+      // the slabs come out of the ring / weight-stage budget; skip if the pipeline would starve
+      const int w_min = p.w_res ? all_w : 2 * wstage_bytes;
+      if (p.nring * p.plane_bytes + w_min + need + 1024 <= budget) {
+        p.tma_epi = 1;
+        budget -= need;
+      }
+    }
+  }
   // deeper input ring when shared memory allows: a plane load is ~3-4K cycles of latency, a small step
   // only ~1.5K cycles of MMA, so one plane of prefetch is not enough to keep the tensor pipe fed
   {
@@ -408,6 +543,7 @@ static bool plan_fwd3(Fwd3Params& p) {
     if (p.wstages < 2) return false;
   }
   p.w_bytes = p.w_res ? all_w : p.wstages * wstage_bytes;
+  p.epi_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 1024);
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.T * p.bn_cols) p.tmem_cols *= 2;
   if (p.kd == 1) { p.zc = 1; }
@@ -448,6 +584,9 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
 struct Fwd3Launch {
   const CUtensorMap& map_a;
   const CUtensorMap& map_b;
+  const CUtensorMap& map_y;
+  const CUtensorMap& map_res;
+  const CUtensorMap& map_mask;
   const float* bias;
   const void* mask;
   const void* res;
@@ -468,7 +607,7 @@ static int launch_fwd3(const Fwd3Launch& L) {
     attr_set = true;
   }
   conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
-      L.map_a, L.map_b, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+      L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
 }
 template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0>
@@ -484,8 +623,13 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled unavailable");
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
-  R2N2_CHECK_ARG(plan_fwd3(p), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
   p.flags = flags & 15;
+  // Measured: on this kernel the smem-slab + TMA epilogue does not pay (conv1b forward 0.55 ms either way, the
+  // masked data gradient 0.66 -> 0.74 ms: one team, so every slab's load -> compute -> store latency is exposed).
+  // It stays available (R2N2_FWD3_TMA_EPI=1, parity-tested) for shapes where the register epilogue would bind.
+  int want = 0;
+  if (const char* e = getenv("R2N2_FWD3_TMA_EPI")) want = out_dtype == R2N2_BF16 ? (atoi(e) ? 2 : 0) : 0;
+  R2N2_CHECK_ARG(plan_fwd3(p, want), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
   p.err_word = get_err_word();
   CUtensorMap map_a, map_b;
   {
@@ -510,19 +654,39 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
   }
-  const size_t smem_bytes = (size_t)p.w_off + (size_t)p.w_bytes +
-                            (2 * p.nring + 2 * p.wstages + 4) * 8 + 16 + 1024;
+  const size_t smem_bytes = p.tma_epi
+      ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) ? 2 : 1) * p.slab_bytes + 1024
+      : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024;
+  CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
+  if (p.tma_epi) {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2,
+                             (cuuint64_t)D * H * W * Cout * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.SC, (cuuint32_t)p.Xb, (cuuint32_t)p.Yb, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    const void* ptrs[3] = {y, (flags & R2N2_EPI_RESIDUAL) ? res : y, (flags & R2N2_EPI_MASK) ? mask : y};
+    CUtensorMap* maps[3] = {&map_y, &map_res, &map_mask};
+    for (int i = 0; i < 3; ++i) {
+      R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, R2N2_ERR_BAD_ALIGN,
+                     "conv_fwd[umma3]: y / residual / mask must be 16-byte aligned");
+      CUresult r = encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptrs[i]), dims, strides, box,
+                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.SC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(epilogue %d) failed (%d)",
+                     i, (int)r);
+    }
+  }
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: smem %zu too large", smem_bytes);
   long long grid = num_sms();
   if (grid > p.items) grid = p.items;
   if (getenv("R2N2_UMMA_DBG"))
     fprintf(stderr, "[umma fwd3] %dx%dx%dx%d Cin %d Cout %d kd %d block %dx%d P %d R %d T %d bands %dx%d zc %d items %lld "
-            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
+            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tma_epi %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
             p.Xb, p.Yb, p.P, p.R, p.T, p.bx, p.by, p.zc, p.items, p.kbox, p.nchunk, p.plane_bytes, p.nring,
-            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tmem_cols, smem_bytes);
+            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tma_epi, p.tmem_cols, smem_bytes);
   R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE,
                  "conv_fwd[umma3]: bad out dtype %d", out_dtype);
-  const Fwd3Launch L{map_a, map_b, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
+  const Fwd3Launch L{map_a, map_b, map_y, map_res, map_mask, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
   int rc;
   const bool k33 = kh == 3 && kw == 3 && !getenv("R2N2_FWD3_GENERIC");
   // specialised (compile-time issue sequence) configurations of the training step
