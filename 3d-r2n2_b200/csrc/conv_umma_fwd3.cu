@@ -37,6 +37,7 @@ struct Fwd3Params {
   int plane_rows, chunk_bytes, plane_bytes, nring;
   int BN, bn_cols, w_sub_bytes, wg, wt, wstages, w_off;   // wt taps (wg = wt * chunks sub-tiles) per weight stage
   int tmem_cols, flags;
+  int no_rot;                              // debugging: all CTAs stream the filter taps in the same order
   int tma_epi, SC, slab_bytes, epi_off;    // epilogue through a dense (Yb x Xb pixels) x SC channels smem slab + TMA
   int* err_word;
 };
@@ -124,6 +125,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t wfull0 = smem_u32(&wfull[0]), wempty0 = smem_u32(&wempty[0]);
   const uint32_t tfull0 = smem_u32(&tfull[0]), tempty0 = smem_u32(&tempty[0]);
   const int pz = (KD_ - 1) / 2;
+  // rotation of the tap order (streamed filters only), in units of one issue group
+  const int grp_taps = WT_ * ((WTT == 1 && RESS == 0) ? 3 : 1);       // taps issued per elected region (never split)
+  const int rot_taps = (!RES_ && !p.no_rot) ? (int)(blockIdx.x % (unsigned)((KD_ * KH_ * KW_) / grp_taps)) * grp_taps : 0;
 
   if (warp == 0) {
     // ================================ input planes (TMA) ====================================
@@ -172,7 +176,11 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
       const Item3 c = decode_item(p, it);
       for (int j = 0; j < c.nz; ++j) {
-        for (int tap = 0; tap < ntaps; tap += WT_) {
+        for (int tap_o = 0; tap_o < ntaps; tap_o += WT_) {
+          // filter-row groups are visited in an order rotated by the CTA index: at any moment the 148 CTAs
+          // stream DIFFERENT taps, which spreads the reads of the (small, shared) weight tensor over L2
+          int tap = tap_o + rot_taps;
+          if (tap >= ntaps) tap -= ntaps;
           mbar_wait(wempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
           const uint32_t bar = wfull0 + 8u * slot;
           uint32_t dst = smem_base + (uint32_t)(p.w_off + slot * p.wg * p.w_sub_bytes);
@@ -233,46 +241,66 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           mbar_wait(wfull0, 0u, abort_flag, p.err_word);
           tc_fence_after();
         }
+        // GR weight stages per elected region: with one tap per stage (big filters) a whole filter row of three
+        // stages is waited for and issued at once, so the per-region overhead (elect, fence, R2UR of the slot
+        // addresses, reconvergence) is paid once per 36 MMAs instead of once per 12
+        constexpr int GR = (WTT == 1 && RESS == 0) ? 3 : 1;
         int tz = 0, ty = 0, tx = 0;                        // first tap of the group (no divisions in this loop)
-        for (int tap = 0; tap < ntaps; tap += WT_) {      // one weight stage = wt taps of ONE plane
+        if (rot_taps) {
+          tz = rot_taps / (KH_ * KW_);
+          const int rem = rot_taps - tz * KH_ * KW_;
+          ty = rem / KW_; tx = rem - ty * KW_;
+        }
+        for (int tap_o = 0; tap_o < ntaps; tap_o += WT_ * GR) {  // one weight stage = wt taps of ONE plane
+          int tap = tap_o + rot_taps;
+          if (tap >= ntaps) tap -= ntaps;
           int ps = pslot + tz;
           if (ps >= p.nring) ps -= p.nring;
+          int slots[GR];
           if (!RES_) {
-            mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
+#pragma unroll
+            for (int g = 0; g < GR; ++g) {
+              slots[g] = wslot;
+              mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
+              if (++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
+            }
             tc_fence_after();
           }
           if (elect_one()) {
             uint64_t a_tap = a_ring + (uint64_t)((uint32_t)ps * plane16 + (uint32_t)ty * rowP16 + (uint32_t)tx * row16);
-            uint64_t b_tap = b_ring + (uint64_t)(RES_ ? (uint32_t)tap * (NCH * wsub16) : (uint32_t)wslot * wstage16);
             int txu = tx;
-            for (int u = 0; u < WT_; ++u) {
-              uint64_t a_t = a_tap;
-              uint32_t d_t = d0;
-              for (int t = 0; t < T_; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                  const int nk = (ch == NCH - 1) ? LASTK : KB;
+            for (int g = 0; g < GR; ++g) {
+              uint64_t b_tap = b_ring + (uint64_t)(RES_ ? (uint32_t)tap * (NCH * wsub16) : (uint32_t)slots[g] * wstage16);
+              for (int u = 0; u < WT_; ++u) {
+                uint64_t a_t = a_tap;
+                uint32_t d_t = d0;
+                for (int t = 0; t < T_; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
 #pragma unroll
-                  for (int k = 0; k < KB; ++k) {
-                    if (k < nk)
-                      umma_bf16(d_t, a_t + (uint64_t)(ch * chunk16 + 2u * k), b_tap + (uint64_t)(ch * wsub16 + 2u * k),
-                                idesc, (ch == 0 && k == 0) ? acc : 1u);
+                  for (int ch = 0; ch < NCH; ++ch) {
+                    const int nk = (ch == NCH - 1) ? LASTK : KB;
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+                      if (k < nk)
+                        umma_bf16(d_t, a_t + (uint64_t)(ch * chunk16 + 2u * k), b_tap + (uint64_t)(ch * wsub16 + 2u * k),
+                                  idesc, (ch == 0 && k == 0) ? acc : 1u);
+                    }
                   }
                 }
+                acc = 1;
+                b_tap += (uint64_t)(NCH * wsub16);
+                a_tap += row16;
+                if (++txu == KW_) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)KW_ * row16); }
               }
-              acc = 1;
-              b_tap += (uint64_t)(NCH * wsub16);
-              a_tap += row16;
-              if (++txu == KW_) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)KW_ * row16); }
+              if (!RES_) umma_commit(wempty0 + 8u * slots[g]);
             }
-            if (!RES_) umma_commit(wempty0 + 8u * wslot);
           }
           __syncwarp();
           acc = 1;
-          if (!RES_ && ++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
-          tx += WT_;
+          tx += WT_ * GR;
           while (tx >= KW_) { tx -= KW_; ++ty; }
           if (ty >= KH_) { ty = 0; ++tz; }
+          if (tz >= KD_) tz = 0;                           // (rotated order wraps around)
         }
         if (elect_one()) {
           umma_commit(tfull0 + 8u * buf);                 // accumulators of this step complete
@@ -624,6 +652,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   p.flags = flags & 15;
+  p.no_rot = getenv("R2N2_FWD3_NO_ROT") ? 1 : 0;
   // Measured: on this kernel the smem-slab + TMA epilogue does not pay (conv1b forward 0.55 ms either way, the
   // masked data gradient 0.66 -> 0.74 ms: one team, so every slab's load -> compute -> store latency is exposed).
   // It stays available (R2N2_FWD3_TMA_EPI=1, parity-tested) for shapes where the register epilogue would bind.
