@@ -92,6 +92,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   const int taps = p.kd * p.kh * p.kw;
   const int nkb = taps * p.kchunks;
+  (void)nkb;
   const int row_bytes = p.kbox * 2;
   const int rows = p.bw * p.bh * p.bd * p.bn;
 

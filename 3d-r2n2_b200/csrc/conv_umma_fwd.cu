@@ -471,7 +471,6 @@ static int launch_fwd_dt(const FwdLaunch& L, int out_dtype) {
 // choose the spatial box (bw,bh,bd,bn), product <= 128, minimising the number of M tiles
 static void choose_box_fwd(int N, int D, int H, int W, int& bw, int& bh, int& bd, int& bn) {
   long long best = -1;
-  int best_rows = 0;
   for (int w = 1; w <= W && w <= 128; ++w)
     for (int h = 1; h <= H && w * h <= 128; ++h)
       for (int d = 1; d <= D && w * h * d <= 128; ++d) {
@@ -480,13 +479,12 @@ static void choose_box_fwd(int N, int D, int H, int W, int& bw, int& bh, int& bd
         if (n < 1) continue;
         long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d) *
                           ((N + n - 1) / n);
-        int rows = w * h * d * n;
         // fewer tiles first; then the most compact box (short TMA rows hurt nothing, but a box that
         // follows the memory order keeps the L2 footprint of the shifted taps small)
         const bool better = best < 0 || tiles < best ||
                             (tiles == best && (w > bw || (w == bw && (h > bh || (h == bh && d > bd)))));
         if (better) {
-          best = tiles; best_rows = rows;
+          best = tiles;
           bw = w; bh = h; bd = d; bn = n;
         }
       }

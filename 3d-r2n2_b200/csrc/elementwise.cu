@@ -848,7 +848,6 @@ int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, in
                          int out_dtype, void* stream) {
   R2N2_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && (kw & 1) && kw * C <= Cpack && (Cpack % 8) == 0,
                  R2N2_ERR_BAD_SHAPE, "nchw_to_rowpack: bad shape");
-  long long total = (long long)N * H * W * (Cpack / (out_dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
     const size_t smem = sizeof(float) * (size_t)C * (W + kw - 1) + sizeof(int) * (size_t)Cpack;
     long long blocks = (long long)N * H;
