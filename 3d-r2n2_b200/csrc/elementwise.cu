@@ -815,6 +815,116 @@ __global__ void voxel_eval_kernel(const float* __restrict__ pred, const float* _
   }
 }
 
+// ------------------------------------------------------------------ average precision per sample
+// lib/test_net.py:69-70: sklearn.metrics.average_precision_score(gt[:,1].flatten(), pred[:,1].flatten()):
+//   AP = sum over DISTINCT score values s (descending) of (R(s) - R(prev)) * P(s),
+//   P(s) = TP(>=s) / #(>=s), R(s) = TP(>=s) / #positives  (0 if there is no positive).
+// One CTA per sample: the nv^3 (<= 32768) scores are sorted in shared memory (bitonic network on the
+// order-preserving 32-bit integer image of the floats, the 0/1 labels are swapped along in a byte array),
+// then two block scans give TP at every position and TP at the end of
+// the previous run of equal scores; the sum is formed in double.
+constexpr int kApThreads = 1024;
+constexpr int kApMax = 32768;
+
+__device__ __forceinline__ unsigned int float_order_key(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // ascending integer order == ascending float order
+}
+
+__global__ void __launch_bounds__(kApThreads, 1)
+average_precision_kernel(const float* __restrict__ pred, const float* __restrict__ gt, double* __restrict__ ap,
+                         int nv) {
+  extern __shared__ unsigned int ap_smem[];                 // [npad] 32-bit score keys, then [npad] 8-bit labels
+  __shared__ unsigned int part[kApThreads];
+  __shared__ double red[kApThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int plane = nv * nv, n = plane * nv;
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  unsigned int* keys = ap_smem;                             // sorted DESCENDING; padding (0) sorts last
+  unsigned char* lab = reinterpret_cast<unsigned char*>(ap_smem + npad);
+  for (int v = tid; v < npad; v += kApThreads) {
+    unsigned int k = 0;
+    unsigned char l = 0;
+    if (v < n) {
+      const int z = v / plane, yx = v - z * plane;
+      const long long o1 = ((long long)(b * nv + z) * 2 + 1) * plane + yx;
+      k = float_order_key(pred[o1]);
+      if (k == 0) k = 1;                                    // (only a NaN pattern maps to 0)
+      l = gt[o1] != 0.f ? 1 : 0;
+    }
+    keys[v] = k;
+    lab[v] = l;
+  }
+  __syncthreads();
+  // bitonic sort, descending (ties keep whatever label order: AP only looks at whole runs of equal scores)
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npad; i += kApThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned int a = keys[i], c = keys[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < c) : (a > c)) {
+            keys[i] = c; keys[l] = a;
+            const unsigned char t = lab[i]; lab[i] = lab[l]; lab[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // each thread owns a contiguous chunk; inclusive scan of the labels
+  const int per = npad / kApThreads > 0 ? npad / kApThreads : 1;
+  const int i0 = tid * per;
+  unsigned int local = 0;
+  for (int i = i0; i < i0 + per && i < n; ++i) local += lab[i];
+  part[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < kApThreads; o <<= 1) {                // Hillis-Steele inclusive scan of the partial sums
+    unsigned int v = part[tid];
+    if (tid >= o) v += part[tid - o];
+    __syncthreads();
+    part[tid] = v;
+    __syncthreads();
+  }
+  const unsigned int total_pos = part[kApThreads - 1];
+  const unsigned int tp0 = part[tid] - local;               // positives before this chunk
+  // a run of equal scores ends at i when keys[i] != keys[i+1] (or i = n-1).  Pass 1: TP at the LAST run end
+  // of every chunk (0xffffffff if it has none), so that each chunk can find TP at the previous run end.
+  unsigned int run_tp = tp0, last_end_tp = 0xffffffffu;
+  for (int i = i0; i < i0 + per && i < n; ++i) {
+    run_tp += lab[i];
+    if (i == n - 1 || keys[i] != keys[i + 1]) last_end_tp = run_tp;
+  }
+  __syncthreads();
+  part[tid] = last_end_tp;
+  __syncthreads();
+  unsigned int prev_tp = 0;
+  for (int t = tid - 1; t >= 0; --t) {
+    const unsigned int v = part[t];
+    if (v != 0xffffffffu) { prev_tp = v; break; }
+  }
+  double acc = 0.0;
+  run_tp = tp0;
+  for (int i = i0; i < i0 + per && i < n; ++i) {
+    run_tp += lab[i];
+    if (i == n - 1 || keys[i] != keys[i + 1]) {
+      if (run_tp != prev_tp && total_pos)
+        acc += ((double)(run_tp - prev_tp) / (double)total_pos) * ((double)run_tp / (double)(i + 1));
+      prev_tp = run_tp;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kApThreads / 32; ++w) t += red[w];
+    ap[b] = t;
+  }
+}
+
 }  // namespace r2n2
 
 using namespace r2n2;
@@ -1169,6 +1279,23 @@ int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long*
   voxel_eval_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
       pred, gt, thresh, (unsigned long long*)counts, nv);
   R2N2_CHECK_LAUNCH("voxel_eval");
+  return R2N2_OK;
+}
+
+int r2n2_average_precision(const float* pred, const float* gt, double* ap, int B, int nv, void* stream) {
+  R2N2_CHECK_ARG(B > 0 && nv > 0 && (long long)nv * nv * nv <= kApMax, R2N2_ERR_BAD_SHAPE,
+                 "average_precision: need 0 < nv^3 <= %d", kApMax);
+  int npad = 1;
+  while (npad < nv * nv * nv) npad <<= 1;
+  if (npad < kApThreads) npad = kApThreads;
+  const size_t smem = (size_t)npad * 5;                     // 4-byte keys + 1-byte labels
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(average_precision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApMax * 5);
+    attr_set = true;
+  }
+  average_precision_kernel<<<B, kApThreads, smem, (cudaStream_t)stream>>>(pred, gt, ap, nv);
+  R2N2_CHECK_LAUNCH("average_precision");
   return R2N2_OK;
 }
 

@@ -57,6 +57,7 @@ __C.TRAIN.SAVE_FREQ = 10000
 __C.TRAIN.PRINT_FREQ = 40
 
 __C.TEST = _AttrDict()
+__C.TEST.EXP_NAME = 'test'                  # lib/config.py:91
 __C.TEST.VOXEL_THRESH = [0.4]
 
 

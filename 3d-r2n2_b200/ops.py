@@ -349,6 +349,15 @@ def voxel_eval(pred, gt, thresh):
     return counts
 
 
+def average_precision(pred, gt):
+    """lib/test_net.py:69-70 on the GPU: float64 tensor [B] of per-sample average precision."""
+    _check(pred, torch.float32), _check(gt, torch.float32)
+    B, nv = pred.shape[0], pred.shape[1]
+    ap = torch.empty(B, dtype=torch.float64, device=pred.device)
+    _call('r2n2_average_precision', _ptr(pred), _ptr(gt), _ptr(ap), B, nv, _stream())
+    return ap
+
+
 # ======================================================================= tape machinery
 class Act:
     """An activation on the tape: channels-last data + gradient bookkeeping."""

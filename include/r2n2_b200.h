@@ -220,6 +220,12 @@ int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, 
 int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long* counts, int B,
                     int nv, void* stream);
 
+/* Per-sample average precision of the occupancy channel (lib/test_net.py:69-70:
+ * sklearn.metrics.average_precision_score(gt[j,:,1].flatten(), pred[j,:,1].flatten())): pred, gt
+ * (B,nv,2,nv,nv) fp32, nv^3 <= 32768; ap[B] float64 = sum over distinct score values (descending) of
+ * (recall - previous recall) * precision, 0 when a sample has no positive voxel. */
+int r2n2_average_precision(const float* pred, const float* gt, double* ap, int B, int nv, void* stream);
+
 int r2n2_fill_zero(void* p, long long bytes, void* stream);
 
 /* 1 if any tcgen05 kernel launched by this process hit its bounded mbarrier wait (a pipeline

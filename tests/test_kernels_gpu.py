@@ -412,3 +412,28 @@ def test_conv_fwd_colsum(case, flags):
     own = cs0 + y.float().cpu().view(-1, Cout).double().sum(0).float()
     assert (cs.cpu() - own).abs().max().item() <= 2e-3 * max(1.0, own.abs().max().item())
     assert (cs.cpu() - want_cs).abs().max().item() <= 5e-2 * max(1.0, want_cs.abs().max().item())
+
+
+def test_average_precision_golden_and_oracle():
+    """r2n2_average_precision (shared-memory bitonic sort + scans, one CTA per sample) against scikit-learn's
+    outputs (golden fixture) and, on other sizes / tie patterns, against the oracle restatement."""
+    import os
+    from oracle import ref_numpy as rn
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'average_precision.npz'))
+    p1 = torch.tensor(z['p1'])
+    oc = torch.tensor(np.unpackbits(z['occ'])[:p1.numel()].reshape(p1.shape).astype(np.float32))
+    pred = torch.stack([1 - p1, p1], dim=2).contiguous()
+    gt = torch.stack([1 - oc, oc], dim=2).contiguous()
+    ap = ops.average_precision(pred.to(DEV), gt.to(DEV)).cpu().numpy()
+    assert np.abs(ap - z['ap']).max() <= 1e-12, (ap, z['ap'])
+    r = np.random.RandomState(5)
+    for nv, B, levels in [(8, 3, 0), (16, 2, 5), (32, 2, 2), (20, 2, 11)]:
+        p = r.rand(B, nv, nv, nv).astype(np.float32)
+        if levels:
+            p = (np.round(p * levels) / levels).astype(np.float32)
+        o = (r.rand(B, nv, nv, nv) < 0.2).astype(np.float32)
+        pr = torch.tensor(np.stack([1 - p, p], axis=2))
+        g = torch.tensor(np.stack([1 - o, o], axis=2))
+        got = ops.average_precision(pr.to(DEV).contiguous(), g.to(DEV).contiguous()).cpu().numpy()
+        want = np.array([rn.average_precision(o[j], p[j]) for j in range(B)])
+        assert np.abs(got - want).max() <= 1e-12, (nv, levels, got, want)

@@ -196,3 +196,33 @@ def test_long_recurrence_config5():
     print('T=24 bf16 vs fp32: max|dp| %.3e, update gates %.3e' % (e16, np.abs(a16[0] - a32[0]).max()))
     assert np.isfinite(p16).all() and e16 < 3e-2
     assert abs(rt.iou(p16, y24, 0.4) - rt.iou(p32, y24, 0.4)) < 5e-3
+
+
+def test_evaluation_loop_matches_host_metrics(tmp_path):
+    """lib/test_net.py mirror: per-batch cost, per-sample IoU counts (lib/voxel.py:4-11) and average precision
+    (sklearn.metrics.average_precision_score) computed on the GPU == the host restatements on the same
+    predictions; result.mat has the reference's keys."""
+    from oracle import ref_numpy as rn
+    from r2n2_b200.lib import test_net as tn
+    import scipy.io as sio
+    net, params = _build('GRUNet', 2)
+    solver = Solver(net)
+    batches = [rt.synthetic_batch(2, 2, seed_x=21), rt.synthetic_batch(1, 2, seed_x=22)]
+    cfg.DIR.OUT_PATH = str(tmp_path)
+    old = list(cfg.TEST.VOXEL_THRESH)
+    cfg.TEST.VOXEL_THRESH = [0.4, 0.5]
+    try:
+        res = tn.test_net(solver, batches)
+    finally:
+        cfg.TEST.VOXEL_THRESH = old
+    assert res['cost'].shape == (2,) and res['mAP'].shape == (2, 2) and res['0.4'].shape == (2, 2, 5)
+    for bi, (x, y) in enumerate(batches):
+        pred, loss, _ = solver.test_output(x, y)
+        assert abs(res['cost'][bi] - loss) < 1e-6
+        for j in range(2):
+            want_ap = rn.average_precision(y[j, :, 1], pred[j, :, 1])
+            assert abs(res['mAP'][bi, j] - want_ap) <= 1e-12
+            for th in (0.4, 0.5):
+                assert np.array_equal(res[str(th)][bi, j], np.asarray(rn.evaluate_voxel_prediction(pred[j], y[j], th), np.float64))
+    mat = sio.loadmat(str(tmp_path / 'test' / 'result.mat'))
+    assert {'cost', 'mAP', '0.4', '0.5'} <= set(mat.keys())
