@@ -815,6 +815,35 @@ __global__ void voxel_eval_kernel(const float* __restrict__ pred, const float* _
   }
 }
 
+// ------------------------------------------------------------------ input pipeline (lib/data_augmentation.py:6-70)
+// One thread per output pixel: background compositing on alpha == 0 (add_random_color_background, 40-54), crop
+// at (cr, cc) and horizontal flip (image_transform, 6-28 / crop_center, 31-38), /255 in fp32 (66), written
+// channels-first like batch_img (lib/data_process.py:145-148).  params[n] = {cr, cc, flip, r, g, b}.
+template <typename T>
+__global__ void preprocess_views_kernel(const uchar4* __restrict__ rgba, const int* __restrict__ params,
+                                        T* __restrict__ out, int n_img, int Hs, int Ws, int Ho, int Wo) {
+  const long long total = (long long)n_img * Ho * Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    long long t = i / Wo;
+    const int y = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int* pr = params + n * 6;
+    const int cr = pr[0], cc = pr[1], flip = pr[2];
+    const int sx = cc + (flip ? (Wo - 1 - x) : x), sy = cr + y;
+    const uchar4 px = rgba[((long long)n * Hs + sy) * Ws + sx];
+    const bool bg = px.w == 0;
+    const float r = (float)(bg ? pr[3] : (int)px.x), g = (float)(bg ? pr[4] : (int)px.y),
+                b = (float)(bg ? pr[5] : (int)px.z);
+    const long long plane = (long long)Ho * Wo;
+    T* o = out + (long long)n * 3 * plane + (long long)y * Wo + x;
+    o[0] = from_float<T>(__fdiv_rn(r, 255.f));
+    o[plane] = from_float<T>(__fdiv_rn(g, 255.f));
+    o[2 * plane] = from_float<T>(__fdiv_rn(b, 255.f));
+  }
+}
+
 // ------------------------------------------------------------------ average precision per sample
 // lib/test_net.py:69-70: sklearn.metrics.average_precision_score(gt[:,1].flatten(), pred[:,1].flatten()):
 //   AP = sum over DISTINCT score values s (descending) of (R(s) - R(prev)) * P(s),
@@ -1279,6 +1308,21 @@ int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long*
   voxel_eval_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
       pred, gt, thresh, (unsigned long long*)counts, nv);
   R2N2_CHECK_LAUNCH("voxel_eval");
+  return R2N2_OK;
+}
+
+int r2n2_preprocess_views(const unsigned char* rgba, const int* params, void* out, int n_img, int Hs, int Ws,
+                          int Ho, int Wo, int out_dtype, void* stream) {
+  R2N2_CHECK_ARG(rgba && params && out, R2N2_ERR_BAD_SHAPE, "preprocess_views: null pointer");
+  R2N2_CHECK_ARG(n_img > 0 && Ho > 0 && Wo > 0 && Ho <= Hs && Wo <= Ws, R2N2_ERR_BAD_SHAPE,
+                 "preprocess_views: bad shape (output %dx%d from %dx%d)", Ho, Wo, Hs, Ws);
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(rgba) & 3) == 0, R2N2_ERR_BAD_ALIGN, "preprocess_views: rgba must be 4-byte aligned");
+  const long long total = (long long)n_img * Ho * Wo;
+  R2N2_DISPATCH_DTYPE(out_dtype, T, {
+    preprocess_views_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uchar4*>(rgba), params, (T*)out, n_img, Hs, Ws, Ho, Wo);
+  })
+  R2N2_CHECK_LAUNCH("preprocess_views");
   return R2N2_OK;
 }
 

@@ -55,9 +55,16 @@ __C.TRAIN.WEIGHT_DECAY = 0.00005
 __C.TRAIN.LOSS_LIMIT = 2
 __C.TRAIN.SAVE_FREQ = 10000
 __C.TRAIN.PRINT_FREQ = 40
+# data augmentation (lib/config.py:62-69), used by lib/data_augmentation.py
+__C.TRAIN.RANDOM_CROP = True
+__C.TRAIN.PAD_X = 10
+__C.TRAIN.PAD_Y = 10
+__C.TRAIN.FLIP = True
+__C.TRAIN.NO_BG_COLOR_RANGE = [[225, 255], [225, 255], [225, 255]]
 
 __C.TEST = _AttrDict()
 __C.TEST.EXP_NAME = 'test'                  # lib/config.py:91
+__C.TEST.NO_BG_COLOR_RANGE = [[240, 240], [240, 240], [240, 240]]   # lib/config.py:98
 __C.TEST.VOXEL_THRESH = [0.4]
 
 

@@ -349,6 +349,17 @@ def voxel_eval(pred, gt, thresh):
     return counts
 
 
+def preprocess_views(rgba, params, out):
+    """rgba uint8 [n,Hs,Ws,4], params int32 [n,6], out [n,3,Ho,Wo] (fp32 / bf16): lib/data_augmentation.py:57-68."""
+    _check(rgba, torch.uint8), _check(params, torch.int32), _check(out)
+    n, Hs, Ws, four = rgba.shape
+    assert four == 4 and params.shape == (n, 6) and out.shape[0] == n and out.shape[1] == 3
+    _work(0.0, (rgba, out))
+    _call('r2n2_preprocess_views', _ptr(rgba), _ptr(params), _ptr(out), n, Hs, Ws, out.shape[2], out.shape[3],
+          _DT[out.dtype], _stream())
+    return out
+
+
 def average_precision(pred, gt):
     """lib/test_net.py:69-70 on the GPU: float64 tensor [B] of per-sample average precision."""
     _check(pred, torch.float32), _check(gt, torch.float32)

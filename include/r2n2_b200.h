@@ -220,6 +220,15 @@ int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, 
 int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long* counts, int B,
                     int nv, void* stream);
 
+/* Input pipeline (lib/data_augmentation.py:6-70, preprocess_img): rgba [n_img,Hs,Ws,4] uint8 renders;
+ * params [n_img][6] int32 = {crop row, crop column, flip, bg r, bg g, bg b} (the caller draws them in the
+ * reference's order; the kernel does not check that the crop window lies inside the source).  Pixels with
+ * alpha == 0 take the background colour, the (Ho,Wo) window is cropped, optionally mirrored, divided by
+ * 255 in fp32 and written channels-first: out [n_img,3,Ho,Wo] in out_dtype (= batch_img of
+ * lib/data_process.py:145-148, viewed as (T,B,3,H,W) by the caller). */
+int r2n2_preprocess_views(const unsigned char* rgba, const int* params, void* out, int n_img, int Hs, int Ws,
+                          int Ho, int Wo, int out_dtype, void* stream);
+
 /* Per-sample average precision of the occupancy channel (lib/test_net.py:69-70:
  * sklearn.metrics.average_precision_score(gt[j,:,1].flatten(), pred[j,:,1].flatten())): pred, gt
  * (B,nv,2,nv,nv) fp32, nv^3 <= 32768; ap[B] float64 = sum over distinct score values (descending) of

@@ -437,3 +437,33 @@ def test_average_precision_golden_and_oracle():
         got = ops.average_precision(pr.to(DEV).contiguous(), g.to(DEV).contiguous()).cpu().numpy()
         want = np.array([rn.average_precision(o[j], p[j]) for j in range(B)])
         assert np.abs(got - want).max() <= 1e-12, (nv, levels, got, want)
+
+
+def test_preprocess_views_golden(monkeypatch):
+    """r2n2_preprocess_views against the outputs of the REAL lib/data_augmentation.preprocess_img (golden
+    fixture; bit-exact fp32), the host mirror's random draws against the reference's (same seed -> same crop /
+    flip / background), and other sizes against the oracle."""
+    import os
+    from oracle import ref_numpy as rn
+    from r2n2_b200.lib import data_augmentation as da
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'preprocess.npz'))
+    out = da.preprocess_views(z['rgba'], params=z['params']).cpu().numpy()          # (n,3,127,127)
+    assert np.array_equal(out.transpose(0, 2, 3, 1), z['out'])
+    for i in range(z['rgba'].shape[0]):                                              # reference-signature wrapper
+        np.random.seed(int(z['seeds'][i]))
+        got = da.preprocess_img(z['rgba'][i], train=bool(z['train'][i]))
+        assert np.array_equal(got, z['out'][i]), i
+    np.random.seed(int(z['seeds'][0]))
+    assert np.array_equal(da.draw_params(1, True)[0], z['params'][0])
+    r = np.random.RandomState(3)
+    rgba = r.randint(0, 256, (5, 40, 52, 4)).astype(np.uint8)
+    rgba[..., 3] = np.where(r.rand(5, 40, 52) < 0.5, 0, rgba[..., 3])
+    prm = np.array([[r.randint(0, 40 - 31 + 1), r.randint(0, 52 - 33 + 1), r.randint(0, 2), 225, 240, 255] for _ in range(5)],
+                   np.int32)
+    o = torch.empty(5, 3, 31, 33, device=DEV)
+    ops.preprocess_views(torch.tensor(rgba).to(DEV), torch.tensor(prm).to(DEV), o)
+    for i in range(5):
+        want = rn.preprocess_img(rgba[i], prm[i], (31, 33))
+        assert np.array_equal(o[i].permute(1, 2, 0).cpu().numpy(), want), i
+    with pytest.raises(ValueError):
+        da.preprocess_views(np.zeros((1, 100, 100, 4), np.uint8))                    # crop window does not fit
