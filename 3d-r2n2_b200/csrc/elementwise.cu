@@ -157,7 +157,7 @@ __device__ __forceinline__ Pack<__nv_bfloat16> unpack16<__nv_bfloat16>(const uin
 }
 
 template <typename T, bool HAS_B>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3)        // (8 raw vectors in flight with b: 3 blocks/SM would spill)
 maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ dy,
                    T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask) {
   // one thread per (output pixel, 16-byte channel group): the up to 8 input vectors of the window stay
