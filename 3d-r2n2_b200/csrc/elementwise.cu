@@ -93,46 +93,6 @@ nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, in
 }
 
 // ------------------------------------------------------------------ max pool 2x2/2 pad 1
-template <typename T>
-__global__ void maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
-                                   T* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
-  constexpr int PN = Pack<T>::N;
-  int CG = C / PN;
-  long long total = (long long)N * Ho * Wo * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long t = i / CG;
-    int wo = (int)(t % Wo);
-    t /= Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
-    Pack<T> m;
-#pragma unroll
-    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      int h = 2 * ho - 1 + dy;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        int w = 2 * wo - 1 + dx;
-        if (w < 0 || w >= W) continue;
-        long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
-        Pack<T> v = Pack<T>::load(a + off);
-        if (b) {
-          Pack<T> u = Pack<T>::load(b + off);
-#pragma unroll
-          for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];
-        }
-#pragma unroll
-        for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
-      }
-    }
-    m.store(y + i * PN);
-  }
-}
-
 // raw 16-byte vector -> floats (4 x fp32 / 8 x bf16): lets a kernel keep many loads in flight in 4
 // registers each and widen them only when they are consumed
 template <typename T>
@@ -154,6 +114,56 @@ __device__ __forceinline__ Pack<__nv_bfloat16> unpack16<__nv_bfloat16>(const uin
     r.v[2 * j] = f.x; r.v[2 * j + 1] = f.y;
   }
   return r;
+}
+
+template <typename T, bool HAS_B>
+__global__ void __launch_bounds__(256, 4)
+maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int N, int H, int W, int C,
+                   int Ho, int Wo) {
+  // one thread per (output pixel, 16-byte channel group); the window's vectors are loaded raw, all before
+  // the first use (memory-level parallelism), and widened when compared
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
+  long long total = (long long)N * Ho * Wo * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % CG);
+    long long t = i / CG;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    uint4 ra[4], rb[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
+      valid[k] = (h >= 0 && h < H && w >= 0 && w < W);
+      ra[k] = make_uint4(0, 0, 0, 0);
+      rb[k] = make_uint4(0, 0, 0, 0);
+      if (valid[k]) {
+        const long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+        ra[k] = *reinterpret_cast<const uint4*>(a + off);
+        if (HAS_B) rb[k] = *reinterpret_cast<const uint4*>(b + off);
+      }
+    }
+    Pack<T> m;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) m.v[e] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      Pack<T> v = unpack16<T>(ra[k]);
+      if (HAS_B) {
+        Pack<T> u = unpack16<T>(rb[k]);
+#pragma unroll
+        for (int e = 0; e < PN; ++e) v.v[e] += u.v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
+    }
+    m.store(y + i * PN);
+  }
 }
 
 template <typename T, bool HAS_B>
@@ -1005,8 +1015,13 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
   int Ho = H / 2 + 1, Wo = W / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    maxpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    if (b) {
+      maxpool_fwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
+    } else {
+      maxpool_fwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
+    }
   })
   R2N2_CHECK_LAUNCH("maxpool2d_fwd");
   return R2N2_OK;
