@@ -717,7 +717,9 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, T* __restri
 template <typename T>
 __global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T* __restrict__ wt_base,
                                               const long long* __restrict__ table, int n) {
-  __shared__ float tile[32][33];
+  // tile = 64 output channels x 32 input channels: 128-byte row reads of w, and the transposed rows are written
+  // as 64 consecutive co (128 bytes of bf16) per ci -- full lines both ways
+  __shared__ float tile[64][33];
   const long long bid = blockIdx.x;
   int e = 0;
   while (e + 1 < n && __ldg(table + (e + 1) * 6 + 5) <= bid) ++e;
@@ -726,19 +728,30 @@ __global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T*
   T* wt = wt_base + __ldg(row + 1);
   const int Cout = (int)__ldg(row + 2), taps = (int)__ldg(row + 3), Cin = (int)__ldg(row + 4);
   long long local = bid - __ldg(row + 5);
-  const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 31) / 32;
+  const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 63) / 64;
   const int ci0 = (int)(local % tiles_ci) * 32; local /= tiles_ci;
-  const int co0 = (int)(local % tiles_co) * 32; local /= tiles_co;
+  const int co0 = (int)(local % tiles_co) * 64; local /= tiles_co;
   const int t = (int)local;
-  for (int j = threadIdx.y; j < 32; j += 8) {
+  for (int j = threadIdx.y; j < 64; j += 8) {
     int co = co0 + j, ci = ci0 + threadIdx.x;
     tile[j][threadIdx.x] = (co < Cout && ci < Cin) ? w[((long long)co * taps + t) * Cin + ci] : 0.f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {
-    int ci = ci0 + j, co = co0 + threadIdx.x;
-    if (ci < Cin && co < Cout)
-      wt[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = from_float<T>(tile[threadIdx.x][j]);
+    const int ci = ci0 + j, co = co0 + 2 * threadIdx.x;
+    if (ci >= Cin) continue;
+    T* dst = wt + ((long long)ci * taps + (taps - 1 - t)) * Cout + co;
+    if (co + 1 < Cout && (Cout & 1) == 0) {
+      if constexpr (sizeof(T) == 2) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(tile[2 * threadIdx.x][j], tile[2 * threadIdx.x + 1][j]);
+        *reinterpret_cast<__nv_bfloat162*>(dst) = h;
+      } else {
+        *reinterpret_cast<float2*>(dst) = make_float2(tile[2 * threadIdx.x][j], tile[2 * threadIdx.x + 1][j]);
+      }
+    } else {
+      if (co < Cout) dst[0] = from_float<T>(tile[2 * threadIdx.x][j]);
+      if (co + 1 < Cout) dst[1] = from_float<T>(tile[2 * threadIdx.x + 1][j]);
+    }
   }
 }
 

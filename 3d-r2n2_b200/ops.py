@@ -180,7 +180,7 @@ class TransposeBatch:
         for p in params:
             rows.append([p.data.storage_offset(), dst, p.cout, p.taps, p.cin, tiles])
             dst += (p.data.numel() + 63) // 64 * 64
-            tiles += ((p.cin + 31) // 32) * ((p.cout + 31) // 32) * p.taps
+            tiles += ((p.cin + 31) // 32) * ((p.cout + 63) // 64) * p.taps
         self.total_tiles = tiles
         self.table = torch.tensor(rows, dtype=torch.int64, device=store.p.device)
         self.wt_all = torch.empty(dst, dtype=dt, device=store.p.device)

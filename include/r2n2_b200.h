@@ -108,8 +108,8 @@ int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin,
 
 /* the same for every weight tensor of a network in one launch (after each optimiser step): `table`
  * is a DEVICE array of n_entries rows of 6 int64 {src offset in floats from base, dst offset in
- * elements from wt_base, Cout, taps, Cin, index of the entry's first 32x32 tile}; total_tiles =
- * sum over entries of ceil(Cin/32) * ceil(Cout/32) * taps. */
+ * elements from wt_base (even), Cout, taps, Cin, index of the entry's first tile}; a tile is 64 output
+ * channels x 32 input channels of one tap: total_tiles = sum over entries of ceil(Cin/32) * ceil(Cout/64) * taps. */
 int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long long* table, int n_entries,
                                 long long total_tiles, int out_dtype, void* stream);
 

@@ -176,14 +176,14 @@ def test_pointwise_and_layout():
     ops.weight_transpose(w.to(DEV), wt, 10, 27, 12)
     _cmp(wt, want, 0.0, 'weight_transpose')
     # every weight tensor of a store in one launch
-    shapes = [(10, 27, 12), (96, 9, 96), (33, 1, 70), (128, 27, 16)]
+    shapes = [(10, 27, 12), (96, 9, 96), (33, 1, 70), (128, 27, 16), (200, 1, 1024)]
     flat, rows, dst, tiles = [], [], 0, 0
     for i, (co, tp, ci) in enumerate(shapes):
         t_ = _r(co * tp * ci, seed=20 + i)
         rows.append([sum(x.numel() for x in flat), dst, co, tp, ci, tiles])
         flat.append(t_)
         dst += co * tp * ci
-        tiles += ((ci + 31) // 32) * ((co + 31) // 32) * tp
+        tiles += ((ci + 31) // 32) * ((co + 63) // 64) * tp
     base = torch.cat(flat).to(DEV)
     for dt in (torch.float32, torch.bfloat16):
         out = torch.full((dst,), float('nan'), dtype=dt, device=DEV)
