@@ -286,11 +286,15 @@ int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int
   plan_stage(p, bestY);
   p.bands = (H + p.Y - 1) / p.Y;
   p.units = (long long)N * D * p.bands;
-  p.stages = (200 * 1024) / p.stage_bytes;
+  // two CTAs per SM (two MMA issuers, two TMEM allocations of <= 256 columns) when two 2-stage pipelines fit:
+  // measured +26..29 % on conv10a / conv10b / conv11 (one CTA: the issuer idles while a stage is refilled)
+  const bool two = p.tmem_cols <= 256 && 2 * p.stage_bytes + 2048 <= 113 * 1024 && !getenv("R2N2_WGRAD3_ONE_CTA");
+  p.stages = ((two ? 111 : 200) * 1024) / p.stage_bytes;
   if (p.stages > 4) p.stages = 4;
+  if (const char* e = getenv("R2N2_WGRAD3_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
   R2N2_CHECK_ARG(p.stages >= 2, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma3]: stage too large");
   p.err_word = get_err_word();
-  long long splits = num_sms() / 3;
+  long long splits = (long long)num_sms() * (two ? 2 : 1) / 3;
   if (const char* e = getenv("R2N2_WGRAD3_SPLITS")) { int v = atoi(e); if (v >= 1) splits = v; }
   if (splits > p.units) splits = p.units;
   if (splits < 1) splits = 1;
