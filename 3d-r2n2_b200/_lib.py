@@ -48,6 +48,7 @@ PROTOTYPES = {
     'r2n2_voxel_eval': [_p, _p, _f, _p, _i, _i, _p],
     'r2n2_preprocess_views': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_average_precision': [_p, _p, _p, _i, _i, _p],
+    'r2n2_voxel_labels': [_p, _p, _i, _i, _p],
     'r2n2_fill_zero': [_p, _ll, _p],
     'r2n2_umma_error_flag': [],
 }

@@ -867,6 +867,23 @@ __global__ void preprocess_views_kernel(const uchar4* __restrict__ rgba, const i
   }
 }
 
+// ------------------------------------------------------------------ voxel labels
+// lib/data_process.py:153-154: batch_voxel[b, :, 0] = voxel_data < 1, batch_voxel[b, :, 1] = voxel_data for
+// a boolean occupancy grid; occ [B,nv,nv,nv] bytes (0 = empty, 1 = occupied, anything else = slot of a short
+// last batch that was never filled: both channels stay 0 like the reference's np.zeros rows), y [B,nv,2,nv,nv] fp32.
+__global__ void voxel_labels_kernel(const unsigned char* __restrict__ occ, float* __restrict__ y, int nv,
+                                    long long total) {
+  const int plane = nv * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long slab = i / plane;                        // b * nv + i0
+    const int jk = (int)(i - slab * plane);
+    const unsigned char v = occ[i];
+    y[(slab * 2) * plane + jk] = v == 0 ? 1.f : 0.f;
+    y[(slab * 2 + 1) * plane + jk] = v == 1 ? 1.f : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ average precision per sample
 // lib/test_net.py:69-70: sklearn.metrics.average_precision_score(gt[:,1].flatten(), pred[:,1].flatten()):
 //   AP = sum over DISTINCT score values s (descending) of (R(s) - R(prev)) * P(s),
@@ -1351,6 +1368,15 @@ int r2n2_preprocess_views(const unsigned char* rgba, const int* params, void* ou
         reinterpret_cast<const uchar4*>(rgba), params, (T*)out, n_img, Hs, Ws, Ho, Wo);
   })
   R2N2_CHECK_LAUNCH("preprocess_views");
+  return R2N2_OK;
+}
+
+int r2n2_voxel_labels(const unsigned char* occ, float* y, int B, int nv, void* stream) {
+  R2N2_CHECK_ARG(occ && y, R2N2_ERR_BAD_SHAPE, "voxel_labels: null pointer");
+  R2N2_CHECK_ARG(B > 0 && nv > 0, R2N2_ERR_BAD_SHAPE, "voxel_labels: bad shape B=%d nv=%d", B, nv);
+  const long long total = (long long)B * nv * nv * nv;
+  voxel_labels_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(occ, y, nv, total);
+  R2N2_CHECK_LAUNCH("voxel_labels");
   return R2N2_OK;
 }
 

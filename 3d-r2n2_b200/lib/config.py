@@ -36,10 +36,20 @@ __C.CONST.COMPUTE = 'fp32'
 __C.CONST.OVERLAP_H2D = True   # new key: training inputs are copied view by view on a side stream, behind the first layers
 __C.CONST.INFER_GRAPH = True   # new key: replay inference (Solver.test_output) as one CUDA graph per (views, has-y)
 
+__C.DATASET = './experiments/dataset/shapenet_1000.json'       # lib/config.py:12
+__C.QUEUE_SIZE = 15                                            # lib/config.py:59
+
 __C.DIR = _AttrDict()
+__C.DIR.SHAPENET_QUERY_PATH = './ShapeNet/ShapeNetVox32/'      # lib/config.py:32-36
+__C.DIR.MODEL_PATH = './ShapeNet/ShapeNetCore.v1/%s/%s/model.obj'
+__C.DIR.VOXEL_PATH = './ShapeNet/ShapeNetVox32/%s/%s/model.binvox'
+__C.DIR.RENDERING_PATH = './ShapeNet/ShapeNetRendering/%s/%s/rendering'
 __C.DIR.OUT_PATH = './output/default'
 
 __C.TRAIN = _AttrDict()
+__C.TRAIN.DATASET_PORTION = [0, 0.8]      # lib/config.py:46-53
+__C.TRAIN.NUM_WORKER = 1
+__C.TRAIN.NUM_RENDERING = 24
 __C.TRAIN.RESUME_TRAIN = False
 __C.TRAIN.INITIAL_ITERATION = 0
 __C.TRAIN.NUM_ITERATION = 60000
@@ -63,6 +73,7 @@ __C.TRAIN.FLIP = True
 __C.TRAIN.NO_BG_COLOR_RANGE = [[225, 255], [225, 255], [225, 255]]
 
 __C.TEST = _AttrDict()
+__C.TEST.DATASET_PORTION = [0.8, 1]        # lib/config.py:94
 __C.TEST.EXP_NAME = 'test'                  # lib/config.py:91
 __C.TEST.NO_BG_COLOR_RANGE = [[240, 240], [240, 240], [240, 240]]   # lib/config.py:98
 __C.TEST.VOXEL_THRESH = [0.4]

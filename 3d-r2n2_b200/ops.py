@@ -369,6 +369,20 @@ def average_precision(pred, gt):
     return ap
 
 
+def voxel_labels(occ, out=None):
+    """occ uint8 [B,nv,nv,nv] (0 empty, 1 occupied, other = unfilled slot) -> y fp32 [B,nv,2,nv,nv] (lib/data_process.py:135-154)."""
+    _check(occ, torch.uint8)
+    B, nv = occ.shape[0], occ.shape[1]
+    assert occ.shape == (B, nv, nv, nv)
+    if out is None:
+        out = torch.empty(B, nv, 2, nv, nv, dtype=torch.float32, device=occ.device)
+    _check(out, torch.float32)
+    assert out.shape == (B, nv, 2, nv, nv)
+    _work(0.0, (occ, out))
+    _call('r2n2_voxel_labels', _ptr(occ), _ptr(out), B, nv, _stream())
+    return out
+
+
 # ======================================================================= tape machinery
 class Act:
     """An activation on the tape: channels-last data + gradient bookkeeping."""

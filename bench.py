@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--cpu-sample-batch', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-infer', action='store_true')
+    ap.add_argument('--no-raw-pipeline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel event table here')
     return ap.parse_args()
 
@@ -261,6 +262,40 @@ def run_ours(args):
     ms_e2e_total, _, _ = timed(step_e2e, e2e_steps, 1)
     e2e_value = B * world / (ms_e2e_total / e2e_steps / 1e3)
 
+    # ---- e2e through the input pipeline: raw uint8 renders -> DeviceBatchQueue -> train_loss ----
+    # (what lib/train_net.train_net() runs: the H2D copy carries 13.5 MB of RGBA bytes instead of 44 MB of
+    # floats, the crop / flip / background / scale and the label expansion are kernels on a side stream one
+    # batch ahead; the workers' PNG decode is not part of it)
+    e2e_raw = None
+    if not args.no_raw_pipeline:
+        import queue as _q
+        from r2n2_b200.lib import data_process as dp
+        rr = np.random.RandomState(77 + rank)
+        n_raw = e2e_steps + 1
+        raw = []
+        for _ in range(2):                                    # two distinct batches, reused in turn
+            rgba = rr.randint(0, 256, (T, B, 137, 137, 4)).astype(np.uint8)
+            params = np.zeros((T, B, 6), np.int32)
+            params[..., 0:2] = rr.randint(0, 10, (T, B, 2))
+            params[..., 2] = rr.randint(0, 2, (T, B))
+            params[..., 3:6] = rr.randint(225, 256, (T, B, 3))
+            occ = (rr.rand(B, 32, 32, 32) < 0.1).astype(np.uint8)
+            raw.append((dp.RawViews(rgba, params), occ))
+        hq = _q.Queue()
+        for i in range(n_raw):
+            hq.put(raw[i % 2])
+        dq = dp.DeviceBatchQueue(hq, depth=2)
+
+        def step_raw():
+            xb, yb = dq.get(timeout=120)
+            solver.train_loss(xb, yb)
+        ms_raw_total, _, _ = timed(step_raw, e2e_steps, 1)
+        dq.close()
+        e2e_raw = {'value': B * world / (ms_raw_total / e2e_steps / 1e3), 'unit': UNIT,
+                   'h2d_bytes_per_step': int(raw[0][0].rgba.nbytes + raw[0][0].params.nbytes + raw[0][1].nbytes),
+                   'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                   'note': 'Solver.train_loss fed by lib/data_process.DeviceBatchQueue from host uint8 RGBA renders'}
+
     # ---- roofline pass: CUDA events around every C-ABI launch of one more step (rank 0) ------
     roofline, table_out = None, None
     pk = peaks()
@@ -340,6 +375,7 @@ def run_ours(args):
                 'e2e': {'value': e2e_value, 'unit': UNIT,
                         'h2d_bytes_per_step': int(x_pin.numel() * 4 + y_pin.numel() * 4),
                         'd2h_bytes_per_step': 4, 'steps': e2e_steps},
+                'e2e_raw_pipeline': e2e_raw,
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
                 'infer': infer,
                 'per_kernel': {k: {'ms': round(v['ms'], 4), 'calls': v['calls'], 'share': round(v['share'], 4),

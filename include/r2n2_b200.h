@@ -229,6 +229,12 @@ int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long*
 int r2n2_preprocess_views(const unsigned char* rgba, const int* params, void* out, int n_img, int Hs, int Ws,
                           int Ho, int Wo, int out_dtype, void* stream);
 
+/* Voxel labels of one batch (lib/data_process.py:135-154): occ [B,nv,nv,nv] bytes, 0 = empty, 1 = occupied
+ * (the boolean grid read from model.binvox), any other value = unfilled slot of a short last batch;
+ * y [B,nv,2,nv,nv] fp32 with y[:,:,0] = (occ == 0), y[:,:,1] = (occ == 1): unfilled slots are zero in both
+ * channels, as the reference leaves them. */
+int r2n2_voxel_labels(const unsigned char* occ, float* y, int B, int nv, void* stream);
+
 /* Per-sample average precision of the occupancy channel (lib/test_net.py:69-70:
  * sklearn.metrics.average_precision_score(gt[j,:,1].flatten(), pred[j,:,1].flatten())): pred, gt
  * (B,nv,2,nv,nv) fp32, nv^3 <= 32768; ap[B] float64 = sum over distinct score values (descending) of

@@ -226,3 +226,41 @@ def test_evaluation_loop_matches_host_metrics(tmp_path):
                 assert np.array_equal(res[str(th)][bi, j], np.asarray(rn.evaluate_voxel_prediction(pred[j], y[j], th), np.float64))
     mat = sio.loadmat(str(tmp_path / 'test' / 'result.mat'))
     assert {'cost', 'mAP', '0.4', '0.5'} <= set(mat.keys())
+
+
+def test_demo_script_writes_reference_obj(tmp_path):
+    """demo.py end to end: PNG views -> Net.load(weights.npy) -> Solver.test_output -> voxel2obj.  The OBJ
+    must be the text the reference's writer produces for the oracle's thresholded prediction."""
+    import hashlib
+    import importlib.util
+    import os
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('r2n2_demo', os.path.join(root, 'demo.py'))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    r = np.random.RandomState(5)
+    paths = []
+    for i in range(3):
+        a = (r.rand(127, 127, 4) * 255).astype(np.uint8)
+        paths.append(str(tmp_path / ('%d.png' % i)))
+        Image.fromarray(a, 'RGBA').save(paths[-1])
+    net, params = _build('ResidualGRUNet', 1)
+    wfile = str(tmp_path / 'weights.npy')
+    net.save(wfile)
+    out_obj = str(tmp_path / 'prediction.obj')
+    assert demo.main([out_obj, '--weights', wfile, '--images'] + paths) == 0
+    x = demo.load_demo_images(paths)
+    assert x.shape == (3, 1, 3, 127, 127) and x.dtype == np.float32
+    ref = rt.RefNet('ResidualGRUNet', params)
+    with torch.no_grad():
+        p = ref.forward(x, None)['pred'].numpy()
+    from r2n2_b200.lib.voxel import voxel2obj
+    ref_obj = str(tmp_path / 'ref.obj')
+    voxel2obj(ref_obj, p[0, :, 1] > 0.4)
+    margin = np.abs(p[0, :, 1] - 0.4).min()
+    if margin > 1e-4:                                   # no voxel sits on the threshold: identical meshes
+        assert hashlib.sha256(open(out_obj, 'rb').read()).hexdigest() == \
+            hashlib.sha256(open(ref_obj, 'rb').read()).hexdigest()
+    assert open(out_obj).readline() == 'g\n'
+    assert demo.main([out_obj, '--weights', str(tmp_path / 'missing.npy'), '--images'] + paths) == 1
