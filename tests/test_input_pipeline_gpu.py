@@ -117,8 +117,9 @@ def test_solver_train_from_worker_processes(tmp_path, restore_cfg):  # noqa: F81
             dq.close()
             data_process.kill_processes(mq, procs)
         assert len(losses_host) == 3 and len(losses_dev) == 3
-        assert losses_host[0] == losses_dev[0]                 # same inputs, same weights: same forward pass
-        assert np.allclose(losses_host, losses_dev, rtol=1e-4)  # later steps see atomically accumulated gradients
+        # same inputs and weights; the host path runs the first layers view by view behind the copies and the
+        # loss / weight-gradient sums are accumulated atomically, so equality holds to rounding only
+        assert np.allclose(losses_host, losses_dev, rtol=1e-4)
     finally:
         cfg.TRAIN.NUM_ITERATION, cfg.DIR.OUT_PATH, cfg.TRAIN.SAVE_FREQ = keep
 
