@@ -17,6 +17,14 @@
 //   * the weights of all taps are streamed through their own small TMA ring once per step and shared
 //     by the T tiles of the step (T accumulators side by side in TMEM, double buffered so that the
 //     epilogue of step i overlaps the MMAs of step i+1).
+// dx-stacked mode (narrow Cout, STK): an SS-mode MMA costs 32 + N/4 cycles (operand reads), so at N = 32 a
+// tap runs at 40 % of the tensor peak however well it is fed.  The three taps (ty, 0..2) of a filter row read
+// the SAME plane rows shifted by 0/1/2 pixels; their weight tiles lie back to back in shared memory, i.e. they
+// ARE one K-major B operand of 3 BN rows.  So ONE MMA with N = 3 BN on the unshifted view computes
+//   D_j[r] = sum_{tz,ty,ci} x[r + ty P (+ plane tz), ci] w[co, (tz,ty,j), ci]      j = 0, 1, 2  (column groups)
+// and the output is  y[r] = D_0[r] + D_1[r+1] + D_2[r+2]:  the shift moves to the epilogue, where it is a
+// warp shuffle across TMEM lanes (+ a 3-value-per-column exchange through shared memory at the 32-row
+// warp boundaries).  N = 96 costs 56 cycles instead of 3 x 40.
 // Warp roles: 0 = input-plane TMA, 1 = MMA issuer, 2..9 = epilogue, 10 = weight TMA.
 #include "umma.cuh"
 
@@ -39,6 +47,8 @@ struct Fwd3Params {
   int tmem_cols, flags;
   int no_rot;                              // debugging: all CTAs stream the filter taps in the same order
   int tma_epi, SC, slab_bytes, epi_off;    // epilogue through a dense (Yb x Xb pixels) x SC channels smem slab + TMA
+  int nslab;                               // output slabs in rotation (2 when no residual / mask slab is loaded)
+  int stk, xch_off, xch_bytes;             // dx-stacked mode: the 3 taps of a filter row share ONE MMA (N = 3 BN)
   int* err_word;
 };
 
@@ -66,7 +76,7 @@ static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long lo
 // compile-time too (3x3 taps) -- the hot configurations get a fully unrolled, branch-free issue sequence
 // (ncu: the generic loop spent 158 instructions per tap for 12 MMAs and the issuing thread, not the tensor
 // pipe, set the pace of conv1b); 0 / -1 = read from the parameter block.
-template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD>
+template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int STK>
 __global__ void __launch_bounds__(kFwd3Threads, 1)
 conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -92,8 +102,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int T_ = TT > 0 ? TT : p.T;
   const int WT_ = WTT > 0 ? WTT : p.wt;
   const bool RES_ = RESS >= 0 ? (RESS != 0) : (p.w_res != 0);
-  const int KD_ = KDD > 0 ? KDD : p.kd;
-  const int KH_ = KDD > 0 ? 3 : p.kh, KW_ = KDD > 0 ? 3 : p.kw;
+  // KDD = 71: the 1 x 7 x 1 filter of the row-packed first layer
+  const int KD_ = KDD == 71 ? 1 : (KDD > 0 ? KDD : p.kd);
+  const int KH_ = KDD == 71 ? 7 : (KDD > 0 ? 3 : p.kh), KW_ = KDD == 71 ? 1 : (KDD > 0 ? 3 : p.kw);
 
   // rows past the loaded halo block are read by the junk rows of the last tile: keep them finite (zero)
   {
@@ -251,6 +262,48 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const int rem = rot_taps - tz * KH_ * KW_;
           ty = rem / KW_; tx = rem - ty * KW_;
         }
+        if constexpr (STK != 0) {
+          // ---- dx-stacked issue: one MMA (N = 3 BN) per filter row (tz, ty), K16 step and tile ----
+          static_assert(NCH == 1, "stacked mode: one channel chunk");
+          const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * p.BN) >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+          const int ngrp = KD_ * 3;                          // filter rows
+          const int gps = RES_ ? ngrp : WT_ / 3;             // filter rows per elected region (= weight stage)
+          int g0 = rot_taps / 3;
+          for (int go = 0; go < ngrp; go += gps) {
+            int slot_w = 0;
+            if (!RES_) {
+              slot_w = wslot;
+              mbar_wait(wfull0 + 8u * wslot, wph, abort_flag, p.err_word);
+              if (++wslot == p.wstages) { wslot = 0; wph ^= 1u; }
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              int g = g0;
+              uint64_t b_g = b_ring + (uint64_t)(RES_ ? (uint32_t)g * 3u * wsub16 : (uint32_t)slot_w * wstage16);
+              for (int u = 0; u < gps; ++u) {
+                const int tz = g / 3, ty = g - tz * 3;
+                int ps = pslot + tz;
+                if (ps >= p.nring) ps -= p.nring;
+                uint64_t a_t = a_ring + (uint64_t)((uint32_t)ps * plane16 + (uint32_t)ty * rowP16);
+                uint32_t d_t = d0;
+                for (int t = 0; t < T_; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
+#pragma unroll
+                  for (int k = 0; k < LASTK; ++k)
+                    umma_bf16(d_t, a_t + (uint64_t)(2u * k), b_g + (uint64_t)(2u * k), idesc_s, k == 0 ? acc : 1u);
+                }
+                acc = 1;
+                b_g += (uint64_t)(3u * wsub16);
+                if (++g == ngrp) { g = 0; if (RES_) b_g = b_ring; }
+              }
+              if (!RES_) umma_commit(wempty0 + 8u * slot_w);
+            }
+            __syncwarp();
+            acc = 1;
+            g0 += gps;
+            if (g0 >= ngrp) g0 -= ngrp;
+          }
+        } else
         for (int tap_o = 0; tap_o < ntaps; tap_o += WT_ * GR) {  // one weight stage = wt taps of ONE plane
           int tap = tap_o + rot_taps;
           if (tap >= ntaps) tap -= ntaps;
@@ -327,7 +380,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int half = (warp - 2) >> 2;
         const bool leader = warp == 2 && lane == 0;
         const uint32_t bufY = smem_base + (uint32_t)p.epi_off;
-        const uint32_t bufM = bufY + (uint32_t)p.slab_bytes;
+        const uint32_t bufM = bufY + (uint32_t)p.slab_bytes;       // (mask slab; second output slab when nslab == 2)
         const uint32_t ef = smem_u32(efull);
         const uint32_t rb = (uint32_t)p.SC * 2u;
         const uint32_t smask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
@@ -337,13 +390,22 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t eph = 0;
         bool pending = false;
         int step = 0;
+        // without input slabs two output slabs rotate: the wait is for the store issued TWO slabs ago, so the
+        // shared-memory read of one slab's store overlaps the next slab's TMEM loads and packing
+        const bool two = p.nslab == 2;
+        const uint32_t bufY0 = bufY;
+        uint32_t sidx = 0;
         for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
           const Item3 c = decode_item(p, it);
           for (int j = 0; j < c.nz; ++j, ++step) {
             const int buf = step & 1;
             const int zz = c.z0 + j;
-            for (int sc = 0; sc < p.BN; sc += p.SC) {
-              if (leader && pending) tma_store_wait_read();
+            for (int sc = 0; sc < p.BN; sc += p.SC, ++sidx) {
+              const uint32_t bufY = two ? bufY0 + (sidx & 1u) * (uint32_t)p.slab_bytes : bufY0;
+              if (leader && pending) {
+                if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else tma_store_wait_read();
+              }
               named_bar_sync(1, 32 * kEpiWarps);
               if (has_in && leader) {
                 mbar_expect_tx(ef, in_tx);
@@ -426,6 +488,108 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         if (leader && pending) tma_store_wait_all();
       }
+    } else if constexpr (STK != 0) {
+    // ---- dx-stacked register epilogue: y[r] = D_0[r] + D_1[r+1] + D_2[r+2] -------------------------------
+    const int nch = p.BN >> 4, half = (warp - 2) >> 2;
+    const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
+    // exchange buffer [2 step parities][T][4 quadrants][BN] x 16 bytes {D1[row 0], D2[row 1], D2[row 0], -}:
+    // lane 31 reads the first pair (its r+1 / r+2 neighbours), lane 30 the second (its r+2 neighbour)
+    const uint32_t xch = smem_base + (uint32_t)p.xch_off;
+    const uint32_t xstep = (uint32_t)(T_ * 4 * p.BN) * 16u;
+    const uint32_t lane_sel = lane == 30 ? 8u : 0u;
+    int step = 0;
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item3 c = decode_item(p, it);
+      for (int j = 0; j < c.nz; ++j, ++step) {
+        const int buf = step & 1;
+        const int zz = c.z0 + j;
+        const uint32_t xb = xch + (uint32_t)(step & 1) * xstep;
+        mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+        tc_fence_after();
+        // phase A: rows 0 and 1 of every (tile, quadrant) are the r+1 / r+2 neighbours of rows 30, 31 of the
+        // quadrant before: they go through shared memory (buffer of this step's parity)
+        for (int t = 0; t < T_; ++t) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols);
+          for (int cc = c_begin; cc < c_end; cc += 16) {
+            uint32_t v1[16], v2[16];
+            tmem_ld16_nowait(taddr + (uint32_t)(p.BN + cc), v1);
+            tmem_ld16_nowait(taddr + (uint32_t)(2 * p.BN + cc), v2);
+            tmem_wait_ld();
+            const uint32_t dst = xb + (uint32_t)((t * 4 + quad) * p.BN + cc) * 16u;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const uint32_t w2 = __shfl_sync(0xffffffffu, v2[q], 1);
+              if (lane == 0)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * q), "r"(v1[q]), "r"(w2), "r"(v2[q]), "r"(0u) : "memory");
+            }
+          }
+        }
+        named_bar_sync(1, 32 * kEpiWarps);
+        for (int t = 0; t < T_; ++t) {
+          const int r = t * 128 + quad * 32 + lane;
+          const int yy = r / p.P, xx = r - yy * p.P;
+          const int gy = c.y0 + yy, gx = c.x0 + xx;
+          const bool valid = r < p.R && xx < p.Xb && gx < p.W && gy < p.H;
+          const long long off = ((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * p.Cout;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols);
+          int nq = quad + 1, nt = t;
+          if (nq == 4) { nq = 0; ++nt; }
+          const bool has_next = nt < T_;                   // (rows past the last tile are junk rows' neighbours)
+          const uint32_t nb = xb + (uint32_t)(has_next ? (nt * 4 + nq) * p.BN : 0) * 16u + lane_sel;
+          const bool use1 = has_next && lane == 31, use2 = has_next && lane >= 30;
+          const bool zero1 = !has_next && lane == 31, zero2 = !has_next && lane >= 30;
+          for (int cc = c_begin; cc < c_end; cc += 16) {
+            EpiPrefetch<TOut> pf;
+            epi_prefetch(pf, p.flags, valid, res + off, mask + off, cc, p.Cout);
+            uint32_t v0[16], v1[16], v2[16];
+            tmem_ld16_nowait(taddr + (uint32_t)cc, v0);
+            tmem_ld16_nowait(taddr + (uint32_t)(p.BN + cc), v1);
+            tmem_ld16_nowait(taddr + (uint32_t)(2 * p.BN + cc), v2);
+            tmem_wait_ld();
+            float f[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              // straight-line: every lane loads a pair (volatile asm: the compiler must not wrap it in a branch)
+              float e0, e1;
+              asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(e0), "=f"(e1) : "r"(nb + (uint32_t)(cc + q) * 16u));
+              float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[q]), 1);
+              float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[q]), 2);
+              a1 = use1 ? e0 : (zero1 ? 0.f : a1);
+              a2 = use2 ? (lane == 31 ? e1 : e0) : (zero2 ? 0.f : a2);
+              f[q] = __uint_as_float(v0[q]) + a1 + a2;
+            }
+            if (!valid) continue;
+            if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc + q));
+                f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
+              }
+            }
+            if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] = lrelu(f[q]);
+            }
+            if (p.flags & R2N2_EPI_RESIDUAL) {
+              float rr[16];
+              pf.r.unpack(rr);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] += rr[q];
+            }
+            if (p.flags & R2N2_EPI_MASK) {
+              float mm[16];
+              pf.m.unpack(mm);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] *= lrelu_slope(mm[q]);
+            }
+            store16(y + off + cc, f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+      }
+    }
     } else {
     const int nch = p.BN >> 4, half = (warp - 2) >> 2;     // two warps per lane quadrant, half the columns each
     const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
@@ -474,9 +638,9 @@ static inline int ru(int v, int m) { return (v + m - 1) / m * m; }
 // Choose the block (Xb, Yb), ring depth and weight staging.  Returns false when the layer does not fit
 // (caller falls back to the per-tap kernel).
 // want_tma_epi: 0 never, 1 if it pays (heuristic), 2 always (bf16 outputs only; decided by the caller)
-static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
+static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   int budget = 222 * 1024;
-  p.tma_epi = 0; p.SC = 32; p.slab_bytes = 0; p.epi_off = 0;
+  p.tma_epi = 0; p.SC = 32; p.slab_bytes = 0; p.epi_off = 0; p.nslab = 1;
   // channel chunk = TMA box / swizzle width; 96 = 3 x 32 (no zero-filled half chunk: 25 % less smem + traffic)
   p.kbox = p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16);
   p.nchunk = (p.Cin + p.kbox - 1) / p.kbox;
@@ -484,10 +648,26 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
   p.full_nk16 = p.kbox >> 4;
   p.last_nk16 = (p.Cin - (p.nchunk - 1) * p.kbox) >> 4;
   p.BN = p.Cout;
-  p.bn_cols = ru(p.BN, 32);
+  p.w_sub_bytes = ru(p.BN * p.rb, 1024);
+  // dx-stacked mode (see the header): 3x3 rows, one channel chunk, the three weight tiles of a filter row
+  // contiguous in shared memory (no padding between them), 3 BN accumulator columns per tile
+  p.stk = (p.kh == 3 && p.kw == 3 && p.nchunk == 1 && 3 * p.BN <= 256 && p.BN * p.rb == p.w_sub_bytes &&
+           !getenv("R2N2_FWD3_NO_STK")) ? 1 : 0;
+  // Measured (B200, 36 x 32^3): the stacked epilogue (2 shuffles + 1 shared load per element, boundary exchange)
+  // costs ~2x the plain one, so stacking pays where a tile carries enough MMA work to hide it: Cin = 64
+  // (conv10a 0.282 -> 0.185 ms, conv9b 0.341 -> 0.323 ms) and the N = 16 layer (conv11 0.115 -> 0.102 ms);
+  // at Cin <= 32 with N = 32 the epilogue binds (conv10b 0.134 -> 0.149 ms).  R2N2_FWD3_STK=0/1 forces it.
+  if (p.stk && !(p.Cin >= 64 || (p.BN <= 16 && p.Cin >= 32))) p.stk = 0;
+  if (const char* e = getenv("R2N2_FWD3_STK")) {
+    if (!atoi(e)) p.stk = 0;
+    else p.stk = (p.kh == 3 && p.kw == 3 && p.nchunk == 1 && 3 * p.BN <= 256 && p.BN * p.rb == p.w_sub_bytes) ? 1 : 0;
+  }
+  if (want_stk == 0) p.stk = 0;
+  p.xch_off = 0; p.xch_bytes = 0;
+  if (p.stk) { budget -= 8 * 1024; want_tma_epi = 0; }
+  p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
   const int Tmax = 256 / p.bn_cols;                       // two accumulator sets in 512 TMEM columns
   if (Tmax < 1) return false;
-  p.w_sub_bytes = ru(p.BN * p.rb, 1024);
   // weight ring: one filter tap (all channel chunks) per stage; depth fixed after the block is chosen
   // (9, 3 or 1 taps: each barrier round costs the issuing thread ~300 cycles, so small taps are grouped)
   const int tpp = p.kh * p.kw, ntaps = p.kd * tpp;
@@ -498,6 +678,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
     while (p.wt > 1 && p.wt * p.nchunk * p.w_sub_bytes > 24 * 1024) p.wt = (p.wt % 3 == 0) ? p.wt / 3 : 1;
     if (const char* e = getenv("R2N2_FWD3_WT")) { int v = atoi(e); if (v >= 1 && tpp % v == 0) p.wt = v; }
   }
+  if (p.stk && !p.w_res && p.wt % 3 != 0) p.wt = 3;       // a weight stage holds whole filter rows
   p.wg = p.wt * p.nchunk;
   const int wstage_bytes = p.wg * p.w_sub_bytes;
   p.wstages = p.w_res ? 1 : 2;
@@ -544,9 +725,15 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
     if (want_tma_epi == 2 || epi_cycles > 0.5 * mma_cycles) {
       p.SC = p.BN % 32 == 0 ? 32 : 16;
       p.slab_bytes = ru(p.Xb * p.Yb * p.SC * 2, 1024);
-      const int need = ((p.flags & R2N2_EPI_MASK) ? 2 : 1) * p.slab_bytes;
+      int need = ((p.flags & R2N2_EPI_MASK) ? 2 : 1) * p.slab_bytes;
       // the slabs come out of the ring / weight-stage budget; skip if the pipeline would starve
       const int w_min = p.w_res ? all_w : 2 * wstage_bytes;
+      // (streamed filters: a second slab would cost a weight stage, measured slower on conv1b: 0.52 -> 0.55 ms)
+      if (nin == 0 && p.w_res && p.nring * p.plane_bytes + w_min + 2 * p.slab_bytes + 1024 <= budget &&
+          !getenv("R2N2_FWD3_ONE_SLAB")) {
+        p.nslab = 2;
+        need = 2 * p.slab_bytes;
+      }
       if (p.nring * p.plane_bytes + w_min + need + 1024 <= budget) {
         p.tma_epi = 1;
         budget -= need;
@@ -572,6 +759,10 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0) {
   }
   p.w_bytes = p.w_res ? all_w : p.wstages * wstage_bytes;
   p.epi_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 1024);
+  if (p.stk) {
+    p.xch_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 16);   // float4 quadruples
+    p.xch_bytes = 2 * p.T * 4 * p.BN * 16;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.T * p.bn_cols) p.tmem_cols *= 2;
   if (p.kd == 1) { p.zc = 1; }
@@ -599,7 +790,9 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
     // its MMA time.  3-D layers with Cin <= 32 (conv10b/c, conv11 and their data gradients) run 1.6-2.3x
     // faster, conv1b (96 -> 96, 127^2) 1.25x; at Cin >= 64 only two weight stages fit beside the plane ring
     // and the weight TMA latency is exposed (conv9b, conv10a, conv2a/b: 0.9-1.0x) -> per-tap kernel.
-    const bool small3d = kd == 3 && (Cin <= 32 || (Cin == 64 && getenv("R2N2_FWD3_C64")));
+    // (Cin = 64: only in dx-stacked mode, i.e. Cout <= 64 -- see plan_fwd3)
+    const bool small3d = kd == 3 && (Cin <= 32 || (Cin == 64 && (3 * Cout <= 256 || getenv("R2N2_FWD3_C64")) &&
+                                                   !getenv("R2N2_FWD3_NO_C64")));
     const bool conv1b_like = kd == 1 && Cin == 96 && Cout == 96;
     // (the row-packed 7x1 first layer is 10 % faster on the per-tap kernel with the TMA epilogue: 0.34 vs 0.38 ms)
     if (!small3d && !conv1b_like && !(k71 && Cin <= 32 && getenv("R2N2_FWD3_K71"))) return false;
@@ -625,23 +818,23 @@ struct Fwd3Launch {
   cudaStream_t st;
 };
 
-template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0>
+template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0>
 static int launch_fwd3(const Fwd3Launch& L) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD>,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
+  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
       L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
 }
-template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0>
+template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0>
 static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
-  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD>(L)
-                                : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD>(L);
+  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>(L)
+                                : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>(L);
 }
 
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
@@ -653,10 +846,12 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   p.flags = flags & 15;
   p.no_rot = getenv("R2N2_FWD3_NO_ROT") ? 1 : 0;
-  // Measured: on this kernel the smem-slab + TMA epilogue does not pay (conv1b forward 0.55 ms either way, the
-  // masked data gradient 0.66 -> 0.74 ms: one team, so every slab's load -> compute -> store latency is exposed).
-  // It stays available (R2N2_FWD3_TMA_EPI=1, parity-tested) for shapes where the register epilogue would bind.
-  int want = 0;
+  // Measured: on this kernel the smem-slab + TMA epilogue pays only without input slabs and where the register
+  // epilogue binds: conv1b forward (96 -> 96, bias + LeakyReLU) 0.553 -> 0.520 ms; with a mask / residual slab
+  // every slab's load -> compute -> store latency is exposed (one team): masked data gradient 0.66 -> 0.74 ms.
+  // R2N2_FWD3_TMA_EPI=0/1 forces it off / on (both parity-tested).
+  const bool has_in = (flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_MASK)) != 0;
+  int want = (out_dtype == R2N2_BF16 && !has_in && kd == 1 && Cin == 96 && Cout == 96) ? 2 : 0;
   if (const char* e = getenv("R2N2_FWD3_TMA_EPI")) want = out_dtype == R2N2_BF16 ? (atoi(e) ? 2 : 0) : 0;
   R2N2_CHECK_ARG(plan_fwd3(p, want), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
   p.err_word = get_err_word();
@@ -684,8 +879,9 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
   }
   const size_t smem_bytes = p.tma_epi
-      ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) ? 2 : 1) * p.slab_bytes + 1024
-      : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024;
+      ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) || p.nslab == 2 ? 2 : 1) * p.slab_bytes + 1024
+      : (p.stk ? (size_t)p.xch_off + (size_t)p.xch_bytes + 1024
+               : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024);
   CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
   if (p.tma_epi) {
     cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
@@ -710,16 +906,30 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   if (grid > p.items) grid = p.items;
   if (getenv("R2N2_UMMA_DBG"))
     fprintf(stderr, "[umma fwd3] %dx%dx%dx%d Cin %d Cout %d kd %d block %dx%d P %d R %d T %d bands %dx%d zc %d items %lld "
-            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tma_epi %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
+            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tma_epi %d stk %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
             p.Xb, p.Yb, p.P, p.R, p.T, p.bx, p.by, p.zc, p.items, p.kbox, p.nchunk, p.plane_bytes, p.nring,
-            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tma_epi, p.tmem_cols, smem_bytes);
+            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tma_epi, p.stk, p.tmem_cols, smem_bytes);
   R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE,
                  "conv_fwd[umma3]: bad out dtype %d", out_dtype);
   const Fwd3Launch L{map_a, map_b, map_y, map_res, map_mask, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
   int rc;
   const bool k33 = kh == 3 && kw == 3 && !getenv("R2N2_FWD3_GENERIC");
+  const bool k71s = kd == 1 && kh == 7 && kw == 1 && !getenv("R2N2_FWD3_GENERIC");
   // specialised (compile-time issue sequence) configurations of the training step
-  if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 1 && !p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 1, 0, 1>(L, out_dtype);
+  if (p.stk) {
+    // dx-stacked configurations (generic issue loop unless listed)
+    if (k33 && Cin == 32 && kd == 3 && p.T == 2 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 2, 9, 1, 3, 1>(L, out_dtype);
+    else if (k33 && Cin == 32 && kd == 3 && p.T == 4 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 4, 9, 1, 3, 1>(L, out_dtype);
+    else if (k33 && Cin == 16 && kd == 3 && p.T == 2 && p.w_res) rc = launch_fwd3_dt<1, 1, 1, 2, 9, 1, 3, 1>(L, out_dtype);
+    else if (k33 && Cin == 32 && kd == 3 && p.T == 1 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<2, 1, 2, 1, 3, 0, 3, 1>(L, out_dtype);
+    else if (k33 && Cin == 64 && kd == 3 && p.T == 2 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<4, 1, 4, 2, 3, 0, 3, 1>(L, out_dtype);
+    else if (k33 && Cin == 64 && kd == 3 && p.T == 1 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<4, 1, 4, 1, 3, 0, 3, 1>(L, out_dtype);
+    else if (Cin == 16) rc = launch_fwd3_dt<1, 1, 1, 0, 0, -1, 0, 1>(L, out_dtype);
+    else if (Cin == 32) rc = launch_fwd3_dt<2, 1, 2, 0, 0, -1, 0, 1>(L, out_dtype);
+    else rc = launch_fwd3_dt<4, 1, 4, 0, 0, -1, 0, 1>(L, out_dtype);
+  }
+  else if (k71s && Cin == 32 && p.T == 2 && p.wt == 7 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 2, 7, 1, 71>(L, out_dtype);
+  else if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 1 && !p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 1, 0, 1>(L, out_dtype);
   else if (k33 && Cin == 32 && kd == 3 && p.T == 3 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 3, 9, 1, 3>(L, out_dtype);
   else if (k33 && Cin == 16 && kd == 3 && p.T == 3 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<1, 1, 1, 3, 9, 1, 3>(L, out_dtype);
   else if (k33 && Cin == 64 && kd == 3 && p.T == 2 && p.wt == 3 && !p.w_res) rc = launch_fwd3_dt<4, 1, 4, 2, 3, 0, 3>(L, out_dtype);

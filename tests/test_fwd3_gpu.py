@@ -37,12 +37,13 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES)
-@pytest.mark.parametrize('tma_epi', ['0', '1'])
+@pytest.mark.parametrize('tma_epi,stk', [('0', '0'), ('1', '0'), ('0', '1')])
 @pytest.mark.parametrize('flags,out_dtype', [(0, torch.float32), (L.EPI_BIAS | L.EPI_LRELU, bf),
                                              (L.EPI_BIAS | L.EPI_RESIDUAL, bf), (L.EPI_RESIDUAL | L.EPI_MASK, bf)])
-def test_conv_fwd3(monkeypatch, case, flags, out_dtype, tma_epi):
+def test_conv_fwd3(monkeypatch, case, flags, out_dtype, tma_epi, stk):
     monkeypatch.setenv('R2N2_FWD3_FORCE', '1')
     monkeypatch.setenv('R2N2_FWD3_TMA_EPI', tma_epi)      # register epilogue / smem-slab + TMA-store epilogue
+    monkeypatch.setenv('R2N2_FWD3_STK', stk)              # one MMA per tap / dx-stacked (N = 3 Cout, shifted sum in the epilogue)
     N, D, H, W, Cin, Cout, k = case
     taps = k[0] * k[1] * k[2]
     P = N * D * H * W

@@ -39,6 +39,7 @@ SHAPES = [
     ('conv9b', (B, 32, 32, 32), 64, 64, (3, 3, 3)),
     ('conv9c', (B, 32, 32, 32), 128, 64, (1, 1, 1)),
     ('conv10a', (B, 32, 32, 32), 64, 32, (3, 3, 3)),
+    ('conv10a_dgrad', (B, 32, 32, 32), 32, 64, (3, 3, 3)),
     ('conv10b', (B, 32, 32, 32), 32, 32, (3, 3, 3)),
     ('conv11', (B, 32, 32, 32), 32, 16, (3, 3, 3)),
     ('conv11_dgrad', (B, 32, 32, 32), 16, 32, (3, 3, 3)),
