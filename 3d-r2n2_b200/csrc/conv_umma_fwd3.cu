@@ -111,6 +111,10 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (int i = threadIdx.x; i < ring_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
   }
+  if constexpr (STK != 0) {
+    uint4* z = reinterpret_cast<uint4*>(smem + p.xch_off + 2 * p.T * 4 * p.BN * 16);
+    for (int i = threadIdx.x; i < p.BN; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), 1); mbar_init(smem_u32(&pempty[s]), 1); }
@@ -492,8 +496,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ---- dx-stacked register epilogue: y[r] = D_0[r] + D_1[r+1] + D_2[r+2] -------------------------------
     const int nch = p.BN >> 4, half = (warp - 2) >> 2;
     const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
-    // exchange buffer [2 step parities][T][4 quadrants][BN] x 16 bytes {D1[row 0], D2[row 1], D2[row 0], -}:
-    // lane 31 reads the first pair (its r+1 / r+2 neighbours), lane 30 the second (its r+2 neighbour)
+    // exchange buffer [2 step parities][T][4 quadrants][BN] x 16 bytes {D2[row 1], D1[row 0], D2[row 0], -}, then
+    // one all-zero block [BN] x 16 bytes (the "neighbour" of the last quadrant of the last tile):
+    // lane 31 reads the first pair (e0 = its r+2, e1 = its r+1 neighbour), lane 30 the second (e0 = its r+2)
     const uint32_t xch = smem_base + (uint32_t)p.xch_off;
     const uint32_t xstep = (uint32_t)(T_ * 4 * p.BN) * 16u;
     const uint32_t lane_sel = lane == 30 ? 8u : 0u;
@@ -515,12 +520,14 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             tmem_ld16_nowait(taddr + (uint32_t)(p.BN + cc), v1);
             tmem_ld16_nowait(taddr + (uint32_t)(2 * p.BN + cc), v2);
             tmem_wait_ld();
-            const uint32_t dst = xb + (uint32_t)((t * 4 + quad) * p.BN + cc) * 16u;
+            // lane 1 stores D2[row 1] at +0, lane 0 stores D1[row 0] at +4 and D2[row 0] at +8
+            const uint32_t dst = xb + (uint32_t)((t * 4 + quad) * p.BN + cc) * 16u + (lane == 0 ? 4u : 0u);
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const uint32_t w2 = __shfl_sync(0xffffffffu, v2[q], 1);
+              if (lane < 2)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 16u * q), "r"(lane == 0 ? v1[q] : v2[q]) : "memory");
               if (lane == 0)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * q), "r"(v1[q]), "r"(w2), "r"(v2[q]), "r"(0u) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 16u * q + 4u), "r"(v2[q]) : "memory");
             }
           }
         }
@@ -535,9 +542,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           int nq = quad + 1, nt = t;
           if (nq == 4) { nq = 0; ++nt; }
           const bool has_next = nt < T_;                   // (rows past the last tile are junk rows' neighbours)
-          const uint32_t nb = xb + (uint32_t)(has_next ? (nt * 4 + nq) * p.BN : 0) * 16u + lane_sel;
-          const bool use1 = has_next && lane == 31, use2 = has_next && lane >= 30;
-          const bool zero1 = !has_next && lane == 31, zero2 = !has_next && lane >= 30;
+          const uint32_t nb = (has_next ? xb + (uint32_t)((nt * 4 + nq) * p.BN) * 16u : xch + 2u * xstep) + lane_sel;
+          const bool use1 = lane == 31, use2 = lane >= 30;
           for (int cc = c_begin; cc < c_end; cc += 16) {
             EpiPrefetch<TOut> pf;
             epi_prefetch(pf, p.flags, valid, res + off, mask + off, cc, p.Cout);
@@ -554,8 +560,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(e0), "=f"(e1) : "r"(nb + (uint32_t)(cc + q) * 16u));
               float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[q]), 1);
               float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[q]), 2);
-              a1 = use1 ? e0 : (zero1 ? 0.f : a1);
-              a2 = use2 ? (lane == 31 ? e1 : e0) : (zero2 ? 0.f : a2);
+              a1 = use1 ? e1 : a1;
+              a2 = use2 ? e0 : a2;
               f[q] = __uint_as_float(v0[q]) + a1 + a2;
             }
             if (!valid) continue;
@@ -664,7 +670,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   }
   if (want_stk == 0) p.stk = 0;
   p.xch_off = 0; p.xch_bytes = 0;
-  if (p.stk) { budget -= 8 * 1024; want_tma_epi = 0; }
+  if (p.stk) { budget -= 10 * 1024; want_tma_epi = 0; }     // (exchange buffer of the stacked epilogue)
   p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
   const int Tmax = 256 / p.bn_cols;                       // two accumulator sets in 512 TMEM columns
   if (Tmax < 1) return false;
@@ -761,7 +767,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   p.epi_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 1024);
   if (p.stk) {
     p.xch_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 16);   // float4 quadruples
-    p.xch_bytes = 2 * p.T * 4 * p.BN * 16;
+    p.xch_bytes = 2 * p.T * 4 * p.BN * 16 + p.BN * 16;     // + the all-zero block
   }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.T * p.bn_cols) p.tmem_cols *= 2;
