@@ -116,6 +116,14 @@ __device__ __forceinline__ Pack<__nv_bfloat16> unpack16<__nv_bfloat16>(const uin
   return r;
 }
 
+// the value a float becomes when it is stored as T and read back
+template <typename T>
+__device__ __forceinline__ float round_as(float x);
+template <>
+__device__ __forceinline__ float round_as<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float round_as<__nv_bfloat16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 template <typename T, bool HAS_B>
 __global__ void __launch_bounds__(256, 4)
 maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int N, int H, int W, int C,
@@ -125,6 +133,9 @@ maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restri
   constexpr int PN = Pack<T>::N;
   int CG = C / PN;
   long long total = (long long)N * Ho * Wo * CG;
+  float sa[PN], sb[PN];
+#pragma unroll
+  for (int e = 0; e < PN; ++e) { sa[e] = 0.f; sb[e] = 0.f; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int cg = (int)(i % CG);
@@ -166,16 +177,25 @@ maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restri
   }
 }
 
-template <typename T, bool HAS_B>
+// EXTRA: additionally (each optional) dxb = dx * LeakyReLU'(b) -- the pre-activation gradient of the branch b =
+// LeakyReLU(z_b) of pool(a + b), written here instead of by a separate pass over dx and b -- and the column
+// sums of dx (after the lrelu_mask, if any) / of dxb into colsum_a / colsum_b (fp32 [C], atomically added):
+// the bias gradients of the convolutions that produced a and b.  The launch makes gridDim * blockDim a
+// multiple of C / PN, so a thread keeps its channel group and sums in registers.
+template <typename T, bool HAS_B, bool EXTRA>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3)        // (8 raw vectors in flight with b: 3 blocks/SM would spill)
 maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ dy,
-                   T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask) {
+                   T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask,
+                   T* __restrict__ dxb, float* __restrict__ colsum_a, float* __restrict__ colsum_b) {
   // one thread per (output pixel, 16-byte channel group): the up to 8 input vectors of the window stay
   // RAW in registers (all loads issued before the first use), the window maximum is formed first, then
   // each position is re-widened, compared and stored (HBM-bound: registers buy loads in flight)
   constexpr int PN = Pack<T>::N;
   int CG = C / PN;
   long long total = (long long)N * Ho * Wo * CG;
+  float sa[PN], sb[PN];
+#pragma unroll
+  for (int e = 0; e < PN; ++e) { sa[e] = 0.f; sb[e] = 0.f; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int cg = (int)(i % CG);
@@ -233,6 +253,41 @@ maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __
         if (lrelu_mask) o.v[e] *= lrelu_slope(av.v[e]);
       }
       o.store(dx + off[k]);
+      if (EXTRA) {
+        // (the sums are formed from the values as STORED, i.e. rounded to T, like a separate pass would see them)
+        if (colsum_a) {
+#pragma unroll
+          for (int e = 0; e < PN; ++e) sa[e] += round_as<T>(o.v[e]);
+        }
+        if (HAS_B && dxb) {
+          const Pack<T> u = unpack16<T>(rb[k]);
+          Pack<T> ob;
+#pragma unroll
+          for (int e = 0; e < PN; ++e) ob.v[e] = o.v[e] * lrelu_slope(u.v[e]);
+          ob.store(dxb + off[k]);
+          if (colsum_b) {
+#pragma unroll
+            for (int e = 0; e < PN; ++e) sb[e] += round_as<T>(ob.v[e]);
+          }
+        }
+      }
+    }
+  }
+  if (EXTRA) {
+    __shared__ float red[2][512];
+    for (int c = threadIdx.x; c < 2 * 512; c += blockDim.x) (&red[0][0])[c] = 0.f;
+    __syncthreads();
+    // the thread's channel group is fixed: (gridDim * blockDim) % CG == 0
+    const int cg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % CG);
+#pragma unroll
+    for (int e = 0; e < PN; ++e) {
+      if (colsum_a) atomicAdd(&red[0][cg * PN + e], sa[e]);
+      if (colsum_b) atomicAdd(&red[1][cg * PN + e], sb[e]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (colsum_a) atomicAdd(colsum_a + c, red[0][c]);
+      if (colsum_b) atomicAdd(colsum_b + c, red[1][c]);
     }
   }
 }
@@ -1057,23 +1112,53 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
   return R2N2_OK;
 }
 
-int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
-                       int C, int lrelu_mask, int dtype, void* stream) {
-  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+int r2n2_maxpool2d_bwd_fused(const void* a, const void* b, const void* dy, void* dx, void* dxb, float* colsum_a,
+                             float* colsum_b, int N, int H, int W, int C, int lrelu_mask, int dtype, void* stream) {
+  const int pn = dtype == R2N2_BF16 ? 8 : 4;
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % pn) == 0,
                  R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd: C must be a multiple of 4 (fp32) / 8 (bf16), got %d", C);
+  R2N2_CHECK_ARG(b || (!dxb && !colsum_b), R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd: dxb / colsum_b need the branch b");
+  R2N2_CHECK_ARG(dxb || !colsum_b, R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd: colsum_b is the column sum of dxb");
   int Ho = H / 2 + 1, Wo = W / 2 + 1;
-  long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
+  long long total = (long long)N * Ho * Wo * (C / pn);
+  const bool extra = dxb || colsum_a || colsum_b;
+  unsigned grid = grid_for(total, 256);
+  if (extra) {
+    R2N2_CHECK_ARG(C <= 512, R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd: fused column sums support C <= 512, got %d", C);
+    // every thread must keep its channel group across the grid-stride loop: grid * 256 % (C / pn) == 0
+    int cg = C / pn, g = 256, r = cg;
+    while (r) { int t = g % r; g = r; r = t; }                 // g = gcd(256, cg)
+    const unsigned m = (unsigned)(cg / g);
+    // one wave of resident blocks (grid-stride): every block ends with C atomic adds per sum on the SAME C
+    // addresses, so 16 blocks per SM would serialise ~2400 atomics per address at L2
+    const unsigned wave = (unsigned)num_sms() * (b ? 2u : 3u);
+    if (grid > wave) grid = wave;
+    grid = (grid + m - 1) / m * m;
+  }
   R2N2_DISPATCH_DTYPE(dtype, T, {
     if (b) {
-      maxpool_bwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
+      if (extra)
+        maxpool_bwd_kernel<T, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, (T*)dxb, colsum_a, colsum_b);
+      else
+        maxpool_bwd_kernel<T, true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, nullptr, nullptr);
     } else {
-      maxpool_bwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask);
+      if (extra)
+        maxpool_bwd_kernel<T, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, colsum_a, nullptr);
+      else
+        maxpool_bwd_kernel<T, false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, nullptr, nullptr);
     }
   })
   R2N2_CHECK_LAUNCH("maxpool2d_bwd");
   return R2N2_OK;
+}
+
+int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
+                       int C, int lrelu_mask, int dtype, void* stream) {
+  return r2n2_maxpool2d_bwd_fused(a, b, dy, dx, nullptr, nullptr, nullptr, N, H, W, C, lrelu_mask, dtype, stream);
 }
 
 int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,

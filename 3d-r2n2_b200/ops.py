@@ -77,6 +77,7 @@ def _work(flops=0.0, tensors=()):
 
 WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
 FUSE_BIAS_GRAD = True     # bias gradients as column sums of the data-gradient epilogue that produces dy
+FUSE_POOL_BWD = True      # max-pool backward also writes the rectified branch's pre-activation gradient + bias sums
 ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
@@ -233,12 +234,22 @@ def maxpool_fwd(a, b, y, N, H, W, C):
     _call('r2n2_maxpool2d_fwd', _ptr(a), _ptr(b), _ptr(y), N, H, W, C, _DT[a.dtype], _stream())
 
 
-def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask):
-    for t in (a, b, dy, dx):
+def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
+    """dxb (optional, needs b): dx * LeakyReLU'(b) written by the same kernel; colsum_a / colsum_b (fp32 [C]):
+    += column sums of dx / dxb (the bias gradients of the layers that produced a and b)."""
+    for t in (a, b, dy, dx, dxb):
         _check(t)
-    _work(0.0, (a, b, dy, dx))
-    _call('r2n2_maxpool2d_bwd', _ptr(a), _ptr(b), _ptr(dy), _ptr(dx), N, H, W, C,
-          1 if lrelu_mask else 0, _DT[a.dtype], _stream())
+    for t in (colsum_a, colsum_b):
+        if t is not None:
+            _check(t, torch.float32)
+            assert t.numel() == C
+    _work(0.0, (a, b, dy, dx, dxb))
+    if dxb is None and colsum_a is None and colsum_b is None:
+        _call('r2n2_maxpool2d_bwd', _ptr(a), _ptr(b), _ptr(dy), _ptr(dx), N, H, W, C,
+              1 if lrelu_mask else 0, _DT[a.dtype], _stream())
+    else:
+        _call('r2n2_maxpool2d_bwd_fused', _ptr(a), _ptr(b), _ptr(dy), _ptr(dx), _ptr(dxb), _ptr(colsum_a),
+              _ptr(colsum_b), N, H, W, C, 1 if lrelu_mask else 0, _DT[a.dtype], _stream())
 
 
 def unpool_fwd(a, b, y, B, D, H, W, C):
@@ -607,8 +618,18 @@ class Ctx:
                 fuse = (b is None and a.lrelu_out and a.n_recv == 0 and a.n_cons == 1
                         and not out.grad_preact)
                 dx = torch.empty_like(a.data)
-                maxpool_bwd(a.data, None if b is None else b.data, out.grad, dx, N, H, W, C, fuse)
+
+                def bias_sum(x, final):
+                    # dx / dxb is the complete pre-activation gradient of x: its column sums are the bias
+                    # gradient of the convolution that produced x (no separate pass)
+                    if (final and FUSE_POOL_BWD and FUSE_BIAS_GRAD and x.bias is not None and not x.bias_done
+                            and x.bias.grad_written and x.n_recv == 0 and x.n_cons == 1):
+                        x.bias_done = True
+                        return x.bias.grad
+                    return None
                 if b is None:
+                    preact = fuse or out.grad_preact or not a.lrelu_out
+                    maxpool_bwd(a.data, None, out.grad, dx, N, H, W, C, fuse, colsum_a=bias_sum(a, preact))
                     if out.grad_preact:         # mask already applied downstream (on the max)
                         assert a.n_cons == 1
                         a.grad_preact = True
@@ -616,8 +637,20 @@ class Ctx:
                         a.grad_preact = True
                     self.accumulate(a, dx)
                 else:
-                    self.accumulate(a, dx, shared=b.requires_grad)
-                    self.accumulate(b, dx, shared=a.requires_grad)
+                    # pool(a + b): both branches receive dx; a rectified branch b that feeds nothing else gets its
+                    # pre-activation gradient dx * LeakyReLU'(b) from the same kernel
+                    split = (FUSE_POOL_BWD and b.requires_grad and b.lrelu_out and not b.grad_preact
+                             and b.n_recv == 0 and b.n_cons == 1)
+                    dxb = torch.empty_like(b.data) if split else None
+                    maxpool_bwd(a.data, b.data, out.grad, dx, N, H, W, C, False, dxb=dxb,
+                                colsum_a=bias_sum(a, not a.lrelu_out), colsum_b=bias_sum(b, True) if split else None)
+                    if split:
+                        self.accumulate(a, dx)
+                        b.grad_preact = True
+                        self.accumulate(b, dxb)
+                    else:
+                        self.accumulate(a, dx, shared=b.requires_grad)
+                        self.accumulate(b, dx, shared=a.requires_grad)
                 out.grad = None
             self.tape.append(bwd)
         return out

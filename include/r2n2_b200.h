@@ -138,6 +138,14 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
 int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, int N, int H, int W,
                        int C, int lrelu_mask, int dtype, void* stream);
 
+/* The same backward pass with what follows it in the graph fused in (each pointer optional):
+ * dxb      = dx * LeakyReLU'(b): the gradient w.r.t. the pre-activation of the branch b = LeakyReLU(z_b) of
+ *            pool(a + b) (res_gru_net.py:100-140: a = 1x1 shortcut, b = rectified 3x3 branch); needs b;
+ * colsum_a = fp32 [C] += column sums of dx (after lrelu_mask), colsum_b += column sums of dxb: the bias
+ *            gradients of the convolutions that produced a and b (atomic adds: zero or accumulate-into). */
+int r2n2_maxpool2d_bwd_fused(const void* a, const void* b, const void* dy, void* dx, void* dxb, float* colsum_a,
+                             float* colsum_b, int N, int H, int W, int C, int lrelu_mask, int dtype, void* stream);
+
 /* Unpool3DLayer (lib/layers.py:375-385): y[B,2D,2H,2W,C], value at the even corner, zeros
  * elsewhere; input is a+b if b != NULL (AddLayer res7/res8, models/res_gru_net.py:171-178). */
 int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,

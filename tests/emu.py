@@ -131,7 +131,7 @@ def maxpool_fwd(a, b, y, N, H, W, C):
     y.copy_(F.max_pool2d(s, 2, 2, 1).permute(0, 2, 3, 1).reshape(-1).to(y.dtype))
 
 
-def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask):
+def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
     s = _pool_in(a, b, N, H, W, C)
     Ho, Wo = H // 2 + 1, W // 2 + 1
     sp = F.pad(s, (0, 0, 1, 2 * Wo - W - 1, 1, 2 * Ho - H - 1), value=float('-inf'))
@@ -144,6 +144,14 @@ def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask):
         av = _f(a).view(N, H, W, C)
         d = d * torch.where(av > 0, torch.ones_like(av), torch.full_like(av, LEAK))
     dx.copy_(d.reshape(-1).to(dx.dtype))
+    if colsum_a is not None:                        # sums of the values as stored
+        colsum_a += _f(dx).view(-1, C).sum(0).to(colsum_a.dtype)
+    if dxb is not None:
+        bv = _f(b).view(N, H, W, C)
+        db = d * torch.where(bv > 0, torch.ones_like(bv), torch.full_like(bv, LEAK))
+        dxb.copy_(db.reshape(-1).to(dxb.dtype))
+        if colsum_b is not None:
+            colsum_b += _f(dxb).view(-1, C).sum(0).to(colsum_b.dtype)
 
 
 def unpool_fwd(a, b, y, B, D, H, W, C):

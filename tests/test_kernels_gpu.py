@@ -117,6 +117,42 @@ def test_dgrad_equals_autograd():
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_pool_bwd_fused(dtype):
+    """r2n2_maxpool2d_bwd_fused: the rectified branch's pre-activation gradient and both bias sums from the
+    pool-backward kernel itself == the separate passes (LeakyReLU', column sums) over its outputs."""
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    for (N, H, W, C) in [(2, 64, 64, 96), (3, 33, 33, 128), (2, 9, 9, 256), (5, 127, 127, 96), (1, 3, 3, 8), (2, 17, 17, 40)]:
+        a, b = _r(N * H * W * C, seed=1).to(dtype), _r(N * H * W * C, seed=2).to(dtype)
+        Ho, Wo = H // 2 + 1, W // 2 + 1
+        dy = _r(N * Ho * Wo * C, seed=3).to(dtype)
+        for bb, mask in ((b, False), (None, True), (None, False)):
+            wdx, wdxb = torch.empty_like(a), (torch.empty_like(a) if bb is not None else None)
+            wsa, wsb = torch.full((C,), 0.5), (torch.full((C,), -0.25) if bb is not None else None)
+            emu.maxpool_bwd(a, bb, dy, wdx, N, H, W, C, mask, wdxb, wsa, wsb)
+            dx = torch.full_like(a, float('nan'), device=DEV)
+            dxb = torch.full_like(a, float('nan'), device=DEV) if bb is not None else None
+            sa = torch.full((C,), 0.5, device=DEV)                 # the sums ACCUMULATE into the buffers
+            sb = torch.full((C,), -0.25, device=DEV) if bb is not None else None
+            ops.maxpool_bwd(a.to(DEV), None if bb is None else bb.to(DEV), dy.to(DEV), dx, N, H, W, C, mask,
+                            dxb, sa, sb)
+            _cmp(dx, wdx, tol, 'fused pool bwd dx')
+            scale = max(1.0, float(wsa.abs().max()))
+            assert (sa.cpu() - wsa).abs().max().item() <= 2e-3 * scale, 'colsum_a'
+            if bb is not None:
+                _cmp(dxb, wdxb, tol, 'fused pool bwd dxb')
+                assert (sb.cpu() - wsb).abs().max().item() <= 2e-3 * max(1.0, float(wsb.abs().max())), 'colsum_b'
+            # only the column sum of a (no second output)
+            dx2 = torch.empty_like(dx)
+            sa2 = torch.zeros(C, device=DEV)
+            ops.maxpool_bwd(a.to(DEV), None if bb is None else bb.to(DEV), dy.to(DEV), dx2, N, H, W, C, mask,
+                            None, sa2, None)
+            assert torch.equal(dx2, dx)
+            assert (sa2.cpu() + 0.5 - wsa).abs().max().item() <= 2e-3 * scale
+    with pytest.raises(RuntimeError):
+        ops.maxpool_bwd(a.to(DEV), None, dy.to(DEV), dx, N, H, W, C, False, torch.empty_like(dx), None, None)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_pool_unpool(dtype):
     tol = 1e-6 if dtype == torch.float32 else 1e-2
     for (N, H, W, C) in [(2, 127, 127, 8), (3, 33, 33, 16), (2, 5, 5, 256), (1, 3, 3, 4), (1, 64, 64, 96)]:
