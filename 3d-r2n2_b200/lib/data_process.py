@@ -239,9 +239,11 @@ def batch_to_device(batch_img, batch_voxel, stream=None, staging=None, out_dtype
                 pr = pr[:batch_img.rgba.size].view(n, Hs, Ws, 4)
                 pp = pp[:n * 6].view(n, 6)
                 po = po[:batch_voxel.size].view(batch_voxel.shape)
-                pr.copy_(torch.from_numpy(batch_img.rgba).view(n, Hs, Ws, 4))
-                pp.copy_(torch.from_numpy(batch_img.params).view(n, 6))
-                po.copy_(torch.from_numpy(np.ascontiguousarray(batch_voxel, dtype=np.uint8)))
+                # plain single-threaded memcpy into the pinned views: torch's copy_ would fan the 13.5 MB out
+                # over every host core in every rank's staging thread and starve the launching threads
+                np.copyto(pr.numpy(), batch_img.rgba.reshape(n, Hs, Ws, 4))
+                np.copyto(pp.numpy(), batch_img.params.reshape(n, 6))
+                np.copyto(po.numpy(), np.asarray(batch_voxel, dtype=np.uint8))
             else:
                 pr = torch.from_numpy(batch_img.rgba).view(n, Hs, Ws, 4)
                 pp = torch.from_numpy(batch_img.params).view(n, 6)
