@@ -12,9 +12,9 @@ echo "ncu launches exit $?" >> gpurun_out/ncu_launches.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fwd_umma_persistent -s 3 -c 1 \
     -o gpurun_out/ncu_conv2b_fwd $CMD > gpurun_out/ncu_full1.log 2>&1
 echo "ncu full1 exit $?" >> gpurun_out/ncu_full1.log
-# flat-halo forward: launch 0 = conv1b, launch 1 = conv10b
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fwd3_umma -s 1 -c 1 \
-    -o gpurun_out/ncu_conv10b_fwd3 $CMD > gpurun_out/ncu_full2.log 2>&1
+# flat-halo forward: launches 0-4 = conv1b (one per view), 5 = conv9b (dx-stacked), 6 = conv10a (dx-stacked), 7 = conv10b
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fwd3_umma -s 5 -c 1 \
+    -o gpurun_out/ncu_conv9b_fwd3_stk $CMD > gpurun_out/ncu_full2.log 2>&1
 echo "ncu full2 exit $?" >> gpurun_out/ncu_full2.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_umma_kernel -s 30 -c 1 \
     -o gpurun_out/ncu_wgrad_v1 $CMD > gpurun_out/ncu_full3.log 2>&1
