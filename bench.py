@@ -13,6 +13,9 @@ Printed JSON (rank 0, one line):
   value   : samples/s, whole job, inputs resident in HBM (CUDA-event timed, max over ranks)
   e2e     : same metric through Solver.train_loss with HOST (pinned) numpy inputs: H2D of x,y and
             D2H of the loss inside the timed region
+  e2e_raw_pipeline: same, fed by lib/data_process.DeviceBatchQueue from host uint8 RGBA renders (what
+            lib/train_net.train_net() runs): H2D of 14.7 MB instead of 44.3 MB, preprocessing kernels included
+  infer   : 1-view inference latencies (the second half of BASELINE.json's metric), CUDA-graph replay
   roofline: dominant kernel (implicit-GEMM conv fwd/dgrad), algorithmic (useful) FLOPs / CUDA-event
             time of its launches, against MEASURED_PEAKS.json
   cpu_baseline: the oracle's torch-CPU restatement of the reference graph timed on the host cores
