@@ -15,6 +15,8 @@ re-scheduled B200-first:
 import math
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib as L
@@ -670,8 +672,19 @@ class Engine:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self.forward(sx, sy, training=False)
+            # thread-local capture mode: the input pipeline's staging thread (lib/data_process.DeviceBatchQueue)
+            # allocates pinned / device memory and copies on its own stream while e.g. a validation pass is being
+            # captured here; under the default global mode any such call from another thread invalidates the capture
+            import gc
+            gc_was = gc.isenabled()
+            if os.environ.get('R2N2_GRAPH_GC_OFF', '1') != '0':
+                gc.disable()            # a cyclic-GC pass inside the capture could destroy old graphs / pools (cudaFree)
+            try:
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    out = self.forward(sx, sy, training=False)
+            finally:
+                if gc_was:
+                    gc.enable()
             self.ctx = None
             ent = dict(graph=g, x=sx, y=sy, out=out, version=self.store.version)
             self._graphs[key] = ent

@@ -12,6 +12,7 @@ r2n2_preprocess_views / r2n2_voxel_labels there, so `get()` hands `Solver.train`
 
 Class and function names, constructor arguments and the shutdown protocol are the reference's."""
 import ctypes
+import os
 import queue as _queue
 import sys
 import threading
@@ -28,14 +29,29 @@ from .data_io import get_rendering_file, get_voxel_file
 
 
 def print_error(func):
-    '''Flush out error messages. Mainly used for debugging separate processes (lib/data_process.py:19-29).'''
+    '''Flush out error messages. Mainly used for debugging separate processes (lib/data_process.py:19-29).
 
-    def func_wrapper(*args, **kwargs):
+    In a forked worker the function never returns: the trainer has usually initialised CUDA before it starts
+    the workers, so the child carries a copy of the parent's CUDA state that must not be torn down by the
+    interpreter's exit handlers (they ran driver calls on inherited handles while the parent was capturing a
+    CUDA graph and invalidated the capture).  The child flushes its queue and leaves through os._exit.'''
+
+    def func_wrapper(self, *args, **kwargs):
         try:
-            return func(*args, **kwargs)
+            return func(self, *args, **kwargs)
         except Exception:
             traceback.print_exception(*sys.exc_info())
             sys.stdout.flush()
+        finally:
+            if getattr(self, '_parent_pid', None) not in (None, os.getpid()):      # running as the child process
+                try:
+                    sys.stdout.flush()
+                    q = self.data_queue
+                    if hasattr(q, 'close') and hasattr(q, 'join_thread'):
+                        q.close()
+                        q.join_thread()                                            # everything put() reaches the pipe
+                finally:
+                    os._exit(0)
 
     return func_wrapper
 

@@ -23,6 +23,16 @@ from test_data_process import RUNS, golden, raw_batches, restore_cfg  # noqa: F4
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def no_leftover_pipeline_threads():
+    """Every DeviceBatchQueue must be closed by its user: a staging thread that outlives its test would keep
+    allocating / copying behind later tests (and CUDA-graph captures)."""
+    yield
+    import threading
+    left = [t.name for t in threading.enumerate() if t.name.startswith('r2n2-device-batch-queue') and t.is_alive()]
+    assert not left, 'staging threads still alive: %s' % left
+
+
 def test_voxel_labels_kernel():
     r = np.random.RandomState(3)
     for B, nv in ((1, 32), (5, 32), (3, 7)):
@@ -154,3 +164,24 @@ def test_train_net_and_test_net_entry_points(tmp_path, restore_cfg):  # noqa: F8
         for k, v in keep.items():
             cfg.TRAIN[k] = v
         cfg.CONST.NETWORK_CLASS, cfg.CONST.WEIGHTS, cfg.DIR.OUT_PATH, cfg.TEST.DATASET_PORTION = keep_c
+
+
+def test_graph_capture_while_pipeline_thread_runs(tmp_path, restore_cfg):  # noqa: F811
+    """Solver.train validates through Solver.test_output, whose first call per view count captures a CUDA graph,
+    while the training queue's staging thread keeps allocating and copying: the capture must survive it."""
+    _, items = raw_batches('train', tmp_path)
+    q = queue.Queue()
+    for it in items * 40:
+        q.put(it)
+    dq = data_process.DeviceBatchQueue(q, depth=2)
+    try:
+        cfg.CONST.BATCH_SIZE = 4
+        net = load_model('GRUNet')()
+        solver = Solver(net)
+        for k in range(6):
+            x, y = dq.get(timeout=60)                       # keeps the thread busy between captures
+            T = 1 + k % 3                                   # three different view counts: three captures
+            pred, loss, _ = solver.test_output(x[:T].contiguous(), y)
+            assert np.isfinite(pred).all() and np.isfinite(loss)
+    finally:
+        dq.close()
