@@ -97,9 +97,10 @@ def synthetic_batch(np, T, B, seed_x=1234, seed_y=4321, n_vox=32, img=127):
 
 
 # ------------------------------------------------------------------------------- CPU reference
-def cpu_reference_step(net_name, B, T, n_steps, warmup):
+def cpu_reference_step(net_name, B, T, n_steps, warmup, min_seconds=0.0):
     """Times training steps of the oracle's torch-CPU restatement of the reference graph
-    (oracle/ref_torch.py: per-view encoder inside the loop, dense convs on zero-stuffed tensors)."""
+    (oracle/ref_torch.py: per-view encoder inside the loop, dense convs on zero-stuffed tensors).
+    min_seconds > 0: keep stepping past n_steps until that much timed CPU work has been done."""
     import torch
     from oracle import ref_torch as rt
     torch.set_num_threads(os.cpu_count() or 1)
@@ -108,12 +109,14 @@ def cpu_reference_step(net_name, B, T, n_steps, warmup):
     net = rt.RefNet(net_name, params)
     adam = rt.RefAdam(net, lr=1e-4)
     times = []
-    for i in range(warmup + n_steps):
+    i = 0
+    while i < warmup + n_steps or (sum(times) < min_seconds and len(times) < 64):
         t0 = time.perf_counter()
         adam.step(x, y)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        i += 1
     return times, torch.get_num_threads()
 
 
@@ -122,8 +125,8 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.cpu_sample_batch
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    steps = max(1, min(args.steps, 240))          # K steps as asked (0.5 s each at batch 2); capped at ~2 minutes
+    warm = max(0, min(args.warmup, 10))
     times, cores = cpu_reference_step(args.net, B, args.views, steps, warm)
     ms = 1e3 * sum(times) / len(times)
     val = B / (ms / 1e3)
@@ -338,11 +341,12 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_sample_batch
-        times, cores = cpu_reference_step(args.net, Bc, T, 1, 1)
+        times, cores = cpu_reference_step(args.net, Bc, T, 3, 1, min_seconds=10.0)
         v = Bc / (sum(times) / len(times))
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': 'oracle torch-CPU fp32 restatement of the reference graph: 1 warm-up + 1 timed '
-                         'training step at batch %d, %d views (batch reduced from %d)' % (Bc, T, B)}
+               'sample': 'oracle torch-CPU fp32 restatement of the reference graph: 1 warm-up + %d timed training '
+                         'steps (%.1f s of CPU work) at batch %d, %d views (batch reduced from %d)'
+                         % (len(times), sum(times), Bc, T, B)}
 
     # ---- 1-view inference latency (second half of BASELINE.json's metric; rank 0, N=1 only) ---------
     infer = None
