@@ -308,21 +308,20 @@ class DeviceBatchQueue(object):
             return None, None
         T, B, Hs, Ws, _ = batch_img.rgba.shape
         need = (max(T, cfg.CONST.N_VIEWS) * B * Hs * Ws * 4, max(T, cfg.CONST.N_VIEWS) * B * 6, batch_voxel.size)
-        if len(self._slots) < self.depth + 1:
-            bufs = (torch.empty(need[0], dtype=torch.uint8).pin_memory(),
+        def alloc():
+            return (torch.empty(need[0], dtype=torch.uint8).pin_memory(),
                     torch.empty(need[1], dtype=torch.int32).pin_memory(),
                     torch.empty(need[2], dtype=torch.uint8).pin_memory())
-            self._slots.append([bufs, None])
-            slot = self._slots[-1]
-        else:
-            slot = self._slots.pop(0)
-            self._slots.append(slot)
-            if slot[1] is not None:
-                slot[1].synchronize()         # the copies out of this pinned slot have finished
-            if any(b.numel() < n for b, n in zip(slot[0], need)):
-                slot[0] = (torch.empty(need[0], dtype=torch.uint8).pin_memory(),
-                           torch.empty(need[1], dtype=torch.int32).pin_memory(),
-                           torch.empty(need[2], dtype=torch.uint8).pin_memory())
+        if not self._slots:
+            # the whole ring at once, on the first batch: page-locking 13.5 MB takes milliseconds and must not
+            # land in the middle of later steps
+            self._slots = [[alloc(), None] for _ in range(self.depth + 1)]
+        slot = self._slots.pop(0)
+        self._slots.append(slot)
+        if slot[1] is not None:
+            slot[1].synchronize()             # the copies out of this pinned slot have finished
+        if any(b.numel() < n for b, n in zip(slot[0], need)):
+            slot[0] = alloc()
         return slot[0], slot
 
     def _work(self):
