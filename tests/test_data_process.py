@@ -117,3 +117,16 @@ def test_bad_render_size_is_reported(tmp_path, restore_cfg):
     proc = data_process.ReconstructionDataProcess(ListQueue(), pairs, repeat=False, train=False)
     with pytest.raises(ValueError):
         proc.make_batch()
+
+
+def test_device_queue_needs_cuda():
+    """No CPU fallback: the trainer-side half of the pipeline refuses to run without a CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    with pytest.raises(RuntimeError):
+        data_process.DeviceBatchQueue(ListQueue())
+    views = data_process.RawViews(np.zeros((1, 1, 137, 137, 4), np.uint8), np.zeros((1, 1, 6), np.int32))
+    assert views.shape == (1, 1, 3, 127, 127)
+    with pytest.raises(RuntimeError):
+        data_process.batch_to_device(views, np.zeros((1, 32, 32, 32), np.uint8))
