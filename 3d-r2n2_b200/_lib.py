@@ -25,6 +25,7 @@ PROTOTYPES = {
     'r2n2_bias_grad': [_p, _p, _ll, _i, _i, _i, _p],
     'r2n2_weight_transpose': [_p, _p, _i, _i, _i, _i, _p],
     'r2n2_weight_transpose_batch': [_p, _p, _p, _i, _ll, _i, _p],
+    'r2n2_weight_transpose_batch_bf16': [_p, _p, _p, _i, _ll, _p],
     'r2n2_cast': [_p, _p, _ll, _i, _p],
     'r2n2_nchw_to_nhwc': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_nchw_to_rowpack': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -810,6 +810,46 @@ __global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T*
   }
 }
 
+// Same, from the bf16 operand mirror (identical layout and offsets as the fp32 master buffer): half the read
+// traffic, 64 x 64 tiles (128-byte segments both ways, a quarter of the blocks of the fp32 version).
+__global__ void weight_transpose_batch_bf16_kernel(const __nv_bfloat16* __restrict__ base,
+                                                   __nv_bfloat16* __restrict__ wt_base,
+                                                   const long long* __restrict__ table, int n) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long bid = blockIdx.x;
+  int e = 0;
+  while (e + 1 < n && __ldg(table + (e + 1) * 6 + 5) <= bid) ++e;
+  const long long* row = table + e * 6;
+  const __nv_bfloat16* w = base + __ldg(row + 0);
+  __nv_bfloat16* wt = wt_base + __ldg(row + 1);
+  const int Cout = (int)__ldg(row + 2), taps = (int)__ldg(row + 3), Cin = (int)__ldg(row + 4);
+  long long local = bid - __ldg(row + 5);
+  const int tiles_ci = (Cin + 63) / 64, tiles_co = (Cout + 63) / 64;
+  const int ci0 = (int)(local % tiles_ci) * 64; local /= tiles_ci;
+  const int co0 = (int)(local % tiles_co) * 64; local /= tiles_co;
+  const int t = (int)local;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int co = co0 + j, ci = ci0 + 2 * threadIdx.x;
+    __nv_bfloat162 v = __halves2bfloat162(zero, zero);
+    if (co < Cout && ci + 1 < Cin) {
+      v = *reinterpret_cast<const __nv_bfloat162*>(w + ((long long)co * taps + t) * Cin + ci);   // (Cin even, ci even)
+    } else if (co < Cout && ci < Cin) {
+      v = __halves2bfloat162(w[((long long)co * taps + t) * Cin + ci], zero);
+    }
+    tile[j][2 * threadIdx.x] = __low2bfloat16(v);
+    tile[j][2 * threadIdx.x + 1] = __high2bfloat16(v);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 64; j += 8) {
+    const int ci = ci0 + j, co = co0 + 2 * threadIdx.x;
+    if (ci >= Cin || co >= Cout) continue;
+    __nv_bfloat16* dst = wt + ((long long)ci * taps + (taps - 1 - t)) * Cout + co;
+    if (co + 1 < Cout) *reinterpret_cast<__nv_bfloat162*>(dst) = __halves2bfloat162(tile[2 * threadIdx.x][j], tile[2 * threadIdx.x + 1][j]);
+    else dst[0] = tile[2 * threadIdx.x][j];
+  }
+}
+
 // ------------------------------------------------------------------ optimisers
 template <typename TM, bool kMirror>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -1387,6 +1427,18 @@ int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long lon
         base, (T*)wt_base, table, n_entries);
   })
   R2N2_CHECK_LAUNCH("weight_transpose_batch");
+  return R2N2_OK;
+}
+
+int r2n2_weight_transpose_batch_bf16(const void* mirror_base, void* wt_base, const long long* table, int n_entries,
+                                     long long total_tiles, void* stream) {
+  R2N2_CHECK_ARG(mirror_base && wt_base && table && n_entries > 0 && total_tiles > 0 && total_tiles < (1LL << 31),
+                 R2N2_ERR_BAD_SHAPE, "weight_transpose_batch_bf16: bad arguments");
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(mirror_base) & 3) == 0 && (reinterpret_cast<uintptr_t>(wt_base) & 3) == 0,
+                 R2N2_ERR_BAD_ALIGN, "weight_transpose_batch_bf16: buffers must be 4-byte aligned");
+  weight_transpose_batch_bf16_kernel<<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)mirror_base, (__nv_bfloat16*)wt_base, table, n_entries);
+  R2N2_CHECK_LAUNCH("weight_transpose_batch_bf16");
   return R2N2_OK;
 }
 

@@ -77,6 +77,7 @@ def _work(flops=0.0, tensors=()):
 
 WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
 FUSE_BIAS_GRAD = True     # bias gradients as column sums of the data-gradient epilogue that produces dy
+TRANSPOSE_FROM_MIRROR = True   # data-gradient operands are transposed from the bf16 mirror (half the reads)
 FUSE_POOL_BWD = True      # max-pool backward also writes the rectified branch's pre-activation gradient + bias sums
 ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
@@ -184,6 +185,16 @@ class TransposeBatch:
             tiles += ((p.cin + 31) // 32) * ((p.cout + 63) // 64) * p.taps
         self.total_tiles = tiles
         self.table = torch.tensor(rows, dtype=torch.int64, device=store.p.device)
+        # from the bf16 mirror (same offsets): 64 x 64 tiles, needs even offsets / channel counts
+        self.table64 = None
+        if (dt == torch.bfloat16 and TRANSPOSE_FROM_MIRROR
+                and all(r[0] % 2 == 0 and r[1] % 2 == 0 and r[2] % 2 == 0 and r[4] % 2 == 0 for r in rows)):
+            rows64, tiles64 = [], 0
+            for r in rows:
+                rows64.append(r[:5] + [tiles64])
+                tiles64 += ((r[4] + 63) // 64) * ((r[2] + 63) // 64) * r[3]
+            self.total_tiles64 = tiles64
+            self.table64 = torch.tensor(rows64, dtype=torch.int64, device=store.p.device)
         self.wt_all = torch.empty(dst, dtype=dt, device=store.p.device)
         for p, r in zip(params, rows):
             p.wt = self.wt_all[r[1]:r[1] + p.data.numel()]
@@ -192,10 +203,16 @@ class TransposeBatch:
 
     def ensure(self):
         if self.version != self.store.version:
-            _check(self.store.p, torch.float32)
-            _work(0.0, (self.store.p, self.wt_all))
-            _call('r2n2_weight_transpose_batch', _ptr(self.store.p), _ptr(self.wt_all), _ptr(self.table),
-                  len(self.params), self.total_tiles, _DT[self.wt_all.dtype], _stream())
+            if self.table64 is not None:
+                _check(self.store.mirror, torch.bfloat16)
+                _work(0.0, (self.store.mirror, self.wt_all))
+                _call('r2n2_weight_transpose_batch_bf16', _ptr(self.store.mirror), _ptr(self.wt_all),
+                      _ptr(self.table64), len(self.params), self.total_tiles64, _stream())
+            else:
+                _check(self.store.p, torch.float32)
+                _work(0.0, (self.store.p, self.wt_all))
+                _call('r2n2_weight_transpose_batch', _ptr(self.store.p), _ptr(self.wt_all), _ptr(self.table),
+                      len(self.params), self.total_tiles, _DT[self.wt_all.dtype], _stream())
             self.version = self.store.version
 
 

@@ -113,6 +113,12 @@ int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin,
 int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long long* table, int n_entries,
                                 long long total_tiles, int out_dtype, void* stream);
 
+/* The same from the bf16 operand mirror (same layout / element offsets as the fp32 master buffer; every segment
+ * offset, Cin and Cout even): table[e][5] = first tile of the entry under a 64 (co) x 64 (ci) tiling, i.e.
+ * ceil(Cin/64) * ceil(Cout/64) * taps tiles per entry.  Bit-identical output, half the read traffic. */
+int r2n2_weight_transpose_batch_bf16(const void* mirror_base, void* wt_base, const long long* table, int n_entries,
+                                     long long total_tiles, void* stream);
+
 /* fp32 -> out_dtype copy (bf16 operand mirrors of the fp32 master weights). */
 int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream);
 

@@ -230,6 +230,24 @@ def test_pointwise_and_layout():
             want = torch.empty(t_.numel())
             emu.weight_transpose(t_, want, co, tp, ci)
             _cmp(out[r_[1]:r_[1] + t_.numel()], want.to(dt), 0.0, 'weight_transpose_batch')
+    # the same from a bf16 mirror (64 x 64 tiles; even offsets and channel counts): bit-identical to the fp32-source path
+    shapes = [(10, 27, 12), (96, 9, 96), (34, 1, 70), (128, 27, 16), (200, 1, 1024), (2, 27, 32), (64, 1, 64)]
+    flat, rows, dst, tiles = [], [], 0, 0
+    for i, (co, tp, ci) in enumerate(shapes):
+        t_ = _r(co * tp * ci, seed=40 + i)
+        rows.append([sum(x.numel() for x in flat), dst, co, tp, ci, tiles])
+        flat.append(t_)
+        dst += (co * tp * ci + 63) // 64 * 64
+        tiles += ((ci + 63) // 64) * ((co + 63) // 64) * tp
+    mirror = torch.cat(flat).to(torch.bfloat16).to(DEV)
+    out = torch.full((dst,), float('nan'), dtype=torch.bfloat16, device=DEV)
+    table = torch.tensor(rows, dtype=torch.int64, device=DEV)
+    L.call('r2n2_weight_transpose_batch_bf16', mirror.data_ptr(), out.data_ptr(), table.data_ptr(), len(rows), tiles, None)
+    for (co, tp, ci), r_, t_ in zip(shapes, rows, flat):
+        want = torch.empty(t_.numel())
+        emu.weight_transpose(t_.to(torch.bfloat16).float(), want, co, tp, ci)
+        got = out[r_[1]:r_[1] + t_.numel()].float().cpu()
+        assert torch.equal(got, want), 'weight_transpose_batch_bf16 %s' % ((co, tp, ci),)
     # flat kernel (C/vector <= 256 vectors per row), ragged row counts, and the generic kernel
     for rows, C in [(1000, 96), (77, 2), (3, 1024), (5000, 256), (40003, 32), (12345, 64), (999, 16),
                     (2, 4096), (70001, 128)]:
