@@ -817,6 +817,12 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   p.ci_cols = (p.ci_tile + 31) / 32 * 32;
   p.G = 512 / p.ci_cols;
   if (p.G > p.taps) p.G = p.taps;
+  // same number of tap groups, evenly filled: 9 taps at G = 4 would be groups of 4, 4, 1 (the CTAs of the
+  // last group idle 3/4 of the time); 3, 3, 3 is the same grid with 25 % less work on the critical CTAs
+  if (!getenv("R2N2_WGRAD_NO_BALANCE")) {
+    const int groups = (p.taps + p.G - 1) / p.G;
+    p.G = (p.taps + groups - 1) / groups;
+  }
   const int co_tiles = (Cout + 127) / 128;
   // bytes per K row (pixel) in one stage
   const int a_row = ((Cout < 128 ? Cout : 128) + p.cw_a - 1) / p.cw_a * p.cw_a * 2;
