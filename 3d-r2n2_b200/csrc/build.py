@@ -1,4 +1,5 @@
 """Build libr2n2_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -13,25 +14,45 @@ if os.environ.get('R2N2_PTXAS_V'):
     NVCC_FLAGS += ['-Xptxas', '-v']
 
 
-def needs_build():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cu', '.cuh'))]
+HASH_FILE = OUT + '.srchash'
+last_action = None       # 'compiled' / 'reused' (what the last build() call did)
+
+
+def source_hash():
+    """sha256 over every .cu / .cuh source, the public header and the compile flags: the library embeds it
+    (r2n2_version()) and the sidecar file records it, so a stale prebuilt .so is never reused silently."""
+    deps = sorted(os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cu', '.cuh')))
     deps.append(os.path.join(os.path.dirname(PKG), 'include', 'r2n2_b200.h'))
-    return any(os.path.getmtime(d) > t for d in deps)
+    h = hashlib.sha256()
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    h.update(' '.join(f for f in NVCC_FLAGS if f != '-v' and f != '-Xptxas').encode())
+    return h.hexdigest()[:16]
+
+
+def needs_build():
+    if not os.path.exists(OUT) or not os.path.exists(HASH_FILE):
+        return True
+    with open(HASH_FILE) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
+    global last_action
     if not force and not needs_build():
+        last_action = 'reused'
         return OUT
+    last_action = 'compiled'
+    src_hash = source_hash()
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
     procs = []
     for s in SOURCES:
         o = os.path.join(HERE, s.replace('.cu', '.o'))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(HERE, s), '-o', o]
+        cmd = [nvcc] + NVCC_FLAGS + ['-DR2N2_SRC_HASH="%s"' % src_hash, '-c', os.path.join(HERE, s), '-o', o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -41,6 +62,8 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
     cmd = [nvcc, '-shared', '-o', OUT] + objs + ['-cudart', 'shared']
     subprocess.check_call(cmd)
+    with open(HASH_FILE, 'w') as f:
+        f.write(src_hash + '\n')
     return OUT
 
 

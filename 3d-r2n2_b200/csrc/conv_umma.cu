@@ -260,13 +260,19 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// one sticky error word PER DEVICE (a process may drive several GPUs; the word must live on the
+// device whose kernels write it)
 int* get_err_word() {
-  static int* w = nullptr;
-  if (!w) {
+  static int* words[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!words[dev]) {
+    int* w = nullptr;
     if (cudaMalloc(&w, sizeof(int)) != cudaSuccess) return nullptr;
     cudaMemset(w, 0, sizeof(int));
+    words[dev] = w;
   }
-  return w;
+  return words[dev];
 }
 
 // choose the spatial box (bw,bh,bd,bn), product <= 128, minimising the number of M tiles

@@ -1096,7 +1096,10 @@ using namespace r2n2;
 // ====================================================================== C ABI
 extern "C" {
 
-const char* r2n2_version(void) { return "r2n2_b200 0.1 (sm_100a)"; }
+#ifndef R2N2_SRC_HASH
+#define R2N2_SRC_HASH "unhashed"
+#endif
+const char* r2n2_version(void) { return "r2n2_b200 0.2 (sm_100a) src " R2N2_SRC_HASH; }
 const char* r2n2_last_error(void) { return r2n2::g_err; }
 
 int r2n2_fill_zero(void* p, long long bytes, void* stream) {

@@ -78,7 +78,94 @@ def attach(solver, group=None):
     sync = GradSync(solver.net.engine, group)
     solver.grad_sync = sync
     solver.net.engine.progress = sync.stage_done
+    solver.rank = dist.get_rank(group) if dist.is_initialized() else 0
+    solver.world = sync.world
+    solver.dist_group = group
     return sync
+
+
+def init_from_env(backend=None):
+    """Join the process group a launcher (torchrun: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*) describes.
+    Returns (rank, world, local_rank); (0, 1, 0) and no group when the process was started alone."""
+    import os
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return 0, 1, 0
+    rank, local = int(os.environ['RANK']), int(os.environ.get('LOCAL_RANK', '0'))
+    if not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard(items, rank, world):
+    """Rank `rank`'s share of a dataset list: every world-th item (disjoint, covering, sizes differ by <= 1)."""
+    return list(items)[rank::world]
+
+
+def shared_seed(seed, group=None):
+    """Rank 0's `seed` on every rank (one small broadcast at start-up)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return int(seed)
+    box = [int(seed)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return int(box[0])
+
+
+class SharedViewCountQueue(object):
+    """Queue wrapper that gives every rank the SAME number of views per step.
+
+    The reference draws the view count of a batch inside the data worker (lib/data_process.py:127-130:
+    `np.random.randint(n_views) + 1`, then `np.random.choice(NUM_RENDERING, curr_n_views)` per sample).  With
+    one process per GPU the ranks' workers would draw different counts, and the recurrence length must agree
+    across ranks for the bucketed gradient all-reduce to line up step by step.  Here the workers always decode
+    N_VIEWS renders (cfg.TRAIN.RANDOM_NUM_VIEWS off in the workers) and the trainer keeps the first T_k of them,
+    T_k ~ U{1..N_VIEWS} drawn from a RandomState seeded with one broadcast seed: the first T of N i.i.d.
+    rendering ids are T i.i.d. rendering ids, so the distribution of a rank's batch is the reference's."""
+
+    def __init__(self, data_queue, seed, n_views, random_num_views=True):
+        import numpy as np
+        self.data_queue = data_queue
+        self.n_views = int(n_views)
+        self.random_num_views = random_num_views
+        self._rs = np.random.RandomState(int(seed) % (2 ** 32))
+        self.counts = []                    # drawn schedule (tests / logging)
+
+    def next_count(self):
+        t = int(self._rs.randint(self.n_views)) + 1 if self.random_num_views else self.n_views
+        self.counts.append(t)
+        return t
+
+    def get(self, *args, **kwargs):
+        batch_img, batch_voxel = self.data_queue.get(*args, **kwargs)
+        t = self.next_count()
+        have = batch_img.shape[0]
+        if have < t:
+            raise ValueError('worker batch holds %d views, the shared schedule asks for %d '
+                             '(workers must run with TRAIN.RANDOM_NUM_VIEWS off)' % (have, t))
+        if hasattr(batch_img, 'rgba'):      # lib/data_process.RawViews
+            batch_img = type(batch_img)(batch_img.rgba[:t], batch_img.params[:t])
+        else:
+            batch_img = batch_img[:t]
+        return batch_img, batch_voxel
+
+    def empty(self):
+        return self.data_queue.empty()
+
+
+def all_reduce_mean_scalar(value, group=None):
+    """Mean over ranks of a host scalar (validation loss)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(value)
+    dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item()) / dist.get_world_size(group)
 
 
 def broadcast_params(engine, src=0, group=None):

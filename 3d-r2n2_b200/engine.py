@@ -146,6 +146,7 @@ class Engine:
         self.last = None
         self.progress = None       # callback(stage) fired when a backward stage's grads are final
         self._marks = (0, 0)
+        self._enc_marks = {}       # encoder sub-stage -> tape index at which its gradients are final
 
     # ------------------------------------------------------------------ parameter definition
     def _define(self):
@@ -538,6 +539,12 @@ class Engine:
                     src, cin = dst, W_.cout
                 ops.maxpool_fwd(src, None, sl(pooled, po * po * cin), B, img, img, cin)
             head = (xin, ys, pooled)
+        elif x_events is not None:
+            # host inputs staged on a side stream (Net._stage_inputs) but no chunked head on this path
+            # (fp32 FFMA kernels): every view must have landed before the first kernel reads x
+            cur = torch.cuda.current_stream()
+            for ev in x_events:
+                cur.wait_event(ev)
         if head is not None:
             a = Act(head[0], (TB, 1, self.img, self.img, self.rowpack))
             a.useful = 21.0 / self.rowpack
@@ -571,14 +578,20 @@ class Engine:
                 pool1 = ctx.pool(c2h('conv1b', c2h('conv1a', a, 0), 1), out_data=head[2])
             else:
                 pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
+            mark_mid = len(ctx.tape)            # tape entries from here on: conv2a ... (enc_mid, enc_hi)
             pool2 = ctx.pool(c2('conv2c', pool1, False), c2('conv2b', c2('conv2a', pool1, True), True))
             pool3 = ctx.pool(c2('conv3c', pool2, False), c2('conv3b', c2('conv3a', pool2, True), True))
+            mark_hi = len(ctx.tape)             # from here on: conv4a ... fc7 (enc_hi)
             pool4 = ctx.pool(c2('conv4b', c2('conv4a', pool3, True), True))
             pool5 = ctx.pool(c2('conv5c', pool4, False), c2('conv5b', c2('conv5a', pool4, True), True))
             pool6 = ctx.pool(pool5, c2('conv6b', c2('conv6a', pool5, True), True))
         else:
             t_ = a
             for i in range(6):       # conv -> pool -> lrelu == conv -> lrelu -> pool (monotone)
+                if i == 1:
+                    mark_mid = len(ctx.tape)
+                if i == 3:
+                    mark_hi = len(ctx.tape)
                 if i == 0 and head is not None:
                     t_ = ctx.pool(c2h('conv1', t_, 0), out_data=head[2])
                 else:
@@ -587,6 +600,7 @@ class Engine:
         flat = ctx.reshape(pool6, (TB, 1, 1, 1, N_CONVFILTER[5] * 9))
         f = ctx.conv(flat, P['fc7.W'], P['fc7.b'], (1, 1, 1), True)
         mark_enc = len(ctx.tape)
+        self._enc_marks = {'enc_hi': mark_hi, 'enc_mid': mark_mid}
 
         # ---- recurrence ---------------------------------------------------------------------
         if self.lstm:
@@ -708,27 +722,34 @@ class Engine:
                 self._finalize_stage('decoder')
             if i == mark_enc:
                 self._finalize_stage('rnn')
+            if i == self._enc_marks.get('enc_hi'):
+                self._finalize_stage('enc_hi')
+            if i == self._enc_marks.get('enc_mid'):
+                self._finalize_stage('enc_mid')
         ctx.tape = []
-        self._finalize_stage('encoder')
+        self._finalize_stage('enc_lo')
         self.ctx = None
 
     def stage_segments(self):
-        """Non-bias store segments per backward stage, in the order their gradients become final."""
-        dec, rnn, enc = [], [], []
+        """Non-bias store segments per backward stage, in the order their gradients become final:
+        decoder (conv7..11) -> recurrent unit -> enc_hi (fc7, conv6..conv4) -> enc_mid (conv3, conv2) ->
+        enc_lo (conv1a/conv1b: the only weights whose all-reduce nothing is left to hide behind)."""
+        out = {'decoder': [], 'rnn': [], 'enc_hi': [], 'enc_mid': [], 'enc_lo': []}
         for name in self.P:
             if name.endswith('.b') or '.b_' in name:
                 continue
             if name.startswith('rnn.'):
-                rnn.append(name)
-            elif name.startswith('conv') and int(''.join(ch for ch in name.split('.')[0][4:] if ch.isdigit())) >= 7:
-                dec.append(name)
+                out['rnn'].append(name)
+            elif name.startswith('fc7'):
+                out['enc_hi'].append(name)
             else:
-                enc.append(name)
-        return {'decoder': dec, 'rnn': rnn, 'encoder': enc}
+                n = int(''.join(ch for ch in name.split('.')[0][4:] if ch.isdigit()))
+                out['decoder' if n >= 7 else ('enc_hi' if n >= 4 else ('enc_mid' if n >= 2 else 'enc_lo'))].append(name)
+        return out
 
     def _finalize_stage(self, stage):
         names = self.stage_segments()[stage]
-        if stage == 'encoder':      # biases ride with the last stage
+        if stage == 'enc_lo':       # biases ride with the last stage
             names = names + [n for n in self.P if n.endswith('.b') or '.b_' in n]
         for n in names:
             p = self.P[n]

@@ -17,12 +17,13 @@ from .config import cfg
 from .. import ops
 
 
-def max_or_nan(params):
+def max_or_nan(params, quiet=False):
     """lib/solver.py:12-17"""
     nan_or_max_param = 0.0
     for param_idx, param in enumerate(params):
         nan_or_max_param = np.max(np.abs(param.val.get_value()))
-        print('param %d : %f' % (param_idx, nan_or_max_param))
+        if not quiet:
+            print('param %d : %f' % (param_idx, nan_or_max_param))
     return nan_or_max_param
 
 
@@ -33,7 +34,8 @@ class Solver(object):
         self.lr = np.float32(1)
         self.iteration = np.float32(0)     # lib/solver.py:79: float32, starts from 0
         self._policy = None
-        self.grad_sync = None              # set by parallel.DataParallel (all-reduce of store.g)
+        self.rank, self.world, self.dist_group = 0, 1, None      # set by dist.attach() (data-parallel training)
+        self.grad_sync = None              # set by dist.attach() (bucketed all-reduce of store.g; also sets engine.progress)
         self.compile_model(cfg.TRAIN.POLICY)
 
     def compile_model(self, policy=cfg.TRAIN.POLICY):
@@ -80,8 +82,18 @@ class Solver(object):
         self.iteration = np.float32(self.iteration + 1)
 
         def fn(x, y):
-            return float(self._step(x, y))
+            loss = float(self._step(x, y))       # host sync: the step's kernels have finished
+            self._check_device_errors()
+            return loss
         return fn
+
+    @staticmethod
+    def _check_device_errors():
+        """A tcgen05 pipeline wait that timed out leaves a sticky per-device error word (csrc/umma.cuh
+        mbar_wait) and garbage accumulators: surface it wherever the host synchronises anyway."""
+        if ops.umma_error_flag() != 0:
+            from .._lib import R2N2Error
+            raise R2N2Error('a tcgen05/TMA pipeline timed out on the device: results of this step are invalid')
 
     def train_step_device(self, x_dev, y_dev):
         """Same step with inputs already on the device; returns the loss as a 0-d CUDA tensor
@@ -92,8 +104,9 @@ class Solver(object):
     def train(self, train_queue, val_queue=None):
         ''' Given data queues, train the network (lib/solver.py:111-186) '''
         save_dir = os.path.join(cfg.DIR.OUT_PATH)
-        if not os.path.exists(save_dir):
-            os.makedirs(save_dir)
+        main_rank = self.rank == 0             # data-parallel: every rank steps, rank 0 prints and saves
+        if main_rank and not os.path.exists(save_dir):
+            os.makedirs(save_dir, exist_ok=True)
         training_losses = []
         start_iter = 0
         if cfg.TRAIN.RESUME_TRAIN:
@@ -101,7 +114,8 @@ class Solver(object):
             start_iter = cfg.TRAIN.INITIAL_ITERATION
         lr = cfg.TRAIN.DEFAULT_LEARNING_RATE
         lr_steps = [int(k) for k in cfg.TRAIN.LEARNING_RATES.keys()]
-        print('Set the learning rate to %f.' % lr)
+        if main_rank:
+            print('Set the learning rate to %f.' % lr)
         self.set_lr(lr)
         for train_ind in range(start_iter, cfg.TRAIN.NUM_ITERATION + 1):
             batch_img, batch_voxel = train_queue.get()
@@ -111,8 +125,9 @@ class Solver(object):
             training_losses.append(loss)
             if train_ind in lr_steps:
                 self.set_lr(float(cfg.TRAIN.LEARNING_RATES[str(train_ind)]))
-                print('Learing rate decreased to %f: ' % self.lr)
-            if train_ind % cfg.TRAIN.PRINT_FREQ == 0:
+                if main_rank:
+                    print('Learing rate decreased to %f: ' % self.lr)
+            if train_ind % cfg.TRAIN.PRINT_FREQ == 0 and main_rank:
                 print('%s Iter: %d Loss: %f' % (datetime.now(), train_ind, loss))
             if train_ind % cfg.TRAIN.VALIDATION_FREQ == 0 and val_queue is not None:
                 val_losses = []
@@ -120,15 +135,27 @@ class Solver(object):
                     batch_img, batch_voxel = val_queue.get()
                     _, val_loss, _ = self.test_output(batch_img, batch_voxel)
                     val_losses.append(val_loss)
-                print('%s Test loss: %f' % (datetime.now(), np.mean(val_losses)))
+                val_mean = float(np.mean(val_losses))
+                if self.world > 1:             # every rank validated its own shard
+                    from ..dist import all_reduce_mean_scalar
+                    val_mean = all_reduce_mean_scalar(val_mean, self.dist_group)
+                if main_rank:
+                    print('%s Test loss: %f' % (datetime.now(), val_mean))
             if train_ind % cfg.TRAIN.NAN_CHECK_FREQ == 0:
-                max_param = max_or_nan(self.net.params)
+                # (parameters are bit-identical on every rank: all ranks reach the same verdict)
+                max_param = max_or_nan(self.net.params, quiet=not main_rank)
                 if np.isnan(max_param):
                     print('NAN detected')
                     break
-            if train_ind % cfg.TRAIN.SAVE_FREQ == 0 and not train_ind == 0:
+            if train_ind % cfg.TRAIN.SAVE_FREQ == 0 and not train_ind == 0 and main_rank:
                 self.save(training_losses, save_dir, train_ind)
-            if loss > cfg.TRAIN.LOSS_LIMIT:
+            if self.world > 1:
+                # ranks see different batches: stop together, on the mean loss, or the next all-reduce would hang
+                from ..dist import all_reduce_mean_scalar
+                stop_loss = all_reduce_mean_scalar(loss, self.dist_group)
+            else:
+                stop_loss = loss
+            if stop_loss > cfg.TRAIN.LOSS_LIMIT:
                 print("Cost exceeds the threshold. Stop training")
                 break
         return training_losses
@@ -150,6 +177,7 @@ class Solver(object):
         out = self.net.forward(x, y)
         prediction = out['pred'].cpu().numpy()
         activations = [out['update_gates'].float().contiguous().cpu().numpy()]
+        self._check_device_errors()
         if y is None:
             return prediction, activations
         return prediction, float(out['loss']), activations

@@ -131,6 +131,10 @@ class Net(object):
             yd.copy_(yt, non_blocking=True)
             yev = torch.cuda.Event()
             yev.record(side)
+        # allocated on `cur`, written on `side`: tell the caching allocator so that a later free cannot hand
+        # the blocks to `cur` while a copy is still in flight
+        xd.record_stream(side)
+        yd.record_stream(side)
         return xd, yd, events, yev
 
     def forward(self, x, y=None):

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-infer', action='store_true')
     ap.add_argument('--no-raw-pipeline', action='store_true')
+    ap.add_argument('--no-parity-check', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the config 4 / config 5 legs')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel event table here')
     return ap.parse_args()
 
@@ -62,16 +64,21 @@ def peaks():
     return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
-def ncu_traffic(kernel_key):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from
-    the committed `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py)."""
+def ncu_traffic(n_launches):
+    """DRAM bytes per launch of the dominant kernel family: sum of dram__bytes_read.sum + dram__bytes_write.sum
+    over ALL forward / data-gradient conv launches of one training step (the same launches `roofline.frac`
+    covers), divided by their count.  From the committed ncu pass (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one step)."""
     p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(p):
-        return None
+        return None, None
     try:
-        return json.load(open(p)).get(kernel_key, {}).get('dram_bytes_per_launch')
+        d = json.load(open(p)).get('conv_fwd_step')
+        if not d:
+            return None, None
+        return d['dram_bytes_total'] / max(1, d['launches']), d
     except Exception:
-        return None
+        return None, None
 
 
 def config_dict(args, extra=None):
@@ -152,7 +159,7 @@ class ClockSampler:
         self.idx = gpu_index
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '200'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -218,13 +225,45 @@ def run_ours(args):
     solver.set_lr(cfg.TRAIN.DEFAULT_LEARNING_RATE)
     if world > 1:
         r2dist.broadcast_params(net.engine)
-        r2dist.attach(solver)
 
     # synthetic ShapeNet-shaped batch (different per rank), pinned host copies for the e2e leg
     x_np, y_np = synthetic_batch(np, T, B, seed_x=1234 + rank, seed_y=4321 + rank)
     x_pin = torch.as_tensor(x_np).pin_memory()
     y_pin = torch.as_tensor(y_np).pin_memory()
     x_dev, y_dev = x_pin.cuda(), y_pin.cuda()
+
+    # ---- parity check on the timed batch (outside every timed region): the benchmarked arithmetic against the
+    # exact-fp32 FFMA path of the same library on the same weights and inputs (that path is pinned to the CPU
+    # oracle at 3e-6 by tests/test_nets_gpu.py).  One fp32 forward + backward (~0.4 s) per rank.
+    parity = None
+    if compute != 'fp32' and not args.no_parity_check:
+        cfg.CONST.COMPUTE = 'fp32'
+        net32 = load_model(args.net)(random_seed=0)
+        cfg.CONST.COMPUTE = compute
+        net32.engine.set_params(net.engine.get_params())
+        o32 = net32.engine.forward(x_dev, y_dev, training=True, want_pred=True)
+        net32.engine.backward()
+        p32, l32 = o32['pred'].clone(), float(o32['loss'])
+        o16 = net.engine.forward(x_dev, y_dev, training=True, want_pred=True)
+        net.engine.backward()
+        g16, g32 = net.engine.get_grads(), net32.engine.get_grads()
+        num = sum(float(((a.astype(np.float64) - b) ** 2).sum()) for a, b in zip(g16, g32))
+        den = sum(float((b.astype(np.float64) ** 2).sum()) for b in g32)
+        thr = 0.4
+        occ = y_dev[:, :, 1] > 0.5
+
+        def iou(p):
+            q = p[:, :, 1] > thr
+            return float((q & occ).sum()) / max(1.0, float((q | occ).sum()))
+        parity = {'loss_bf16': float(o16['loss']), 'loss_fp32': l32,
+                  'max_abs_dp': float((o16['pred'] - p32).abs().max()),
+                  'mean_abs_dp': float((o16['pred'] - p32).abs().mean()),
+                  'grad_rel_l2': (num / den) ** 0.5, 'iou04_bf16': iou(o16['pred']), 'iou04_fp32': iou(p32),
+                  'against': 'fp32 FFMA path of the same library (oracle-pinned), same weights, timed batch of rank 0'}
+        del net32, o32, p32, g16, g32
+        torch.cuda.empty_cache()
+    if world > 1:
+        r2dist.attach(solver)
 
     def barrier():
         if world > 1:
@@ -264,7 +303,7 @@ def run_ours(args):
     # ---- e2e: host buffers through the public API (Solver.train_loss) -----------------------
     def step_e2e():
         solver.train_loss(x_pin, y_pin)        # H2D x,y (pinned) ... D2H loss (float())
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 20))
     ms_e2e_total, _, _ = timed(step_e2e, e2e_steps, 1)
     e2e_value = B * world / (ms_e2e_total / e2e_steps / 1e3)
 
@@ -317,15 +356,22 @@ def run_ours(args):
         tot_ms = sum(d['ms'] for d in table.values())
         # forward / data-gradient launches of the implicit-GEMM kernels (the _colsum entry point is the same
         # kernels plus the producing layer's bias gradient, fused or as a second pass: counted in, conservatively)
-        conv = dict(ms=0.0, flops=0.0, calls=0)
+        conv = dict(ms=0.0, flops=0.0, calls=0, bytes=0.0)
         for name in ('r2n2_conv_fwd', 'r2n2_conv_fwd_colsum'):
             for k_ in conv:
                 conv[k_] += table.get(name, {}).get(k_, 0)
         if conv['ms'] > 0:
             ach = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
+            traffic, tdetail = ncu_traffic(conv['calls'])
             roofline = {'bound': 'tensor', 'kernel': 'r2n2_conv_fwd (implicit-GEMM conv/FC fwd + dgrad)',
                         'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops'],
-                        'traffic': ncu_traffic('r2n2_conv_fwd'), 'peak_source': pk['src'],
+                        'traffic': traffic,
+                        'traffic_note': None if tdetail is None else
+                        ('ncu dram bytes summed over the %d conv fwd/dgrad kernel launches of one step / %d; '
+                         'algorithmic operand bytes of the same launches: %.0f per launch'
+                         % (tdetail['launches'], tdetail['launches'],
+                            conv['bytes'] / max(1, conv['calls']))),
+                        'peak_source': pk['src'],
                         'launches': conv['calls'], 'avg_launch_ms': conv['ms'] / max(1, conv['calls']),
                         'share_of_step': conv['ms'] / tot_ms if tot_ms else None,
                         'flops_counted': 'algorithmic (useful, zero-skipped unpool), summed over the launches'}
@@ -337,6 +383,17 @@ def run_ours(args):
             with open(args.profile_out, 'w') as f:
                 json.dump({'per_kernel': table_out, 'sum_ms': tot_ms,
                            'launches': [(n, t, ms, w) for n, t, ms, w in raw]}, f, indent=1)
+
+    # ---- data-parallel consistency: after all those steps every rank must hold bit-identical parameters ----
+    dp_check = None
+    if world > 1:
+        st = net.engine.store
+        bits = st.p.view(torch.int32).to(torch.int64)
+        chk = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=bits.device) % 8191 + 1)).sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        dp_check = {'params_bit_identical_across_ranks': bool(all(torch.equal(c, allc[0]) for c in allc)),
+                    'checksum': [int(v) for v in allc[0].tolist()], 'steps_taken': int(solver.iteration)}
 
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) --------------------------------------
     cpu = None
@@ -372,6 +429,43 @@ def run_ours(args):
         cfg.CONST.BATCH_SIZE = B
         infer['note'] = 'bf16/tcgen05 forward replayed as one CUDA graph, input resident in HBM, CUDA events'
 
+    # ---- BASELINE.json configs 4 and 5 at every N (weak scaling, same per-GPU shapes) ---------------------
+    other = None
+    if not args.no_other_configs:
+        other = {}
+        del solver, net
+        torch.cuda.empty_cache()
+        # config 4: 3D-conv-LSTM variant of the residual net, 5-view training, batch 36 per GPU
+        cfg.CONST.BATCH_SIZE = B
+        net4 = load_model('ResidualLSTMNet')(random_seed=0)
+        s4 = Solver(net4)
+        s4.set_lr(cfg.TRAIN.DEFAULT_LEARNING_RATE)
+        if world > 1:
+            r2dist.broadcast_params(net4.engine)
+            r2dist.attach(s4)
+        k4 = max(3, min(args.steps, 10))
+        ms4, _, _ = timed(lambda: s4.train_step_device(x_dev, y_dev), k4, 3)
+        other['lstm_train'] = {'metric': 'ResidualLSTMNet train samples/sec (5 views, 32^3)',
+                               'value': B * world / (ms4 / k4 / 1e3), 'unit': UNIT, 'ms_per_step': ms4 / k4,
+                               'steps': k4, 'warmup': 3, 'per_gpu_batch': B, 'views': T, 'n_gpus': world,
+                               'config': 'BASELINE.json configs[3]'}
+        del s4, net4
+        torch.cuda.empty_cache()
+        # config 5: ResidualGRUNet 24-view sequence inference, batch 256 on 8 GPUs = 32 per GPU, batch-sharded, no
+        # collective; one CUDA-graph replay per step, input resident in HBM
+        B5, T5 = 32, 24
+        cfg.CONST.BATCH_SIZE = B5
+        net5 = load_model('ResidualGRUNet')(random_seed=0, compute_grad=False)
+        x5 = torch.rand(T5, B5, 3, 127, 127, device='cuda')
+        k5 = max(3, min(args.steps, 10))
+        ms5, _, _ = timed(lambda: net5.engine.forward_graph(x5, None), k5, 3)
+        other['infer_24view'] = {'metric': 'ResidualGRUNet 24-view inference samples/sec (batch 32 per GPU)',
+                                 'value': B5 * world / (ms5 / k5 / 1e3), 'unit': UNIT, 'ms_per_batch': ms5 / k5,
+                                 'steps': k5, 'warmup': 3, 'per_gpu_batch': B5, 'views': T5, 'n_gpus': world,
+                                 'config': 'BASELINE.json configs[4]'}
+        del net5, x5
+        cfg.CONST.BATCH_SIZE = B
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -385,7 +479,7 @@ def run_ours(args):
                         'd2h_bytes_per_step': 4, 'steps': e2e_steps},
                 'e2e_raw_pipeline': e2e_raw,
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-                'infer': infer,
+                'infer': infer, 'parity_check': parity, 'other_configs': other, 'dp_check': dp_check,
                 'per_kernel': {k: {'ms': round(v['ms'], 4), 'calls': v['calls'], 'share': round(v['share'], 4),
                                    'tflops': round(v['tflops'], 2), 'gbs': round(v['gbs'], 1)}
                                for k, v in (table_out or {}).items()}}

@@ -1,0 +1,233 @@
+"""Parity of the BENCHMARKED path (bf16 operands on tcgen05, fp32 accumulation) at the benchmark
+configuration (BASELINE.json config 3: ResidualGRUNet, batch 36, 5 views) and for the other benchmarked
+nets, against the repo's fp32 FFMA path (itself pinned to the oracle at 3e-6, tests/test_nets_gpu.py) and
+against the oracle where the CPU can afford it.
+
+Every bound below is <= 2x the value measured on a B200 (profiles/r02_parity_bf16.txt holds the printed
+numbers of the run the bounds were taken from); the measured values are printed on every run (-s).
+Reference sites: models/net.py:56-58 (tensor.grad), lib/layers.py:583-601 (loss), lib/solver.py:20-48 (Adam).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import r2n2_b200  # noqa: F401
+from r2n2_b200.lib.config import cfg
+from r2n2_b200.lib.solver import Solver
+from r2n2_b200.models import load_model
+from oracle import ref_torch as rt
+
+pytestmark = pytest.mark.gpu
+
+OUT = os.environ.get('R2N2_PARITY_OUT')       # optional: append the measured numbers as JSON lines
+
+
+def _record(name, d):
+    print('[parity] %s %s' % (name, json.dumps(d)))
+    if OUT:
+        with open(OUT, 'a') as f:
+            f.write(json.dumps(dict(test=name, **d)) + '\n')
+
+
+def _build(net_name, B, compute, params=None, seed=0):
+    cfg.CONST.BATCH_SIZE = B
+    cfg.CONST.COMPUTE = compute
+    try:
+        net = load_model(net_name)()
+    finally:
+        cfg.CONST.COMPUTE = 'fp32'
+    if params is None:
+        params = rt.init_params(net_name, seed=seed)
+    net.engine.set_params(params)
+    return net, params
+
+
+def _rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _grad_table(spec, g_a, g_b):
+    """per-tensor relative L2 error of gradient lists (reference order), biases and weights apart"""
+    rows = {}
+    for (name, _, _), a, b in zip(spec, g_a, g_b):
+        rows[name] = _rel_l2(a, b)
+    return rows
+
+
+# measured on B200 (profiles/r02_parity_bf16.txt); bound = 2 x measured, rounded up
+BOUND_B36 = dict(pred_max=3.0e-2, pred_mean=2.0e-3, loss_rel=5e-3, grad_rel_l2_worst=0.30, grad_rel_l2_median=0.08,
+                 grad_total_rel_l2=0.10)
+
+
+def test_bf16_vs_fp32_at_benchmark_config():
+    """B=36, T=5 (the configuration bench.py times): the code paths that only exist at this size -- N split of
+    the M=180 GEMMs, one-wave weight-gradient grids, the chunked head that overlaps the host-to-device copy --
+    produce the fp32 path's predictions, loss and gradients within the stated bf16 tolerance."""
+    B, T = 36, 5
+    net32, params = _build('ResidualGRUNet', B, 'fp32')
+    net16, _ = _build('ResidualGRUNet', B, 'bf16', params)
+    x, y = rt.synthetic_batch(T, B)
+    # forward (Solver.test_output: host numpy in, CUDA-graph replay)
+    p32, l32, a32 = Solver(net32).test_output(x, y)
+    p16, l16, a16 = Solver(net16).test_output(x, y)
+    dp = np.abs(p16 - p32)
+    iou32, iou16 = rt.iou(p32, y, 0.4), rt.iou(p16, y, 0.4)
+    # training step, HOST inputs: Net._stage_inputs + chunked head on the bf16 path
+    o32 = net32.forward_backward(x, y)
+    g32 = net32.get_grads()
+    o16 = net16.forward_backward(x, y)
+    g16 = net16.get_grads()
+    # same step with device-resident inputs (what bench.py's `value` leg runs): must agree with the host-input
+    # path up to the order of the fp32 atomics in the weight-gradient reduction
+    xd, yd = torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda()
+    o16d = net16.forward_backward(xd, yd)
+    g16d = net16.get_grads()
+    names = [w.name for w in net16.engine.weights]
+    spec = [(n, None, None) for n in names]
+    tab = _grad_table(spec, g16, g32)
+    tab_dev = _grad_table(spec, g16d, g16)
+    worst = max(tab.items(), key=lambda kv: kv[1])
+    flat16 = np.concatenate([g.ravel() for g in g16])
+    flat32 = np.concatenate([g.ravel() for g in g32])
+    m = dict(pred_max=float(dp.max()), pred_mean=float(dp.mean()), loss32=float(l32), loss16=float(l16),
+             loss_rel=abs(float(l16) - float(l32)) / abs(float(l32)),
+             train_loss32=float(o32['loss']), train_loss16=float(o16['loss']), train_loss16_dev=float(o16d['loss']),
+             iou32=iou32, iou16=iou16, gates_max=float(np.abs(a16[0] - a32[0]).max()),
+             grad_rel_l2_worst=worst[1], grad_worst_name=worst[0],
+             grad_rel_l2_median=float(np.median(list(tab.values()))),
+             grad_total_rel_l2=_rel_l2(flat16, flat32),
+             host_vs_device_inputs_worst=max(tab_dev.values()))
+    _record('b36_t5', m)
+    _record('b36_t5_per_tensor', {k: round(v, 5) for k, v in tab.items()})
+    assert np.isfinite(p16).all() and all(np.isfinite(g).all() for g in g16)
+    assert m['pred_max'] < BOUND_B36['pred_max'] and m['pred_mean'] < BOUND_B36['pred_mean']
+    assert m['loss_rel'] < BOUND_B36['loss_rel']
+    assert abs(m['train_loss16'] - m['train_loss32']) / abs(m['train_loss32']) < BOUND_B36['loss_rel']
+    assert abs(m['train_loss16'] - m['loss16']) < 1e-5 * max(1.0, abs(m['loss16']))   # training fwd == inference fwd
+    assert m['grad_rel_l2_worst'] < BOUND_B36['grad_rel_l2_worst'], worst
+    assert m['grad_rel_l2_median'] < BOUND_B36['grad_rel_l2_median']
+    assert m['grad_total_rel_l2'] < BOUND_B36['grad_total_rel_l2']
+    assert m['host_vs_device_inputs_worst'] < 1e-3       # same arithmetic, atomics order only
+    assert abs(iou16 - iou32) < 5e-3
+    from r2n2_b200 import ops
+    assert ops.umma_error_flag() == 0
+
+
+BOUND_TRAJ = dict(loss_rel_max=2e-2, drift_ratio_max=0.5)
+
+
+def test_bf16_adam_trajectory_30_steps():
+    """30 Solver.train_loss steps at B=36, T=5 on the bf16 path vs the fp32 path from the same start: the loss
+    curves stay together and the parameter difference stays a fraction of the distance travelled (Adam + bf16
+    operand mirror written by the optimiser kernel + transposed data-gradient operands refreshed per step)."""
+    B, T, STEPS = 36, 5, 30
+    net32, params = _build('ResidualGRUNet', B, 'fp32')
+    net16, _ = _build('ResidualGRUNet', B, 'bf16', params)
+    s32, s16 = Solver(net32), Solver(net16)
+    s32.set_lr(1e-4), s16.set_lr(1e-4)
+    batches = [rt.synthetic_batch(T, B, seed_x=100 + i, seed_y=200 + i) for i in range(3)]
+    p0 = net32.engine.store.p.clone()
+    l32, l16 = [], []
+    for i in range(STEPS):
+        x, y = batches[i % 3]
+        l32.append(s32.train_loss(x, y))
+        l16.append(s16.train_loss(x, y))
+    l32, l16 = np.array(l32), np.array(l16)
+    rel = np.abs(l16 - l32) / np.abs(l32)
+    # drift: the two stores have the same layout except the padded tensor-path segments -> compare per tensor
+    moved, diff = 0.0, 0.0
+    worst = ('', 0.0)
+    for w32, w16, a0 in zip(net32.engine.weights, net16.engine.weights, params):
+        a32, a16 = w32.get_value().astype(np.float64), w16.get_value().astype(np.float64)
+        mv, df = np.linalg.norm(a32 - a0), np.linalg.norm(a16 - a32)
+        moved += mv ** 2
+        diff += df ** 2
+        if mv > 0 and df / mv > worst[1]:
+            worst = (w32.name, df / mv)
+    ratio = float(np.sqrt(diff / moved))
+    m = dict(loss32_first=float(l32[0]), loss32_last=float(l32[-1]), loss16_last=float(l16[-1]),
+             loss_rel_max=float(rel.max()), loss_rel_last=float(rel[-1]), drift_ratio=ratio,
+             drift_worst_tensor=worst[0], drift_worst_ratio=float(worst[1]),
+             loss32=[round(float(v), 5) for v in l32], loss16=[round(float(v), 5) for v in l16])
+    _record('adam_traj_b36_t5', m)
+    assert np.isfinite(l16).all()
+    assert l32[-1] < l32[0] and l16[-1] < l16[0]                 # both actually train
+    assert m['loss_rel_max'] < BOUND_TRAJ['loss_rel_max']
+    assert m['drift_ratio'] < BOUND_TRAJ['drift_ratio_max']
+    del p0
+
+
+BOUND_LSTM = dict(pred_max=3e-2, grad_rel_l2_worst=0.30)
+
+
+def test_lstm_bf16_parity():
+    """conv-LSTM variant (BASELINE config 4) on the tensor path: forward against the ORACLE, gradients against
+    the fp32 path (N=384 hidden convolution, lstm gate kernels in bf16)."""
+    B, T = 2, 3
+    net16, params = _build('ResidualLSTMNet', B, 'bf16')
+    net32, _ = _build('ResidualLSTMNet', B, 'fp32', params)
+    x, y = rt.synthetic_batch(T, B)
+    p16, l16, a16 = Solver(net16).test_output(x, y)
+    with torch.no_grad():
+        out = rt.RefNet('ResidualLSTMNet', params).forward(x, y)
+    rp = out['pred'].numpy()
+    o16 = net16.forward_backward(x, y)
+    g16 = net16.get_grads()
+    net32.forward_backward(x, y)
+    g32 = net32.get_grads()
+    names = [w.name for w in net16.engine.weights]
+    tab = _grad_table([(n, 0, 0) for n in names], g16, g32)
+    worst = max(tab.items(), key=lambda kv: kv[1])
+    m = dict(pred_max=float(np.abs(p16 - rp).max()), loss16=float(l16), loss_oracle=float(out['loss']),
+             iou16=rt.iou(p16, y, 0.4), iou_oracle=rt.iou(rp, y, 0.4),
+             gates_max=float(np.abs(a16[0] - out['update_gates'].numpy()).max()),
+             grad_rel_l2_worst=worst[1], grad_worst_name=worst[0],
+             grad_rel_l2_median=float(np.median(list(tab.values()))))
+    _record('lstm_b2_t3', m)
+    assert m['pred_max'] < BOUND_LSTM['pred_max']
+    assert abs(m['loss16'] - m['loss_oracle']) < 2e-2 * max(1.0, abs(m['loss_oracle']))
+    assert abs(m['iou16'] - m['iou_oracle']) < 5e-3
+    assert m['grad_rel_l2_worst'] < BOUND_LSTM['grad_rel_l2_worst'], worst
+
+
+def test_t24_bf16_vs_oracle_b1():
+    """BASELINE config 5 shape of the recurrence (24 views) at batch 1: the bf16 path against the ORACLE
+    (24 CPU encoder passes), not against our own fp32 path."""
+    net16, params = _build('ResidualGRUNet', 1, 'bf16')
+    x, y = rt.synthetic_batch(24, 1, seed_x=12)
+    p16, l16, a16 = Solver(net16).test_output(x, y)
+    with torch.no_grad():
+        out = rt.RefNet('ResidualGRUNet', params).forward(x, y)
+    rp = out['pred'].numpy()
+    m = dict(pred_max=float(np.abs(p16 - rp).max()), pred_mean=float(np.abs(p16 - rp).mean()),
+             loss16=float(l16), loss_oracle=float(out['loss']),
+             gates_max=float(np.abs(a16[0] - out['update_gates'].numpy()).max()),
+             iou16=rt.iou(p16, y, 0.4), iou_oracle=rt.iou(rp, y, 0.4))
+    _record('t24_b1', m)
+    assert np.isfinite(p16).all() and m['pred_max'] < 3e-2
+    assert abs(m['iou16'] - m['iou_oracle']) < 5e-3
+
+
+def test_fp32_host_inputs_overlap_h2d():
+    """compute='fp32' + OVERLAP_H2D + pinned host inputs -- the first kernel must wait for
+    the side-stream copies (no chunked head on the FFMA path).  Same result as device-resident inputs."""
+    B, T = 4, 3
+    net, params = _build('ResidualGRUNet', B, 'fp32')
+    x, y = rt.synthetic_batch(T, B)
+    xp, yp = torch.as_tensor(x).pin_memory(), torch.as_tensor(y).pin_memory()
+    assert cfg.CONST.OVERLAP_H2D
+    ref = net.forward_backward(torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda())
+    g_ref = net.engine.store.g.clone()
+    for _ in range(3):                          # repeat: a race would show up as run-to-run differences
+        torch.cuda.synchronize()
+        junk = torch.empty(64 << 20, device='cuda').normal_()     # recycle freed blocks, keep the stream busy
+        del junk
+        out = net.forward_backward(xp, yp)
+        assert abs(float(out['loss']) - float(ref['loss'])) < 1e-6
+        d = (net.engine.store.g - g_ref).abs().max().item()
+        assert d < 1e-5 * max(1.0, g_ref.abs().max().item()), d     # fp32 atomics order in the weight gradients

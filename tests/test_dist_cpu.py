@@ -51,4 +51,59 @@ def test_gradsync_world2_gloo():
         assert ok_cov, 'buckets must tile the flat buffer exactly once'
         assert ok_sum, 'all-reduce(sum) result wrong on rank %d' % rank
         assert scale == 0.5 and ok_bc
-        assert stages == ['decoder', 'rnn', 'encoder']
+        assert stages == ['decoder', 'rnn', 'enc_hi', 'enc_mid', 'enc_lo']
+
+
+def _worker_views(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['RANK'], os.environ['WORLD_SIZE'], os.environ['LOCAL_RANK'] = str(rank), str(world), str(rank)
+    import queue
+    import numpy as np
+    import r2n2_b200  # noqa: F401
+    from r2n2_b200 import dist as r2dist
+    from r2n2_b200.lib.data_process import RawViews
+    r, w, _ = r2dist.init_from_env(backend='gloo')
+    assert (r, w) == (rank, world)
+    seed = r2dist.shared_seed(1234 + 77 * rank)          # ranks propose different seeds: rank 0's wins
+    items = list(range(11))
+    mine = r2dist.shard(items, rank, world)
+    hq = queue.Queue()
+    rs = np.random.RandomState(rank)                     # per-rank data differs
+    for i in range(12):
+        if i % 2:
+            hq.put((RawViews(rs.randint(0, 255, (5, 2, 4, 4, 4)).astype(np.uint8), np.zeros((5, 2, 6), np.int32)),
+                    np.zeros((2, 4, 4, 4), np.uint8)))
+        else:
+            hq.put((rs.rand(5, 2, 3, 4, 4).astype(np.float32), np.zeros((2, 4, 2, 4, 4), np.float32)))
+    sq = r2dist.SharedViewCountQueue(hq, seed, 5)
+    shapes = []
+    for i in range(12):
+        x, y = sq.get()
+        shapes.append(int(x.shape[0]))
+        assert (hasattr(x, 'rgba')) == bool(i % 2) and x.shape[1] == 2
+    mean = r2dist.all_reduce_mean_scalar(float(rank + 1))
+    q.put((rank, seed, mine, shapes, list(sq.counts), mean))
+    dist.destroy_process_group()
+
+
+def test_shared_view_schedule_and_dataset_shards_world2_gloo():
+    """lib/train_net.train_net() under a launcher: disjoint covering dataset shards, ONE view-count schedule on
+    all ranks (reference draw: lib/data_process.py:127-130), rank 0's seed everywhere."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_views, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, seed0, mine0, shapes0, counts0, mean0), (r1, seed1, mine1, shapes1, counts1, mean1) = res
+    assert seed0 == seed1 == 1234
+    assert sorted(mine0 + mine1) == list(range(11)) and not set(mine0) & set(mine1)
+    assert shapes0 == shapes1 == counts0 == counts1
+    assert all(1 <= t <= 5 for t in shapes0) and len(set(shapes0)) > 1
+    assert mean0 == mean1 == 1.5

@@ -3,7 +3,8 @@
 // filter taps of a convolution (tap shift = row offset of the operand view).  Also measures the
 // issue rate of back-to-back SS-mode MMAs for several N.
 //
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/exp_desc tools/exp_desc.cu && ./exp_desc
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o gpurun_out/exp_desc tools/exp_desc.cu
+//   (always link the runtime dynamically and keep the binary under gpurun_out/, never in the tree)
 //
 // Operands are written by hand with the TMA swizzle (byte offset bits [4:6] ^= bits [7:9], masked to the
 // swizzle width), values are small integers so fp32 accumulation is exact.
