@@ -10,9 +10,11 @@ LIB_PATH = os.path.join(_HERE, 'libr2n2_b200.so')
 
 F32, BF16 = 0, 1
 EPI_BIAS, EPI_LRELU, EPI_RESIDUAL, EPI_MASK = 1, 2, 4, 8
+EPI_RES_PRE = 64
 CONV_UP2, CONV_DOWN2 = 16, 32
 WGRAD_ACCUMULATE, WGRAD_UP2 = 1, 2
 ALGO_SIMT, ALGO_UMMA = 0, 1
+ALGO_SPLIT = 2      # host-level only: three ALGO_UMMA passes over hi/lo split operands (COMPUTE='bf16x3')
 ELT_SIGMOID, ELT_TANH, ELT_COMPLEMENT, ELT_MUL = 0, 1, 2, 3
 
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -27,6 +29,7 @@ PROTOTYPES = {
     'r2n2_weight_transpose_batch': [_p, _p, _p, _i, _ll, _i, _p],
     'r2n2_weight_transpose_batch_bf16': [_p, _p, _p, _i, _ll, _p],
     'r2n2_cast': [_p, _p, _ll, _i, _p],
+    'r2n2_split_bf16': [_p, _p, _p, _ll, _p],
     'r2n2_nchw_to_nhwc': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_nchw_to_rowpack': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_maxpool2d_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _p],

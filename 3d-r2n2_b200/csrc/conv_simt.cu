@@ -158,7 +158,9 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
     }
   }
 
-  // ---- epilogue: bias -> lrelu -> +residual -> *mask
+  // ---- epilogue: [+residual (RES_PRE)] -> bias -> lrelu -> [+residual] -> *mask
+  const bool res_pre = (flags & R2N2_EPI_RESIDUAL) && (flags & R2N2_EPI_RES_PRE);
+  const bool res_post = (flags & R2N2_EPI_RESIDUAL) && !(flags & R2N2_EPI_RES_PRE);
   const int co0 = n0 + tx * 4;
   float bv[4] = {0.f, 0.f, 0.f, 0.f};
   if (flags & R2N2_EPI_BIAS) {
@@ -175,11 +177,13 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[j] = acc[i][j] + bv[j];
+      v[j] = acc[i][j];
+      if (res_pre && co0 + j < g.Cout) v[j] += to_float<TOut>(res[off + j]);
+      v[j] += bv[j];
       if (flags & R2N2_EPI_LRELU) v[j] = lrelu(v[j]);
     }
     if (vec_ok) {
-      if (flags & R2N2_EPI_RESIDUAL) {
+      if (res_post) {
         float4 r = Vec4<TOut>::load(res + off);
         v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
       }
@@ -194,7 +198,7 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
       for (int j = 0; j < 4; ++j) {
         if (co0 + j >= g.Cout) continue;
         float o = v[j];
-        if (flags & R2N2_EPI_RESIDUAL) o += to_float<TOut>(res[off + j]);
+        if (res_post) o += to_float<TOut>(res[off + j]);
         if (flags & R2N2_EPI_MASK) o *= lrelu_slope(to_float<TOut>(mask[off + j]));
         y[off + j] = from_float<TOut>(o);
       }

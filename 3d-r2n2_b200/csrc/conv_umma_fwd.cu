@@ -604,7 +604,12 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.stages = stages;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.bn_cols) p.tmem_cols *= 2;
-  p.flags = flags & 15;
+  p.flags = flags & (15 | R2N2_EPI_RES_PRE);
+  if (flags & R2N2_EPI_RES_PRE) {          // partial-sum accumulation (fp32 outputs): register epilogue only
+    R2N2_CHECK_ARG(out_dtype == R2N2_F32 && (flags & R2N2_EPI_RESIDUAL), R2N2_ERR_UNSUPPORTED,
+                   "conv_fwd[umma]: RES_PRE needs RESIDUAL and an fp32 output");
+    p.tma_epi = 0;
+  }
   p.err_word = get_err_word();
   // [stages][barriers ...][1024-aligned epilogue slabs]
   p.epi_off = (int)(((size_t)p.stages * p.stage_bytes + (2 * p.stages + 6) * 8 + 16 + 1023) / 1024 * 1024);

@@ -565,6 +565,12 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               f[q] = __uint_as_float(v0[q]) + a1 + a2;
             }
             if (!valid) continue;
+            if ((p.flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) == (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) {
+              float rr[16];
+              pf.r.unpack(rr);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] += rr[q];
+            }
             if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
               for (int q = 0; q < 16; q += 4) {
@@ -576,7 +582,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
               for (int q = 0; q < 16; ++q) f[q] = lrelu(f[q]);
             }
-            if (p.flags & R2N2_EPI_RESIDUAL) {
+            if ((p.flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) == R2N2_EPI_RESIDUAL) {
               float rr[16];
               pf.r.unpack(rr);
 #pragma unroll
@@ -850,7 +856,9 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled unavailable");
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
-  p.flags = flags & 15;
+  p.flags = flags & (15 | R2N2_EPI_RES_PRE);
+  R2N2_CHECK_ARG(!(flags & R2N2_EPI_RES_PRE) || (out_dtype == R2N2_F32 && (flags & R2N2_EPI_RESIDUAL)),
+                 R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: RES_PRE needs RESIDUAL and an fp32 output");
   p.no_rot = getenv("R2N2_FWD3_NO_ROT") ? 1 : 0;
   // Measured: on this kernel the smem-slab + TMA epilogue pays only without input slabs and where the register
   // epilogue binds: conv1b forward (96 -> 96, bias + LeakyReLU) 0.553 -> 0.520 ms; with a mask / residual slab

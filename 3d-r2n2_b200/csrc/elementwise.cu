@@ -414,6 +414,34 @@ __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, long
   }
 }
 
+// ------------------------------------------------------------------ hi / lo operand split (COMPUTE = 'bf16x3')
+// x = hi + lo + O(2^-17 |x|):  hi = bf16_rn(x), lo = bf16_rn(x - hi).  A contraction of split operands
+// (hi*hi + lo*hi + hi*lo, fp32 accumulation) carries ~16 mantissa bits instead of bf16's 8.
+__global__ void split_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+  const long long n8 = n >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(s)[2 * i], b = reinterpret_cast<const float4*>(s)[2 * i + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    Pack<__nv_bfloat16> ph, pl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = __bfloat162float(__float2bfloat16_rn(v[j]));
+      ph.v[j] = h;
+      pl.v[j] = v[j] - h;          // exact in fp32 (Sterbenz), rounded to bf16 by the store
+    }
+    ph.store(hi + 8 * i);
+    pl.store(lo + 8 * i);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long j = (n8 << 3) + threadIdx.x;
+    const __nv_bfloat16 h = __float2bfloat16_rn(s[j]);
+    hi[j] = h;
+    lo[j] = __float2bfloat16_rn(s[j] - __bfloat162float(h));
+  }
+}
+
 // ------------------------------------------------------------------ conv-GRU gate math
 // hidden grid rows: pr = b*64 + pos ; 128 channels -> 32 float4 groups per row
 template <typename T>
@@ -1280,6 +1308,17 @@ int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* str
     cast_kernel<T><<<grid_for((n >> 2) + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, n);
   })
   R2N2_CHECK_LAUNCH("cast");
+  return R2N2_OK;
+}
+
+int r2n2_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream) {
+  R2N2_CHECK_ARG(n > 0 && src && hi && lo, R2N2_ERR_BAD_SHAPE, "split_bf16: bad arguments");
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(lo) & 15) == 0,
+                 R2N2_ERR_BAD_ALIGN, "split_bf16: pointers must be 16-byte aligned");
+  split_bf16_kernel<<<grid_for((n >> 3) + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  R2N2_CHECK_LAUNCH("split_bf16");
   return R2N2_OK;
 }
 

@@ -234,6 +234,12 @@ static __device__ __forceinline__ void epi_row(EpiPrefetch<TOut>& pf, uint32_t t
     float f[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = empty_acc ? 0.f : __uint_as_float(v[j]);
+    if ((flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) == (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) {
+      float r[16];
+      cur.r.unpack(r);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] += r[j];
+    }
     if (flags & R2N2_EPI_BIAS) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
@@ -245,7 +251,7 @@ static __device__ __forceinline__ void epi_row(EpiPrefetch<TOut>& pf, uint32_t t
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j]);
     }
-    if (flags & R2N2_EPI_RESIDUAL) {
+    if ((flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_RES_PRE)) == R2N2_EPI_RESIDUAL) {
       float r[16];
       cur.r.unpack(r);
 #pragma unroll

@@ -62,9 +62,11 @@ class ParamStore:
     """Flat fp32 parameter / gradient / moment buffers.  Non-bias segments first (L2 decay
     applies to [0, n_decay)), biases after.  Segments are 64-element aligned."""
 
-    def __init__(self, device, mirror_dtype=None):
+    def __init__(self, device, mirror_dtype=None, split=False):
         self.device = device
         self.mirror_dtype = mirror_dtype
+        self.split = split            # bf16x3: mirror = hi, mirror_lo = lo operand halves
+        self.mirror_lo = None
         self._plan = []           # (name, numel, is_bias)
         self.offsets = {}
         self.version = 0
@@ -87,6 +89,8 @@ class ParamStore:
         self.g = torch.zeros(self.n, dtype=torch.float32, device=self.device)
         if self.mirror_dtype is not None:
             self.mirror = torch.zeros(self.n, dtype=self.mirror_dtype, device=self.device)
+            if self.split:
+                self.mirror_lo = torch.zeros(self.n, dtype=self.mirror_dtype, device=self.device)
 
     def seg(self, name, buf=None):
         off, numel = self.offsets[name]
@@ -102,7 +106,9 @@ class ParamStore:
         self.version += 1
 
     def refresh_mirror(self):
-        if self.mirror is not None and self.p.is_cuda:
+        if self.mirror_lo is not None:
+            ops.split_bf16(self.p, self.mirror, self.mirror_lo)
+        elif self.mirror is not None and self.p.is_cuda:
             ops.cast(self.p, self.mirror)
 
 
@@ -122,9 +128,12 @@ class Engine:
         self.device = torch.device(device)
         self.compute = compute
         self._graphs = {}
-        self.dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16}[compute]
+        # 'fp32': FFMA kernels (exact parity path); 'bf16': tcgen05, bf16 operands and activations;
+        # 'bf16x3': tcgen05 over hi/lo split operands, fp32 activations (fp32 accuracy at 1/3 of the bf16 rate)
+        self.dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'bf16x3': torch.float32}[compute]
+        self.split = compute == 'bf16x3'
         if conv_algo is None:
-            conv_algo = L.ALGO_SIMT if compute == 'fp32' else L.ALGO_UMMA
+            conv_algo = {'fp32': L.ALGO_SIMT, 'bf16': L.ALGO_UMMA, 'bf16x3': L.ALGO_SPLIT}[compute]
         self.algo = conv_algo
         self.wgrad_algo = conv_algo if wgrad_algo is None else wgrad_algo
         self.residual = net_name != 'GRUNet'
@@ -138,7 +147,8 @@ class Engine:
         # tensor path: the 7x7x3 first layer runs on a row-packed input (7 taps x 3 channels packed
         # into 32 channels by r2n2_nchw_to_rowpack) as a 7x1 convolution: K = 7*32 instead of 49*16
         self.rowpack = 0 if self.algo == L.ALGO_SIMT else 32
-        self.store = ParamStore(self.device, None if self.dtype == torch.float32 else self.dtype)
+        self.store = ParamStore(self.device, torch.bfloat16 if self.split else
+                                (None if self.dtype == torch.float32 else self.dtype), split=self.split)
         self.P = {}
         self.weights = []      # RefWeight list in reference creation order
         self._define()
@@ -147,6 +157,7 @@ class Engine:
         self.progress = None       # callback(stage) fired when a backward stage's grads are final
         self._marks = (0, 0)
         self._enc_marks = {}       # encoder sub-stage -> tape index at which its gradients are final
+        self.debug = None          # dict: forward() drops named intermediate buffers here (tools/diag_head.py)
 
     # ------------------------------------------------------------------ parameter definition
     def _define(self):
@@ -212,7 +223,8 @@ class Engine:
 
         def mk_param(seg, cout, taps, cin):
             p = Param(st.seg(seg), st.seg(seg, st.g),
-                      None if st.mirror is None else st.seg(seg, st.mirror), cout, taps, cin, st)
+                      None if st.mirror is None else st.seg(seg, st.mirror), cout, taps, cin, st,
+                      None if st.mirror_lo is None else st.seg(seg, st.mirror_lo))
             self.P[seg] = p
             return p
 
@@ -289,8 +301,10 @@ class Engine:
 
         if st.p.is_cuda:
             # conv1's input has no gradient: its transposed operand is never used
-            self.tbatch = ops.TransposeBatch(
-                [p for n, p in self.P.items() if p.taps * p.cin > 1 and not n.startswith(('conv1a.', 'conv1.'))], st)
+            tparams = [p for n, p in self.P.items() if p.taps * p.cin > 1 and not n.startswith(('conv1a.', 'conv1.'))]
+            self.tbatch = ops.TransposeBatch(tparams, st)
+            if self.split:
+                self.tbatch_lo = ops.TransposeBatch(tparams, st, 'mirror_lo', 'wt_lo')
 
     # ------------------------------------------------------------------ parameter I/O
     def set_params(self, arrays):
@@ -324,7 +338,7 @@ class Engine:
         for gname, members in self.groups:
             n = HID_POS * len(members) * HID_C
             xp = ctx.empty(TB * n, f.data)
-            ops.conv_fwd(f.data, self.P['rnn.Wx_' + gname].operand(), None, None, None, xp,
+            ops.conv_fwd_x(f.data, self.P['rnn.Wx_' + gname].operand(), None, None, None, xp,
                          (TB, 1, 1, 1, N_FC), n, (1, 1, 1), 0, ctx.algo)
             xps[gname] = xp
         return xps
@@ -341,16 +355,16 @@ class Engine:
             d = dxp[gname]                                     # [T,B,64,cg]
             ops.bias_grad(d, bb.grad, cg, bb.grad_written); bb.grad_written = True
             if T > 1:                                          # step 0 has h == 0: no conv term
-                ops.conv_wgrad(hin[gname][:(T - 1) * B * HID_POS * HID_C], d[B * HID_POS * cg:],
+                ops.conv_wgrad_x(hin[gname][:(T - 1) * B * HID_POS * HID_C], d[B * HID_POS * cg:],
                                Wh.grad, ((T - 1) * B, g4, g4, g4, HID_C), cg, (3, 3, 3),
                                ctx.wgrad_algo, Wh.grad_written)
                 Wh.grad_written = True
-            ops.conv_wgrad(f.data, d, Wx.grad, (TB, 1, 1, 1, N_FC), HID_POS * cg, (1, 1, 1),
+            ops.conv_wgrad_x(f.data, d, Wx.grad, (TB, 1, 1, 1, N_FC), HID_POS * cg, (1, 1, 1),
                            ctx.wgrad_algo, Wx.grad_written)
             Wx.grad_written = True
             if idx < len(self.groups) - 1:
                 first = ctx.empty(TB * N_FC, f.data)
-                ops.conv_fwd(d, Wx.operand_t(), None, None, None, first,
+                ops.conv_fwd_x(d, Wx.operand_t(), None, None, None, first,
                              (TB, 1, 1, 1, HID_POS * cg), N_FC, (1, 1, 1), 0, ctx.algo)
             else:
                 # last group: fuse the accumulation and fc7's LeakyReLU' into the epilogue
@@ -369,7 +383,7 @@ class Engine:
             mask = f.data
             f.grad_preact = True
         out = extra if extra is not None else ctx.empty(TB * N_FC, f.data)
-        ops.conv_fwd(d, Wx.operand_t(), None, mask, res, out, (TB, 1, 1, 1, kdim), N_FC, (1, 1, 1),
+        ops.conv_fwd_x(d, Wx.operand_t(), None, mask, res, out, (TB, 1, 1, 1, kdim), N_FC, (1, 1, 1),
                      flags, ctx.algo)
         f.grad, f.grad_shared = out, False
         f.n_recv += 1
@@ -397,12 +411,12 @@ class Engine:
                 continue
             hp = sl(h, t - 1)
             a_ur = ctx.empty(B * 2 * hn, f.data)
-            ops.conv_fwd(hp, P['rnn.Wh_ur'].operand(), None, None, None, a_ur, geom_h, 2 * HID_C,
+            ops.conv_fwd_x(hp, P['rnn.Wh_ur'].operand(), None, None, None, a_ur, geom_h, 2 * HID_C,
                          (3, 3, 3), 0, ctx.algo)
             ops.gru_ur_fwd(a_ur, sl(xp_ur, t, 2 * hn), P['rnn.b_ur'].data, hp, sl(u, t), sl(r, t),
                            sl(rh, t), B)
             a_c = ctx.empty(B * hn, f.data)
-            ops.conv_fwd(sl(rh, t), P['rnn.Wh_c'].operand(), None, None, None, a_c, geom_h, HID_C,
+            ops.conv_fwd_x(sl(rh, t), P['rnn.Wh_c'].operand(), None, None, None, a_c, geom_h, HID_C,
                          (3, 3, 3), 0, ctx.algo)
             ops.gru_out_fwd(a_c, sl(xp_c, t), P['rnn.b_c'].data, sl(u, t), hp, sl(c, t), sl(h, t), B)
         h_last = Act(sl(h, T - 1), geom_h, requires_grad=ctx.training)
@@ -424,10 +438,10 @@ class Engine:
                     if t == 0:
                         break
                     d_rh = ctx.empty(B * hn, f.data)
-                    ops.conv_fwd(sl(dxp_c, t), P['rnn.Wh_c'].operand_t(), None, None, None, d_rh,
+                    ops.conv_fwd_x(sl(dxp_c, t), P['rnn.Wh_c'].operand_t(), None, None, None, d_rh,
                                  geom_h, HID_C, (3, 3, 3), 0, ctx.algo)
                     ops.gru_r_bwd(d_rh, hp, sl(r, t), sl(dxp_ur, t, 2 * hn), dh_prev, B)
-                    ops.conv_fwd(sl(dxp_ur, t, 2 * hn), P['rnn.Wh_ur'].operand_t(), None, None, dh_prev,
+                    ops.conv_fwd_x(sl(dxp_ur, t, 2 * hn), P['rnn.Wh_ur'].operand_t(), None, None, dh_prev,
                                  dh_prev, geom_ur, HID_C, (3, 3, 3), L.EPI_RESIDUAL, ctx.algo)
                     dh = dh_prev
                 self._rnn_param_grads(ctx, f, {'ur': dxp_ur, 'c': dxp_c}, {'ur': h, 'c': rh[B * hn:]},
@@ -452,7 +466,7 @@ class Engine:
             a = None
             if t > 0:
                 a = ctx.empty(B * 3 * hn, f.data)
-                ops.conv_fwd(sl(h, t - 1), P['rnn.Wh_fig'].operand(), None, None, None, a, geom_h,
+                ops.conv_fwd_x(sl(h, t - 1), P['rnn.Wh_fig'].operand(), None, None, None, a, geom_h,
                              3 * HID_C, (3, 3, 3), 0, ctx.algo)
             ops.lstm_fwd(a, sl(xp, t, 3 * hn), P['rnn.b_fig'].data, sl(s, t - 1) if t > 0 else None,
                          sl(fig, t, 3 * hn), sl(s, t), sl(h, t), B)
@@ -473,7 +487,7 @@ class Engine:
                     if t == 0:
                         break
                     dh = ctx.empty(B * hn, f.data)
-                    ops.conv_fwd(sl(dxp, t, 3 * hn), P['rnn.Wh_fig'].operand_t(), None, None, None, dh,
+                    ops.conv_fwd_x(sl(dxp, t, 3 * hn), P['rnn.Wh_fig'].operand_t(), None, None, None, dh,
                                  geom_3, HID_C, (3, 3, 3), 0, ctx.algo)
                     ds = ds_prev
                 self._rnn_param_grads(ctx, f, {'fig': dxp}, {'fig': h}, T, B)
@@ -497,6 +511,8 @@ class Engine:
         TB = T * B
         ctx = Ctx(self.dtype, self.algo, self.wgrad_algo, training)
         self.ctx = ctx
+        if self.split:
+            ops.split_cache_clear()
         if training:
             for p in self.P.values():
                 p.grad_written = False
@@ -533,7 +549,7 @@ class Engine:
                     kk = (1, 7, 1) if i == 0 else (1, 3, 3)
                     ops.useful_frac = 21.0 / rp if i == 0 else 1.0
                     dst = sl(ys[i], img * img * W_.cout)
-                    ops.conv_fwd(src, W_.operand(), b_.data, None, None, dst, (B, 1, img, img, cin), W_.cout, kk,
+                    ops.conv_fwd_x(src, W_.operand(), b_.data, None, None, dst, (B, 1, img, img, cin), W_.cout, kk,
                                  L.EPI_BIAS | L.EPI_LRELU, ctx.algo)
                     ops.useful_frac = 1.0
                     src, cin = dst, W_.cout
@@ -578,6 +594,8 @@ class Engine:
                 pool1 = ctx.pool(c2h('conv1b', c2h('conv1a', a, 0), 1), out_data=head[2])
             else:
                 pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
+            if self.debug is not None:
+                self.debug['xin'], self.debug['pool1'] = a.data, pool1.data
             mark_mid = len(ctx.tape)            # tape entries from here on: conv2a ... (enc_mid, enc_hi)
             pool2 = ctx.pool(c2('conv2c', pool1, False), c2('conv2b', c2('conv2a', pool1, True), True))
             pool3 = ctx.pool(c2('conv3c', pool2, False), c2('conv3b', c2('conv3a', pool2, True), True))
@@ -599,6 +617,8 @@ class Engine:
             pool6 = t_
         flat = ctx.reshape(pool6, (TB, 1, 1, 1, N_CONVFILTER[5] * 9))
         f = ctx.conv(flat, P['fc7.W'], P['fc7.b'], (1, 1, 1), True)
+        if self.debug is not None:
+            self.debug['pool6'], self.debug['f'] = pool6.data, f.data
         mark_enc = len(ctx.tape)
         self._enc_marks = {'enc_hi': mark_hi, 'enc_mid': mark_mid}
 
@@ -658,6 +678,8 @@ class Engine:
                          B, nv, 1.0 / (B * nv ** 3), self.logit_c)
         if training:
             logits.grad, logits.n_recv = dlogits, 1
+        if self.debug is not None:
+            self.debug['h'], self.debug['logits'] = h.data, logits.data
         loss = None if loss_sum is None else loss_sum[0] / float(B * nv ** 3)
         g5 = N_GRU_VOX
         gates_ref = gates.reshape(T, B, g5, g5, g5, HID_C).permute(0, 1, 2, 5, 3, 4)
@@ -729,6 +751,8 @@ class Engine:
         ctx.tape = []
         self._finalize_stage('enc_lo')
         self.ctx = None
+        if self.split:
+            ops.split_cache_clear()
 
     def stage_segments(self):
         """Non-bias store segments per backward stage, in the order their gradients become final:

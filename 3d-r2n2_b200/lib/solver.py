@@ -58,13 +58,19 @@ class Solver(object):
             t = float(self.iteration)
             lr_t = float(self.lr) * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
             st.ensure_moments()
-            ops.adam(st.p, st.g, st.m, st.v, st.mirror, st.n_decay, lr_t, self.beta_1, self.beta_2,
-                     self.epsilon, self.w_decay, grad_scale)
+            split = getattr(st, 'mirror_lo', None) is not None       # bf16x3: hi / lo operand halves, one extra pass
+            ops.adam(st.p, st.g, st.m, st.v, None if split else st.mirror, st.n_decay, lr_t, self.beta_1,
+                     self.beta_2, self.epsilon, self.w_decay, grad_scale)
+            if split:
+                st.refresh_mirror()
         else:
             if st.m is None:
                 st.m = torch.zeros_like(st.p)
-            ops.sgd(st.p, st.g, st.m, st.mirror, st.n_decay, float(self.lr), self.momentum,
+            split = getattr(st, 'mirror_lo', None) is not None
+            ops.sgd(st.p, st.g, st.m, None if split else st.mirror, st.n_decay, float(self.lr), self.momentum,
                     self.w_decay, grad_scale)
+            if split:
+                st.refresh_mirror()
         st.touch()
 
     def _step(self, x, y):

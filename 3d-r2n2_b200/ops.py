@@ -157,6 +157,105 @@ def conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate, up2=False):
           _stream())
 
 
+# ======================================================================= hi/lo operand split (COMPUTE='bf16x3')
+class SplitPair:
+    """(hi, lo) bf16 tensors with hi + lo == the fp32 source up to 2^-17 relative."""
+    __slots__ = ('hi', 'lo', 'src')
+
+    def __init__(self, hi, lo, src=None):
+        self.hi, self.lo, self.src = hi, lo, src
+
+
+def split_bf16(src, hi, lo):
+    _check(src, torch.float32), _check(hi, torch.bfloat16), _check(lo, torch.bfloat16)
+    assert hi.numel() == src.numel() == lo.numel()
+    _work(0.0, (src, hi, lo))
+    _call('r2n2_split_bf16', _ptr(src), _ptr(hi), _ptr(lo), src.numel(), _stream())
+
+
+# activations split during the current step: (data_ptr, numel) -> SplitPair.  The pair keeps a reference to its
+# source, so the allocator cannot hand the same address to another tensor while the entry lives; cleared by the
+# engine at the start of every forward pass and at the end of every backward pass.
+_split_cache = {}
+
+
+def split_cache_clear():
+    _split_cache.clear()
+
+
+def split_invalidate(t):
+    """t was overwritten in place (gradient accumulation, LeakyReLU' applied to a handed-over buffer): a split
+    taken before the write is stale."""
+    if _split_cache and t is not None:
+        _split_cache.pop((t.data_ptr(), t.numel()), None)
+
+
+def split_of(x):
+    """x: fp32 tensor (an activation / gradient that is complete) or an existing SplitPair."""
+    if isinstance(x, SplitPair):
+        return x
+    key = (x.data_ptr(), x.numel())
+    sp = _split_cache.get(key)
+    if sp is None:
+        hi = torch.empty(x.numel(), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty(x.numel(), dtype=torch.bfloat16, device=x.device)
+        split_bf16(x, hi, lo)
+        sp = SplitPair(hi, lo, x)
+        _split_cache[key] = sp
+    return sp
+
+
+def conv_fwd_x(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo, colsum=None):
+    """conv_fwd, or -- algo == L.ALGO_SPLIT -- the same contraction at fp32 accuracy on the tensor cores:
+    x and w are split into bf16 (hi, lo) pairs and  hi*hi + lo*hi + hi*lo  is accumulated over three tcgen05
+    passes into the fp32 output (R2N2_EPI_RES_PRE: the partial sum enters before bias / LeakyReLU / mask;
+    the dropped lo*lo term is 2^-18 relative).  w is then a SplitPair of packed operands."""
+    if algo != L.ALGO_SPLIT:
+        return conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo, colsum)
+    Cin = geom[4]
+    assert isinstance(w, SplitPair) and y.dtype == torch.float32
+    if not umma_ok(Cin, cout):
+        raise RuntimeError('bf16x3: Cin %d / Cout %d is not a tcgen05 shape (multiples of 16)' % (Cin, cout))
+    xs = split_of(x)
+    global useful_frac
+    uf = useful_frac
+    useful_frac = uf / 3.0          # (profiler bookkeeping: the three passes are ONE algorithmic contraction)
+    try:
+        return _conv_fwd_split(xs, w, bias, mask_src, residual, y, geom, cout, k, flags, colsum)
+    finally:
+        useful_frac = uf
+
+
+def _conv_fwd_split(xs, w, bias, mask_src, residual, y, geom, cout, k, flags, colsum):
+    geo = flags & (L.CONV_UP2 | L.CONV_DOWN2)
+    real_res = residual if flags & L.EPI_RESIDUAL else None
+    assert not (real_res is not None and flags & L.EPI_LRELU), 'a post-activation residual cannot ride the split passes'
+    conv_fwd(xs.hi, w.hi, None, None, real_res, y, geom, cout, k, geo | (L.EPI_RESIDUAL if real_res is not None else 0),
+             L.ALGO_UMMA)
+    conv_fwd(xs.lo, w.hi, None, None, y, y, geom, cout, k, geo | L.EPI_RESIDUAL, L.ALGO_UMMA)
+    conv_fwd(xs.hi, w.lo, bias, mask_src, y, y, geom, cout, k,
+             geo | L.EPI_RESIDUAL | L.EPI_RES_PRE | (flags & (L.EPI_BIAS | L.EPI_LRELU | L.EPI_MASK)), L.ALGO_UMMA,
+             colsum)
+    return y
+
+
+def conv_wgrad_x(x, dy, dw, geom, cout, k, algo, accumulate, up2=False):
+    if algo != L.ALGO_SPLIT:
+        return conv_wgrad(x, dy, dw, geom, cout, k, algo, accumulate, up2)
+    if not umma_ok(geom[4], cout):
+        raise RuntimeError('bf16x3: Cin %d / Cout %d is not a tcgen05 shape (multiples of 16)' % (geom[4], cout))
+    xs, ds = split_of(x), split_of(dy)
+    global useful_frac
+    uf = useful_frac
+    useful_frac = uf / 3.0
+    try:
+        conv_wgrad(xs.hi, ds.hi, dw, geom, cout, k, L.ALGO_UMMA, accumulate, up2)
+        conv_wgrad(xs.lo, ds.hi, dw, geom, cout, k, L.ALGO_UMMA, True, up2)
+        conv_wgrad(xs.hi, ds.lo, dw, geom, cout, k, L.ALGO_UMMA, True, up2)
+    finally:
+        useful_frac = uf
+
+
 def bias_grad(dy, db, C, accumulate):
     _check(dy), _check(db, torch.float32)
     _work(0.0, (dy,))
@@ -174,10 +273,12 @@ class TransposeBatch:
     """Transposed (data-gradient) operands of ALL weight tensors of a flat store, refreshed by one
     launch per parameter version instead of one launch per layer."""
 
-    def __init__(self, params, store):
+    def __init__(self, params, store, mirror_attr='mirror', wt_attr='wt'):
         self.store = store
         self.params = params
-        dt = store.mirror.dtype if store.mirror is not None else torch.float32
+        self.mirror_attr = mirror_attr            # 'mirror' (bf16 / hi operands) or 'mirror_lo' (bf16x3 lo operands)
+        mirror = getattr(store, mirror_attr)
+        dt = mirror.dtype if mirror is not None else torch.float32
         rows, dst, tiles = [], 0, 0
         for p in params:
             rows.append([p.data.storage_offset(), dst, p.cout, p.taps, p.cin, tiles])
@@ -197,16 +298,20 @@ class TransposeBatch:
             self.table64 = torch.tensor(rows64, dtype=torch.int64, device=store.p.device)
         self.wt_all = torch.empty(dst, dtype=dt, device=store.p.device)
         for p, r in zip(params, rows):
-            p.wt = self.wt_all[r[1]:r[1] + p.data.numel()]
-            p.tbatch = self
+            setattr(p, wt_attr, self.wt_all[r[1]:r[1] + p.data.numel()])
+            if wt_attr == 'wt':
+                p.tbatch = self
+            else:
+                p.tbatch_lo = self
         self.version = -1
 
     def ensure(self):
         if self.version != self.store.version:
             if self.table64 is not None:
-                _check(self.store.mirror, torch.bfloat16)
-                _work(0.0, (self.store.mirror, self.wt_all))
-                _call('r2n2_weight_transpose_batch_bf16', _ptr(self.store.mirror), _ptr(self.wt_all),
+                mirror = getattr(self.store, self.mirror_attr)
+                _check(mirror, torch.bfloat16)
+                _work(0.0, (mirror, self.wt_all))
+                _call('r2n2_weight_transpose_batch_bf16', _ptr(mirror), _ptr(self.wt_all),
                       _ptr(self.table64), len(self.params), self.total_tiles64, _stream())
             else:
                 _check(self.store.p, torch.float32)
@@ -438,28 +543,45 @@ class Param:
     grad: fp32, same shape.  mirror: compute-dtype copy (bf16 path) or None.
     wt:   [cin, taps(reversed), cout] compute-dtype copy for the data-gradient GEMM."""
 
-    def __init__(self, data, grad, mirror, cout, taps, cin, store=None):
+    def __init__(self, data, grad, mirror, cout, taps, cin, store=None, mirror_lo=None):
         self.data, self.grad, self.mirror = data, grad, mirror
+        self.mirror_lo = mirror_lo      # bf16x3: low half of the operand split (mirror = high half)
         self.cout, self.taps, self.cin = cout, taps, cin
         self.store = store
         self.wt = None
+        self.wt_lo = None
+        self.tbatch_lo = None
         self.wt_version = -1
         self.tbatch = None       # TransposeBatch: all transposed operands refreshed by one launch
         self.grad_written = False
 
     def operand(self):
+        if self.mirror_lo is not None:
+            return SplitPair(self.mirror, self.mirror_lo, self.data)
         return self.mirror if self.mirror is not None else self.data
 
     def operand_t(self):
         if self.tbatch is not None:
             self.tbatch.ensure()
+            if self.tbatch_lo is not None:
+                self.tbatch_lo.ensure()
+                return SplitPair(self.wt, self.wt_lo)
             return self.wt
         ver = self.store.version if self.store is not None else 0
+        n = self.cin * self.taps * self.cout
+        if self.mirror_lo is not None:                       # bf16x3 without the batched transposes (host tests)
+            if self.wt is None or self.wt_version != ver:
+                t32 = torch.empty(n, dtype=torch.float32, device=self.data.device)
+                weight_transpose(self.data, t32, self.cout, self.taps, self.cin)
+                self.wt = torch.empty(n, dtype=torch.bfloat16, device=self.data.device)
+                self.wt_lo = torch.empty(n, dtype=torch.bfloat16, device=self.data.device)
+                split_bf16(t32, self.wt, self.wt_lo)
+                self.wt_version = ver
+            return SplitPair(self.wt, self.wt_lo)
         if self.wt is None or self.wt_version != ver:
             dt = self.mirror.dtype if self.mirror is not None else torch.float32
             if self.wt is None:
-                self.wt = torch.empty(self.cin * self.taps * self.cout, dtype=dt,
-                                      device=self.data.device)
+                self.wt = torch.empty(n, dtype=dt, device=self.data.device)
             weight_transpose(self.data, self.wt, self.cout, self.taps, self.cin)
             self.wt_version = ver
         return self.wt
@@ -495,6 +617,7 @@ class Ctx:
             x.grad, x.grad_shared = new, False
         else:
             add(x.grad, g, x.grad)
+            split_invalidate(x.grad)
         x.n_recv += 1
 
     def ensure_preact(self, out):
@@ -502,6 +625,7 @@ class Ctx:
         if out.lrelu_out and not out.grad_preact:
             dst = torch.empty_like(out.grad) if out.grad_shared else out.grad
             lrelu_bwd(out.data, out.grad, None, dst)
+            split_invalidate(dst)
             out.grad, out.grad_shared, out.grad_preact = dst, False, True
 
     def dgrad_into(self, x, dy, W, k, extra=None, down2=False):
@@ -520,6 +644,7 @@ class Ctx:
             flags |= L.EPI_RESIDUAL
             if extra is not None:
                 add(extra, res, extra)
+                split_invalidate(extra)
                 res = extra
         elif extra is not None:
             res = extra
@@ -538,13 +663,14 @@ class Ctx:
         if last and x.bias is not None and not x.bias_done and FUSE_BIAS_GRAD and x.bias.grad_written:
             colsum = x.bias.grad
             x.bias_done = True
-        conv_fwd(dy, W.operand_t(), None, mask, res, out_buf, (N, D, H, Wd, W.cout), Cin, k,
-                 flags, self.algo, colsum)
+        conv_fwd_x(dy, W.operand_t(), None, mask, res, out_buf, (N, D, H, Wd, W.cout), Cin, k,
+                   flags, self.algo, colsum)
+        split_invalidate(out_buf)
         x.grad, x.grad_shared = out_buf, False
         x.n_recv += 1
 
     def weight_grads(self, x_data, dy, geom, W, b, k, up2=False):
-        conv_wgrad(x_data, dy, W.grad, geom, W.cout, k, self.wgrad_algo, W.grad_written, up2)
+        conv_wgrad_x(x_data, dy, W.grad, geom, W.cout, k, self.wgrad_algo, W.grad_written, up2)
         W.grad_written = True
         if b is not None:
             bias_grad(dy, b.grad, W.cout, b.grad_written)
@@ -558,8 +684,8 @@ class Ctx:
     # ---- differentiable ops --------------------------------------------------------------
     def zero_skip(self, cin, cout):
         """Unpool3D+Conv3D can run fused (UP2: only the taps that meet a stored value)."""
-        return (self.algo == L.ALGO_UMMA and umma_ok(cin, cout)
-                and (self.dtype == torch.bfloat16 or ZERO_SKIP_ANY_DTYPE))
+        return (self.algo in (L.ALGO_UMMA, L.ALGO_SPLIT) and umma_ok(cin, cout)
+                and (self.dtype == torch.bfloat16 or self.algo == L.ALGO_SPLIT or ZERO_SKIP_ANY_DTYPE))
 
     def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False, out_data=None):
         """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw).
@@ -585,8 +711,8 @@ class Ctx:
             if up2:
                 flags |= L.CONV_UP2
             useful_frac = x.useful
-            conv_fwd(x.data, W.operand(), None if b is None else b.data, None,
-                     None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
+            conv_fwd_x(x.data, W.operand(), None if b is None else b.data, None,
+                       None if residual is None else residual.data, y, x.geom, cout, k, flags, self.algo)
             useful_frac = 1.0
         out = Act(y, og, requires_grad=self.training, lrelu_out=lrelu)
         out.bias = b

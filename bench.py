@@ -470,9 +470,10 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if compute == 'bf16' else 'f32', 'data': 'synthetic',
+                'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (hi/lo operand split, fp32 accumulate and storage)'}.get(compute, 'f32'),
+                'data': 'synthetic',
                 'config': config_dict(args, {'compute': compute,
-                                             'conv_algo': 'tcgen05/TMA' if compute == 'bf16' else 'fp32 FFMA',
+                                             'conv_algo': 'tcgen05/TMA' if compute.startswith('bf16') else 'fp32 FFMA',
                                              'final_loss': final_loss}),
                 'e2e': {'value': e2e_value, 'unit': UNIT,
                         'h2d_bytes_per_step': int(x_pin.numel() * 4 + y_pin.numel() * 4),

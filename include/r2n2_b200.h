@@ -49,6 +49,9 @@ extern "C" {
 #define R2N2_EPI_LRELU 2
 #define R2N2_EPI_RESIDUAL 4
 #define R2N2_EPI_MASK 8
+#define R2N2_EPI_RES_PRE 64  /* with R2N2_EPI_RESIDUAL: the residual is added to the accumulator BEFORE bias / LeakyReLU
+                                (a partial sum of the same contraction, e.g. the hi/lo operand-split passes of
+                                COMPUTE='bf16x3'), instead of after the activation */
 /* geometry flags of r2n2_conv_fwd (R2N2_ALGO_UMMA only), N,D,H,W always name the SMALL grid:
  * UP2  : fused Unpool3DLayer + Conv3DLayer (lib/layers.py:375-385 + 441): x is [N,D,H,W,Cin], the
  *        convolution runs over its zero-stuffed x2 upsampling and y / residual / mask_src are
@@ -121,6 +124,11 @@ int r2n2_weight_transpose_batch_bf16(const void* mirror_base, void* wt_base, con
 
 /* fp32 -> out_dtype copy (bf16 operand mirrors of the fp32 master weights). */
 int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream);
+
+/* fp32 -> (hi, lo) bf16 pair with src = hi + lo up to 2^-17 relative: the operand split of the
+ * COMPUTE='bf16x3' path (three tcgen05 passes hi*hi + lo*hi + hi*lo accumulated in fp32 reach the
+ * reference's float32 accuracy, .theanorc:2, at a third of the bf16 tensor rate). */
+int r2n2_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
 
 /* ---- bandwidth-bound kernels ----------------------------------------------------------
  * input images: x (N,C,H,W) fp32 as delivered by lib/data_process.py:133-148 -> channels-last

@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 LEAK = 0.01
 EPI_BIAS, EPI_LRELU, EPI_RESIDUAL, EPI_MASK = 1, 2, 4, 8
+EPI_RES_PRE = 64
 
 
 def _f(t):
@@ -41,11 +42,13 @@ def conv_fwd(x, w, bias, mask_src, residual, y, geom, cout, k, flags, algo, cols
     if flags & CONV_DOWN2:
         o = o[:, :, ::2, ::2, ::2]
     o = o.permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    if (flags & EPI_RESIDUAL) and (flags & EPI_RES_PRE):
+        o = o + _f(residual).view(-1, cout)
     if flags & EPI_BIAS:
         o = o + _f(bias).view(1, cout)
     if flags & EPI_LRELU:
         o = torch.where(o > 0, o, LEAK * o)
-    if flags & EPI_RESIDUAL:
+    if (flags & EPI_RESIDUAL) and not (flags & EPI_RES_PRE):
         o = o + _f(residual).view(-1, cout)
     if flags & EPI_MASK:
         m = _f(mask_src).view(-1, cout)
@@ -97,6 +100,12 @@ def fill_zero(t):
 
 def cast(src, dst):
     dst.copy_(src.to(dst.dtype))
+
+
+def split_bf16(src, hi, lo):
+    h = src.to(torch.bfloat16)
+    hi.copy_(h)
+    lo.copy_((src - h.float()).to(torch.bfloat16))
 
 
 def nchw_to_nhwc(x, y, cpad, wpad=None, xoff=0):
@@ -292,7 +301,7 @@ def voxel_eval(pred, gt, thresh):
     return torch.stack([f(occ ^ g1), f(occ & g1), f(occ | g1), f(occ & g0), f(~occ & g1)], 1)
 
 
-ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
+ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'split_bf16', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
        'maxpool_fwd', 'maxpool_bwd', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
        'eltwise', 'gru_ur_fwd', 'gru_out_fwd', 'gru_out_bwd', 'gru_r_bwd', 'lstm_fwd', 'lstm_bwd',
        'softmax_ce3d', 'adam', 'sgd', 'voxel_eval']

