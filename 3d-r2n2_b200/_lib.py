@@ -16,6 +16,7 @@ WGRAD_ACCUMULATE, WGRAD_UP2 = 1, 2
 ALGO_SIMT, ALGO_UMMA = 0, 1
 ALGO_SPLIT = 2      # host-level only: three ALGO_UMMA passes over hi/lo split operands (COMPUTE='bf16x3')
 ELT_SIGMOID, ELT_TANH, ELT_COMPLEMENT, ELT_MUL = 0, 1, 2, 3
+ELT_SIGMOID_BWD, ELT_TANH_BWD, ELT_NEG = 4, 5, 6
 
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 

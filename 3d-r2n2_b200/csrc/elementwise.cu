@@ -394,9 +394,19 @@ __global__ void eltwise_kernel(int op, const T* __restrict__ a, const T* __restr
       o = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
     } else if (op == R2N2_ELT_COMPLEMENT) {
       o = make_float4(1.f - v.x, 1.f - v.y, 1.f - v.z, 1.f - v.w);
+    } else if (op == R2N2_ELT_NEG) {
+      o = make_float4(-v.x, -v.y, -v.z, -v.w);
     } else {
       float4 u = Vec4<T>::load(b + i * 4);
-      o = make_float4(v.x * u.x, v.y * u.y, v.z * u.z, v.w * u.w);
+      if (op == R2N2_ELT_MUL) {
+        o = make_float4(v.x * u.x, v.y * u.y, v.z * u.z, v.w * u.w);
+      } else if (op == R2N2_ELT_SIGMOID_BWD) {      // a = sigmoid output, b = dL/dy
+        o = make_float4(u.x * v.x * (1.f - v.x), u.y * v.y * (1.f - v.y), u.z * v.z * (1.f - v.z),
+                        u.w * v.w * (1.f - v.w));
+      } else {                                      // R2N2_ELT_TANH_BWD: a = tanh output
+        o = make_float4(u.x * (1.f - v.x * v.x), u.y * (1.f - v.y * v.y), u.z * (1.f - v.z * v.z),
+                        u.w * (1.f - v.w * v.w));
+      }
     }
     Vec4<T>::store(y + i * 4, o);
   }
@@ -1292,8 +1302,9 @@ int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, 
 int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int dtype,
                  void* stream) {
   R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "eltwise: n must be a multiple of 4");
-  R2N2_CHECK_ARG(op >= R2N2_ELT_SIGMOID && op <= R2N2_ELT_MUL, R2N2_ERR_UNSUPPORTED, "eltwise: bad op %d", op);
-  R2N2_CHECK_ARG(op != R2N2_ELT_MUL || b, R2N2_ERR_BAD_SHAPE, "eltwise: MUL needs two operands");
+  R2N2_CHECK_ARG(op >= R2N2_ELT_SIGMOID && op <= R2N2_ELT_NEG, R2N2_ERR_UNSUPPORTED, "eltwise: bad op %d", op);
+  R2N2_CHECK_ARG(!(op == R2N2_ELT_MUL || op == R2N2_ELT_SIGMOID_BWD || op == R2N2_ELT_TANH_BWD) || b,
+                 R2N2_ERR_BAD_SHAPE, "eltwise: op %d needs two operands", op);
   R2N2_DISPATCH_DTYPE(dtype, T, {
     eltwise_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
         op, (const T*)a, (const T*)b, (T*)y, n >> 2);

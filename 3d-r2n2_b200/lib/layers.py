@@ -24,6 +24,51 @@ trainable_params = []          # lib/layers.py:10 (module-global, never cleared:
 _rng = np.random.RandomState()  # lib/layers.py:31 uses an unseeded RandomState per Weight
 _ctx = None
 DEVICE = 'cuda'              # the kernels only run on CUDA; tests of the host logic override it
+_replay = None               # active replay_weights context (define-by-run nets, models/net.py)
+
+
+class _LayerStore:
+    """What ops.Param needs from a parameter store: a version that moves when the optimiser (or set_value)
+    changes the values, so that transposed data-gradient operands are rebuilt."""
+    version = 0
+
+
+_layer_store = _LayerStore()
+
+
+class replay_weights:
+    """A user-defined `network_definition` (models/net.py:43-51) runs once per call here instead of once per
+    Theano compile.  Inside this context every `Weight(...)` construction returns the tensor created at the same
+    position of the FIRST run instead of a new one, so the body needs no change."""
+
+    def __init__(self, weights):
+        self.weights, self.pos = list(weights), 0
+
+    def __enter__(self):
+        global _replay
+        if _replay is not None:
+            raise RuntimeError('nested network_definition replay')
+        _replay = self
+        self.pos = 0
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global _replay
+        _replay = None
+        if et is None and self.pos != len(self.weights):
+            raise RuntimeError('network_definition created %d Weights, %d on the first run'
+                               % (self.pos, len(self.weights)))
+        return False
+
+    def next(self, w_shape, is_bias):
+        if self.pos >= len(self.weights):
+            raise RuntimeError('network_definition creates more Weights than on its first run')
+        w = self.weights[self.pos]
+        self.pos += 1
+        if tuple(np.atleast_1d(w.shape)) != tuple(np.atleast_1d(w_shape)) or w.is_bias != is_bias:
+            raise RuntimeError('network_definition is not deterministic: Weight %d was %s, now %s'
+                               % (self.pos - 1, tuple(np.atleast_1d(w.shape)), tuple(np.atleast_1d(w_shape))))
+        return w
 
 
 def get_trainable_params():
@@ -58,6 +103,7 @@ class _Shared:
         self._owner = owner
 
     def get_value(self):
+        self._owner.sync_host()
         return self._owner.np_values
 
     def set_value(self, v):
@@ -65,14 +111,22 @@ class _Shared:
         if tuple(v.shape) != tuple(np.shape(self._owner.np_values)):
             raise ValueError('shape mismatch: %s vs %s' % (v.shape, np.shape(self._owner.np_values)))
         self._owner.np_values = v
-        self._owner._param = None      # re-pack lazily
+        self._owner._host_stale = False
+        self._owner.repack()
 
 
 class Weight(object):
     """lib/layers.py:18-79: same signature, same fillers, same fan-in/out rules."""
 
+    def __new__(cls, w_shape, is_bias, *args, **kwargs):
+        if _replay is not None:
+            return _replay.next(w_shape, is_bias)
+        return super(Weight, cls).__new__(cls)
+
     def __init__(self, w_shape, is_bias, mean=0, std=0.01, filler='msra', fan_in=None,
                  fan_out=None, name=None):
+        if getattr(self, '_defined', False):      # handed out again by replay_weights
+            return
         super(Weight, self).__init__()
         assert (is_bias in [True, False])
         rng = _rng
@@ -115,6 +169,10 @@ class Weight(object):
         self.name = name
         self._kind = None      # how the owning layer packs it: ('conv2d', cin_pad) ...
         self._param = None
+        self._host_stale = False   # the optimiser moved the device copy: np_values is refreshed on get_value
+        self._m = self._v = None   # optimiser moments (packed layout, like the parameter)
+        self.grad_seen = False
+        self._defined = True
         global trainable_params
         trainable_params.append(self)
 
@@ -123,10 +181,50 @@ class Weight(object):
         if self._kind is None:
             self._kind = kind
 
-    def param(self, ctx):
-        if self._param is not None and self._param_dtype == ctx.dtype:
-            return self._param
-        t = torch.as_tensor(self.np_values).to(DEVICE)
+    def repack(self):
+        """Values changed on the host: refill the packed device copy IN PLACE (optimiser moments and the
+        gradient buffer stay attached) or drop it when the layout is not known yet."""
+        if self._param is None:
+            return
+        fresh = self._pack(torch.as_tensor(self.np_values).to(self._param.data.device))[0]
+        self._param.data.copy_(fresh.contiguous().view(-1))
+        if self._param.mirror is not None:
+            ops.cast(self._param.data, self._param.mirror)
+        _layer_store.version += 1
+
+    def sync_host(self):
+        """Device copy -> np_values in the reference layout (after optimiser steps)."""
+        if not self._host_stale or self._param is None:
+            return
+        self.np_values = self._unpack(self._param.data)
+        self._host_stale = False
+
+    def grad_value(self):
+        """tensor.grad(loss, self.val) of the last forward_backward, reference layout (models/net.py:58)."""
+        if self._param is None:
+            return np.zeros(tuple(np.atleast_1d(self.shape)), np.float32)
+        return self._unpack(self._param.grad)
+
+    def _unpack(self, v):
+        kind, shp = self._kind, tuple(int(d) for d in np.atleast_1d(self.shape))
+        if kind is None or kind[0] == 'bias':
+            r = v.view(shp)
+        elif kind[0] == 'conv2d':
+            r = pk.unpack_conv2d(v.view(shp[0], shp[2], shp[3], kind[1]), shp[1])
+        elif kind[0] == 'conv3d':
+            r = pk.unpack_conv3d(v.view(shp[0], shp[1], shp[3], shp[4], shp[2]))
+        elif kind[0] == 'fc':
+            r = pk.unpack_fc(v.view(shp[1], shp[0]), kind[1])
+        elif kind[0] == 'wx':
+            d, c, h, w = kind[1]
+            r = pk.unpack_fcconv_wx(v.view(d * h * w, c, shp[0]), d, c, h, w)
+        elif kind[0] == 'blockdiag':
+            r = v.view(shp[:-2] + (shp[-1], shp[-2])).transpose(-1, -2)
+        else:
+            raise ValueError(kind)
+        return r.contiguous().cpu().numpy().reshape(shp)
+
+    def _pack(self, t):
         kind = self._kind
         if kind is None or kind[0] == 'bias':
             p, cout, taps, cin = t.contiguous(), t.numel(), 1, 1
@@ -143,15 +241,26 @@ class Weight(object):
             d, c, h, w = kind[1]
             p = pk.pack_fcconv_wx(t, d, c, h, w).contiguous()
             cout, taps, cin = d * h * w * c, 1, t.shape[0]
+        elif kind[0] == 'blockdiag':          # (D_1..D_{n-1}, n_in, n_out) -> per position [n_out][n_in]
+            p = t.transpose(-1, -2).contiguous()
+            cout, taps, cin = t.shape[-1], 1, t.shape[-2]
         else:
             raise ValueError(kind)
+        return p, cout, taps, cin
+
+    def param(self, ctx):
+        if self._param is not None and self._param_dtype == ctx.dtype:
+            return self._param
+        self.sync_host()
+        p, cout, taps, cin = self._pack(torch.as_tensor(self.np_values).to(DEVICE))
         p = p.contiguous().view(-1)
         mirror = None
         if ctx.dtype != torch.float32 and not self.is_bias:
             mirror = torch.empty_like(p, dtype=ctx.dtype)
             ops.cast(p, mirror)
-        self._param = Param(p, None, mirror, cout, taps, cin, None)
+        self._param = Param(p, torch.zeros_like(p), mirror, cout, taps, cin, _layer_store)
         self._param_dtype = ctx.dtype
+        self._m = self._v = None
         return self._param
 
 
@@ -165,6 +274,8 @@ def _as_act(t, shape, ctx):
     """Reference-layout tensor / ndarray (or an Act) -> channels-last Act."""
     if isinstance(t, Act):
         return t
+    if getattr(t, '_r2n2_act', None) is not None:      # a Layer's .output: stay on the tape
+        return t._r2n2_act
     if isinstance(t, np.ndarray):
         t = torch.as_tensor(t)
     if not isinstance(t, torch.Tensor):
@@ -185,6 +296,8 @@ def _as_act(t, shape, ctx):
         return Act(y, (B, D, H, W, C))
     if t.dim() == 2:
         return Act(t.to(ctx.dtype).contiguous().view(-1), (t.shape[0], 1, 1, 1, t.shape[1]))
+    if t.dim() == 3:
+        return Act(t.to(ctx.dtype).contiguous().view(-1), (t.shape[0], 1, 1, t.shape[1], t.shape[2]))
     raise ValueError('unsupported input rank %d' % t.dim())
 
 
@@ -193,12 +306,20 @@ def _ref_view(act, shape):
     N, D, H, W, C = act.geom
     d = act.data.view(N, D, H, W, C)
     if len(shape) == 4:
-        return d[:, 0].permute(0, 3, 1, 2)[:, :shape[1]]
-    if len(shape) == 5:
-        return d.permute(0, 1, 4, 2, 3)
-    if len(shape) == 2:
-        return d.reshape(N, -1)
-    raise ValueError(shape)
+        v = d[:, 0].permute(0, 3, 1, 2)[:, :shape[1]]
+    elif len(shape) == 5:
+        v = d.permute(0, 1, 4, 2, 3)
+    elif len(shape) == 2:
+        v = d.reshape(N, -1)
+    elif len(shape) == 3:
+        v = d.reshape(N, shape[1], shape[2])
+    else:
+        raise ValueError(shape)
+    if v.data_ptr() == act.data.data_ptr() and v.numel() == act.data.numel():
+        # the symbolic variable of the reference: feeding it to InputLayer / SoftmaxWithLoss3D / scan keeps the
+        # producing Act (and with it the gradient path), like passing a Theano variable does
+        v._r2n2_act = act
+    return v
 
 
 class InputLayer(object):
@@ -289,7 +410,7 @@ class TensorProductLayer(Layer):
         ctx = get_context()
         x = self._prev_layer.act
         N = x.geom[0]
-        xin = Act(x.data, (N, 1, 1, 1, x.data.numel() // N))
+        xin = ctx.view(x, (N, 1, 1, 1, x.data.numel() // N))
         self._act = ctx.conv(xin, self.W.param(ctx), self.b.param(ctx) if self._bias else None,
                              (1, 1, 1))
 
@@ -315,10 +436,7 @@ class EltwiseMultiplyLayer(Layer):
         self._mult_layer = mult_layer
 
     def set_output(self):
-        a, b = self._prev_layer.act, self._mult_layer.act
-        y = torch.empty_like(a.data)
-        ops.eltwise(L.ELT_MUL, a.data, b.data, y)
-        self._act = Act(y, a.geom)
+        self._act = get_context().mul(self._prev_layer.act, self._mult_layer.act)
 
 
 class FlattenLayer(Layer):
@@ -332,8 +450,7 @@ class FlattenLayer(Layer):
 
     def set_output(self):
         x = self._prev_layer.act
-        self._act = Act(x.data, (x.geom[0], 1, 1, 1, x.data.numel() // x.geom[0]),
-                        lrelu_out=x.lrelu_out)
+        self._act = get_context().view(x, (x.geom[0], 1, 1, 1, x.data.numel() // x.geom[0]))
 
     @property
     def output(self):
@@ -492,9 +609,9 @@ class FCConv3DLayer(Layer):
         h = self._prev_layer.act
         f = self._fc_layer.act
         B = f.geom[0]
-        fin = Act(f.data, (B, 1, 1, 1, f.data.numel() // B))
+        fin = ctx.view(f, (B, 1, 1, 1, f.data.numel() // B))
         xp = ctx.conv(fin, self.Wx.param(ctx), None, (1, 1, 1))
-        xp = Act(xp.data, (h.geom[0], h.geom[1], h.geom[2], h.geom[3], self._output_shape[2]))
+        xp = ctx.view(xp, (h.geom[0], h.geom[1], h.geom[2], h.geom[3], self._output_shape[2]))
         fs = self._filter_shape
         self._act = ctx.conv(h, self.Wh.param(ctx), self.b.param(ctx), (fs[1], fs[3], fs[4]),
                              residual=xp)
@@ -512,6 +629,7 @@ class SoftmaxWithLoss3D(object):
         if not isinstance(input, Act):
             t = input
             input = _as_act(t, tuple(t.shape), Ctx(torch.float32, ctx.algo))
+        self._src = input               # the Act on the tape: dL/dlogits is delivered here by loss()
         if input.data.dtype != torch.float32:
             input = Act(input.data.float(), input.geom)
         self.input = input
@@ -520,7 +638,7 @@ class SoftmaxWithLoss3D(object):
             raise ValueError('SoftmaxWithLoss3D is accelerated for (B,n,2,n,n) inputs only')
         self._B, self._nv = B, D
 
-    def _run(self, y, want_pred):
+    def _run(self, y, want_pred, want_grad=False):
         B, nv = self._B, self._nv
         dev = self.input.data.device
         pred = torch.empty(B, nv, 2, nv, nv, dtype=torch.float32, device=dev) if want_pred else None
@@ -529,7 +647,14 @@ class SoftmaxWithLoss3D(object):
         if y is not None:
             yt = torch.as_tensor(y).to(dev).float().contiguous()
             loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        ops.softmax_ce3d(self.input.data, yt, pred, loss, None, B, nv, 1.0)
+        dlogits = None
+        src = self._src
+        if want_grad and y is not None and src.requires_grad and src.n_recv == 0:
+            # tensor.grad(loss, ...) starts here (models/net.py:56-58): d(mean CE)/dlogits from the same pass
+            dlogits = torch.empty(src.data.numel(), dtype=src.data.dtype, device=dev)
+        ops.softmax_ce3d(self.input.data, yt, pred, loss, dlogits, B, nv, 1.0 / float(B * nv ** 3))
+        if dlogits is not None:
+            src.grad, src.n_recv = dlogits, 1
         return pred, (None if loss is None else loss[0] / float(B * nv ** 3))
 
     def prediction(self):
@@ -541,7 +666,7 @@ class SoftmaxWithLoss3D(object):
         return torch.mean(((p >= threshold).float() == yt).float())
 
     def loss(self, y):
-        return self._run(y, False)[1]
+        return self._run(y, False, want_grad=get_context().training)[1]
 
 
 class LeakyReLU(Layer):
@@ -559,29 +684,239 @@ class LeakyReLU(Layer):
 
 
 class _Elt(Layer):
-    _op = None
+    _op = None        # name of the tape-aware Ctx op (forward kernel + its derivative)
 
     def __init__(self, prev_layer):
         super().__init__(prev_layer)
         self._output_shape = self._input_shape
 
     def set_output(self):
-        a = self._prev_layer.act
-        y = torch.empty_like(a.data)
-        ops.eltwise(self._op, a.data, None, y)
-        self._act = Act(y, a.geom)
+        self._act = getattr(get_context(), self._op)(self._prev_layer.act)
 
 
 class SigmoidLayer(_Elt):
     """lib/layers.py:649-656"""
-    _op = L.ELT_SIGMOID
+    _op = 'sigmoid'
 
 
 class TanhLayer(_Elt):
     """lib/layers.py:659-665 (the reference forgets to set _output_shape there)"""
-    _op = L.ELT_TANH
+    _op = 'tanh'
 
 
 class ComplementLayer(_Elt):
     """lib/layers.py:668-676: 1 - input"""
-    _op = L.ELT_COMPLEMENT
+    _op = 'complement'
+
+
+# ------------------------------------------------------------------------------------------------------
+# Layer classes no shipped model instantiates (lib/layers.py:164-203, 239-263, 508-575, 604-625); kept so that
+# `from lib.layers import ...` of a user's network file resolves and trains.  Pure data movement (dimshuffle,
+# reshape, concatenate) is torch plumbing between channels-last buffers; the arithmetic is C-ABI calls.
+def _geom_of(shape):
+    """channels-last geometry (N,D,H,W,C) that stores a reference-layout tensor of this shape"""
+    s = [int(v) for v in shape]
+    if len(s) == 2:
+        return (s[0], 1, 1, 1, s[1])
+    if len(s) == 3:
+        return (s[0], 1, 1, s[1], s[2])
+    if len(s) == 4:
+        return (s[0], 1, s[2], s[3], s[1])
+    if len(s) == 5:
+        return (s[0], s[1], s[3], s[4], s[2])
+    raise ValueError('unsupported rank %d' % len(s))
+
+
+def _logical(data, shape):
+    """channels-last buffer -> tensor with the reference's logical shape (a view)"""
+    g = _geom_of(shape)
+    d = data.view(g)
+    if len(shape) == 2:
+        return d.view(g[0], g[4])
+    if len(shape) == 3:
+        return d.view(g[0], g[3], g[4])
+    if len(shape) == 4:
+        return d[:, 0].permute(0, 3, 1, 2)
+    return d.permute(0, 1, 4, 2, 3)
+
+
+def _physical(t, shape):
+    """reference-layout tensor -> contiguous channels-last buffer (flat)"""
+    if len(shape) == 4:
+        t = t.permute(0, 2, 3, 1)
+    elif len(shape) == 5:
+        t = t.permute(0, 1, 3, 4, 2)
+    return t.contiguous().view(-1)
+
+
+def _movement(ctx, layers, fn, out_shape):
+    """out = fn(*[layer.output]) for a pure data-movement fn; the gradient is the same movement backwards."""
+    acts = [l.act for l in layers]
+    shapes = [tuple(l.output_shape) for l in layers]
+    for a, s in zip(acts, shapes):
+        if a.data.numel() != int(np.prod(s)):
+            raise NotImplementedError('data-movement layers need unpadded channel counts')
+    ins = [_logical(a.data, s) for a, s in zip(acts, shapes)]
+    out = Act(_physical(fn(*ins), out_shape), _geom_of(out_shape),
+              requires_grad=ctx.training and any(a.requires_grad for a in acts))
+    if out.requires_grad:
+        for a in acts:
+            ctx.consume(a)
+
+        def bwd():
+            if out.grad is None:
+                return
+            with torch.enable_grad():
+                leaves = [torch.zeros_like(i, dtype=torch.float32).requires_grad_(True) for i in ins]
+                gs = torch.autograd.grad(fn(*leaves), leaves, _logical(out.grad, out_shape).float())
+            for a, s, g in zip(acts, shapes, gs):
+                if a.requires_grad:
+                    ctx.accumulate(a, _physical(g, s).to(a.data.dtype))
+            out.grad = None
+        ctx.tape.append(bwd)
+    return out
+
+
+class DimShuffleLayer(Layer):
+    """lib/layers.py:239-250"""
+
+    def __init__(self, prev_layer, shuffle_pattern):
+        super().__init__(prev_layer)
+        self._shuffle_pattern = shuffle_pattern
+        self._output_shape = list(self._input_shape)
+        for out_dim, in_dim in enumerate(shuffle_pattern):
+            self._output_shape[out_dim] = self._input_shape[in_dim]
+        self._output_shape = tuple(self._output_shape)
+
+    def set_output(self):
+        pat = tuple(self._shuffle_pattern)
+        self._act = _movement(get_context(), [self._prev_layer], lambda t: t.permute(pat), self._output_shape)
+
+    @property
+    def output(self):
+        return _logical(self.act.data, self._output_shape)
+
+
+class ReshapeLayer(Layer):
+    """lib/layers.py:253-263"""
+
+    def __init__(self, prev_layer, reshape):
+        super().__init__(prev_layer)
+        self._output_shape = [self._prev_layer.output_shape[0]]
+        self._output_shape.extend(reshape)
+        self._output_shape = tuple(self._output_shape)
+        print('Reshape the prev layer to [%s]' % ','.join(str(x) for x in self._output_shape))
+
+    def set_output(self):
+        shp = tuple(int(v) for v in self._output_shape)
+        self._act = _movement(get_context(), [self._prev_layer], lambda t: t.reshape(shp), shp)
+
+    @property
+    def output(self):
+        return _logical(self.act.data, self._output_shape)
+
+
+class ConcatLayer(Layer):
+    """lib/layers.py:604-625"""
+
+    def __init__(self, prev_layers, axis=1):
+        assert (len(prev_layers) > 1)
+        super().__init__(prev_layers[0])
+        self._axis = axis
+        self._prev_layers = prev_layers
+        self._output_shape = list(self._input_shape).copy()
+        for prev_layer in prev_layers[1:]:
+            self._output_shape[axis] += prev_layer._output_shape[axis]
+        print('Concat the prev layer to [%s]' % ','.join(str(x) for x in self._output_shape))
+
+    def set_output(self):
+        ax = self._axis
+        self._act = _movement(get_context(), list(self._prev_layers), lambda *ts: torch.cat(ts, dim=ax),
+                              self._output_shape)
+
+    @property
+    def output(self):
+        return _logical(self.act.data, self._output_shape)
+
+
+class Conv3DLSTMLayer(Conv3DLayer):
+    """lib/layers.py:508-575.  The reference class is a stub: it computes an unused gate filter shape and then
+    exactly Conv3DLayer's output (zero pad + conv3d2d.conv3d(W) + b); the conv-LSTM *network* of BASELINE.json
+    config 4 is models.ResidualLSTMNet."""
+
+    def __init__(self, prev_layer, filter_shape, padding=None, params=None):
+        super().__init__(prev_layer, filter_shape, padding, params)
+        n_c, n_x = filter_shape[0], self._input_shape[2]
+        self._gate_filter_shape = [4 * n_c, 1, n_x + n_c, 1, 1]
+
+
+class BlockDiagonalLayer(Layer):
+    """lib/layers.py:164-203: out[n, d.., o] = sum_k x[n, d.., k] * W[d.., k, o] (+ b[d.., o]) -- one small GEMM
+    per position d, each a C-ABI contraction call (forward, weight gradient, data gradient)."""
+
+    def __init__(self, prev_layer, n_out, params=None, bias=True):
+        super().__init__(prev_layer)
+        self._bias = bias
+        self._output_shape = list(self._input_shape)
+        self._output_shape[-1] = n_out
+        self._output_shape = tuple(self._output_shape)
+        if params is None:
+            self._W_shape = tuple(list(self._input_shape[1:]) + [n_out])
+            self.W = Weight(self._W_shape, is_bias=False)
+            if bias:
+                self.b = Weight(self._output_shape[1:], is_bias=True, mean=0.1, filler='constant')
+        else:
+            self.W = params[0]
+            if bias:
+                self.b = params[1]
+        self.W.bind(('blockdiag',))
+        self.params = [self.W]
+        if bias:
+            self.params.append(self.b)
+
+    def set_output(self):
+        ctx = get_context()
+        x = self._prev_layer.act
+        ishape = tuple(int(v) for v in self._input_shape)
+        N, K, O = ishape[0], ishape[-1], int(self._output_shape[-1])
+        P = int(np.prod(ishape[1:-1]))
+        W, b = self.W.param(ctx), (self.b.param(ctx) if self._bias else None)
+        xt = _logical(x.data, ishape).reshape(N, P, K).transpose(0, 1).contiguous()          # [P,N,K]
+        y = torch.empty(P, N, O, dtype=x.data.dtype, device=x.data.device)
+        wop = W.operand().view(P, O * K)
+        for p in range(P):
+            ops.conv_fwd(xt[p].reshape(-1), wop[p], None if b is None else b.data[p * O:(p + 1) * O], None, None,
+                         y[p].view(-1), (N, 1, 1, 1, K), O, (1, 1, 1), L.EPI_BIAS if b is not None else 0, ctx.algo)
+        oshape = tuple(int(v) for v in self._output_shape)
+        out = Act(_physical(y.transpose(0, 1).reshape(oshape), oshape), _geom_of(oshape), requires_grad=ctx.training)
+        self._act = out
+        if not ctx.training:
+            return
+        ctx.consume(x)
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = _logical(out.grad, oshape).reshape(N, P, O).transpose(0, 1).contiguous()   # [P,N,O]
+            dx = torch.empty(P, N, K, dtype=x.data.dtype, device=x.data.device)
+            wt = torch.empty(K * O, dtype=W.operand().dtype, device=x.data.device)
+            for p in range(P):
+                ops.conv_wgrad(xt[p].reshape(-1), dy[p].reshape(-1), W.grad[p * O * K:(p + 1) * O * K],
+                               (N, 1, 1, 1, K), O, (1, 1, 1), ctx.wgrad_algo, W.grad_written)
+                if b is not None:
+                    ops.bias_grad(dy[p].reshape(-1), b.grad[p * O:(p + 1) * O], O, b.grad_written)
+                if x.requires_grad:
+                    ops.weight_transpose(W.data[p * O * K:(p + 1) * O * K], wt, O, 1, K)
+                    ops.conv_fwd(dy[p].reshape(-1), wt, None, None, None, dx[p].view(-1), (N, 1, 1, 1, O), K,
+                                 (1, 1, 1), 0, ctx.algo)
+            W.grad_written = True
+            if b is not None:
+                b.grad_written = True
+            if x.requires_grad:
+                ctx.accumulate(x, _physical(dx.transpose(0, 1).reshape(ishape), ishape))
+            out.grad = None
+        ctx.tape.append(bwd)
+
+    @property
+    def output(self):
+        return _logical(self.act.data, self._output_shape)

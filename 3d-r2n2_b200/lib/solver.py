@@ -51,7 +51,32 @@ class Solver(object):
         self.lr = np.float32(lr)
 
     # ---- one optimisation step -----------------------------------------------------------
+    def _apply_updates_layerwise(self, grad_scale):
+        """A user-defined network (models.net.Net define-by-run): one optimiser launch per Weight of
+        lib/layers.py, same update rules (lib/solver.py:20-71), L2 decay on non-bias tensors only."""
+        from . import layers as ly
+        t = float(self.iteration)
+        for w in self.net._weights:
+            p = w._param
+            if p is None:
+                continue
+            n_decay = 0 if w.is_bias else p.data.numel()
+            if w._m is None:
+                w._m = torch.zeros_like(p.data)
+                w._v = torch.zeros_like(p.data)
+            if self._policy == 'adam':
+                lr_t = float(self.lr) * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+                ops.adam(p.data, p.grad, w._m, w._v, p.mirror, n_decay, lr_t, self.beta_1, self.beta_2,
+                         self.epsilon, self.w_decay, grad_scale)
+            else:
+                ops.sgd(p.data, p.grad, w._m, p.mirror, n_decay, float(self.lr), self.momentum, self.w_decay,
+                        grad_scale)
+            w._host_stale = True
+        ly._layer_store.version += 1
+
     def _apply_updates(self, grad_scale=1.0):
+        if getattr(self.net, 'engine', None) is None:
+            return self._apply_updates_layerwise(grad_scale)
         st = self.net.engine.store
         if self._policy == 'adam':
             # lib/solver.py:24-25: lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t), t float32
@@ -76,6 +101,8 @@ class Solver(object):
     def _step(self, x, y):
         out = self.net.forward_backward(x, y)
         scale = 1.0
+        if self.grad_sync is not None and getattr(self.net, 'engine', None) is None:
+            raise NotImplementedError('data-parallel training needs the flat gradient store of an engine network')
         if self.grad_sync is not None:
             scale = self.grad_sync(self.net.engine.store.g)
         self._apply_updates(scale)

@@ -2,28 +2,66 @@
 models/res_gru_net.py:16-204) executed through the drop-in layer classes of lib/layers.py,
 one C-ABI kernel call per layer, with the per-view encoder INSIDE the recurrence exactly as the
 reference's theano.scan step has it.  The only textual change w.r.t. the reference is that
-`theano.scan(recurrence, sequences=[x], outputs_info=[0, 0])` is a host loop.
+`theano` is lib/theano_compat (scan = host loop).
 
-This is the demonstration that each layer is a drop-in (and a parity aid for the fused
-engine); the networks themselves run through engine.py.
+`LayerwiseGRUNet` / `LayerwiseResidualGRUNet` are ordinary user-defined networks in the sense of
+models/net.py:43-51: `Net` runs them define-by-run, `Solver.train_loss` trains them (tensor.grad = the
+tape the layers record).  They demonstrate that each layer is a drop-in and serve as a parity aid for
+the fused engine; the shipped networks themselves run through engine.py.
 """
 import numpy as np
 import torch
 
 from ..lib import layers as ly
+from ..lib import theano_compat as theano
+from ..lib.theano_compat import tensor
+from ..lib.config import cfg
 from ..lib.layers import TensorProductLayer, ConvLayer, PoolLayer, Unpool3DLayer, \
     LeakyReLU, SoftmaxWithLoss3D, Conv3DLayer, InputLayer, FlattenLayer, \
     FCConv3DLayer, TanhLayer, SigmoidLayer, ComplementLayer, AddLayer, \
-    EltwiseMultiplyLayer
-from ..ops import Ctx
-from .. import _lib as L
+    EltwiseMultiplyLayer, get_trainable_params
+from .net import Net, tensor5
+
+
+class LayerwiseResidualGRUNet(Net):
+    RESIDUAL = True
+
+    def network_definition(self):
+        # (multi_views, self.batch_size, 3, self.img_h, self.img_w)
+        self.x = tensor5()
+        self.is_x_tensor4 = False
+        _define(self, self.RESIDUAL)
+
+
+class LayerwiseGRUNet(LayerwiseResidualGRUNet):
+    RESIDUAL = False
+
+
+_cache = {}
 
 
 def run(net, x, y, residual):
-    ctx = Ctx(net.engine.dtype, net.engine.algo, training=False)
-    ly.set_context(ctx)
-    n0 = len(ly.trainable_params)
-    x = torch.as_tensor(np.asarray(x, dtype=np.float32)).to(ly.DEVICE)
+    """Forward pass of an engine network's current parameters through the layer-by-layer definition."""
+    compute = net.engine.compute
+    key = (residual, net.batch_size, net.img_w, net.img_h, compute)
+    lw = _cache.get(key)
+    saved = (cfg.CONST.BATCH_SIZE, cfg.CONST.COMPUTE, cfg.CONST.IMG_W, cfg.CONST.IMG_H)
+    cfg.CONST.BATCH_SIZE, cfg.CONST.COMPUTE = net.batch_size, compute
+    cfg.CONST.IMG_W, cfg.CONST.IMG_H = net.img_w, net.img_h
+    try:
+        if lw is None:
+            n0 = len(ly.trainable_params)
+            lw = (LayerwiseResidualGRUNet if residual else LayerwiseGRUNet)()
+            del ly.trainable_params[n0:]         # do not leak into the module-global list (quirk 13)
+            _cache[key] = lw
+        for w, v in zip(lw._weights, net.engine.get_params()):
+            w.val.set_value(v)
+        return lw.forward(x, y)
+    finally:
+        cfg.CONST.BATCH_SIZE, cfg.CONST.COMPUTE, cfg.CONST.IMG_W, cfg.CONST.IMG_H = saved
+
+
+def _define(net, residual):
     batch_size, img_w, img_h = net.batch_size, net.img_w, net.img_h
     n_gru_vox = 4
     n_convfilter = [96, 128, 256, 256, 256, 256]
@@ -184,22 +222,13 @@ def run(net, x, y, residual):
         conv10 = Conv3DLayer(conv9, (n_deconvfilter[4], 3, 3, 3))
         conv11 = Conv3DLayer(conv10, (n_deconvfilter[5], 3, 3, 3))
 
-    # ---- load the net's current parameter values into the freshly created Weights ---------
-    new_params = ly.trainable_params[n0:]
-    values = net.engine.get_params()
-    assert len(new_params) == len(values), (len(new_params), len(values))
-    for w, v in zip(new_params, values):
-        w.val.set_value(v)
-    del ly.trainable_params[n0:]         # do not leak into the module-global list (quirk 13)
-
-    # ---- theano.scan -> host loop ----------------------------------------------------------
-    s_prev = torch.zeros(s_shape, dtype=torch.float32, device=x.device)
-    u_prev = torch.zeros(s_shape, dtype=torch.float32, device=x.device)
-    u_all = []
-    for t in range(x.shape[0]):
-        s_prev, u_prev = recurrence(x[t], s_prev, u_prev)
-        u_all.append(u_prev)
-    s_last = s_prev
+    s_update, _ = theano.scan(recurrence,
+                              sequences=[net.x],
+                              outputs_info=[tensor.zeros_like(np.zeros(s_shape), dtype=theano.config.floatX),
+                                            tensor.zeros_like(np.zeros(s_shape), dtype=theano.config.floatX)])
+    update_all = s_update[-1]
+    s_all = s_update[0]
+    s_last = s_all[-1]
 
     gru_s = InputLayer(s_shape, s_last)
     if residual:
@@ -242,6 +271,9 @@ def run(net, x, y, residual):
         conv10_ = Conv3DLayer(rect9, (n_deconvfilter[4], 3, 3, 3), params=conv10.params)
         rect10 = LeakyReLU(conv10_)
         conv11_ = Conv3DLayer(rect10, (n_deconvfilter[5], 3, 3, 3), params=conv11.params)
-    softmax_loss = SoftmaxWithLoss3D(conv11_)
-    loss = softmax_loss.loss(y) if y is not None else None
-    return dict(pred=softmax_loss.prediction(), loss=loss, update_gates=torch.stack(u_all))
+    softmax_loss = SoftmaxWithLoss3D(conv11_.output)
+    net.loss = softmax_loss.loss(net.y)
+    net.error = softmax_loss.error(net.y)
+    net.params = get_trainable_params()
+    net.output = softmax_loss.prediction()
+    net.activations = [update_all]

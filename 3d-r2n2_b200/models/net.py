@@ -6,9 +6,14 @@ import numpy as np
 import torch
 
 from ..lib.config import cfg
+from ..lib import theano_compat as theano
+from ..lib import layers as ly
 from ..engine import Engine
 from ..ops import Ctx
 from .. import _lib as L
+
+tensor = theano.tensor
+tensor5 = tensor.TensorType(theano.config.floatX, (False,) * 5)     # models/net.py:9
 
 
 class _SharedView:
@@ -36,6 +41,14 @@ class NetWeight:
 
 
 class Net(object):
+    """Two kinds of subclass:
+      * the shipped networks set NET_NAME and run on the fused engine (engine.py);
+      * a subclass that overrides `network_definition` the way the reference's model files do
+        (models/net.py:43-51: builds layers from self.x / self.y, sets self.loss / error / params / output /
+        activations) runs DEFINE-BY-RUN: the body is executed once at construction (creating the Weights, on a
+        zero batch) and again on every call with the real batch fed through self.x / self.y, Weight
+        constructions replaying the tensors of the first run (lib.layers.replay_weights); `tensor.grad` is the
+        reverse pass over the tape the layers recorded (models/net.py:56-58)."""
     NET_NAME = None   # engine network name, set by subclasses
 
     def __init__(self, random_seed=dt.datetime.now().microsecond, compute_grad=True):
@@ -45,9 +58,14 @@ class Net(object):
         self.img_h = cfg.CONST.IMG_H
         self.n_vox = cfg.CONST.N_VOX
         self.compute_grad = compute_grad
+        self.engine = None
+        self._feed = {'x': None, 'y': None}
+        self._sym = {'x': None, 'y': None}
+        # (self.batch_size, 3, self.img_h, self.img_w); a multi-view network re-declares x as tensor5 and
+        # clears is_x_tensor4 in its network_definition (models/net.py:23-29)
+        self.x = tensor.tensor4()
         self.is_x_tensor4 = True
-        self.x = None            # fed per call (reference: symbolic tensor5)
-        self.y = None
+        self.y = tensor5()
         self.activations = []
         self.loss = []
         self.output = []
@@ -56,9 +74,56 @@ class Net(object):
         self.grads = []
         self.setup()
 
+    # ---- self.x / self.y: symbolic declarations in the reference, the fed batch here ----------------------
+    def _get_input(self, k):
+        if self._feed[k] is None:
+            sym = self._sym[k]
+            if k == 'y' or sym is None:
+                shape = (self.batch_size, self.n_vox, 2, self.n_vox, self.n_vox)
+            elif sym.ndim == 5:
+                shape = (1, self.batch_size, 3, self.img_h, self.img_w)
+            else:
+                shape = (self.batch_size, 3, self.img_h, self.img_w)
+            self._feed[k] = torch.zeros(shape, dtype=torch.float32, device=ly.DEVICE)   # construction-time batch
+        return self._feed[k]
+
+    def _set_input(self, k, v):
+        if isinstance(v, theano.Symbol):
+            self._sym[k] = v             # a (re-)declaration: the fed batch stays
+        else:
+            self._feed[k] = v
+
+    x = property(lambda self: self._get_input('x'), lambda self, v: self._set_input('x', v))
+    y = property(lambda self: self._get_input('y'), lambda self, v: self._set_input('y', v))
+
     def setup(self):
-        self.network_definition()
+        self._generic = type(self).network_definition is not Net.network_definition
+        if self._generic:
+            self._run_definition(None, None, False, first=True)
+        else:
+            self.network_definition()
         self.post_processing()
+
+    def _run_definition(self, x, y, training, first=False):
+        compute = cfg.CONST.COMPUTE
+        if compute not in ('fp32', 'bf16'):
+            raise NotImplementedError("user-defined networks run with CONST.COMPUTE 'fp32' or 'bf16'")
+        dtype, algo = {'fp32': (torch.float32, L.ALGO_SIMT), 'bf16': (torch.bfloat16, L.ALGO_UMMA)}[compute]
+        ctx = Ctx(dtype, algo, training=training)
+        ly.set_context(ctx)
+        self._feed = {'x': x, 'y': y}
+        if first:
+            n0 = len(ly.trainable_params)
+            self.network_definition()
+            self._weights = list(ly.trainable_params[n0:])
+        else:
+            if training:
+                for w in self._weights:
+                    if w._param is not None:
+                        w._param.grad_written = False
+            with ly.replay_weights(self._weights):
+                self.network_definition()
+        return ctx
 
     def network_definition(self):
         """Subclasses with a NET_NAME get the fused engine; anything else must override."""
@@ -102,6 +167,8 @@ class Net(object):
         t = torch.as_tensor(a)
         if t.dtype != torch.float32:
             t = t.float()
+        if self.engine is None:
+            return t.to(ly.DEVICE)
         return t.cuda(non_blocking=True)
 
     def _stage_inputs(self, x, y):
@@ -137,9 +204,22 @@ class Net(object):
         yd.record_stream(side)
         return xd, yd, events, yev
 
+    def _generic_out(self, training):
+        gates = None
+        if self.activations:
+            a = self.activations[0]
+            gates = a.stack() if hasattr(a, 'stack') else a
+        return dict(pred=None if training else self.output, loss=self.loss, update_gates=gates)
+
     def forward(self, x, y=None):
         """(prediction, loss, activations) as CUDA tensors; the compiled test function of
         lib/solver.py:215-218."""
+        if self._generic:
+            self._run_definition(self._to_dev(x), self._to_dev(y), False)
+            out = self._generic_out(False)
+            if y is None:
+                out['loss'] = None
+            return out
         xd, yd = self._to_dev(x), self._to_dev(y)
         if cfg.CONST.INFER_GRAPH and xd.is_cuda:
             out = self.engine.forward_graph(xd.contiguous(), None if yd is None else yd.contiguous())
@@ -153,6 +233,13 @@ class Net(object):
         the engine's flat buffer; `self.grads` materialises them in reference layout lazily."""
         if not self.compute_grad:
             raise RuntimeError('net was built with compute_grad=False')
+        if self._generic:
+            ctx = self._run_definition(self._to_dev(x), self._to_dev(y), True)
+            ctx.backward()
+            for w in self._weights:          # a parameter the loss does not depend on: zero gradient
+                if w._param is not None and not w._param.grad_written:
+                    w._param.grad.zero_()
+            return self._generic_out(True)
         xe = ye = None
         if cfg.CONST.OVERLAP_H2D and self.engine.store.p.is_cuda and not (torch.is_tensor(x) and x.is_cuda):
             x, y, xe, ye = self._stage_inputs(x, y)
@@ -163,6 +250,8 @@ class Net(object):
         return out
 
     def get_grads(self):
+        if self._generic:
+            return [w.grad_value() for w in self._weights]
         return self.engine.get_grads()
 
     # ---- checkpoint format of the reference ------------------------------------------------
@@ -186,11 +275,15 @@ class Net(object):
         succ_ind = 0
         for param_idx, param in enumerate(self.params):
             try:
-                param.val._w.set_value(params_cpu[succ_ind])
+                if self.engine is not None:
+                    param.val._w.set_value(params_cpu[succ_ind])     # one operand refresh after the loop
+                else:
+                    param.val.set_value(params_cpu[succ_ind])
                 succ_ind += 1
             except IndexError:
                 if ignore_param:
                     print('Ignore mismatch')
                 else:
                     raise
-        self.engine.params_changed()
+        if self.engine is not None:
+            self.engine.params_changed()

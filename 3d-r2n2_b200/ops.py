@@ -864,3 +864,75 @@ class Ctx:
                 out.grad = None
             self.tape.append(bwd)
         return out
+
+    # ---- ops of the layer-by-layer API (user-defined network_definition; models/net.py:56-58) -----------
+    def view(self, x, geom):
+        """The same buffer under another geometry (FlattenLayer, the (B,1,1,1,n) input of a dot, the
+        reshape of dot(f, Wx) onto the hidden grid): a new Act whose gradient flows back to x."""
+        geom = tuple(int(g) for g in geom)
+        assert x.data.numel() == geom[0] * geom[1] * geom[2] * geom[3] * geom[4], (x.geom, geom)
+        out = Act(x.data, geom, requires_grad=self.training and x.requires_grad)
+        out.useful = x.useful
+        if out.requires_grad:
+            self.consume(x)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                self.accumulate(x, out.grad)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def _unary(self, x, op, bwd_op):
+        y = torch.empty_like(x.data)
+        eltwise(op, x.data, None, y)
+        out = Act(y, x.geom, requires_grad=self.training and x.requires_grad)
+        if out.requires_grad:
+            self.consume(x)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                dx = torch.empty_like(y)
+                if bwd_op == L.ELT_NEG:
+                    eltwise(L.ELT_NEG, out.grad, None, dx)
+                else:
+                    eltwise(bwd_op, y, out.grad, dx)
+                self.accumulate(x, dx)
+                out.grad = None
+            self.tape.append(bwd)
+        return out
+
+    def sigmoid(self, x):
+        """SigmoidLayer (lib/layers.py:649-656)"""
+        return self._unary(x, L.ELT_SIGMOID, L.ELT_SIGMOID_BWD)
+
+    def tanh(self, x):
+        """TanhLayer (lib/layers.py:659-665)"""
+        return self._unary(x, L.ELT_TANH, L.ELT_TANH_BWD)
+
+    def complement(self, x):
+        """ComplementLayer (lib/layers.py:668-676): 1 - x"""
+        return self._unary(x, L.ELT_COMPLEMENT, L.ELT_NEG)
+
+    def mul(self, a, b):
+        """EltwiseMultiplyLayer (lib/layers.py:217-225)"""
+        assert a.data.numel() == b.data.numel()
+        y = torch.empty_like(a.data)
+        eltwise(L.ELT_MUL, a.data, b.data, y)
+        out = Act(y, a.geom, requires_grad=self.training and (a.requires_grad or b.requires_grad))
+        if out.requires_grad:
+            self.consume(a), self.consume(b)
+
+            def bwd():
+                if out.grad is None:
+                    return
+                for x, other in ((a, b), (b, a)):
+                    if x.requires_grad:
+                        dx = torch.empty_like(y)
+                        eltwise(L.ELT_MUL, out.grad, other.data, dx)
+                        self.accumulate(x, dx)
+                out.grad = None
+            self.tape.append(bwd)
+        return out

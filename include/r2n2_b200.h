@@ -181,6 +181,12 @@ int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, 
 #define R2N2_ELT_TANH 1
 #define R2N2_ELT_COMPLEMENT 2
 #define R2N2_ELT_MUL 3
+/* their derivatives (tensor.grad through a user-defined network_definition, models/net.py:56-58):
+ * SIGMOID_BWD: y = b * a * (1 - a) with a = the sigmoid OUTPUT, b = dL/d(output); TANH_BWD: y = b * (1 - a^2);
+ * NEG: y = -a (ComplementLayer). */
+#define R2N2_ELT_SIGMOID_BWD 4
+#define R2N2_ELT_TANH_BWD 5
+#define R2N2_ELT_NEG 6
 int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int dtype,
                  void* stream);
 

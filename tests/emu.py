@@ -195,7 +195,16 @@ def lrelu_bwd(a, dy, addend, dx):
 
 def eltwise(op, a, b, y):
     v = _f(a)
-    o = [torch.sigmoid(v), torch.tanh(v), 1 - v, None][op] if op < 3 else v * _f(b)
+    if op < 3:
+        o = [torch.sigmoid(v), torch.tanh(v), 1 - v][op]
+    elif op == 3:
+        o = v * _f(b)
+    elif op == 4:
+        o = _f(b) * v * (1 - v)
+    elif op == 5:
+        o = _f(b) * (1 - v * v)
+    else:
+        o = -v
     y.copy_(o.to(y.dtype))
 
 

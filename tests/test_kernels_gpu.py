@@ -194,7 +194,7 @@ def test_pointwise_and_layout():
         getattr(emu, name)(*args, want)
         getattr(ops, name)(*[None if t is None else t.to(DEV) for t in args], y)
         _cmp(y, want, 1e-6, name)
-    for op in range(4):
+    for op in range(7):       # forward ops 0..3, SIGMOID_BWD / TANH_BWD / NEG (lib/layers.py:649-676 under tensor.grad)
         want, y = torch.empty(n), torch.empty(n, device=DEV)
         emu.eltwise(op, a, b, want)
         ops.eltwise(op, a.to(DEV), b.to(DEV), y)
