@@ -7,6 +7,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libr2n2_b200.so')
+if os.environ.get('R2N2_WAITSTAT'):      # diagnostic build with per-warp mbarrier wait statistics (tools/waitstat.py)
+    LIB_PATH = os.path.join(_HERE, 'libr2n2_b200_ws.so')
 
 F32, BF16 = 0, 1
 EPI_BIAS, EPI_LRELU, EPI_RESIDUAL, EPI_MASK = 1, 2, 4, 8

@@ -12,6 +12,11 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets']
 if os.environ.get('R2N2_PTXAS_V'):
     NVCC_FLAGS += ['-Xptxas', '-v']
+# diagnostic build (tools/waitstat.py): per-warp mbarrier wait statistics; a SEPARATE library, never the product's
+WAITSTAT = bool(os.environ.get('R2N2_WAITSTAT'))
+if WAITSTAT:
+    NVCC_FLAGS += ['-DR2N2_WAITSTAT']
+    OUT = os.path.join(PKG, 'libr2n2_b200_ws.so')
 
 
 HASH_FILE = OUT + '.srchash'
@@ -50,7 +55,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, s.replace('.cu', '.o'))
+        o = os.path.join(HERE, s.replace('.cu', '.ws.o' if WAITSTAT else '.o'))
         objs.append(o)
         cmd = [nvcc] + NVCC_FLAGS + ['-DR2N2_SRC_HASH="%s"' % src_hash, '-c', os.path.join(HERE, s), '-o', o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -45,6 +45,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  R2N2_WS_BEGIN(bars);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tmem_full_bar = bars + 2 * p.stages;
@@ -230,6 +231,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       store16(y + off, f);
     }
   }
+  R2N2_WS_END(p.err_word);
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[5] = clock64();
@@ -268,8 +270,13 @@ int* get_err_word() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!words[dev]) {
     int* w = nullptr;
-    if (cudaMalloc(&w, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(w, 0, sizeof(int));
+#ifdef R2N2_WAITSTAT
+    const size_t bytes = 64 + (size_t)512 * 16 * 40 * sizeof(long long);     // error word + wait statistics
+#else
+    const size_t bytes = sizeof(int);
+#endif
+    if (cudaMalloc(&w, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(w, 0, bytes);
     words[dev] = w;
   }
   return words[dev];
@@ -499,6 +506,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  R2N2_WS_BEGIN(bars);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tmem_full_bar = bars + 2 * p.stages;
@@ -718,6 +726,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       }
     }
   }
+  R2N2_WS_END(p.err_word);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -986,3 +995,17 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
 }  // namespace r2n2
 
 extern "C" int r2n2_umma_error_flag(void) { return r2n2::umma_error_flag(); }
+
+#ifdef R2N2_WAITSTAT
+// diagnostic build only (tools/waitstat.py): copy the wait statistics of the last tcgen05 launch to the host and clear them
+extern "C" int r2n2_waitstat_read(long long* dst, long long n_words) {
+  int* w = r2n2::get_err_word();
+  if (!w) return 1;
+  const long long cap = 512LL * 16 * 40;
+  if (n_words > cap) n_words = cap;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+  if (cudaMemcpy(dst, reinterpret_cast<long long*>(w) + 8, (size_t)n_words * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 3;
+  cudaMemset(reinterpret_cast<long long*>(w) + 8, 0, (size_t)cap * sizeof(long long));
+  return 0;
+}
+#endif

@@ -49,6 +49,11 @@ struct Fwd3Params {
   int tma_epi, SC, slab_bytes, epi_off;    // epilogue through a dense (Yb x Xb pixels) x SC channels smem slab + TMA
   int nslab;                               // output slabs in rotation (2 when no residual / mask slab is loaded)
   int stk, xch_off, xch_bytes;             // dx-stacked mode: the 3 taps of a filter row share ONE MMA (N = 3 BN)
+  int out_bytes;                           // sizeof(output element)
+  int stage_epi, stg_off;                  // warp-staged epilogue: per-warp 32 pixels x 64 bytes staging tiles at this smem offset
+  int pair;                                // CTA-pair mode (cluster of 2, cta_group::2 MMAs with M = 256, each CTA holds half of the filter rows)
+  int skip;                                // TIMING EXPERIMENTS ONLY (R2N2_FWD3_SKIP bit mask): 1 no plane loads, 2 no weight loads,
+                                           // 4 no epilogue work, 8 no MMAs -- results are garbage, the barrier protocol is kept
   int* err_word;
 };
 
@@ -68,6 +73,26 @@ static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long lo
   return c;
 }
 
+// CTA-pair mode: the pair walks the items two at a time in lockstep (leader = even item, peer = odd item); an odd
+// tail gives the peer a GHOST item (n = N: its TMA loads are zero-filled, its stores clipped, its rows invalid)
+template <int PAIR>
+static __device__ __forceinline__ Item3 decode_item_pair(const Fwd3Params& p, long long itp, uint32_t crank) {
+  if (!PAIR) return decode_item(p, itp);
+  const long long it = 2 * itp + crank;
+  const bool ghost = it >= p.items;
+  Item3 c = decode_item(p, ghost ? p.items - 1 : it);
+  if (ghost) c.n = p.N;
+  return c;
+}
+template <int PAIR>
+static __device__ __forceinline__ void mma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+}
+template <int PAIR>
+static __device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if (PAIR) umma_commit_2cta(bar); else umma_commit(bar);
+}
+
 // KB = K16 steps per full channel chunk (row bytes = 32 KB), NCH = channel chunks, LASTK = K16 steps of
 // the last chunk: compile-time so that the MMA issue sequence of one tap is straight-line code with
 // immediate descriptor offsets (a single thread issues every MMA of the SM: each extra instruction per
@@ -76,7 +101,7 @@ static __device__ __forceinline__ Item3 decode_item(const Fwd3Params& p, long lo
 // compile-time too (3x3 taps) -- the hot configurations get a fully unrolled, branch-free issue sequence
 // (ncu: the generic loop spent 158 instructions per tap for 12 MMAs and the issuing thread, not the tensor
 // pipe, set the pace of conv1b); 0 / -1 = read from the parameter block.
-template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int STK>
+template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int STK, int PAIR>
 __global__ void __launch_bounds__(kFwd3Threads, 1)
 conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
@@ -87,6 +112,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int ring_bytes = p.nring * p.plane_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.w_off + p.w_bytes);
+  R2N2_WS_BEGIN(bars);
   uint64_t* pfull = bars;                              // [nring]   plane TMA -> MMA
   uint64_t* pempty = pfull + p.nring;                  // [nring]   MMA -> plane TMA
   uint64_t* wfull = pempty + p.nring;                  // [wstages] weight TMA -> MMA
@@ -99,6 +125,11 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  static_assert(!(STK != 0 && PAIR != 0), "the dx-stacked mode has no CTA-pair variant");
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;             // 0 = leader (issues the MMAs of the pair)
+  const unsigned cid = PAIR ? (blockIdx.x >> 1) : blockIdx.x, ncta = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const long long pitems = PAIR ? (p.items + 1) / 2 : p.items;
+  const int bn_local = PAIR ? (p.BN >> 1) : p.BN;                     // filter rows held by this CTA
   const int T_ = TT > 0 ? TT : p.T;
   const int WT_ = WTT > 0 ? WTT : p.wt;
   const bool RES_ = RESS >= 0 ? (RESS != 0) : (p.w_res != 0);
@@ -117,22 +148,32 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), 1); mbar_init(smem_u32(&pempty[s]), 1); }
-    for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), 1); mbar_init(smem_u32(&wempty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), kEpiWarps); }
+    // pair mode: the leader's `full` barriers collect one expect_tx arrival + the TMA bytes of EACH CTA, its
+    // `tempty` barriers the epilogue warps of both; `empty` / `tfull` are per CTA (multicast tcgen05.commit)
+    const uint32_t np = PAIR ? 2u : 1u;
+    for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), np); mbar_init(smem_u32(&pempty[s]), 1); }
+    for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), np); mbar_init(smem_u32(&wempty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), np * kEpiWarps); }
     mbar_init(smem_u32(efull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // both CTAs' barriers initialised and rings zero-filled before any remote arrive / MMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t smem_base = smem_u32(smem);
@@ -142,26 +183,33 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int pz = (KD_ - 1) / 2;
   // rotation of the tap order (streamed filters only), in units of one issue group
   const int grp_taps = WT_ * ((WTT == 1 && RESS == 0) ? 3 : 1);       // taps issued per elected region (never split)
-  const int rot_taps = (!RES_ && !p.no_rot) ? (int)(blockIdx.x % (unsigned)((KD_ * KH_ * KW_) / grp_taps)) * grp_taps : 0;
+  const int rot_taps = (!RES_ && !p.no_rot) ? (int)(cid % (unsigned)((KD_ * KH_ * KW_) / grp_taps)) * grp_taps : 0;
 
   if (warp == 0) {
     // ================================ input planes (TMA) ====================================
     int slot = 0;
     uint32_t ph = 0;
     const uint32_t tx = (uint32_t)(p.nchunk * p.plane_rows * p.rb);
-    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const Item3 c = decode_item(p, it);
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
       const int nplanes = c.nz + KD_ - 1;
       for (int i = 0; i < nplanes; ++i) {
         mbar_wait(pempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
-        const uint32_t bar = pfull0 + 8u * slot;
+        const uint32_t bar = PAIR ? mapa_shared(pfull0 + 8u * slot, 0) : pfull0 + 8u * slot;
         const uint32_t dst = smem_base + (uint32_t)(slot * p.plane_bytes);
         if (elect_one()) {
-          mbar_expect_tx(bar, tx);
+          if (PAIR) mbar_expect_tx_cluster(bar, (p.skip & 1) ? 0u : tx); else mbar_expect_tx(bar, (p.skip & 1) ? 0u : tx);
+          if (!(p.skip & 1)) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (KW_ - 1) / 2, c.y0 - (KH_ - 1) / 2,
-                        c.z0 + i - pz, c.n);
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (PAIR)
+              tma_load_5d_2sm(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (KW_ - 1) / 2,
+                              c.y0 - (KH_ - 1) / 2, c.z0 + i - pz, c.n);
+            else
+              tma_load_5d(dst + (uint32_t)(ch * p.chunk_bytes), &map_a, bar, ch * p.kbox, c.x0 - (KW_ - 1) / 2, c.y0 - (KH_ - 1) / 2,
+                          c.z0 + i - pz, c.n);
+          }
+          }
         }
         __syncwarp();
         if (++slot == p.nring) { slot = 0; ph ^= 1u; }
@@ -171,25 +219,29 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ================================ weights (TMA): wt filter taps per stage ==================
     int slot = 0;
     uint32_t ph = 0;
-    const uint32_t stage_tx = (uint32_t)(p.BN * p.rb * NCH * WT_);
+    const uint32_t stage_tx = (uint32_t)(bn_local * p.rb * NCH * WT_);
+    const int wrow0 = PAIR ? (int)crank * bn_local : 0;          // this CTA's half of the filter rows
     const int ntaps = KD_ * KH_ * KW_;
     if (RES_) {
       // small filters: every tap is loaded once and stays in shared memory for the whole kernel
       uint32_t dst = smem_base + (uint32_t)p.w_off;
       if (elect_one()) {
-        mbar_expect_tx(wfull0, (uint32_t)(p.BN * p.rb * NCH * ntaps));
+        const uint32_t wbar = PAIR ? mapa_shared(wfull0, 0) : wfull0;
+        if (PAIR) mbar_expect_tx_cluster(wbar, (uint32_t)(bn_local * p.rb * NCH * ntaps));
+        else mbar_expect_tx(wbar, (uint32_t)(bn_local * p.rb * NCH * ntaps));
         for (int tap = 0; tap < ntaps; ++tap) {
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
-            tma_load_2d(dst, &map_b, wfull0, tap * p.Cin + ch * p.kbox, 0);
+            if (PAIR) tma_load_2d_2sm(dst, &map_b, wbar, tap * p.Cin + ch * p.kbox, wrow0);
+            else tma_load_2d(dst, &map_b, wbar, tap * p.Cin + ch * p.kbox, 0);
             dst += (uint32_t)p.w_sub_bytes;
           }
         }
       }
       __syncwarp();
     } else
-    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const Item3 c = decode_item(p, it);
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
       for (int j = 0; j < c.nz; ++j) {
         for (int tap_o = 0; tap_o < ntaps; tap_o += WT_) {
           // filter-row groups are visited in an order rotated by the CTA index: at any moment the 148 CTAs
@@ -197,14 +249,15 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           int tap = tap_o + rot_taps;
           if (tap >= ntaps) tap -= ntaps;
           mbar_wait(wempty0 + 8u * slot, ph ^ 1u, abort_flag, p.err_word);
-          const uint32_t bar = wfull0 + 8u * slot;
+          const uint32_t bar = PAIR ? mapa_shared(wfull0 + 8u * slot, 0) : wfull0 + 8u * slot;
           uint32_t dst = smem_base + (uint32_t)(p.w_off + slot * p.wg * p.w_sub_bytes);
           if (elect_one()) {
-            mbar_expect_tx(bar, stage_tx);
-            for (int u = 0; u < WT_; ++u) {
+            if (PAIR) mbar_expect_tx_cluster(bar, (p.skip & 2) ? 0u : stage_tx); else mbar_expect_tx(bar, (p.skip & 2) ? 0u : stage_tx);
+            for (int u = 0; u < ((p.skip & 2) ? 0 : WT_); ++u) {
 #pragma unroll
               for (int ch = 0; ch < NCH; ++ch) {
-                tma_load_2d(dst, &map_b, bar, (tap + u) * p.Cin + ch * p.kbox, 0);
+                if (PAIR) tma_load_2d_2sm(dst, &map_b, bar, (tap + u) * p.Cin + ch * p.kbox, wrow0);
+                else tma_load_2d(dst, &map_b, bar, (tap + u) * p.Cin + ch * p.kbox, 0);
                 dst += (uint32_t)p.w_sub_bytes;
               }
             }
@@ -215,9 +268,10 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ============================================
+    // ================================ MMA issuer (pair mode: the leader CTA only) ============
+    if (PAIR == 0 || crank == 0) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                           ((uint32_t)(128 >> 4) << 24);
+                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     constexpr uint32_t kRb = 32u * KB;
     constexpr uint32_t layout_type = (kRb == 128) ? 2u : (kRb == 64 ? 4u : 6u);
     const uint64_t desc_hi = make_kmajor_desc(0, 8u * kRb, layout_type);
@@ -236,8 +290,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int wslot = 0;
     uint32_t wph = 0;
     int step = 0;
-    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const Item3 c = decode_item(p, it);
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
       int waited = 0;              // planes of this item already seen full
       pslot = wait_slot;
       for (int j = 0; j < c.nz; ++j, ++step) {
@@ -332,15 +386,15 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               for (int u = 0; u < WT_; ++u) {
                 uint64_t a_t = a_tap;
                 uint32_t d_t = d0;
-                for (int t = 0; t < T_; ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
+                for (int t = 0; t < ((p.skip & 8) ? 0 : T_); ++t, a_t += tile16, d_t += (uint32_t)p.bn_cols) {
 #pragma unroll
                   for (int ch = 0; ch < NCH; ++ch) {
                     const int nk = (ch == NCH - 1) ? LASTK : KB;
 #pragma unroll
                     for (int k = 0; k < KB; ++k) {
                       if (k < nk)
-                        umma_bf16(d_t, a_t + (uint64_t)(ch * chunk16 + 2u * k), b_tap + (uint64_t)(ch * wsub16 + 2u * k),
-                                  idesc, (ch == 0 && k == 0) ? acc : 1u);
+                        mma_issue<PAIR>(d_t, a_t + (uint64_t)(ch * chunk16 + 2u * k), b_tap + (uint64_t)(ch * wsub16 + 2u * k),
+                                        idesc, (ch == 0 && k == 0) ? acc : 1u);
                     }
                   }
                 }
@@ -349,7 +403,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 a_tap += row16;
                 if (++txu == KW_) { txu = 0; a_tap += (uint64_t)(rowP16 - (uint32_t)KW_ * row16); }
               }
-              if (!RES_) umma_commit(wempty0 + 8u * slots[g]);
+              if (!RES_) mma_commit<PAIR>(wempty0 + 8u * slots[g]);
             }
           }
           __syncwarp();
@@ -360,18 +414,19 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (tz >= KD_) tz = 0;                           // (rotated order wraps around)
         }
         if (elect_one()) {
-          umma_commit(tfull0 + 8u * buf);                 // accumulators of this step complete
-          umma_commit(pempty0 + 8u * pslot);              // plane z-1 is not needed by later steps
+          mma_commit<PAIR>(tfull0 + 8u * buf);            // accumulators of this step complete
+          mma_commit<PAIR>(pempty0 + 8u * pslot);         // plane z-1 is not needed by later steps
           if (j == c.nz - 1)
             for (int e = 1; e < KD_; ++e) {
               int ps = pslot + e;
               if (ps >= p.nring) ps -= p.nring;
-              umma_commit(pempty0 + 8u * ps);
+              mma_commit<PAIR>(pempty0 + 8u * ps);
             }
         }
         __syncwarp();
         if (++pslot == p.nring) pslot = 0;
       }
+    }
     }
   } else if (warp >= 2 && warp < 2 + kEpiWarps) {
     // ================================ epilogue ==============================================
@@ -399,8 +454,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const bool two = p.nslab == 2;
         const uint32_t bufY0 = bufY;
         uint32_t sidx = 0;
-        for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-          const Item3 c = decode_item(p, it);
+        for (long long it = cid; it < pitems; it += ncta) {
+          const Item3 c = decode_item_pair<PAIR>(p, it, crank);
           for (int j = 0; j < c.nz; ++j, ++step) {
             const int buf = step & 1;
             const int zz = c.z0 + j;
@@ -424,7 +479,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 mbar_wait(ef, eph, abort_flag, p.err_word);
                 eph ^= 1u;
               }
-              for (int t = half; t < T_; t += 2) {
+              for (int t = half; t < ((p.skip & 4) ? 0 : T_); t += 2) {
                 const int r = t * 128 + quad * 32 + lane;
                 const int yy = r / p.P, xx = r - yy * p.P;
                 const bool valid = r < p.R && xx < p.Xb;
@@ -480,14 +535,17 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               named_bar_sync(1, 32 * kEpiWarps);
-              if (leader) {
+              if (leader && !(p.skip & 4)) {
                 tma_store_5d(&map_y, bufY, sc, c.x0, c.y0, zz, c.n);
                 pending = true;
               }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(mapa_shared(tempty0 + 8u * buf, 0));
+              else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+            }
           }
         }
         if (leader && pending) tma_store_wait_all();
@@ -503,8 +561,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t xstep = (uint32_t)(T_ * 4 * p.BN) * 16u;
     const uint32_t lane_sel = lane == 30 ? 8u : 0u;
     int step = 0;
-    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const Item3 c = decode_item(p, it);
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
       for (int j = 0; j < c.nz; ++j, ++step) {
         const int buf = step & 1;
         const int zz = c.z0 + j;
@@ -599,24 +657,203 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(tempty0 + 8u * buf, 0));
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        }
+      }
+    }
+    } else if (p.stage_epi) {
+    // ---- warp-staged epilogue ---------------------------------------------------------------------------
+    // A thread owns one accumulator row (= one pixel); writing its channels with 16-byte accesses makes every
+    // store / load instruction of the warp touch 32 different 128-byte lines (32 L1 wavefronts).  Here the warp
+    // exchanges a ROUND of 64 bytes per pixel (32 bf16 / 16 fp32 channels) through a private, XOR-swizzled
+    // 2 KB shared-memory tile and accesses global memory as 8 pixels x 64 contiguous bytes per instruction
+    // (a quarter of the wavefronts, full 32-byte sectors).  Warp-local only: no CTA barrier, no TMA store
+    // whose shared-memory read would have to drain before the next slab (what bounded the TMA epilogue).
+    constexpr int RC = 64 / (int)sizeof(TOut);            // channels per round
+    const int nrounds = p.BN / RC;
+    const int half = (warp - 2) >> 2;
+    const uint32_t stg = smem_base + (uint32_t)p.stg_off + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t my_row = stg + (uint32_t)lane * 64u, my_sw = (uint32_t)((lane >> 1) & 3);
+    const int q_lo = lane >> 2;                           // pixel (of 8) this lane moves in each of the 4 global accesses
+    const uint32_t u_g = (uint32_t)(lane & 3);            // its 16-byte unit
+    const bool has_res = (p.flags & R2N2_EPI_RESIDUAL) != 0, has_mask = (p.flags & R2N2_EPI_MASK) != 0;
+    const bool res_pre = (p.flags & R2N2_EPI_RES_PRE) != 0;
+    int step = 0;
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
+      for (int j = 0; j < c.nz; ++j, ++step) {
+        const int buf = step & 1;
+        const int zz = c.z0 + j;
+        bool first = true;
+        const int nitems = T_ * nrounds;
+        for (int wi = half; wi < ((p.skip & 4) ? 0 : nitems); wi += 2) {
+          const int t = wi / nrounds, rd = wi - t * nrounds;
+          // the 4 pixels whose 16-byte unit u_g this lane loads / stores: rows q = 8 k + q_lo of the warp's 32
+          long long goff[4];
+          bool gok[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = t * 128 + quad * 32 + 8 * k + q_lo;
+            const int yy = r / p.P, xx = r - yy * p.P;
+            const int gy = c.y0 + yy, gx = c.x0 + xx;
+            gok[k] = r < p.R && xx < p.Xb && gx < p.W && gy < p.H && c.n < p.N;
+            goff[k] = (((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * p.Cout + rd * RC) * (long long)sizeof(TOut) +
+                      (long long)u_g * 16;
+          }
+          uint4 gin[2][4];
+          if (has_res || has_mask) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (gok[k]) {
+                if (has_res) gin[0][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(res) + goff[k]);
+                if (has_mask) gin[1][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(mask) + goff[k]);
+              }
+            }
+          }
+          if (first) {
+            mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+            tc_fence_after();
+            first = false;
+          }
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols + rd * RC);
+          float f[RC];
+          if (p.skip & 16) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) f[q] = 0.f;
+          } else {
+            uint32_t v[16];
+            tmem_ld16_nowait(taddr, v);
+            if (RC == 32) {
+              uint32_t v2[16];
+              tmem_ld16_nowait(taddr + 16u, v2);
+              tmem_wait_ld();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[(RC == 32 ? 16 : 0) + q] = __uint_as_float(v2[q]);
+            } else {
+              tmem_wait_ld();
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+          }
+          // inputs of this round: global (8 pixels x 64 B per access) -> staging tile -> the pixel's owner
+          float rin[RC], min_[RC];
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            if (which == 0 ? !has_res : !has_mask) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t row = (uint32_t)(8 * k + q_lo);
+              const uint32_t a = stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4);
+              const uint4 g = gok[k] ? gin[which][k] : make_uint4(0, 0, 0, 0);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(g.x), "r"(g.y), "r"(g.z), "r"(g.w) : "memory");
+            }
+            __syncwarp();
+            uint4 o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[u].x), "=r"(o[u].y), "=r"(o[u].z), "=r"(o[u].w)
+                           : "r"(my_row + (((uint32_t)u ^ my_sw) << 4)));
+            __syncwarp();
+            float* dst = which == 0 ? rin : min_;
+            if (sizeof(TOut) == 2) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t w4[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                  dst[u * 8 + 2 * e] = t2.x; dst[u * 8 + 2 * e + 1] = t2.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                dst[(u * 4) % RC] = __uint_as_float(o[u].x); dst[(u * 4 + 1) % RC] = __uint_as_float(o[u].y);
+                dst[(u * 4 + 2) % RC] = __uint_as_float(o[u].z); dst[(u * 4 + 3) % RC] = __uint_as_float(o[u].w);
+              }
+            }
+          }
+          if (has_res && res_pre) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) f[q] += rin[q];
+          }
+          if (p.flags & R2N2_EPI_BIAS) {
+#pragma unroll
+            for (int q = 0; q < RC; q += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + rd * RC + q));
+              f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
+            }
+          }
+          if (p.flags & R2N2_EPI_LRELU) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) f[q] = lrelu(f[q]);
+          }
+          if (has_res && !res_pre) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) f[q] += rin[q];
+          }
+          if (has_mask) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) f[q] *= lrelu_slope(min_[q]);
+          }
+          // results: owner -> staging tile -> global
+          uint32_t w[16];
+          if (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[(2 * q) % RC], f[(2 * q + 1) % RC]);
+              w[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q] = __float_as_uint(f[q % RC]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (((uint32_t)u ^ my_sw) << 4)), "r"(w[4 * u]),
+                         "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                         : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t row = (uint32_t)(8 * k + q_lo);
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4)));
+            if (gok[k] && !(p.skip & 32)) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + goff[k]) = o;
+          }
+          __syncwarp();
+        }
+        if (first) {          // (no work item for this warp in this step: still a consumer of the accumulator barrier)
+          mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
+          tc_fence_after();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(tempty0 + 8u * buf, 0));
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        }
       }
     }
     } else {
     const int nch = p.BN >> 4, half = (warp - 2) >> 2;     // two warps per lane quadrant, half the columns each
     const int c_begin = half ? ((nch + 1) >> 1) << 4 : 0, c_end = half ? p.BN : ((nch + 1) >> 1) << 4;
     int step = 0;
-    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
-      const Item3 c = decode_item(p, it);
+    for (long long it = cid; it < pitems; it += ncta) {
+      const Item3 c = decode_item_pair<PAIR>(p, it, crank);
       for (int j = 0; j < c.nz; ++j, ++step) {
         const int buf = step & 1;
         const int zz = c.z0 + j;
         bool first = true;
-        for (int t = 0; t < T_; ++t) {
+        if (p.skip & 4) { mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word); first = false; }
+        for (int t = 0; t < ((p.skip & 4) ? 0 : T_); ++t) {
           const int r = t * 128 + quad * 32 + lane;
           const int yy = r / p.P, xx = r - yy * p.P;
           const int gy = c.y0 + yy, gx = c.x0 + xx;
-          const bool valid = r < p.R && xx < p.Xb && gx < p.W && gy < p.H;
+          const bool valid = r < p.R && xx < p.Xb && gx < p.W && gy < p.H && c.n < p.N;
           const long long off = ((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * p.Cout;
           EpiPrefetch<TOut> pf;
           epi_prefetch(pf, p.flags, valid, res + off, mask + off, c_begin, p.Cout);
@@ -630,18 +867,24 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(tempty0 + 8u * buf, 0));
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8u * buf) : "memory");
+        }
       }
     }
     }
   }
+  R2N2_WS_END(p.err_word);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal it / read its smem
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -660,11 +903,11 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   p.full_nk16 = p.kbox >> 4;
   p.last_nk16 = (p.Cin - (p.nchunk - 1) * p.kbox) >> 4;
   p.BN = p.Cout;
-  p.w_sub_bytes = ru(p.BN * p.rb, 1024);
+  p.w_sub_bytes = ru((p.pair ? p.BN / 2 : p.BN) * p.rb, 1024);     // pair mode: each CTA holds half of the filter rows
   // dx-stacked mode (see the header): 3x3 rows, one channel chunk, the three weight tiles of a filter row
   // contiguous in shared memory (no padding between them), 3 BN accumulator columns per tile
   p.stk = (p.kh == 3 && p.kw == 3 && p.nchunk == 1 && 3 * p.BN <= 256 && p.BN * p.rb == p.w_sub_bytes &&
-           !getenv("R2N2_FWD3_NO_STK")) ? 1 : 0;
+           !getenv("R2N2_FWD3_NO_STK") && !p.pair) ? 1 : 0;
   // Measured (B200, 36 x 32^3): the stacked epilogue (2 shuffles + 1 shared load per element, boundary exchange)
   // costs ~2x the plain one, so stacking pays where a tile carries enough MMA work to hide it: Cin = 64
   // (conv10a 0.282 -> 0.185 ms, conv9b 0.341 -> 0.323 ms) and the N = 16 layer (conv11 0.115 -> 0.102 ms);
@@ -672,11 +915,19 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   if (p.stk && !(p.Cin >= 64 || (p.BN <= 16 && p.Cin >= 32))) p.stk = 0;
   if (const char* e = getenv("R2N2_FWD3_STK")) {
     if (!atoi(e)) p.stk = 0;
-    else p.stk = (p.kh == 3 && p.kw == 3 && p.nchunk == 1 && 3 * p.BN <= 256 && p.BN * p.rb == p.w_sub_bytes) ? 1 : 0;
+    else p.stk = (p.kh == 3 && p.kw == 3 && p.nchunk == 1 && 3 * p.BN <= 256 && p.BN * p.rb == p.w_sub_bytes && !p.pair) ? 1 : 0;
   }
   if (want_stk == 0) p.stk = 0;
   p.xch_off = 0; p.xch_bytes = 0;
   if (p.stk) { budget -= 10 * 1024; want_tma_epi = 0; }     // (exchange buffer of the stacked epilogue)
+  // warp-staged epilogue (8 warps x 2 KB): whenever a pixel's channels are whole 64-byte rounds and no other epilogue is chosen
+  p.stage_epi = 0; p.stg_off = 0;
+  {
+    const int out_bytes = p.out_bytes;
+    int want_stage = (!p.stk && want_tma_epi != 2 && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
+    if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
+    if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
+  }
   p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
   const int Tmax = 256 / p.bn_cols;                       // two accumulator sets in 512 TMEM columns
   if (Tmax < 1) return false;
@@ -684,7 +935,9 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   // (9, 3 or 1 taps: each barrier round costs the issuing thread ~300 cycles, so small taps are grouped)
   const int tpp = p.kh * p.kw, ntaps = p.kd * tpp;
   const int all_w = ntaps * p.nchunk * p.w_sub_bytes;
-  p.w_res = (all_w <= 64 * 1024 && !getenv("R2N2_FWD3_NO_RES")) ? 1 : 0;
+  // (pair mode: half the filter per CTA -- conv1b's 9 x 96 x 96 taps are 81 KB per CTA and stay resident, which removes
+  //  the weight ring whose refill round trip bounded that layer: tools/r02 R2N2_FWD3_SKIP experiments)
+  p.w_res = (all_w <= (p.pair ? 96 : 64) * 1024 && !getenv("R2N2_FWD3_NO_RES")) ? 1 : 0;
   p.wt = tpp;                                            // a stage never straddles two planes
   if (!p.w_res) {
     while (p.wt > 1 && p.wt * p.nchunk * p.w_sub_bytes > 24 * 1024) p.wt = (p.wt % 3 == 0) ? p.wt / 3 : 1;
@@ -771,6 +1024,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   }
   p.w_bytes = p.w_res ? all_w : p.wstages * wstage_bytes;
   p.epi_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 1024);
+  p.stg_off = p.epi_off;
   if (p.stk) {
     p.xch_off = ru(p.w_off + p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16, 16);   // float4 quadruples
     p.xch_bytes = 2 * p.T * 4 * p.BN * 16 + p.BN * 16;     // + the all-zero block
@@ -811,6 +1065,7 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
   }
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
+  p.pair = 0; p.skip = 0; p.flags = 0; p.out_bytes = 2;
   return plan_fwd3(p);
 }
 
@@ -830,23 +1085,40 @@ struct Fwd3Launch {
   cudaStream_t st;
 };
 
-template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0>
+template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0, int PAIR = 0>
 static int launch_fwd3(const Fwd3Launch& L) {
+  auto kern = conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK><<<L.grid, kFwd3Threads, L.smem, L.st>>>(
+  if (PAIR) {
+    // clusters of two CTAs (one TPC): tcgen05 cta_group::2
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid, 1, 1);
+    cfg.blockDim = dim3(kFwd3Threads, 1, 1);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = L.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias,
+                                       (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: cluster launch: %s", cudaGetErrorString(e));
+    return R2N2_OK;
+  }
+  kern<<<L.grid, kFwd3Threads, L.smem, L.st>>>(
       L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
 }
-template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0>
+template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0, int PAIR = 0>
 static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
-  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>(L)
-                                : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK>(L);
+  return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>(L)
+                                : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>(L);
 }
 
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
@@ -857,15 +1129,24 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;
   p.flags = flags & (15 | R2N2_EPI_RES_PRE);
+  p.out_bytes = out_dtype == R2N2_F32 ? 4 : 2;
   R2N2_CHECK_ARG(!(flags & R2N2_EPI_RES_PRE) || (out_dtype == R2N2_F32 && (flags & R2N2_EPI_RESIDUAL)),
                  R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: RES_PRE needs RESIDUAL and an fp32 output");
   p.no_rot = getenv("R2N2_FWD3_NO_ROT") ? 1 : 0;
+  // CTA-pair mode (cta_group::2): where half of the filter per CTA fits next to the plane ring and N >= 96 makes the
+  // B-operand read worth halving.  R2N2_FWD3_PAIR=0/1 forces it off / on (any 2-D or 3-D layer with Cout % 32 == 0).
+  p.pair = (kd == 1 && Cin == 96 && Cout == 96 && (num_sms() % 2) == 0) ? 1 : 0;
+  if (const char* e = getenv("R2N2_FWD3_PAIR")) p.pair = (atoi(e) != 0 && Cout % 32 == 0 && Cout >= 32 && (num_sms() % 2) == 0) ? 1 : 0;
+  p.skip = getenv("R2N2_FWD3_SKIP") ? atoi(getenv("R2N2_FWD3_SKIP")) : 0;
   // Measured: on this kernel the smem-slab + TMA epilogue pays only without input slabs and where the register
   // epilogue binds: conv1b forward (96 -> 96, bias + LeakyReLU) 0.553 -> 0.520 ms; with a mask / residual slab
   // every slab's load -> compute -> store latency is exposed (one team): masked data gradient 0.66 -> 0.74 ms.
   // R2N2_FWD3_TMA_EPI=0/1 forces it off / on (both parity-tested).
   const bool has_in = (flags & (R2N2_EPI_RESIDUAL | R2N2_EPI_MASK)) != 0;
-  int want = (out_dtype == R2N2_BF16 && !has_in && kd == 1 && Cin == 96 && Cout == 96) ? 2 : 0;
+  // (round 2: the warp-staged epilogue -- plan_fwd3 -- replaces it by default: no slab hand-over between CTA-wide barriers
+  //  and no wait for the TMA store's shared-memory read; the TMA path stays selectable and tested)
+  int want = 0;
+  (void)has_in;
   if (const char* e = getenv("R2N2_FWD3_TMA_EPI")) want = out_dtype == R2N2_BF16 ? (atoi(e) ? 2 : 0) : 0;
   R2N2_CHECK_ARG(plan_fwd3(p, want), R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: layer does not fit the flat-halo kernel");
   p.err_word = get_err_word();
@@ -885,7 +1166,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
     const long long K = (long long)kd * kh * kw * Cin;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbox, (cuuint32_t)(p.pair ? p.BN / 2 : p.BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.rb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -895,7 +1176,8 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   const size_t smem_bytes = p.tma_epi
       ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) || p.nslab == 2 ? 2 : 1) * p.slab_bytes + 1024
       : (p.stk ? (size_t)p.xch_off + (size_t)p.xch_bytes + 1024
-               : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024);
+               : (p.stage_epi ? (size_t)p.stg_off + 16 * 1024 + 1024
+                              : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024));
   CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
   if (p.tma_epi) {
     cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
@@ -917,12 +1199,16 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   }
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma3]: smem %zu too large", smem_bytes);
   long long grid = num_sms();
-  if (grid > p.items) grid = p.items;
+  if (p.pair) {
+    const long long pitems = (p.items + 1) / 2;
+    if (grid > 2 * pitems) grid = 2 * pitems;
+    grid &= ~1LL;
+  } else if (grid > p.items) grid = p.items;
   if (getenv("R2N2_UMMA_DBG"))
     fprintf(stderr, "[umma fwd3] %dx%dx%dx%d Cin %d Cout %d kd %d block %dx%d P %d R %d T %d bands %dx%d zc %d items %lld "
-            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tma_epi %d stk %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
+            "kbox %d nchunk %d plane %d ring %d wsub %d wt %d wstages %d resident %d tma_epi %d stk %d pair %d tmem %d smem %zu\n", N, D, H, W, Cin, Cout, kd,
             p.Xb, p.Yb, p.P, p.R, p.T, p.bx, p.by, p.zc, p.items, p.kbox, p.nchunk, p.plane_bytes, p.nring,
-            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tma_epi, p.stk, p.tmem_cols, smem_bytes);
+            p.w_sub_bytes, p.wt, p.wstages, p.w_res, p.tma_epi, p.stk, p.pair, p.tmem_cols, smem_bytes);
   R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE,
                  "conv_fwd[umma3]: bad out dtype %d", out_dtype);
   const Fwd3Launch L{map_a, map_b, map_y, map_res, map_mask, bias, mask, res, y, p, (unsigned)grid, smem_bytes, st};
@@ -930,7 +1216,16 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   const bool k33 = kh == 3 && kw == 3 && !getenv("R2N2_FWD3_GENERIC");
   const bool k71s = kd == 1 && kh == 7 && kw == 1 && !getenv("R2N2_FWD3_GENERIC");
   // specialised (compile-time issue sequence) configurations of the training step
-  if (p.stk) {
+  if (p.pair) {
+    // CTA-pair configurations (cta_group::2)
+    if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 9, 1, 1, 0, 1>(L, out_dtype);
+    else if (Cin == 96) rc = launch_fwd3_dt<2, 3, 2, 0, 0, -1, 0, 0, 1>(L, out_dtype);
+    else if (Cin == 128) rc = launch_fwd3_dt<4, 2, 4, 0, 0, -1, 0, 0, 1>(L, out_dtype);
+    else if (Cin == 64) rc = launch_fwd3_dt<4, 1, 4, 0, 0, -1, 0, 0, 1>(L, out_dtype);
+    else if (Cin == 32) rc = launch_fwd3_dt<2, 1, 2, 0, 0, -1, 0, 0, 1>(L, out_dtype);
+    else rc = launch_fwd3_dt<1, 1, 1, 0, 0, -1, 0, 0, 1>(L, out_dtype);
+  }
+  else if (p.stk) {
     // dx-stacked configurations (generic issue loop unless listed)
     if (k33 && Cin == 32 && kd == 3 && p.T == 2 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 2, 9, 1, 3, 1>(L, out_dtype);
     else if (k33 && Cin == 32 && kd == 3 && p.T == 4 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 4, 9, 1, 3, 1>(L, out_dtype);

@@ -45,6 +45,7 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  R2N2_WS_BEGIN(bars);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tmem_full_bar = bars + 2 * p.stages;
@@ -212,6 +213,7 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         }
       }
   }
+  R2N2_WS_END(p.err_word);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

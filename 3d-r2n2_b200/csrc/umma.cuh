@@ -43,6 +43,50 @@ static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, 
     }
   }
 }
+#ifdef R2N2_WAITSTAT
+// DIAGNOSTIC BUILD ONLY (libr2n2_b200_ws.so, tools/waitstat.py): cycles each warp spends inside mbar_wait, per
+// barrier slot, written at kernel exit to the device buffer behind the error word:
+//   out[(block * 16 + warp) * 40 + i]: i < 38 = wait cycles on barrier i (8-byte slots from the kernel's first
+//   mbarrier), 38 = cycles from kernel entry to exit, 39 = number of waits that actually blocked.
+struct WaitStat {
+  long long bin[38];
+  long long t0, blocked;
+  uint32_t base;
+};
+static __device__ __forceinline__ void ws_begin(WaitStat& w, const void* bars) {
+  for (int i = 0; i < 38; ++i) w.bin[i] = 0;
+  w.blocked = 0;
+  w.base = smem_u32(bars);
+  w.t0 = clock64();
+}
+static __device__ __forceinline__ void ws_end(const WaitStat& w, int* err_word) {
+  if ((threadIdx.x & 31) != 0 || err_word == nullptr) return;
+  const unsigned blk = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const unsigned warp = threadIdx.x >> 5;
+  if (blk >= 512 || warp >= 16) return;
+  long long* out = reinterpret_cast<long long*>(err_word) + 8 + (size_t)(blk * 16 + warp) * 40;
+  for (int i = 0; i < 38; ++i) out[i] = w.bin[i];
+  out[38] = clock64() - w.t0;
+  out[39] = w.blocked;
+}
+static __device__ __forceinline__ void mbar_wait_ws(WaitStat& w, uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                             int* err_word) {
+  // (mbarrier.try_wait may itself suspend the thread for a while before it returns true: time the whole call)
+  const long long t = clock64();
+  mbar_wait(bar, parity, abort_flag, err_word);
+  const long long dt = clock64() - t;
+  uint32_t idx = (bar - w.base) >> 3;
+  if (idx > 37) idx = 37;
+  w.bin[idx] += dt;
+  if (dt > 200) ++w.blocked;
+}
+#define R2N2_WS_BEGIN(bars_ptr) WaitStat ws_; ws_begin(ws_, bars_ptr)
+#define R2N2_WS_END(err_word_ptr) ws_end(ws_, err_word_ptr)
+#define mbar_wait(bar, parity, af, ew) mbar_wait_ws(ws_, bar, parity, af, ew)
+#else
+#define R2N2_WS_BEGIN(bars_ptr)
+#define R2N2_WS_END(err_word_ptr)
+#endif
 static __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -94,6 +138,61 @@ static __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_
 }
 static __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// ---- CTA pair (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA spans both SMs' tensor cores, each CTA
+// supplies its own 128 A rows and HALF of the B (N) rows from its own shared memory at the same offsets.
+static __device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address of this CTA -> shared::cluster address of the same location in CTA `rank` of the cluster
+static __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+static __device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes)
+               : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA loads into THIS CTA's shared memory whose completion is signalled on an mbarrier of the pair's leader CTA
+static __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
+                                                int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+static __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+static __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs
+static __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
                : "memory");
 }
 static __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {

@@ -37,13 +37,19 @@ CASES = [
 
 
 @pytest.mark.parametrize('case', CASES)
-@pytest.mark.parametrize('tma_epi,stk', [('0', '0'), ('1', '0'), ('0', '1')])
+@pytest.mark.parametrize('tma_epi,stk,stage', [('0', '0', '1'), ('0', '0', '0'), ('1', '0', '1'), ('0', '1', '1')])
 @pytest.mark.parametrize('flags,out_dtype', [(0, torch.float32), (L.EPI_BIAS | L.EPI_LRELU, bf),
                                              (L.EPI_BIAS | L.EPI_RESIDUAL, bf), (L.EPI_RESIDUAL | L.EPI_MASK, bf)])
-def test_conv_fwd3(monkeypatch, case, flags, out_dtype, tma_epi, stk):
+def test_conv_fwd3(monkeypatch, case, flags, out_dtype, tma_epi, stk, stage):
     monkeypatch.setenv('R2N2_FWD3_FORCE', '1')
     monkeypatch.setenv('R2N2_FWD3_TMA_EPI', tma_epi)      # register epilogue / smem-slab + TMA-store epilogue
+    monkeypatch.setenv('R2N2_FWD3_STAGE_EPI', stage)      # warp-staged (8 pixels x 64 B per access) / thread-per-pixel epilogue
     monkeypatch.setenv('R2N2_FWD3_STK', stk)              # one MMA per tap / dx-stacked (N = 3 Cout, shifted sum in the epilogue)
+    monkeypatch.setenv('R2N2_FWD3_PAIR', '0')             # single-CTA path (the CTA-pair path: test_conv_fwd3_pair)
+    _run_case(case, flags, out_dtype)
+
+
+def _run_case(case, flags, out_dtype):
     N, D, H, W, Cin, Cout, k = case
     taps = k[0] * k[1] * k[2]
     P = N * D * H * W
@@ -67,6 +73,32 @@ def test_conv_fwd3(monkeypatch, case, flags, out_dtype, tma_epi, stk):
         bad = ((got - want).abs() > tol * max(1.0, want.abs().max().item())).nonzero().flatten()
         pix = torch.unique(bad // Cout)[:12].tolist()
         raise AssertionError('fwd3 %s flags %d: max err %.3e, %d bad, first pixels %s' % (case, flags, err, bad.numel(), pix))
+
+
+PAIR_CASES = [
+    (3, 1, 17, 17, 96, 96, (1, 3, 3)),       # conv1b-like, resident half filters; 3 items -> the peer's last item is a ghost
+    (2, 1, 127, 127, 96, 96, (1, 3, 3)),     # conv1b itself (two views): T = 2 specialised issue sequence
+    (5, 1, 30, 61, 96, 96, (1, 3, 3)),       # ragged blocks, odd number of items
+    (2, 1, 40, 70, 96, 128, (1, 3, 3)),      # conv2a-like: streamed half filters (N = 128 across the pair)
+    (2, 1, 33, 33, 128, 128, (1, 3, 3)),     # two 64-channel chunks, streamed
+    (1, 1, 9, 9, 64, 64, (1, 3, 3)),         # a single item: the peer works on a ghost only
+    (1, 16, 16, 16, 32, 32, (3, 3, 3)),      # 3-D rolling plane ring in lockstep
+    (2, 11, 12, 32, 64, 64, (3, 3, 3)),      # two z items with different plane counts (8 + 3)
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CASES)
+@pytest.mark.parametrize('tma_epi', ['0', '1'])
+@pytest.mark.parametrize('flags,out_dtype', [(0, torch.float32), (L.EPI_BIAS | L.EPI_LRELU, bf),
+                                             (L.EPI_BIAS | L.EPI_RESIDUAL, bf), (L.EPI_RESIDUAL | L.EPI_MASK, bf)])
+def test_conv_fwd3_pair(monkeypatch, case, flags, out_dtype, tma_epi):
+    """CTA-pair mode (cluster of two, tcgen05 cta_group::2, M = 256 MMAs, half of the filter rows per CTA,
+    multicast commits): same results as the emulated ABI for resident and streamed filters, 2-D and 3-D,
+    odd item counts (ghost item) and both epilogues."""
+    monkeypatch.setenv('R2N2_FWD3_FORCE', '1')
+    monkeypatch.setenv('R2N2_FWD3_TMA_EPI', tma_epi)
+    monkeypatch.setenv('R2N2_FWD3_PAIR', '1')
+    _run_case(case, flags, out_dtype)
 
 
 def test_fwd3_matches_per_tap_kernel_bitwise_shape(monkeypatch):
