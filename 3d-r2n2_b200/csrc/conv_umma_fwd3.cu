@@ -50,6 +50,7 @@ struct Fwd3Params {
   int nslab;                               // output slabs in rotation (2 when no residual / mask slab is loaded)
   int stk, xch_off, xch_bytes;             // dx-stacked mode: the 3 taps of a filter row share ONE MMA (N = 3 BN)
   int out_bytes;                           // sizeof(output element)
+  unsigned P_magic;                        // ceil(2^32 / P): r / P == __umulhi(r, P_magic) for r, P < 2^16
   int stage_epi, stg_off;                  // warp-staged epilogue: per-warp 32 pixels x 64 bytes staging tiles at this smem offset
   int pair;                                // CTA-pair mode (cluster of 2, cta_group::2 MMAs with M = 256, each CTA holds half of the filter rows)
   int skip;                                // TIMING EXPERIMENTS ONLY (R2N2_FWD3_SKIP bit mask): 1 no plane loads, 2 no weight loads,
@@ -687,36 +688,44 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int buf = step & 1;
         const int zz = c.z0 + j;
         bool first = true;
-        const int nitems = T_ * nrounds;
-        for (int wi = half; wi < ((p.skip & 4) ? 0 : nitems); wi += 2) {
-          const int t = wi / nrounds, rd = wi - t * nrounds;
+        // work split between the two warps of a quadrant: whole tiles when there are several (the pixel geometry
+        // is computed once per tile), else alternate rounds
+        const bool by_tile = T_ >= 2;
+        const int t_step = by_tile ? 2 : 1, rd0 = by_tile ? 0 : half, rd_step = by_tile ? 1 : 2;
+        for (int t = by_tile ? half : 0; t < ((p.skip & 4) ? 0 : T_); t += t_step) {
+          R2N2_WS_T0();
           // the 4 pixels whose 16-byte unit u_g this lane loads / stores: rows q = 8 k + q_lo of the warp's 32
-          long long goff[4];
+          long long goff0[4];
           bool gok[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int r = t * 128 + quad * 32 + 8 * k + q_lo;
-            const int yy = r / p.P, xx = r - yy * p.P;
+            const unsigned r = (unsigned)(t * 128 + quad * 32 + 8 * k + q_lo);
+            const int yy = (int)__umulhi(r, (unsigned)p.P_magic), xx = (int)r - yy * p.P;     // r / P (exact for r, P < 2^16)
             const int gy = c.y0 + yy, gx = c.x0 + xx;
-            gok[k] = r < p.R && xx < p.Xb && gx < p.W && gy < p.H && c.n < p.N;
-            goff[k] = (((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * p.Cout + rd * RC) * (long long)sizeof(TOut) +
-                      (long long)u_g * 16;
+            gok[k] = (int)r < p.R && xx < p.Xb && gx < p.W && gy < p.H && c.n < p.N;
+            goff0[k] = ((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * (long long)(p.Cout * (int)sizeof(TOut)) +
+                       (long long)u_g * 16;
           }
+          R2N2_WS_ACC(30);                       // geometry
+        for (int rd = rd0; rd < nrounds; rd += rd_step) {
+          const long long rdo = (long long)(rd * 64);
           uint4 gin[2][4];
           if (has_res || has_mask) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (gok[k]) {
-                if (has_res) gin[0][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(res) + goff[k]);
-                if (has_mask) gin[1][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(mask) + goff[k]);
+                if (has_res) gin[0][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(res) + goff0[k] + rdo);
+                if (has_mask) gin[1][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(mask) + goff0[k] + rdo);
               }
             }
           }
+          R2N2_WS_ACC(31);                       // input loads issued
           if (first) {
             mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
             tc_fence_after();
             first = false;
           }
+          R2N2_WS_ACC(32);                       // accumulator wait
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols + rd * RC);
           float f[RC];
           if (p.skip & 16) {
@@ -737,48 +746,44 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
           }
-          // inputs of this round: global (8 pixels x 64 B per access) -> staging tile -> the pixel's owner
-          float rin[RC], min_[RC];
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-            if (which == 0 ? !has_res : !has_mask) continue;
+          R2N2_WS_ACC(33);                       // TMEM loads
+          // an input of this round: global (8 pixels x 64 B per access, issued above) -> staging tile -> the pixel's
+          // owner, folded into f at once (op 0: f += v, op 1: f *= LeakyReLU'(v)) so that no second row stays live
+          auto fold = [&](const uint4 (&g4)[4], int op) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t row = (uint32_t)(8 * k + q_lo);
               const uint32_t a = stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4);
-              const uint4 g = gok[k] ? gin[which][k] : make_uint4(0, 0, 0, 0);
+              const uint4 g = gok[k] ? g4[k] : make_uint4(0, 0, 0, 0);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(g.x), "r"(g.y), "r"(g.z), "r"(g.w) : "memory");
             }
             __syncwarp();
-            uint4 o[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[u].x), "=r"(o[u].y), "=r"(o[u].z), "=r"(o[u].w)
+            for (int u = 0; u < 4; ++u) {
+              uint4 o;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                            : "r"(my_row + (((uint32_t)u ^ my_sw) << 4)));
-            __syncwarp();
-            float* dst = which == 0 ? rin : min_;
-            if (sizeof(TOut) == 2) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t w4[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
+              const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+              if (sizeof(TOut) == 2) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                  dst[u * 8 + 2 * e] = t2.x; dst[u * 8 + 2 * e + 1] = t2.y;
+                  const int q = (u * 8 + 2 * e) % RC;
+                  if (op == 0) { f[q] += t2.x; f[q + 1] += t2.y; }
+                  else { f[q] *= lrelu_slope(t2.x); f[q + 1] *= lrelu_slope(t2.y); }
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float tv = __uint_as_float(w4[e]);
+                  const int q = (u * 4 + e) % RC;
+                  if (op == 0) f[q] += tv; else f[q] *= lrelu_slope(tv);
                 }
               }
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                dst[(u * 4) % RC] = __uint_as_float(o[u].x); dst[(u * 4 + 1) % RC] = __uint_as_float(o[u].y);
-                dst[(u * 4 + 2) % RC] = __uint_as_float(o[u].z); dst[(u * 4 + 3) % RC] = __uint_as_float(o[u].w);
-              }
             }
-          }
-          if (has_res && res_pre) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) f[q] += rin[q];
-          }
+            __syncwarp();
+          };
+          if (has_res && res_pre) fold(gin[0], 0);
           if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
             for (int q = 0; q < RC; q += 4) {
@@ -790,14 +795,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int q = 0; q < RC; ++q) f[q] = lrelu(f[q]);
           }
-          if (has_res && !res_pre) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) f[q] += rin[q];
-          }
-          if (has_mask) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) f[q] *= lrelu_slope(min_[q]);
-          }
+          if (has_res && !res_pre) fold(gin[0], 0);
+          if (has_mask) fold(gin[1], 1);
+          R2N2_WS_ACC(34);                       // inputs folded, bias, LeakyReLU
           // results: owner -> staging tile -> global
           uint32_t w[16];
           if (sizeof(TOut) == 2) {
@@ -822,9 +822,11 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint4 o;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                          : "r"(stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4)));
-            if (gok[k] && !(p.skip & 32)) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + goff[k]) = o;
+            if (gok[k] && !(p.skip & 32)) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + goff0[k] + rdo) = o;
           }
           __syncwarp();
+          R2N2_WS_ACC(35);                       // pack, staging exchange, global stores
+        }
         }
         if (first) {          // (no work item for this warp in this step: still a consumer of the accumulator barrier)
           mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
@@ -924,7 +926,9 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   p.stage_epi = 0; p.stg_off = 0;
   {
     const int out_bytes = p.out_bytes;
-    int want_stage = (!p.stk && want_tma_epi != 2 && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
+    // (measured: it pays from 192 bytes per pixel on -- conv1b forward 0.51 -> 0.44 ms; the 64 / 128-byte layers of the
+    //  decoder run 2-5 % faster on the thread-per-pixel epilogue, whose column split balances the two warps of a quadrant)
+    int want_stage = (!p.stk && want_tma_epi != 2 && (p.BN * out_bytes) % 64 == 0 && p.BN * out_bytes >= 192) ? 1 : 0;
     if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
     if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
   }
@@ -975,6 +979,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   p.Xb = bX; p.Yb = bY; p.P = bX + p.kw - 1;
   p.bx = (p.W + bX - 1) / bX; p.by = (p.H + bY - 1) / bY;
   p.R = bY * p.P;
+  p.P_magic = (unsigned)((0x100000000ULL + (unsigned long long)p.P - 1) / (unsigned long long)p.P);
   p.T = (p.R + 127) / 128;
   p.plane_rows = (bY + p.kh - 1) * p.P;
   const int reach = p.T * 128 + (p.kh - 1) * p.P + p.kw - 1;
@@ -1060,8 +1065,13 @@ bool conv_fwd3_applicable(int N, int D, int H, int W, int Cin, int Cout, int kd,
     const bool small3d = kd == 3 && (Cin <= 32 || (Cin == 64 && (3 * Cout <= 256 || getenv("R2N2_FWD3_C64")) &&
                                                    !getenv("R2N2_FWD3_NO_C64")));
     const bool conv1b_like = kd == 1 && Cin == 96 && Cout == 96;
-    // (the row-packed 7x1 first layer is 10 % faster on the per-tap kernel with the TMA epilogue: 0.34 vs 0.38 ms)
-    if (!small3d && !conv1b_like && !(k71 && Cin <= 32 && getenv("R2N2_FWD3_K71"))) return false;
+    // round 2, with the warp-staged epilogue (>= 192 output bytes per pixel): conv2a (96 -> 128) 0.220 -> 0.192 ms and the
+    // row-packed 7x1 first layer 0.333 -> 0.279 ms (resident filter, input loaded once instead of once per tap);
+    // conv2b / the 128 -> 96 data gradient stay on the per-tap kernel (0.216 vs 0.316 ms, 0.171 vs 0.222 ms: their
+    // streamed filters leave too few weight stages).  R2N2_FWD3_K71=0 / R2N2_FWD3_C96=0 restore the round-1 routing.
+    const bool conv2a_like = kd == 1 && Cin == 96 && Cout == 128 && !(getenv("R2N2_FWD3_C96") && !atoi(getenv("R2N2_FWD3_C96")));
+    const bool k71_on = k71 && Cin <= 32 && Cout * 2 >= 192 && !(getenv("R2N2_FWD3_K71") && !atoi(getenv("R2N2_FWD3_K71")));
+    if (!small3d && !conv1b_like && !conv2a_like && !k71_on) return false;
   }
   Fwd3Params p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kd = kd; p.kh = kh; p.kw = kw;

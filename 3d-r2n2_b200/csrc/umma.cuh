@@ -82,10 +82,15 @@ static __device__ __forceinline__ void mbar_wait_ws(WaitStat& w, uint32_t bar, u
 }
 #define R2N2_WS_BEGIN(bars_ptr) WaitStat ws_; ws_begin(ws_, bars_ptr)
 #define R2N2_WS_END(err_word_ptr) ws_end(ws_, err_word_ptr)
+// section timers (bins 30..36 by convention): R2N2_WS_T0() ... R2N2_WS_ACC(slot) adds the cycles since the last mark
+#define R2N2_WS_T0() long long ws_t_ = clock64()
+#define R2N2_WS_ACC(slot) do { const long long ws_n_ = clock64(); ws_.bin[slot] += ws_n_ - ws_t_; ws_t_ = ws_n_; } while (0)
 #define mbar_wait(bar, parity, af, ew) mbar_wait_ws(ws_, bar, parity, af, ew)
 #else
 #define R2N2_WS_BEGIN(bars_ptr)
 #define R2N2_WS_END(err_word_ptr)
+#define R2N2_WS_T0()
+#define R2N2_WS_ACC(slot)
 #endif
 static __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {

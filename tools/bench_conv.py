@@ -22,6 +22,7 @@ SHAPES = [
     ('conv1b', (TB, 1, 127, 127), 96, 96, (1, 3, 3)),
     ('conv2a', (TB, 1, 64, 64), 96, 128, (1, 3, 3)),
     ('conv2b', (TB, 1, 64, 64), 128, 128, (1, 3, 3)),
+    ('conv2a_dgrad', (TB, 1, 64, 64), 128, 96, (1, 3, 3)),
     ('conv2c', (TB, 1, 64, 64), 96, 128, (1, 1, 1)),
     ('conv3a', (TB, 1, 33, 33), 128, 256, (1, 3, 3)),
     ('conv3b', (TB, 1, 33, 33), 256, 256, (1, 3, 3)),
