@@ -324,6 +324,10 @@ int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void
                  "conv_fwd[umma]: Cin (%d) and Cout (%d) must be multiples of 16 (use ALGO_SIMT)", Cin, Cout);
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 31) == 0 &&
+                     (!(flags & R2N2_EPI_RESIDUAL) || (reinterpret_cast<uintptr_t>(res) & 31) == 0) &&
+                     (!(flags & R2N2_EPI_MASK) || (reinterpret_cast<uintptr_t>(mask) & 31) == 0),
+                 R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: y / residual / mask must be 32-byte aligned");
   EncodeTiledFn encode = get_encode();
   R2N2_CHECK_ARG(encode != nullptr, R2N2_ERR_CUDA, "conv_fwd[umma]: cuTensorMapEncodeTiled unavailable");
 

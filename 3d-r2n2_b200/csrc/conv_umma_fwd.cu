@@ -522,6 +522,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
                  "conv_fwd[umma]: Cin (%d) and Cout (%d) must be multiples of 16 (use ALGO_SIMT)", Cin, Cout);
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: x / w must be 16-byte aligned");
+  // the register epilogues move 32 bytes per instruction (256-bit global loads / stores)
+  R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 31) == 0 &&
+                     (!(flags & R2N2_EPI_RESIDUAL) || (reinterpret_cast<uintptr_t>(res) & 31) == 0) &&
+                     (!(flags & R2N2_EPI_MASK) || (reinterpret_cast<uintptr_t>(mask) & 31) == 0),
+                 R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: y / residual / mask must be 32-byte aligned");
   // 3x3 / 3x3x3 layers with <= 128 output channels: input loaded once, taps as descriptor views
   if (mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw)) {
     int rc = conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, out_dtype, st);

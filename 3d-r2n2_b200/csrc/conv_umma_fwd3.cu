@@ -926,9 +926,10 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
   p.stage_epi = 0; p.stg_off = 0;
   {
     const int out_bytes = p.out_bytes;
-    // (measured: it pays from 192 bytes per pixel on -- conv1b forward 0.51 -> 0.44 ms; the 64 / 128-byte layers of the
-    //  decoder run 2-5 % faster on the thread-per-pixel epilogue, whose column split balances the two warps of a quadrant)
-    int want_stage = (!p.stk && want_tma_epi != 2 && (p.BN * out_bytes) % 64 == 0 && p.BN * out_bytes >= 192) ? 1 : 0;
+    // (measured: it pays at 192 bytes per pixel -- conv1b forward 0.51 -> 0.44 ms, conv1a 0.30 -> 0.28 ms; the 64 / 128-byte
+    //  layers of the decoder run 2-5 % faster on the thread-per-pixel epilogue, whose column split balances the two warps)
+    // (with 256-bit thread-per-pixel accesses the other widths are as fast or faster without staging: conv2a 0.171 vs 0.179 ms)
+    int want_stage = (!p.stk && want_tma_epi != 2 && p.BN * out_bytes == 192) ? 1 : 0;
     if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
     if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
   }

@@ -262,14 +262,19 @@ static __device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (
     __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
     w[j] = *reinterpret_cast<uint32_t*>(&h);
   }
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  // one 256-bit store (sm_100: STG.256): a warp's thread-per-pixel accesses cost one L1 wavefront per lane and
+  // instruction, so 32 bytes per instruction halve the epilogue's LSU time (dst is 32-byte aligned: channel counts
+  // are multiples of 16 and the dispatchers check the base pointers)
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
 }
 static __device__ __forceinline__ void store16(float* dst, const float (&f)[16]) {
-  float4* d = reinterpret_cast<float4*>(dst);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  for (int j = 0; j < 2; ++j)
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * j), "f"(f[8 * j]), "f"(f[8 * j + 1]),
+                 "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]), "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
+                 : "memory");
 }
 
 
@@ -280,8 +285,9 @@ template <>
 struct Row16<__nv_bfloat16> {
   uint4 a, b;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    a = reinterpret_cast<const uint4*>(p)[0];
-    b = reinterpret_cast<const uint4*>(p)[1];
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
   }
   __device__ __forceinline__ void unpack(float (&f)[16]) const {
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -298,7 +304,11 @@ struct Row16<float> {
   float4 q[4];
   __device__ __forceinline__ void load(const float* p) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = reinterpret_cast<const float4*>(p)[j];
+    for (int j = 0; j < 2; ++j)
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(q[2 * j].x), "=f"(q[2 * j].y), "=f"(q[2 * j].z), "=f"(q[2 * j].w), "=f"(q[2 * j + 1].x),
+                     "=f"(q[2 * j + 1].y), "=f"(q[2 * j + 1].z), "=f"(q[2 * j + 1].w)
+                   : "l"(p + 8 * j));
   }
   __device__ __forceinline__ void unpack(float (&f)[16]) const {
 #pragma unroll
