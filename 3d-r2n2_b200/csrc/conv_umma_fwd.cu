@@ -35,6 +35,9 @@ struct FwdParams {
   int SC, slab_bytes, epi_off;             // slab = 128 rows x SC output channels; smem offset of the staging buffers
   float* colsum;                           // TMA epilogue, one N tile: colsum[c] += sum over pixels of y[p, c] (fp32), or NULL
   int csum_off;                            //   smem offset of the per-team partial sums (2 x BN floats)
+  int mc;                                  // multicast cluster: the mc CTAs of a cluster compute mc N tiles of ONE M tile; each loads
+  int mc_rows;                             //   mc_rows rows of every A box and multicasts them to all (slice r at smem row r * mc_rows)
+  signed char mc_dn[8], mc_dd[8];          //   box-relative (image, plane) coordinates of the slice of cluster rank r
   int mode;                                // 0 plain, 1 UP2 (zero-stuffed x2 input, 8 parity classes), 2 DOWN2
   int cls_tiles;                           // tiles per parity class (= m_tiles * n_tiles)
   int* err_word;
@@ -76,8 +79,8 @@ constexpr int kFwdThreads = 64 + 32 * kEpiWarps;
 // NK16 / NSUB > 0: K16 steps per sub-block and sub-blocks per stage are compile-time (every stage full, every
 // channel chunk full): the MMA issue sequence of a stage is straight-line code with immediate descriptor
 // offsets -- the issuing thread, not the tensor pipe, sets the pace when it spends ~17 instructions per MMA.
-template <typename TOut, int NK16, int NSUB>
-__global__ void __launch_bounds__(kFwdThreads, 2)
+template <typename TOut, int NK16, int NSUB, int MC>
+__global__ void __launch_bounds__(kFwdThreads, MC ? 1 : 2)
 conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
                          const __grid_constant__ CUtensorMap map_mask,
@@ -102,7 +105,8 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     *abort_flag = 0;
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      // multicast: a stage may be refilled (by every CTA's slice) only when ALL CTAs of the cluster have consumed it
+      mbar_init(smem_u32(&empty_bar[s]), MC ? (uint32_t)p.mc : 1u);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
@@ -126,8 +130,11 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();            // every CTA's barriers exist before the first multicast load / commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const uint16_t cmask = MC ? (uint16_t)((1u << p.mc) - 1u) : (uint16_t)1;
 
   const int taps = p.kd * p.kh * p.kw;
   const int nq = taps * p.kchunks;                  // sub-blocks per tile
@@ -165,7 +172,11 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         uint32_t dst = smem_base + (uint32_t)(s * p.stage_bytes);
         for (int u = 0; u < ns; ++u) {
           if (leader) {
-            tma_load_5d(dst, &map_a, bar, c0, cx + jx, cy + jy, cz + jz, n0);
+            if (MC)       // this CTA's slice of the box, to every CTA of the cluster (each full barrier expects the whole box)
+              tma_load_5d_mc(dst + (uint32_t)((int)crank * p.mc_rows * row_bytes), &map_a, bar, cmask, c0, cx + jx, cy + jy,
+                             cz + jz + p.mc_dd[crank], n0 + p.mc_dn[crank]);
+            else
+              tma_load_5d(dst, &map_a, bar, c0, cx + jx, cy + jy, cz + jz, n0);
             tma_load_2d(dst + (uint32_t)p.a_bytes, &map_b, bar, kcol + c0, col0);
           }
           dst += (uint32_t)sub_bytes;
@@ -223,7 +234,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
                 umma_bf16(d_tmem, da0 + (uint64_t)(u * sub16 + 2u * k), db0 + (uint64_t)(u * sub16 + 2u * k), idesc,
                           (u == 0 && k == 0) ? acc : 1u);
             }
-            umma_commit(empty0 + 8u * s);
+            if (MC) umma_commit_mc(empty0 + 8u * s, cmask); else umma_commit(empty0 + 8u * s);
           }
         } else if (elect_one()) {
           uint32_t addr = a_addr;
@@ -240,7 +251,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
             addr += (uint32_t)sub_bytes;
             if (++c == p.kchunks) c = 0;
           }
-          umma_commit(empty0 + 8u * s);                 // stage free once these MMAs retire
+          if (MC) umma_commit_mc(empty0 + 8u * s, cmask); else umma_commit(empty0 + 8u * s);   // stage free once these MMAs retire
         }
         __syncwarp();
         acc = 1;
@@ -437,6 +448,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
   R2N2_WS_END(p.err_word);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();            // no CTA exits while a peer may still multicast into its shared memory / barriers
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -452,18 +464,65 @@ struct FwdLaunch {
   const FwdParams& p;
   int grid; size_t smem; cudaStream_t st;
 };
-template <typename TOut, int NK16, int NSUB>
-static int launch_fwd(const FwdLaunch& L) {
+template <typename TOut, int NK16, int NSUB, int MC>
+static int launch_fwd_k(const FwdLaunch& L) {
+  auto kern = conv_fwd_umma_persistent<TOut, NK16, NSUB, MC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_umma_persistent<TOut, NK16, NSUB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  conv_fwd_umma_persistent<TOut, NK16, NSUB><<<L.grid, kFwdThreads, L.smem, L.st>>>(
+  if (MC) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid, 1, 1);
+    cfg.blockDim = dim3(kFwdThreads, 1, 1);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = L.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)L.p.mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias,
+                                       (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: cluster launch: %s", cudaGetErrorString(e));
+    return R2N2_OK;
+  }
+  kern<<<L.grid, kFwdThreads, L.smem, L.st>>>(
       L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
+}
+template <typename TOut, int NK16, int NSUB>
+static int launch_fwd(const FwdLaunch& L) {
+  // multicast clusters: only the generic and the (4, 2) / (4, 3) / (4, 4) issue sequences are instantiated
+  if (L.p.mc > 1) {
+    if constexpr (NK16 == 4 && (NSUB == 2 || NSUB == 3 || NSUB == 4)) return launch_fwd_k<TOut, NK16, NSUB, 1>(L);
+    else return launch_fwd_k<TOut, 0, 0, 1>(L);
+  }
+  return launch_fwd_k<TOut, NK16, NSUB, 0>(L);
+}
+
+// resident clusters of `c` CTAs (one CTA per SM, full shared memory) the device can hold at once
+static int max_active_clusters(int c) {
+  static int cache[9] = {0};
+  if (c < 2 || c > 8) return 0;
+  if (cache[c]) return cache[c];
+  auto kern = conv_fwd_umma_persistent<__nv_bfloat16, 0, 0, 1>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms() / c * c, 1, 1);
+  cfg.blockDim = dim3(kFwdThreads, 1, 1);
+  cfg.dynamicSmemBytes = 200 * 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[c] = n > 0 ? n : -1;
+  return cache[c];
 }
 template <int NK16, int NSUB>
 static int launch_fwd_dt(const FwdLaunch& L, int out_dtype) {
@@ -550,6 +609,46 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     p.BN /= 2;
   if (const char* e = getenv("R2N2_UMMA_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && v <= Cout) p.BN = v; }
   p.n_tiles = (Cout + p.BN - 1) / p.BN;
+  // Multicast clusters for the layers that were split along N to cover the SMs (recurrent unit, FC layers, conv6): the N
+  // tiles of one M tile re-load the same A boxes, and their CTAs are bound by the ~55 B/clk of TMA traffic one SM takes
+  // (tools/waitstat.py: the producer warp is busy 93 % of the kernel, nobody waits).  In a cluster of C such CTAs each
+  // loads 1/C of every A box and multicasts it: per-CTA traffic A/C + B.  Needs all clusters resident at once (one
+  // tile per CTA, lockstep) -- C = 8 fits 16 clusters on a B200, so N is re-merged where that gives a resident shape.
+  p.mc = 0; p.mc_rows = 0;
+  int mc_sd = 0, mc_sn = 0;
+  // MEASURED (CUDA-graph replay, no host launch time): no gain -- GRU hidden conv 13 us with or without (only C = 2 leaves
+  // all 72 clusters resident), fc7 10 -> 11 us with C = 8, x-projection 17 -> 18 us: at ~10 us these kernels sit on their
+  // launch + prologue + first-load latency floor, not on the A traffic.  Kept as an opt-in (R2N2_UMMA_MC=1), parity-tested.
+  if (mode == 0 && getenv("R2N2_UMMA_MC") && atoi(getenv("R2N2_UMMA_MC")) && !getenv("R2N2_UMMA_BN")) {
+    const int rows = p.bw * p.bh * p.bd * p.bn, c3 = p.bw * p.bh * p.bd, c2 = p.bw * p.bh;
+    double best_traffic = 1e30;
+    int bBN = 0, bC = 0;
+    for (int BN = p.BN; BN <= 256 && BN <= Cout; BN *= 2) {
+      if (Cout % BN) continue;
+      const int nt = Cout / BN;
+      if ((long long)p.m_tiles * nt > num_sms()) continue;
+      for (int C = 8; C >= 2; C >>= 1) {
+        if (nt % C || rows % C || (rows / C) % 8) continue;
+        const int sr = rows / C;
+        if (!(sr % c3 == 0 || (c3 % sr == 0 && sr % c2 == 0))) continue;
+        if (p.m_tiles * nt / C > max_active_clusters(C)) continue;
+        const double traffic = 128.0 / C + BN;              // rows of A + rows of B per K element and CTA
+        if (traffic < best_traffic) { best_traffic = traffic; bBN = BN; bC = C; }
+      }
+    }
+    if (bC && best_traffic < 0.8 * (128.0 + p.BN)) {
+      p.BN = bBN;
+      p.n_tiles = Cout / p.BN;
+      p.mc = bC;
+      p.mc_rows = rows / bC;
+      if (p.mc_rows % c3 == 0) { mc_sn = p.mc_rows / c3; mc_sd = p.bd; }
+      else { mc_sn = 1; mc_sd = p.mc_rows / c2; }
+      for (int r = 0; r < 8; ++r) {
+        if (p.mc_rows % c3 == 0) { p.mc_dn[r] = (signed char)(r * mc_sn); p.mc_dd[r] = 0; }
+        else { const int per = c3 / p.mc_rows; p.mc_dn[r] = (signed char)(r / per); p.mc_dd[r] = (signed char)((r % per) * mc_sd); }
+      }
+    }
+  }
   p.mode = mode;
   p.cls_tiles = p.m_tiles * p.n_tiles;
   p.total_tiles = p.cls_tiles * (mode == 1 ? 8 : 1);
@@ -572,6 +671,10 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   (void)sub_cycles;
   if (const char* e = getenv("R2N2_UMMA_CTAS")) { int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
   if (2 * p.bn_cols * ctas > 512) ctas = 1;
+  // no more tiles than SMs (recurrent unit, FC layers, conv5/6): every CTA is alone on its SM anyway, so it gets the
+  // whole shared memory -- 5 pipeline stages instead of 2 hide the TMA round trip of these latency-bound layers
+  if (p.total_tiles <= num_sms() && !getenv("R2N2_UMMA_CTAS")) ctas = 1;
+  if (p.mc > 1) ctas = 1;
   // epilogue through shared memory + TMA (bf16 outputs; UP2 writes strided positions and keeps the register path)
   // Worth its shared memory only where the register epilogue would be the critical path: thread-per-pixel
   // accesses cost ~66 L1 wavefront cycles per 16-byte instruction (2 stores + 2 loads per input tensor per
@@ -601,6 +704,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   if (nsub > 8) nsub = 8;
   while (nsub > 1 && nsub * sub_bytes > stage_cap) --nsub;
   if (nsub > nq) nsub = nq;
+  // a stage count that divides the tile's sub-blocks keeps every stage full, i.e. on the compile-time issue sequence
+  // (the generic loop costs the issuing thread ~100 cycles per MMA on the N = 32 / 64 tiles of the small layers)
+  if (mode != 1 && Cin % p.kbox == 0 && nq % nsub != 0 && !getenv("R2N2_UMMA_NO_DIV_NSUB"))
+    for (int v = nsub; v >= 1; --v)
+      if (nq % v == 0 && (v <= 4 || v == 6 || v == 8)) { if (2 * v >= nsub || v >= 3) nsub = v; break; }
   if (const char* e = getenv("R2N2_UMMA_NSUB")) { int v = atoi(e); if (v >= 1 && v <= 8) nsub = v < nq ? v : nq; }
   p.nsub = nsub;
   p.stage_bytes = nsub * sub_bytes;
@@ -633,7 +741,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Wi * Cin * 2, (cuuint64_t)Hi * Wi * Cin * 2,
                              (cuuint64_t)Di * Hi * Wi * Cin * 2};
     cuuint32_t box[5] = {(cuuint32_t)p.kbox, (cuuint32_t)(p.bw * sc), (cuuint32_t)(p.bh * sc),
-                         (cuuint32_t)(p.bd * sc), (cuuint32_t)p.bn};
+                         (cuuint32_t)((p.mc > 1 ? mc_sd : p.bd) * sc), (cuuint32_t)(p.mc > 1 ? mc_sn : p.bn)};
     cuuint32_t es[5] = {1, (cuuint32_t)sc, (cuuint32_t)sc, (cuuint32_t)sc, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides,
                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes),
@@ -677,7 +785,8 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   int grid = num_sms() * ctas;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (getenv("R2N2_UMMA_DBG"))
-    fprintf(stderr, "[umma fwd] tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d tma_epi %d SC %d smem %zu\n",
+    fprintf(stderr, "[umma fwd] mc %d(%d rows) spec %d tiles %d (m %d x n %d) box %dx%dx%dx%d BN %d kbox %d nsub %d stages %d ctas %d tma_epi %d SC %d smem %zu\n",
+            p.mc, p.mc_rows, (int)(mode != 1 && Cin % p.kbox == 0 && nq % p.nsub == 0),
             p.total_tiles, p.m_tiles, p.n_tiles, p.bw, p.bh, p.bd, p.bn, p.BN, p.kbox, p.nsub, p.stages, ctas,
             p.tma_epi, p.SC, smem_bytes);
   R2N2_CHECK_ARG(out_dtype == R2N2_BF16 || out_dtype == R2N2_F32, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d",
@@ -691,6 +800,12 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   else if (spec && nk16 == 4 && p.nsub == 2) rc = launch_fwd_dt<4, 2>(L, out_dtype);
   else if (spec && nk16 == 2 && p.nsub == 3) rc = launch_fwd_dt<2, 3>(L, out_dtype);
   else if (spec && nk16 == 2 && p.nsub == 4) rc = launch_fwd_dt<2, 4>(L, out_dtype);
+  else if (spec && nk16 == 4 && p.nsub == 3) rc = launch_fwd_dt<4, 3>(L, out_dtype);
+  else if (spec && nk16 == 4 && p.nsub == 4) rc = launch_fwd_dt<4, 4>(L, out_dtype);
+  else if (spec && nk16 == 4 && p.nsub == 6) rc = launch_fwd_dt<4, 6>(L, out_dtype);
+  else if (spec && nk16 == 4 && p.nsub == 8) rc = launch_fwd_dt<4, 8>(L, out_dtype);
+  else if (spec && nk16 == 2 && p.nsub == 6) rc = launch_fwd_dt<2, 6>(L, out_dtype);
+  else if (spec && nk16 == 2 && p.nsub == 8) rc = launch_fwd_dt<2, 8>(L, out_dtype);
   else rc = launch_fwd_dt<0, 0>(L, out_dtype);
   if (rc != R2N2_OK) return rc;
   R2N2_CHECK_LAUNCH("conv_fwd[umma]");

@@ -194,6 +194,22 @@ static __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TMA multicast: the box lands at the same shared-memory offset in every CTA of `mask`, and each of them gets the
+// complete_tx on its own mbarrier at the same offset
+static __device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, uint16_t mask, int c0,
+                                               int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5, %6, %7, %8}], [%2], %3;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// tcgen05.commit of a single-CTA MMA stream that arrives on the barrier at this offset in every CTA of `mask`
+static __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
 // arrives (once the MMAs issued so far have retired) on the barrier at this shared-memory offset in BOTH CTAs
 static __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

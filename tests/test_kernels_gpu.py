@@ -398,6 +398,14 @@ UMMA_CASES = [
     (1, 8, 8, 8, 128, 64, (1, 1, 1)),       # conv9c
     (180, 1, 1, 1, 1024, 512, (1, 1, 1)),   # x-projection slice
     (2, 6, 5, 7, 64, 64, (3, 3, 3)),        # ragged 3-D
+    # the single-wave layers that run on MULTICAST CLUSTERS (each CTA loads 1/C of every A box for the whole cluster)
+    (36, 4, 4, 4, 128, 256, (3, 3, 3)),     # GRU hidden conv at batch 36: 18 M tiles, slices = planes of one image
+    (36, 4, 4, 4, 256, 128, (3, 3, 3)),     # its data gradient (u/r gates): K = 6912
+    (32, 4, 4, 4, 128, 128, (3, 3, 3)),     # candidate conv at batch 32 (config 5)
+    (180, 1, 1, 1, 2304, 1024, (1, 1, 1)),  # fc7 at T*B = 180: second M tile mostly out of bounds, slices = images
+    (180, 1, 1, 1, 1024, 2304, (1, 1, 1)),  # fc7 data gradient
+    (180, 1, 5, 5, 256, 256, (1, 3, 3)),    # conv6a: 125-row boxes (no aligned slices -> no cluster)
+    (7, 4, 4, 4, 128, 384, (3, 3, 3)),      # LSTM hidden conv, odd batch (last box half out of bounds)
 ]
 
 
@@ -405,7 +413,11 @@ UMMA_CASES = [
 @pytest.mark.parametrize('flags,out_dtype', [(0, torch.float32), (L.EPI_BIAS | L.EPI_LRELU, torch.bfloat16),
                                              (L.EPI_BIAS | L.EPI_RESIDUAL, torch.bfloat16),
                                              (L.EPI_RESIDUAL | L.EPI_MASK, torch.bfloat16)])
-def test_conv_fwd_umma_bf16(case, flags, out_dtype):
+@pytest.mark.parametrize('mc', ['0', '1'])
+def test_conv_fwd_umma_bf16(monkeypatch, case, flags, out_dtype, mc):
+    if mc == '1' and case[0] * case[1] * case[2] * case[3] > 128 * 148:
+        pytest.skip('multicast clusters only exist for single-wave layers')
+    monkeypatch.setenv('R2N2_UMMA_MC', mc)        # multicast clusters (opt-in) for the single-wave layers
     N, D, H, W, Cin, Cout, k = case
     taps = k[0] * k[1] * k[2]
     P = N * D * H * W

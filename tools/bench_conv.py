@@ -53,6 +53,7 @@ def main():
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--what', default='fwd,wgrad')
     ap.add_argument('--json', default=None)
+    ap.add_argument('--graph', action='store_true', help='time the launches replayed from a CUDA graph (no host launch overhead)')
     args = ap.parse_args()
     dev = 'cuda'
     bf = torch.bfloat16
@@ -79,10 +80,28 @@ def main():
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.iters):
-                fn()
-            e1.record()
+            if args.graph:
+                # small layers: a python launch (~20 us) is longer than the kernel; replay the launches from a CUDA graph
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(args.iters):
+                        fn()
+                g.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                g.replay()
+                e1.record()
+            else:
+                e0.record()
+                for _ in range(args.iters):
+                    fn()
+                e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
             res[what] = dict(ms=ms, tflops=flops / ms / 1e9)
