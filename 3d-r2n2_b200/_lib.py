@@ -59,6 +59,7 @@ PROTOTYPES = {
     'r2n2_voxel_labels': [_p, _p, _i, _i, _p],
     'r2n2_fill_zero': [_p, _ll, _p],
     'r2n2_umma_error_flag': [],
+    'r2n2_set_sm_limit': [_i],
 }
 
 _lib = None

@@ -132,6 +132,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+inline int& sm_limit_ref() {
+  static int limit = 0;          // r2n2_set_sm_limit (0 = none)
+  return limit;
+}
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -140,7 +144,8 @@ inline int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  const int lim = sm_limit_ref();
+  return (lim >= 16 && lim < n) ? (lim & ~1) : n;
 }
 
 // dispatch on dtype code

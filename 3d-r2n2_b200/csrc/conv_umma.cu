@@ -999,6 +999,7 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
 }  // namespace r2n2
 
 extern "C" int r2n2_umma_error_flag(void) { return r2n2::umma_error_flag(); }
+extern "C" int r2n2_set_sm_limit(int n_sms) { r2n2::sm_limit_ref() = n_sms; return R2N2_OK; }
 
 #ifdef R2N2_WAITSTAT
 // diagnostic build only (tools/waitstat.py): copy the wait statistics of the last tcgen05 launch to the host and clear them

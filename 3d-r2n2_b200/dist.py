@@ -49,6 +49,27 @@ class GradSync:
             self.ranges[last] = self.ranges[last] + [(st.n_decay, st.n)]
         self.pending = []
         self.launched = set()
+        # OPTIONAL SM partition while an all-reduce is in flight (csrc: r2n2_set_sm_limit): the compute grids leave
+        # `reserve` TPCs (2 SMs each: the CTA-pair kernels need whole TPCs) to the NCCL kernels, which init_from_env caps
+        # at NCCL_MAX_CTAS = reserve channels.  Measured on 8 x B200 (profiles/r02_scaling_experiments.txt): no gain --
+        # 11.52 ms/step without, 11.56 / 11.59 / 11.87 ms with 4 / 8 / 16 reserved -- so it is OFF by default
+        # (R2N2_COMM_SMS=0); the step-time gap to N=1 is the slowest GPU of the box, see bench.py dp_check.
+        import os
+        self.reserve = int(os.environ.get('R2N2_COMM_SMS', '0')) if st.p.is_cuda else 0
+        self.n_sm = torch.cuda.get_device_properties(st.p.device).multi_processor_count if st.p.is_cuda else 0
+        self._limited = False
+
+    def _set_limit(self, on):
+        if self.reserve <= 0 or on == self._limited:
+            return
+        from . import _lib as L
+        L.call('r2n2_set_sm_limit', self.n_sm - 2 * self.reserve if on else 0)
+        self._limited = on
+
+    def poll(self):
+        """ops.pre_launch hook: give the SMs back as soon as every launched all-reduce has completed."""
+        if self._limited and all(w.is_completed() for w in self.pending):
+            self._set_limit(False)
 
     def coverage(self):
         """all (lo, hi) ranges, sorted: must tile [0, n) exactly once (checked in tests)."""
@@ -62,6 +83,7 @@ class GradSync:
         for lo, hi in self.ranges[stage]:
             self.pending.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
                                                 async_op=True))
+        self._set_limit(True)
 
     def __call__(self, g):
         if self.world > 1:
@@ -70,6 +92,7 @@ class GradSync:
             for w in self.pending:
                 w.wait()
         self.pending, self.launched = [], set()
+        self._set_limit(False)
         return 1.0 / self.world
 
 
@@ -78,6 +101,9 @@ def attach(solver, group=None):
     sync = GradSync(solver.net.engine, group)
     solver.grad_sync = sync
     solver.net.engine.progress = sync.stage_done
+    if sync.world > 1 and sync.reserve > 0:
+        from . import ops
+        ops.pre_launch = sync.poll
     solver.rank = dist.get_rank(group) if dist.is_initialized() else 0
     solver.world = sync.world
     solver.dist_group = group
@@ -92,6 +118,11 @@ def init_from_env(backend=None):
     if world <= 1:
         return 0, 1, 0
     rank, local = int(os.environ['RANK']), int(os.environ.get('LOCAL_RANK', '0'))
+    # SM partition between the step's persistent kernels and the overlapped all-reduce (GradSync._set_limit):
+    # NCCL gets at most NCCL_MAX_CTAS channels (= SMs); must be set before the communicator exists; explicit settings win.
+    reserve = int(os.environ.get('R2N2_COMM_SMS', '0'))
+    if reserve > 0 and torch.cuda.is_available():
+        os.environ.setdefault('NCCL_MAX_CTAS', str(reserve))
     if not dist.is_initialized():
         if backend is None:
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'

@@ -49,9 +49,14 @@ _next_work = None        # work description (flops / bytes) attached by the wrap
 _next_tag = ''
 
 
+pre_launch = None         # optional host callback before every launch (dist.GradSync polls its all-reduces here)
+
+
 def _call(name, *args):
     global launch_count, _next_work, _next_tag
     launch_count += 1
+    if pre_launch is not None:
+        pre_launch()
     if profiler is None:
         L.call(name, *args)
         return

@@ -211,7 +211,7 @@ def run_ours(args):
         args.gpus = world
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        r2dist.init_from_env('nccl')        # (also caps the SMs NCCL may take: NCCL_MAX_CTAS, see dist.py)
     _lib.load()
 
     compute = args.compute
@@ -388,12 +388,41 @@ def run_ours(args):
     dp_check = None
     if world > 1:
         st = net.engine.store
+        # where does the step time beyond the 1-GPU figure go?  Each rank's own forward+backward+Adam with the gradient
+        # synchronisation switched OFF (parameters restored afterwards): the slowest of N GPUs sets the synchronous step
+        # (GPUs of one box differ by a few % under the power cap); what is left over is communication.
+        p_keep, m_keep, v_keep = st.p.clone(), None if st.m is None else st.m.clone(), None if st.v is None else st.v.clone()
+        it_keep = solver.iteration
+        sync_keep, prog_keep, hook_keep = solver.grad_sync, net.engine.progress, ops.pre_launch
+        solver.grad_sync, net.engine.progress, ops.pre_launch = None, None, None
+        for _ in range(3):
+            solver.train_step_device(x_dev, y_dev)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(10):
+            solver.train_step_device(x_dev, y_dev)
+        eb.record()
+        torch.cuda.synchronize()
+        own = torch.tensor([ea.elapsed_time(eb) / 10.0], device='cuda')
+        solver.grad_sync, net.engine.progress, ops.pre_launch = sync_keep, prog_keep, hook_keep
+        st.p.copy_(p_keep)
+        if m_keep is not None:
+            st.m.copy_(m_keep), st.v.copy_(v_keep)
+        solver.iteration = it_keep
+        net.engine.params_changed()
+        owns = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(owns, own)
+        own_ms = [round(float(o.item()), 3) for o in owns]
         bits = st.p.view(torch.int32).to(torch.int64)
         chk = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=bits.device) % 8191 + 1)).sum()])
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         dp_check = {'params_bit_identical_across_ranks': bool(all(torch.equal(c, allc[0]) for c in allc)),
-                    'checksum': [int(v) for v in allc[0].tolist()], 'steps_taken': int(solver.iteration)}
+                    'checksum': [int(v) for v in allc[0].tolist()], 'steps_taken': int(solver.iteration),
+                    'per_rank_ms_without_sync': own_ms, 'slowest_rank_ms': max(own_ms),
+                    'sync_overhead_ms': round(ms_step - max(own_ms), 3),
+                    'note': 'ms_per_step = slowest rank + sync_overhead; the N=1 figure is one GPU of the box'}
 
     # ---- CPU baseline (rank 0, N=1 only, bounded sample) --------------------------------------
     cpu = None

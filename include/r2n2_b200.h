@@ -275,6 +275,11 @@ int r2n2_fill_zero(void* p, long long bytes, void* stream);
  * protocol failure: results of that launch are garbage); synchronises the device. */
 int r2n2_umma_error_flag(void);
 
+/* Upper bound on the SMs the persistent (one CTA per SM) grids of later launches occupy; 0 = all.  The data-parallel
+ * trainer lowers it while a gradient all-reduce is in flight: a 148-CTA grid that finds SMs taken by the NCCL kernels
+ * runs its last CTAs as a second wave.  Process-wide, takes effect at the next launch.  Returns R2N2_OK. */
+int r2n2_set_sm_limit(int n_sms);
+
 #ifdef __cplusplus
 }
 #endif
