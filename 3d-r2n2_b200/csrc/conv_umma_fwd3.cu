@@ -50,6 +50,7 @@ struct Fwd3Params {
   int nslab;                               // output slabs in rotation (2 when no residual / mask slab is loaded)
   int stk, xch_off, xch_bytes;             // dx-stacked mode: the 3 taps of a filter row share ONE MMA (N = 3 BN)
   int out_bytes;                           // sizeof(output element)
+  int ew;                                  // epilogue warps (8, or 16 on the warp-staged bf16 epilogue)
   unsigned P_magic;                        // ceil(2^32 / P): r / P == __umulhi(r, P_magic) for r, P < 2^16
   int stage_epi, stg_off;                  // warp-staged epilogue: per-warp 32 pixels x 64 bytes staging tiles at this smem offset
   int pair;                                // CTA-pair mode (cluster of 2, cta_group::2 MMAs with M = 256, each CTA holds half of the filter rows)
@@ -102,8 +103,8 @@ static __device__ __forceinline__ void mma_commit(uint32_t bar) {
 // compile-time too (3x3 taps) -- the hot configurations get a fully unrolled, branch-free issue sequence
 // (ncu: the generic loop spent 158 instructions per tap for 12 MMAs and the issuing thread, not the tensor
 // pipe, set the pace of conv1b); 0 / -1 = read from the parameter block.
-template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int STK, int PAIR>
-__global__ void __launch_bounds__(kFwd3Threads, 1)
+template <typename TOut, int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int STK, int PAIR, int EW>
+__global__ void __launch_bounds__(96 + 32 * EW, 1)
 conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
                       const __grid_constant__ CUtensorMap map_mask,
@@ -154,7 +155,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t np = PAIR ? 2u : 1u;
     for (int s = 0; s < p.nring; ++s) { mbar_init(smem_u32(&pfull[s]), np); mbar_init(smem_u32(&pempty[s]), 1); }
     for (int s = 0; s < p.wstages; ++s) { mbar_init(smem_u32(&wfull[s]), np); mbar_init(smem_u32(&wempty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), np * kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tfull[b]), 1); mbar_init(smem_u32(&tempty[b]), np * (uint32_t)EW); }
     mbar_init(smem_u32(efull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,7 +217,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (++slot == p.nring) { slot = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 2 + kEpiWarps) {
+  } else if (warp == 2 + EW) {
     // ================================ weights (TMA): wt filter taps per stage ==================
     int slot = 0;
     uint32_t ph = 0;
@@ -429,7 +430,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
     }
-  } else if (warp >= 2 && warp < 2 + kEpiWarps) {
+  } else if (warp >= 2 && warp < 2 + EW) {
     // ================================ epilogue ==============================================
     const int quad = warp & 3;
     if (p.tma_epi) {
@@ -466,7 +467,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else tma_store_wait_read();
               }
-              named_bar_sync(1, 32 * kEpiWarps);
+              named_bar_sync(1, 32 * EW);
               if (has_in && leader) {
                 mbar_expect_tx(ef, in_tx);
                 if (p.flags & R2N2_EPI_RESIDUAL) tma_load_5d(bufY, &map_res, ef, sc, c.x0, c.y0, zz, c.n);
@@ -535,7 +536,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
               }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              named_bar_sync(1, 32 * kEpiWarps);
+              named_bar_sync(1, 32 * EW);
               if (leader && !(p.skip & 4)) {
                 tma_store_5d(&map_y, bufY, sc, c.x0, c.y0, zz, c.n);
                 pending = true;
@@ -590,7 +591,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
         }
-        named_bar_sync(1, 32 * kEpiWarps);
+        named_bar_sync(1, 32 * EW);
         for (int t = 0; t < T_; ++t) {
           const int r = t * 128 + quad * 32 + lane;
           const int yy = r / p.P, xx = r - yy * p.P;
@@ -668,17 +669,29 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ---- warp-staged epilogue ---------------------------------------------------------------------------
     // A thread owns one accumulator row (= one pixel); writing its channels with 16-byte accesses makes every
     // store / load instruction of the warp touch 32 different 128-byte lines (32 L1 wavefronts).  Here the warp
-    // exchanges a ROUND of 64 bytes per pixel (32 bf16 / 16 fp32 channels) through a private, XOR-swizzled
-    // 2 KB shared-memory tile and accesses global memory as 8 pixels x 64 contiguous bytes per instruction
-    // (a quarter of the wavefronts, full 32-byte sectors).  Warp-local only: no CTA barrier, no TMA store
-    // whose shared-memory read would have to drain before the next slab (what bounded the TMA epilogue).
-    constexpr int RC = 64 / (int)sizeof(TOut);            // channels per round
+    // exchanges a ROUND of RB bytes per pixel through a private, XOR-swizzled shared-memory tile (32 pixels x RB)
+    // and accesses global memory as (32 / NU) pixels x RB contiguous bytes per instruction (full 32-byte sectors,
+    // 1/4 - 1/2 of the wavefronts).  Warp-local only: no CTA barrier, no TMA store whose shared-memory read would
+    // have to drain before the next slab (what bounded the TMA epilogue).
+    // EW = 8: RB = 64 (32 bf16 / 16 fp32 channels), two warps per TMEM lane quadrant.  EW = 16 (bf16 outputs): RB = 32
+    // (16 channels, one tcgen05.ld), four warps per quadrant -- the epilogue is latency-bound (IPC ~0.4 of 4 with
+    // two warps per scheduler), so twice the warps on half the registers each move twice the data.
+    constexpr int RB = EW == 16 ? 32 : 64;                // bytes per pixel and round
+    constexpr int RC = RB / (int)sizeof(TOut);            // channels per round
+    constexpr int NU = RB / 16;                           // 16-byte units per pixel and round = global accesses per round
+    constexpr int PPA = 32 / NU;                          // pixels per global access
+    static_assert(EW == 8 || sizeof(TOut) == 2, "16 epilogue warps: bf16 outputs");
     const int nrounds = p.BN / RC;
-    const int half = (warp - 2) >> 2;
-    const uint32_t stg = smem_base + (uint32_t)p.stg_off + (uint32_t)(warp - 2) * 2048u;
-    const uint32_t my_row = stg + (uint32_t)lane * 64u, my_sw = (uint32_t)((lane >> 1) & 3);
-    const int q_lo = lane >> 2;                           // pixel (of 8) this lane moves in each of the 4 global accesses
-    const uint32_t u_g = (uint32_t)(lane & 3);            // its 16-byte unit
+    const int sub = (warp - 2) >> 2, nsubw = EW / 4;     // this warp among the warps of its quadrant
+    const uint32_t stg = smem_base + (uint32_t)p.stg_off + (uint32_t)(warp - 2) * (32u * RB);
+    // XOR swizzle of the 16-byte unit index: conflict-free for the owner pattern (32 rows, fixed unit) and for the
+    // global-access pattern (PPA rows x NU units)
+    auto swz = [&](uint32_t row, uint32_t u) -> uint32_t {
+      return RB == 64 ? (u ^ ((row >> 1) & 3u)) : (u ^ ((row >> 2) & 1u));
+    };
+    const uint32_t my_row = stg + (uint32_t)lane * RB;
+    const int q_lo = lane / NU;                           // pixel (of PPA) this lane moves in each global access
+    const uint32_t u_g = (uint32_t)(lane % NU);           // its 16-byte unit
     const bool has_res = (p.flags & R2N2_EPI_RESIDUAL) != 0, has_mask = (p.flags & R2N2_EPI_MASK) != 0;
     const bool res_pre = (p.flags & R2N2_EPI_RES_PRE) != 0;
     int step = 0;
@@ -688,34 +701,34 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int buf = step & 1;
         const int zz = c.z0 + j;
         bool first = true;
-        // work split between the two warps of a quadrant: whole tiles when there are several (the pixel geometry
-        // is computed once per tile), else alternate rounds
-        const bool by_tile = T_ >= 2;
-        const int t_step = by_tile ? 2 : 1, rd0 = by_tile ? 0 : half, rd_step = by_tile ? 1 : 2;
-        for (int t = by_tile ? half : 0; t < ((p.skip & 4) ? 0 : T_); t += t_step) {
+        // work items (tile, round) dealt round-robin to the warps of a quadrant; whole tiles when that balances
+        const int nitems = T_ * nrounds;
+        const bool by_tile = (T_ % nsubw) == 0;
+        for (int wi0 = sub; wi0 < ((p.skip & 4) ? 0 : nitems); wi0 += nsubw) {
+          // by_tile: warp `sub` takes the tiles t = sub, sub + nsubw, ... with all their rounds
+          const int t = by_tile ? (wi0 / (nrounds * nsubw)) * nsubw + sub : wi0 / nrounds;
+          const int rd = by_tile ? (wi0 / nsubw) % nrounds : wi0 - (wi0 / nrounds) * nrounds;
           R2N2_WS_T0();
-          // the 4 pixels whose 16-byte unit u_g this lane loads / stores: rows q = 8 k + q_lo of the warp's 32
-          long long goff0[4];
-          bool gok[4];
+          // the NU pixels whose 16-byte unit u_g this lane loads / stores: rows q = PPA k + q_lo of the warp's 32
+          long long goff0[NU];
+          bool gok[NU];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const unsigned r = (unsigned)(t * 128 + quad * 32 + 8 * k + q_lo);
+          for (int k = 0; k < NU; ++k) {
+            const unsigned r = (unsigned)(t * 128 + quad * 32 + PPA * k + q_lo);
             const int yy = (int)__umulhi(r, (unsigned)p.P_magic), xx = (int)r - yy * p.P;     // r / P (exact for r, P < 2^16)
             const int gy = c.y0 + yy, gx = c.x0 + xx;
             gok[k] = (int)r < p.R && xx < p.Xb && gx < p.W && gy < p.H && c.n < p.N;
             goff0[k] = ((((long long)c.n * p.D + zz) * p.H + gy) * p.W + gx) * (long long)(p.Cout * (int)sizeof(TOut)) +
-                       (long long)u_g * 16;
+                       (long long)(rd * RB) + (long long)u_g * 16;
           }
           R2N2_WS_ACC(30);                       // geometry
-        for (int rd = rd0; rd < nrounds; rd += rd_step) {
-          const long long rdo = (long long)(rd * 64);
-          uint4 gin[2][4];
+          uint4 gin[2][NU];
           if (has_res || has_mask) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NU; ++k) {
               if (gok[k]) {
-                if (has_res) gin[0][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(res) + goff0[k] + rdo);
-                if (has_mask) gin[1][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(mask) + goff0[k] + rdo);
+                if (has_res) gin[0][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(res) + goff0[k]);
+                if (has_mask) gin[1][k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(mask) + goff0[k]);
               }
             }
           }
@@ -747,22 +760,22 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
           }
           R2N2_WS_ACC(33);                       // TMEM loads
-          // an input of this round: global (8 pixels x 64 B per access, issued above) -> staging tile -> the pixel's
+          // an input of this round: global (PPA pixels x RB bytes per access, issued above) -> staging tile -> the pixel's
           // owner, folded into f at once (op 0: f += v, op 1: f *= LeakyReLU'(v)) so that no second row stays live
-          auto fold = [&](const uint4 (&g4)[4], int op) {
+          auto fold = [&](const uint4 (&g4)[NU], int op) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t row = (uint32_t)(8 * k + q_lo);
-              const uint32_t a = stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4);
+            for (int k = 0; k < NU; ++k) {
+              const uint32_t row = (uint32_t)(PPA * k + q_lo);
+              const uint32_t a = stg + row * RB + (swz(row, u_g) << 4);
               const uint4 g = gok[k] ? g4[k] : make_uint4(0, 0, 0, 0);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(g.x), "r"(g.y), "r"(g.z), "r"(g.w) : "memory");
             }
             __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NU; ++u) {
               uint4 o;
               asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                           : "r"(my_row + (((uint32_t)u ^ my_sw) << 4)));
+                           : "r"(my_row + (swz((uint32_t)lane, (uint32_t)u) << 4)));
               const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
               if (sizeof(TOut) == 2) {
 #pragma unroll
@@ -799,34 +812,33 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (has_mask) fold(gin[1], 1);
           R2N2_WS_ACC(34);                       // inputs folded, bias, LeakyReLU
           // results: owner -> staging tile -> global
-          uint32_t w[16];
+          uint32_t w[4 * NU];
           if (sizeof(TOut) == 2) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+            for (int q = 0; q < 4 * NU; ++q) {
               __nv_bfloat162 h = __floats2bfloat162_rn(f[(2 * q) % RC], f[(2 * q + 1) % RC]);
               w[q] = *reinterpret_cast<uint32_t*>(&h);
             }
           } else {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) w[q] = __float_as_uint(f[q % RC]);
+            for (int q = 0; q < 4 * NU; ++q) w[q] = __float_as_uint(f[q % RC]);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (((uint32_t)u ^ my_sw) << 4)), "r"(w[4 * u]),
+          for (int u = 0; u < NU; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (swz((uint32_t)lane, (uint32_t)u) << 4)), "r"(w[4 * u]),
                          "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
                          : "memory");
           __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t row = (uint32_t)(8 * k + q_lo);
+          for (int k = 0; k < NU; ++k) {
+            const uint32_t row = (uint32_t)(PPA * k + q_lo);
             uint4 o;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                         : "r"(stg + row * 64u + ((u_g ^ ((row >> 1) & 3u)) << 4)));
-            if (gok[k] && !(p.skip & 32)) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + goff0[k] + rdo) = o;
+                         : "r"(stg + row * RB + (swz(row, u_g) << 4)));
+            if (gok[k] && !(p.skip & 32)) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(y) + goff0[k]) = o;
           }
           __syncwarp();
           R2N2_WS_ACC(35);                       // pack, staging exchange, global stores
-        }
         }
         if (first) {          // (no work item for this warp in this step: still a consumer of the accumulator barrier)
           mbar_wait(tfull0 + 8u * buf, (uint32_t)(step >> 1) & 1u, abort_flag, p.err_word);
@@ -932,6 +944,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
     int want_stage = (!p.stk && want_tma_epi != 2 && p.BN * out_bytes == 192) ? 1 : 0;
     if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
     if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
+    p.ew = (p.stage_epi && out_bytes == 2 && !(getenv("R2N2_FWD3_EW") && atoi(getenv("R2N2_FWD3_EW")) == 8)) ? 16 : 8;
   }
   p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
   const int Tmax = 256 / p.bn_cols;                       // two accumulator sets in 512 TMEM columns
@@ -1096,9 +1109,10 @@ struct Fwd3Launch {
   cudaStream_t st;
 };
 
-template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0, int PAIR = 0>
+template <typename TOut, int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, int KDD = 0, int STK = 0, int PAIR = 0, int EW = 8>
 static int launch_fwd3(const Fwd3Launch& L) {
-  auto kern = conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>;
+  auto kern = conv_fwd3_umma_kernel<TOut, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR, EW>;
+  constexpr int kThreads = 96 + 32 * EW;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1109,7 +1123,7 @@ static int launch_fwd3(const Fwd3Launch& L) {
     // clusters of two CTAs (one TPC): tcgen05 cta_group::2
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid, 1, 1);
-    cfg.blockDim = dim3(kFwd3Threads, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = L.smem;
     cfg.stream = L.st;
     cudaLaunchAttribute at[1];
@@ -1122,7 +1136,7 @@ static int launch_fwd3(const Fwd3Launch& L) {
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma3]: cluster launch: %s", cudaGetErrorString(e));
     return R2N2_OK;
   }
-  kern<<<L.grid, kFwd3Threads, L.smem, L.st>>>(
+  kern<<<L.grid, kThreads, L.smem, L.st>>>(
       L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
   return R2N2_OK;
 }
@@ -1130,6 +1144,11 @@ template <int KB, int NCH, int LASTK, int TT = 0, int WTT = 0, int RESS = -1, in
 static int launch_fwd3_dt(const Fwd3Launch& L, int out_dtype) {
   return out_dtype == R2N2_BF16 ? launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>(L)
                                 : launch_fwd3<float, KB, NCH, LASTK, TT, WTT, RESS, KDD, STK, PAIR>(L);
+}
+// bf16 outputs through the warp-staged epilogue with 16 epilogue warps
+template <int KB, int NCH, int LASTK, int TT, int WTT, int RESS, int KDD, int PAIR>
+static int launch_fwd3_ew16(const Fwd3Launch& L) {
+  return launch_fwd3<__nv_bfloat16, KB, NCH, LASTK, TT, WTT, RESS, KDD, 0, PAIR, 16>(L);
 }
 
 int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* mask, const void* res, void* y,
@@ -1229,7 +1248,8 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   // specialised (compile-time issue sequence) configurations of the training step
   if (p.pair) {
     // CTA-pair configurations (cta_group::2)
-    if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 9, 1, 1, 0, 1>(L, out_dtype);
+    if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 9 && p.w_res && p.ew == 16) rc = launch_fwd3_ew16<2, 3, 2, 2, 9, 1, 1, 1>(L);
+    else if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 9, 1, 1, 0, 1>(L, out_dtype);
     else if (Cin == 96) rc = launch_fwd3_dt<2, 3, 2, 0, 0, -1, 0, 0, 1>(L, out_dtype);
     else if (Cin == 128) rc = launch_fwd3_dt<4, 2, 4, 0, 0, -1, 0, 0, 1>(L, out_dtype);
     else if (Cin == 64) rc = launch_fwd3_dt<4, 1, 4, 0, 0, -1, 0, 0, 1>(L, out_dtype);
@@ -1248,6 +1268,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
     else if (Cin == 32) rc = launch_fwd3_dt<2, 1, 2, 0, 0, -1, 0, 1>(L, out_dtype);
     else rc = launch_fwd3_dt<4, 1, 4, 0, 0, -1, 0, 1>(L, out_dtype);
   }
+  else if (k71s && Cin == 32 && p.T == 2 && p.wt == 7 && p.w_res && p.ew == 16) rc = launch_fwd3_ew16<2, 1, 2, 2, 7, 1, 71, 0>(L);
   else if (k71s && Cin == 32 && p.T == 2 && p.wt == 7 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 2, 7, 1, 71>(L, out_dtype);
   else if (k33 && Cin == 96 && kd == 1 && p.T == 2 && p.wt == 1 && !p.w_res) rc = launch_fwd3_dt<2, 3, 2, 2, 1, 0, 1>(L, out_dtype);
   else if (k33 && Cin == 32 && kd == 3 && p.T == 3 && p.wt == 9 && p.w_res) rc = launch_fwd3_dt<2, 1, 2, 3, 9, 1, 3>(L, out_dtype);
