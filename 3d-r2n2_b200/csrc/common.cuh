@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <utility>
 #include "../../include/r2n2_b200.h"
 
 namespace r2n2 {
@@ -146,6 +148,51 @@ inline int num_sms() {
   }
   const int lim = sm_limit_ref();
   return (lim >= 16 && lim < n) ? (lim & ~1) : n;
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the library is launched with programmaticStreamSerialization: the next kernel of the stream may be
+// scheduled while this one still runs (its CTAs land on SMs as ours exit), run its prologue (barrier init, TMEM
+// allocation, shared-memory zero fill, descriptor fetch) and then block in griddepcontrol.wait until this grid has
+// completed and its memory is visible.  Hides the launch latency + prologue of ~170 launches per training step.
+// RULE: a kernel executes pdl_wait() before its FIRST global-memory access (read or write).  R2N2_PDL=0 switches the
+// launch attribute off (then griddepcontrol.* are no-ops).
+static __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("R2N2_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+// <<<grid, block, smem, stream>>> with the PDL attribute (and an optional cluster size along x)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster_x;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // dispatch on dtype code

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 conv_fwd_simt_kernel(const TIn* __restrict__ x, const TIn* __restrict__ w,
                      const float* __restrict__ bias, const TOut* mask,
                      const TOut* res, TOut* y, ConvGeom g, int flags) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   __shared__ __align__(16) float As[2][16][128];
   __shared__ __align__(16) float Bs[2][16][64];
   __shared__ int tap_dz[kMaxTaps], tap_dy[kMaxTaps], tap_dx[kMaxTaps];
@@ -213,6 +215,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                        ConvGeom g, long long p_per_split, int use_atomics) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   __shared__ __align__(16) float As[2][16][64];
   __shared__ __align__(16) float Bs[2][16][64];
   const int tid = threadIdx.x;
@@ -355,10 +359,10 @@ int conv_fwd_simt(const void* x, const void* w, const float* bias, const void* m
 #define R2N2_LAUNCH_FWD(TI, TO)                                                              \
   do {                                                                                       \
     if (vec)                                                                                 \
-      conv_fwd_simt_kernel<TI, TO, true><<<grid, 256, 0, st>>>(                              \
+      r2n2::launch_k((conv_fwd_simt_kernel<TI, TO, true>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0,                              \
           (const TI*)x, (const TI*)w, bias, (const TO*)mask, (const TO*)res, (TO*)y, g, flags); \
     else                                                                                     \
-      conv_fwd_simt_kernel<TI, TO, false><<<grid, 256, 0, st>>>(                             \
+      r2n2::launch_k((conv_fwd_simt_kernel<TI, TO, false>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0,                             \
           (const TI*)x, (const TI*)w, bias, (const TO*)mask, (const TO*)res, (TO*)y, g, flags); \
   } while (0)
   if (in_dtype == R2N2_F32 && out_dtype == R2N2_F32) R2N2_LAUNCH_FWD(float, float);
@@ -391,7 +395,7 @@ int conv_wgrad_simt(const void* x, const void* dy, float* dw, int N, int D, int 
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * g.K, st);
   dim3 grid(gx, gy, (unsigned)splits);
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)dy, dw, g, pps,
+    r2n2::launch_k((conv_wgrad_simt_kernel<T>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0, (const T*)x, (const T*)dy, dw, g, pps,
                                                    use_atomics);
   })
   R2N2_CHECK_LAUNCH("conv_wgrad[simt]");

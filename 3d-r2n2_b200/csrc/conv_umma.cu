@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kUmmaThreads)
 conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
                      const UmmaConvParams p) {
+  r2n2::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] [full[stages]] [empty[stages]] [tmem_full] [tmem_ptr] [abort]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,6 +90,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  r2n2::pdl_wait();            // prologue done; from here on global memory of the preceding kernels may be touched
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   const int taps = p.kd * p.kh * p.kw;
@@ -407,7 +409,7 @@ int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void
                      cudaGetErrorString(e));
       attr_set = true;
     }
-    conv_fwd_umma_kernel<__nv_bfloat16><<<grid, kUmmaThreads, smem_bytes, st>>>(
+    r2n2::launch_k((conv_fwd_umma_kernel<__nv_bfloat16>), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0,
         map_a, map_b, bias, (const __nv_bfloat16*)mask, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, p);
   } else if (out_dtype == R2N2_F32) {
     static bool attr_set = false;
@@ -418,7 +420,7 @@ int conv_fwd_umma_v1(const void* x, const void* w, const float* bias, const void
                      cudaGetErrorString(e));
       attr_set = true;
     }
-    conv_fwd_umma_kernel<float><<<grid, kUmmaThreads, smem_bytes, st>>>(
+    r2n2::launch_k((conv_fwd_umma_kernel<float>), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0,
         map_a, map_b, bias, (const float*)mask, (const float*)res, (float*)y, p);
   } else {
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd[umma]: bad out dtype %d", out_dtype);
@@ -507,6 +509,7 @@ struct UmmaWgradParams {
 __global__ void __launch_bounds__(kUmmaThreads)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                        float* __restrict__ dw, const UmmaWgradParams p) {
+  r2n2::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -570,6 +573,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  r2n2::pdl_wait();            // prologue done; from here on global memory of the preceding kernels may be touched
 
   const int rb_a = p.cw_a * 2, rb_b = p.cw_b * 2;        // smem row pitch (bytes) of dy / x chunks
   const int chunk_a = p.rows * rb_a, chunk_b = p.rows * rb_b;
@@ -991,7 +995,7 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
             "smem %zu grid %ux%ux%u tmem %d ci_cols %d\n", Cin, Cout, p.taps, p.G, p.bw, p.bh, p.bd, p.bn, p.rows, p.dxh,
             p.ystack, p.up2, p.stage_bytes, p.stages, smem_bytes, grid.x, grid.y, grid.z, p.tmem_cols, p.ci_cols);
   R2N2_CHECK_ARG(smem_bytes <= 200 * 1024, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: smem %zu too large", smem_bytes);
-  conv_wgrad_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
+  r2n2::launch_k((conv_wgrad_umma_kernel), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0, map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma]");
   return R2N2_OK;
 }

@@ -86,6 +86,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
                          const __grid_constant__ CUtensorMap map_mask,
                          const float* __restrict__ bias, const TOut* mask, const TOut* res, TOut* y,
                          const FwdParams p) {
+  r2n2::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -133,6 +134,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
   if (MC) cluster_sync_all();            // every CTA's barriers exist before the first multicast load / commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  r2n2::pdl_wait();            // prologue done; from here on global memory of the preceding kernels may be touched
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
   const uint16_t cmask = MC ? (uint16_t)((1u << p.mc) - 1u) : (uint16_t)1;
 
@@ -473,24 +475,9 @@ static int launch_fwd_k(const FwdLaunch& L) {
     R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  if (MC) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(L.grid, 1, 1);
-    cfg.blockDim = dim3(kFwdThreads, 1, 1);
-    cfg.dynamicSmemBytes = L.smem;
-    cfg.stream = L.st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)L.p.mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias,
-                                       (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
-    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: cluster launch: %s", cudaGetErrorString(e));
-    return R2N2_OK;
-  }
-  kern<<<L.grid, kFwdThreads, L.smem, L.st>>>(
+  cudaError_t le = r2n2::launch_k((kern), dim3(L.grid), dim3(kFwdThreads), L.smem, (cudaStream_t)(L.st), MC ? L.p.mc : 0,
       L.map_a, L.map_b, L.map_y, L.map_res, L.map_mask, L.bias, (const TOut*)L.mask, (const TOut*)L.res, (TOut*)L.y, L.p);
+  R2N2_CHECK_ARG(le == cudaSuccess, R2N2_ERR_CUDA, "conv_fwd[umma]: launch: %s", cudaGetErrorString(le));
   return R2N2_OK;
 }
 template <typename TOut, int NK16, int NSUB>

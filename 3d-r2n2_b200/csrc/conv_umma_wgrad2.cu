@@ -32,6 +32,7 @@ struct Wgrad2Params {
 __global__ void __launch_bounds__(kUmmaThreads)
 conv_wgrad2_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                         float* __restrict__ dw, const Wgrad2Params p) {
+  r2n2::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -86,6 +87,7 @@ conv_wgrad2_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  r2n2::pdl_wait();            // prologue done; from here on global memory of the preceding kernels may be touched
 
   const int rb_x = p.cw_x * 2, rb_y = p.cw_y * 2;          // smem row pitch of x / dy chunks
   const int chunk_x = p.rows * rb_x, chunk_y = p.rows * rb_y;
@@ -333,7 +335,7 @@ int conv_wgrad2_umma(const void* x, const void* dy, float* dw, int N, int D, int
             "grid %lldx%dx%d tmem %d\n", Cin, Cout, p.taps, p.TS, gpc, p.bw, p.bh, p.bd, p.bn, p.rows, p.stage_bytes,
             smem_bytes, splits, p.ci_tiles, tap_group_ctas, p.tmem_cols);
   dim3 grid((unsigned)splits, (unsigned)p.ci_tiles, (unsigned)tap_group_ctas);
-  conv_wgrad2_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
+  r2n2::launch_k((conv_wgrad2_umma_kernel), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0, map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma2]");
   return R2N2_OK;
 }

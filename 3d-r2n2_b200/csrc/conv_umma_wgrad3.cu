@@ -42,6 +42,7 @@ struct Wgrad3Params {
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                         float* __restrict__ dw, const Wgrad3Params p) {
+  r2n2::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -84,6 +85,7 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  r2n2::pdl_wait();            // prologue done; from here on global memory of the preceding kernels may be touched
 
   const long long u_begin = (long long)blockIdx.x * p.units_per_cta;
   long long u_end = u_begin + p.units_per_cta;
@@ -341,7 +343,7 @@ int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int
             "units %lld per cta %lld grid %lldx3 tmem %d\n", Cin, Cout, p.s_is_x ? "x" : "dy", p.cs, p.nshift, p.nmma,
             p.Y, p.bands, p.R, p.nk, p.stage_bytes, p.stages, p.units, p.units_per_cta, splits, p.tmem_cols);
   dim3 grid((unsigned)splits, 3);
-  conv_wgrad3_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(map_dy, map_x, dw, p);
+  r2n2::launch_k((conv_wgrad3_umma_kernel), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0, map_dy, map_x, dw, p);
   R2N2_CHECK_LAUNCH("conv_wgrad[umma3]");
   return R2N2_OK;
 }

@@ -28,6 +28,8 @@ static inline int grid_for(long long work_items, int block) {
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C,
                                     int H, int W, int Cpad, int Wpad, int xoff) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = (long long)N * H * Wpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -54,6 +56,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int H, int W,
                        int kw, int Cpack) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   // one block per image row (n, h): the C channel rows are staged in shared memory with (kw-1)/2
   // zero columns either side (coalesced fp32 reads, each input element read once), then every
   // thread assembles 16-byte groups of packed channels from a per-block offset table and stores them
@@ -128,6 +132,8 @@ template <typename T, bool HAS_B>
 __global__ void __launch_bounds__(256, 4)
 maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int N, int H, int W, int C,
                    int Ho, int Wo) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   // one thread per (output pixel, 16-byte channel group); the window's vectors are loaded raw, all before
   // the first use (memory-level parallelism), and widened when compared
   constexpr int PN = Pack<T>::N;
@@ -187,6 +193,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3)        // (8 raw vectors i
 maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ dy,
                    T* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask,
                    T* __restrict__ dxb, float* __restrict__ colsum_a, float* __restrict__ colsum_b) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   // one thread per (output pixel, 16-byte channel group): the up to 8 input vectors of the window stay
   // RAW in registers (all loads issued before the first use), the window maximum is formed first, then
   // each position is re-widened, compared and stored (HBM-bound: registers buy loads in flight)
@@ -296,6 +304,8 @@ maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __
 template <typename T>
 __global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                   T* __restrict__ y, int B, int D, int H, int W, int C) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   constexpr int PN = Pack<T>::N;
   int CG = C / PN;
   int D2 = 2 * D, H2 = 2 * H, W2 = 2 * W;
@@ -327,6 +337,8 @@ __global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__
 template <typename T>
 __global__ void unpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int D,
                                   int H, int W, int C) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   constexpr int PN = Pack<T>::N;
   int CG = C / PN;
   long long total = (long long)B * D * H * W * CG;
@@ -348,6 +360,8 @@ __global__ void unpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, 
 template <typename T>
 __global__ void add_kernel(const T* a, const T* b, T* y,
                            long long n4) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 u = Vec4<T>::load(a + i * 4), v = Vec4<T>::load(b + i * 4);
@@ -357,6 +371,8 @@ __global__ void add_kernel(const T* a, const T* b, T* y,
 
 template <typename T>
 __global__ void lrelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n4) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = Vec4<T>::load(x + i * 4);
@@ -367,6 +383,8 @@ __global__ void lrelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, lon
 template <typename T>
 __global__ void lrelu_bwd_kernel(const T* a, const T* dy,
                                  const T* addend, T* dx, long long n4) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 av = Vec4<T>::load(a + i * 4), g = Vec4<T>::load(dy + i * 4);
@@ -384,6 +402,8 @@ __global__ void lrelu_bwd_kernel(const T* a, const T* dy,
 template <typename T>
 __global__ void eltwise_kernel(int op, const T* __restrict__ a, const T* __restrict__ b,
                                T* __restrict__ y, long long n4) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = Vec4<T>::load(a + i * 4);
@@ -414,6 +434,8 @@ __global__ void eltwise_kernel(int op, const T* __restrict__ a, const T* __restr
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, long long n) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x)
@@ -429,6 +451,8 @@ __global__ void cast_kernel(const float* __restrict__ s, T* __restrict__ d, long
 // (hi*hi + lo*hi + hi*lo, fp32 accumulation) carries ~16 mantissa bits instead of bf16's 8.
 __global__ void split_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   const long long n8 = n >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
@@ -459,6 +483,8 @@ __global__ void gru_ur_fwd_kernel(const T* __restrict__ conv_ur, const T* __rest
                                   const float* __restrict__ bias, const T* __restrict__ h,
                                   T* __restrict__ u, T* __restrict__ r, T* __restrict__ rh,
                                   long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -492,6 +518,8 @@ __global__ void gru_out_fwd_kernel(const T* __restrict__ conv_c, const T* __rest
                                    const float* __restrict__ bias, const T* __restrict__ u,
                                    const T* __restrict__ h, T* __restrict__ cc,
                                    T* __restrict__ hn, long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -521,6 +549,8 @@ __global__ void gru_out_bwd_kernel(const T* __restrict__ dh, const T* __restrict
                                    const T* __restrict__ cc, const T* __restrict__ h,
                                    T* __restrict__ da_ur, T* __restrict__ da_c,
                                    T* __restrict__ dh_prev, long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -546,6 +576,8 @@ template <typename T>
 __global__ void gru_r_bwd_kernel(const T* __restrict__ d_rh, const T* __restrict__ h,
                                  const T* __restrict__ r, T* __restrict__ da_ur,
                                  T* __restrict__ dh_prev, long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -568,6 +600,8 @@ __global__ void lstm_fwd_kernel(const T* __restrict__ conv, const T* __restrict_
                                 const float* __restrict__ bias, const T* __restrict__ s,
                                 T* __restrict__ fig, T* __restrict__ sn, T* __restrict__ hn,
                                 long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -603,6 +637,8 @@ __global__ void lstm_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ 
                                 const T* __restrict__ fig, const T* __restrict__ s,
                                 const T* __restrict__ hn, T* __restrict__ da,
                                 T* __restrict__ ds_prev, long long rows) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long total = rows * 32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -638,6 +674,8 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
                                     float* __restrict__ pred, float* __restrict__ loss_sum,
                                     TD* __restrict__ dlogits, long long nvox_total, int nv,
                                     float grad_scale, int cstride) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   const long long plane = (long long)nv * nv;  // one (y,x) plane
   float local = 0.f;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox_total;
@@ -700,6 +738,8 @@ __global__ void softmax_ce3d_kernel(const float* __restrict__ logits, const floa
 template <typename T>
 __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows,
                                  int C, long long rows_per_block) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   constexpr int PN = Pack<T>::N;
   __shared__ float red[8][32 * PN + 1];
   const int cx = threadIdx.x, ry = threadIdx.y;
@@ -746,6 +786,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bias_grad_flat_kernel(const T* __restrict__ dy, float* __restrict__ db, long long rows, int C,
                       long long rows_per_block) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   constexpr int PN = Pack<T>::N;
   __shared__ float red[256 * PN];
   const int CV = C / PN;
@@ -789,6 +831,8 @@ bias_grad_flat_kernel(const T* __restrict__ dy, float* __restrict__ db, long lon
 template <typename T>
 __global__ void weight_transpose_kernel(const float* __restrict__ w, T* __restrict__ wt, int Cout,
                                         int taps, int Cin) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   __shared__ float tile[32][33];
   int t = blockIdx.z;
   int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -810,6 +854,8 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, T* __restri
 template <typename T>
 __global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T* __restrict__ wt_base,
                                               const long long* __restrict__ table, int n) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   // tile = 64 output channels x 32 input channels: 128-byte row reads of w, and the transposed rows are written
   // as 64 consecutive co (128 bytes of bf16) per ci -- full lines both ways
   __shared__ float tile[64][33];
@@ -853,6 +899,8 @@ __global__ void weight_transpose_batch_kernel(const float* __restrict__ base, T*
 __global__ void weight_transpose_batch_bf16_kernel(const __nv_bfloat16* __restrict__ base,
                                                    __nv_bfloat16* __restrict__ wt_base,
                                                    const long long* __restrict__ table, int n) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   __shared__ __nv_bfloat16 tile[64][66];
   const long long bid = blockIdx.x;
   int e = 0;
@@ -894,6 +942,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, TM* __restrict__ mirror,
                             long long n, long long n_decay, float lr_t, float b1, float b2,
                             float eps, float wd, float gscale) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   long long n4 = (n + 3) >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -934,6 +984,8 @@ template <typename TM, bool kMirror>
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                            float* __restrict__ vel, TM* __restrict__ mirror, long long n,
                            long long n_decay, float lr, float mom, float wd, float gscale) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     float rg = g[j] * gscale;
@@ -949,6 +1001,8 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
 // ------------------------------------------------------------------ voxel IoU counts
 __global__ void voxel_eval_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                   float thresh, unsigned long long* __restrict__ counts, int nv) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   int b = blockIdx.y;
   long long plane = (long long)nv * nv;
   long long nvox = plane * nv;
@@ -978,6 +1032,8 @@ __global__ void voxel_eval_kernel(const float* __restrict__ pred, const float* _
 template <typename T>
 __global__ void preprocess_views_kernel(const uchar4* __restrict__ rgba, const int* __restrict__ params,
                                         T* __restrict__ out, int n_img, int Hs, int Ws, int Ho, int Wo) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   const long long total = (long long)n_img * Ho * Wo;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1006,6 +1062,8 @@ __global__ void preprocess_views_kernel(const uchar4* __restrict__ rgba, const i
 // last batch that was never filled: both channels stay 0 like the reference's np.zeros rows), y [B,nv,2,nv,nv] fp32.
 __global__ void voxel_labels_kernel(const unsigned char* __restrict__ occ, float* __restrict__ y, int nv,
                                     long long total) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   const int plane = nv * nv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1036,6 +1094,8 @@ __device__ __forceinline__ unsigned int float_order_key(float f) {
 __global__ void __launch_bounds__(kApThreads, 1)
 average_precision_kernel(const float* __restrict__ pred, const float* __restrict__ gt, double* __restrict__ ap,
                          int nv) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
   extern __shared__ unsigned int ap_smem[];                 // [npad] 32-bit score keys, then [npad] 8-bit labels
   __shared__ unsigned int part[kApThreads];
   __shared__ double red[kApThreads / 32];
@@ -1152,7 +1212,7 @@ int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int C
                  R2N2_ERR_BAD_SHAPE, "nchw_to_nhwc: bad shape");
   long long total = (long long)N * H * Wpad;
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((nchw_to_nhwc_kernel<T>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         x, (T*)y, N, C, H, W, Cpad, Wpad, xoff);
   })
   R2N2_CHECK_LAUNCH("nchw_to_nhwc");
@@ -1167,7 +1227,7 @@ int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, in
     const size_t smem = sizeof(float) * (size_t)C * (W + kw - 1) + sizeof(int) * (size_t)Cpack;
     long long blocks = (long long)N * H;
     if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-    nchw_to_rowpack_kernel<T><<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
+    r2n2::launch_k((nchw_to_rowpack_kernel<T>), dim3((unsigned)blocks), dim3(128), smem, (cudaStream_t)((cudaStream_t)stream), 0,
         x, (T*)y, N, C, H, W, kw, Cpack);
   })
   R2N2_CHECK_LAUNCH("nchw_to_rowpack");
@@ -1182,10 +1242,10 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
   long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
     if (b) {
-      maxpool_fwd_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      r2n2::launch_k((maxpool_fwd_kernel<T, true>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
     } else {
-      maxpool_fwd_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      r2n2::launch_k((maxpool_fwd_kernel<T, false>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
     }
   })
@@ -1219,17 +1279,17 @@ int r2n2_maxpool2d_bwd_fused(const void* a, const void* b, const void* dy, void*
   R2N2_DISPATCH_DTYPE(dtype, T, {
     if (b) {
       if (extra)
-        maxpool_bwd_kernel<T, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        r2n2::launch_k((maxpool_bwd_kernel<T, true, true>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
           (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, (T*)dxb, colsum_a, colsum_b);
       else
-        maxpool_bwd_kernel<T, true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        r2n2::launch_k((maxpool_bwd_kernel<T, true, false>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
           (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, nullptr, nullptr);
     } else {
       if (extra)
-        maxpool_bwd_kernel<T, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        r2n2::launch_k((maxpool_bwd_kernel<T, false, true>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
           (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, colsum_a, nullptr);
       else
-        maxpool_bwd_kernel<T, false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        r2n2::launch_k((maxpool_bwd_kernel<T, false, false>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
           (const T*)a, (const T*)b, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, nullptr, nullptr, nullptr);
     }
   })
@@ -1248,7 +1308,7 @@ int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H
                  R2N2_ERR_BAD_SHAPE, "unpool3d_fwd: bad shape");
   long long total = (long long)B * D * H * W * 8 * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    unpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((unpool_fwd_kernel<T>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)a, (const T*)b, (T*)y, B, D, H, W, C);
   })
   R2N2_CHECK_LAUNCH("unpool3d_fwd");
@@ -1261,7 +1321,7 @@ int r2n2_unpool3d_bwd(const void* dy, void* dx, int B, int D, int H, int W, int 
                  R2N2_ERR_BAD_SHAPE, "unpool3d_bwd: bad shape");
   long long total = (long long)B * D * H * W * (C / (dtype == R2N2_BF16 ? 8 : 4));
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    unpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((unpool_bwd_kernel<T>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)dy, (T*)dx, B, D, H, W, C);
   })
   R2N2_CHECK_LAUNCH("unpool3d_bwd");
@@ -1271,7 +1331,7 @@ int r2n2_unpool3d_bwd(const void* dy, void* dx, int B, int D, int H, int W, int 
 int r2n2_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
   R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "add: n must be a multiple of 4");
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    add_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b,
+    r2n2::launch_k((add_kernel<T>), dim3(grid_for(n >> 2, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0, (const T*)a, (const T*)b,
                                                                            (T*)y, n >> 2);
   })
   R2N2_CHECK_LAUNCH("add");
@@ -1281,7 +1341,7 @@ int r2n2_add(const void* a, const void* b, void* y, long long n, int dtype, void
 int r2n2_lrelu_fwd(const void* x, void* y, long long n, int dtype, void* stream) {
   R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "lrelu_fwd: n must be a multiple of 4");
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    lrelu_fwd_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y,
+    r2n2::launch_k((lrelu_fwd_kernel<T>), dim3(grid_for(n >> 2, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0, (const T*)x, (T*)y,
                                                                                  n >> 2);
   })
   R2N2_CHECK_LAUNCH("lrelu_fwd");
@@ -1292,7 +1352,7 @@ int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, 
                    int dtype, void* stream) {
   R2N2_CHECK_ARG(n > 0 && (n & 3) == 0, R2N2_ERR_BAD_SHAPE, "lrelu_bwd: n must be a multiple of 4");
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    lrelu_bwd_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((lrelu_bwd_kernel<T>), dim3(grid_for(n >> 2, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)a, (const T*)dy, (const T*)addend, (T*)dx, n >> 2);
   })
   R2N2_CHECK_LAUNCH("lrelu_bwd");
@@ -1306,7 +1366,7 @@ int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int
   R2N2_CHECK_ARG(!(op == R2N2_ELT_MUL || op == R2N2_ELT_SIGMOID_BWD || op == R2N2_ELT_TANH_BWD) || b,
                  R2N2_ERR_BAD_SHAPE, "eltwise: op %d needs two operands", op);
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    eltwise_kernel<T><<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((eltwise_kernel<T>), dim3(grid_for(n >> 2, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         op, (const T*)a, (const T*)b, (T*)y, n >> 2);
   })
   R2N2_CHECK_LAUNCH("eltwise");
@@ -1316,7 +1376,7 @@ int r2n2_eltwise(int op, const void* a, const void* b, void* y, long long n, int
 int r2n2_cast(const float* src, void* dst, long long n, int out_dtype, void* stream) {
   R2N2_CHECK_ARG(n > 0, R2N2_ERR_BAD_SHAPE, "cast: n <= 0");
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    cast_kernel<T><<<grid_for((n >> 2) + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, n);
+    r2n2::launch_k((cast_kernel<T>), dim3(grid_for((n >> 2) + 1, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0, src, (T*)dst, n);
   })
   R2N2_CHECK_LAUNCH("cast");
   return R2N2_OK;
@@ -1327,7 +1387,7 @@ int r2n2_split_bf16(const float* src, void* hi, void* lo, long long n, void* str
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(lo) & 15) == 0,
                  R2N2_ERR_BAD_ALIGN, "split_bf16: pointers must be 16-byte aligned");
-  split_bf16_kernel<<<grid_for((n >> 3) + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+  r2n2::launch_k((split_bf16_kernel), dim3(grid_for((n >> 3) + 1, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
       src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
   R2N2_CHECK_LAUNCH("split_bf16");
   return R2N2_OK;
@@ -1339,7 +1399,7 @@ int r2n2_gru_gates_ur_fwd(const void* conv_ur, const void* xp_ur, const float* b
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_ur_fwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    gru_ur_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((gru_ur_fwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)conv_ur, (const T*)xp_ur, bias_ur, (const T*)h, (T*)u, (T*)r, (T*)rh, rows);
   })
   R2N2_CHECK_LAUNCH("gru_gates_ur_fwd");
@@ -1351,7 +1411,7 @@ int r2n2_gru_gates_out_fwd(const void* conv_c, const void* xp_c, const float* bi
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_out_fwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    gru_out_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((gru_out_fwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)conv_c, (const T*)xp_c, bias_c, (const T*)u, (const T*)h, (T*)c, (T*)h_new, rows);
   })
   R2N2_CHECK_LAUNCH("gru_gates_out_fwd");
@@ -1363,7 +1423,7 @@ int r2n2_gru_gates_out_bwd(const void* dh, const void* u, const void* c, const v
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_out_bwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    gru_out_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((gru_out_bwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)dh, (const T*)u, (const T*)c, (const T*)h, (T*)da_ur, (T*)da_c, (T*)dh_prev, rows);
   })
   R2N2_CHECK_LAUNCH("gru_gates_out_bwd");
@@ -1375,7 +1435,7 @@ int r2n2_gru_gates_r_bwd(const void* d_rh, const void* h, const void* r, void* d
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "gru_gates_r_bwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    gru_r_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((gru_r_bwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)d_rh, (const T*)h, (const T*)r, (T*)da_ur, (T*)dh_prev, rows);
   })
   R2N2_CHECK_LAUNCH("gru_gates_r_bwd");
@@ -1388,7 +1448,7 @@ int r2n2_lstm_gates_fwd(const void* conv_fig, const void* xp_fig, const float* b
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "lstm_gates_fwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    lstm_fwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((lstm_fwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)conv_fig, (const T*)xp_fig, bias_fig, (const T*)s, (T*)fig, (T*)s_new, (T*)h_new,
         rows);
   })
@@ -1402,7 +1462,7 @@ int r2n2_lstm_gates_bwd(const void* dh, const void* ds_in, const void* fig, cons
   R2N2_CHECK_ARG(B > 0, R2N2_ERR_BAD_SHAPE, "lstm_gates_bwd: B <= 0");
   long long rows = (long long)B * 64;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    lstm_bwd_kernel<T><<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((lstm_bwd_kernel<T>), dim3(grid_for(rows * 32, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)dh, (const T*)ds_in, (const T*)fig, (const T*)s, (const T*)h_new, (T*)da_fig,
         (T*)ds_prev, rows);
   })
@@ -1417,7 +1477,7 @@ int r2n2_softmax_ce3d(const float* logits, const float* y, float* pred, float* l
                  "softmax_ce3d: bad shape");
   long long total = (long long)B * nv * nv * nv;
   R2N2_DISPATCH_DTYPE(ddtype, T, {
-    softmax_ce3d_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((softmax_ce3d_kernel<T>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         logits, y, pred, loss_sum, (T*)dlogits, total, nv, grad_scale, cstride);
   })
   R2N2_CHECK_LAUNCH("softmax_ce3d");
@@ -1437,7 +1497,7 @@ int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, 
     const long long rpb = (rows + blocks - 1) / blocks;
     blocks = (rows + rpb - 1) / rpb;
     R2N2_DISPATCH_DTYPE(dtype, T, {
-      bias_grad_flat_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)dy, db, rows, C, rpb);
+      r2n2::launch_k((bias_grad_flat_kernel<T>), dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0, (const T*)dy, db, rows, C, rpb);
     })
     R2N2_CHECK_LAUNCH("bias_grad");
     return R2N2_OK;
@@ -1450,7 +1510,7 @@ int r2n2_bias_grad(const void* dy, float* db, long long rows, int C, int dtype, 
   long long rpb = (rows + gy - 1) / gy;
   gy = (rows + rpb - 1) / rpb;
   R2N2_DISPATCH_DTYPE(dtype, T, {
-    bias_grad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((bias_grad_kernel<T>), dim3(dim3(gx, (unsigned)gy)), dim3(dim3(32, 8)), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         (const T*)dy, db, rows, C, rpb);
   })
   R2N2_CHECK_LAUNCH("bias_grad");
@@ -1464,7 +1524,7 @@ int r2n2_weight_transpose(const float* w, void* wt, int Cout, int taps, int Cin,
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps);
   R2N2_CHECK_ARG(grid.y <= 65535, R2N2_ERR_BAD_SHAPE, "weight_transpose: Cout too large");
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    weight_transpose_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, (T*)wt, Cout,
+    r2n2::launch_k((weight_transpose_kernel<T>), dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)((cudaStream_t)stream), 0, w, (T*)wt, Cout,
                                                                                 taps, Cin);
   })
   R2N2_CHECK_LAUNCH("weight_transpose");
@@ -1476,7 +1536,7 @@ int r2n2_weight_transpose_batch(const float* base, void* wt_base, const long lon
   R2N2_CHECK_ARG(base && wt_base && table && n_entries > 0 && total_tiles > 0 && total_tiles < (1LL << 31),
                  R2N2_ERR_BAD_SHAPE, "weight_transpose_batch: bad arguments");
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    weight_transpose_batch_kernel<T><<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((weight_transpose_batch_kernel<T>), dim3((unsigned)total_tiles), dim3(dim3(32, 8)), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         base, (T*)wt_base, table, n_entries);
   })
   R2N2_CHECK_LAUNCH("weight_transpose_batch");
@@ -1489,7 +1549,7 @@ int r2n2_weight_transpose_batch_bf16(const void* mirror_base, void* wt_base, con
                  R2N2_ERR_BAD_SHAPE, "weight_transpose_batch_bf16: bad arguments");
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(mirror_base) & 3) == 0 && (reinterpret_cast<uintptr_t>(wt_base) & 3) == 0,
                  R2N2_ERR_BAD_ALIGN, "weight_transpose_batch_bf16: buffers must be 4-byte aligned");
-  weight_transpose_batch_bf16_kernel<<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  r2n2::launch_k((weight_transpose_batch_bf16_kernel), dim3((unsigned)total_tiles), dim3(dim3(32, 8)), 0, (cudaStream_t)((cudaStream_t)stream), 0,
       (const __nv_bfloat16*)mirror_base, (__nv_bfloat16*)wt_base, table, n_entries);
   R2N2_CHECK_LAUNCH("weight_transpose_batch_bf16");
   return R2N2_OK;
@@ -1502,10 +1562,10 @@ int r2n2_adam(float* p, const float* g, float* m, float* v, void* p_mirror, long
   int grid = grid_for((n + 3) >> 2, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (!p_mirror) {
-    adam_kernel<float, false><<<grid, 256, 0, st>>>(p, g, m, v, nullptr, n, n_decay, lr_t, beta1,
+    r2n2::launch_k((adam_kernel<float, false>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0, p, g, m, v, nullptr, n, n_decay, lr_t, beta1,
                                                     beta2, eps, wd, grad_scale);
   } else if (mirror_dtype == R2N2_BF16) {
-    adam_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_mirror, n,
+    r2n2::launch_k((adam_kernel<__nv_bfloat16, true>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0, p, g, m, v, (__nv_bfloat16*)p_mirror, n,
                                                            n_decay, lr_t, beta1, beta2, eps, wd,
                                                            grad_scale);
   } else {
@@ -1521,10 +1581,10 @@ int r2n2_sgd(float* p, const float* g, float* vel, void* p_mirror, long long n, 
   int grid = grid_for(n, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (!p_mirror) {
-    sgd_kernel<float, false><<<grid, 256, 0, st>>>(p, g, vel, nullptr, n, n_decay, lr, momentum, wd,
+    r2n2::launch_k((sgd_kernel<float, false>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0, p, g, vel, nullptr, n, n_decay, lr, momentum, wd,
                                                    grad_scale);
   } else if (mirror_dtype == R2N2_BF16) {
-    sgd_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(p, g, vel, (__nv_bfloat16*)p_mirror, n,
+    r2n2::launch_k((sgd_kernel<__nv_bfloat16, true>), dim3(grid), dim3(256), 0, (cudaStream_t)(st), 0, p, g, vel, (__nv_bfloat16*)p_mirror, n,
                                                           n_decay, lr, momentum, wd, grad_scale);
   } else {
     R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "sgd: mirror dtype must be bf16");
@@ -1540,7 +1600,7 @@ int r2n2_voxel_eval(const float* pred, const float* gt, float thresh, long long*
   long long nvox = (long long)nv * nv * nv;
   int gx = (int)((nvox + 255) / 256);
   if (gx > 64) gx = 64;
-  voxel_eval_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+  r2n2::launch_k((voxel_eval_kernel), dim3(dim3(gx, B)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
       pred, gt, thresh, (unsigned long long*)counts, nv);
   R2N2_CHECK_LAUNCH("voxel_eval");
   return R2N2_OK;
@@ -1554,7 +1614,7 @@ int r2n2_preprocess_views(const unsigned char* rgba, const int* params, void* ou
   R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(rgba) & 3) == 0, R2N2_ERR_BAD_ALIGN, "preprocess_views: rgba must be 4-byte aligned");
   const long long total = (long long)n_img * Ho * Wo;
   R2N2_DISPATCH_DTYPE(out_dtype, T, {
-    preprocess_views_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    r2n2::launch_k((preprocess_views_kernel<T>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
         reinterpret_cast<const uchar4*>(rgba), params, (T*)out, n_img, Hs, Ws, Ho, Wo);
   })
   R2N2_CHECK_LAUNCH("preprocess_views");
@@ -1565,7 +1625,7 @@ int r2n2_voxel_labels(const unsigned char* occ, float* y, int B, int nv, void* s
   R2N2_CHECK_ARG(occ && y, R2N2_ERR_BAD_SHAPE, "voxel_labels: null pointer");
   R2N2_CHECK_ARG(B > 0 && nv > 0, R2N2_ERR_BAD_SHAPE, "voxel_labels: bad shape B=%d nv=%d", B, nv);
   const long long total = (long long)B * nv * nv * nv;
-  voxel_labels_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(occ, y, nv, total);
+  r2n2::launch_k((voxel_labels_kernel), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0, occ, y, nv, total);
   R2N2_CHECK_LAUNCH("voxel_labels");
   return R2N2_OK;
 }
@@ -1582,7 +1642,7 @@ int r2n2_average_precision(const float* pred, const float* gt, double* ap, int B
     cudaFuncSetAttribute(average_precision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApMax * 5);
     attr_set = true;
   }
-  average_precision_kernel<<<B, kApThreads, smem, (cudaStream_t)stream>>>(pred, gt, ap, nv);
+  r2n2::launch_k((average_precision_kernel), dim3(B), dim3(kApThreads), smem, (cudaStream_t)((cudaStream_t)stream), 0, pred, gt, ap, nv);
   R2N2_CHECK_LAUNCH("average_precision");
   return R2N2_OK;
 }
