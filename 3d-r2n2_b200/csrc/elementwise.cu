@@ -71,7 +71,7 @@ nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, in
   const int groups = Cpack / PN;
   for (int j = threadIdx.x; j < Cpack; j += blockDim.x) {
     const int kx = j / C, c = j - kx * C;
-    lut[j] = (kx < kw) ? c * pitch + kx : -1;
+    lut[j] = (kx < kw) ? c * pitch + kx : (j == kw * C ? -2 : -1);      // -2: the constant-one channel
   }
   for (long long rh = blockIdx.x; rh < (long long)N * H; rh += gridDim.x) {
     const int h = (int)(rh % H);
@@ -89,7 +89,7 @@ nchw_to_rowpack_kernel(const float* __restrict__ x, T* __restrict__ y, int N, in
 #pragma unroll
       for (int e = 0; e < PN; ++e) {
         const int off = lut[gq * PN + e];
-        o.v[e] = off >= 0 ? row[off + w] : 0.f;
+        o.v[e] = off >= 0 ? row[off + w] : (off == -2 ? 1.f : 0.f);
       }
       o.store(out + (long long)i * PN);
     }

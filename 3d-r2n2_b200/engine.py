@@ -575,10 +575,14 @@ class Engine:
             a = Act(xin, (TB, 1, self.img, self.img, self.cin_pad))
             a.useful = 3.0 / self.cin_pad          # RGB padded with zero channels
 
+        # row-packed first layer: packed channel 21 is the constant 1 -> bias gradient = dW[:, centre tap, 21]
+        ones = (3, 21) if (self.rowpack and self.rowpack > 21) else None
+
         def c2(name, inp, lrelu, residual=None):
             k = 7 if name in ('conv1a', 'conv1') else (1 if name.endswith('c') else 3)
             kk = (1, k, 1) if (k == 7 and self.rowpack) else (1, k, k)
-            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, lrelu, residual)
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, lrelu, residual,
+                            bias_via_ones=ones if (k == 7 and self.rowpack) else None)
 
         def c3(name, inp, lrelu, residual=None, out_dtype=None, up2=False):
             k = 1 if name == 'conv9c' else 3
@@ -587,7 +591,8 @@ class Engine:
         # ---- encoder over all T*B views (hoisted out of the scan) ----------------------------
         def c2h(name, inp, i):          # chunked head: outputs exist already
             kk = (1, 7, 1) if i == 0 else (1, 3, 3)
-            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, True, out_data=head[1][i])
+            return ctx.conv(inp, P[name + '.W'], P[name + '.b'], kk, True, out_data=head[1][i],
+                            bias_via_ones=ones if i == 0 else None)
 
         if self.residual:
             if head is not None:

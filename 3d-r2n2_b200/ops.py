@@ -692,12 +692,15 @@ class Ctx:
         return (self.algo in (L.ALGO_UMMA, L.ALGO_SPLIT) and umma_ok(cin, cout)
                 and (self.dtype == torch.bfloat16 or self.algo == L.ALGO_SPLIT or ZERO_SKIP_ANY_DTYPE))
 
-    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False, out_data=None):
+    def conv(self, x, W, b, k, lrelu=False, residual=None, out_dtype=None, up2=False, out_data=None, bias_via_ones=None):
         """y = [lrelu](conv(x; W) + b) [+ residual].  x: Act; W,b: Param; k=(kd,kh,kw).
         up2: the convolution runs over Unpool3D(x) (lib/layers.py:375-385) without materialising
         the 7/8-zero tensor; y lives on the x2 grid and the gradient reaches x directly.
         out_data: the output was already computed into this buffer (chunked head of the step, overlapped
-        with the host-to-device copy): only the tape entry is made."""
+        with the host-to-device copy): only the tape entry is made.
+        bias_via_ones=(tap, channel): input channel `channel` is the constant 1 (r2n2_nchw_to_rowpack) and its weights
+        are zero, so dW[:, tap, channel] of the CENTRE tap is sum_p dy[p, :] -- the bias gradient comes out of the
+        weight-gradient GEMM and no column-sum pass over dy (557 MB for conv1a) is needed."""
         N, D, H, Wd, Cin = x.geom
         assert Cin == W.cin and k[0] * k[1] * k[2] == W.taps, (x.geom, W.cin, W.taps, k)
         assert not (lrelu and residual is not None)
@@ -721,6 +724,8 @@ class Ctx:
             useful_frac = 1.0
         out = Act(y, og, requires_grad=self.training, lrelu_out=lrelu)
         out.bias = b
+        if bias_via_ones is not None and b is not None:
+            out.bias_done = True          # neither a fused column sum nor a bias_grad pass: see bwd()
         if self.training:
             self.consume(x)
             if residual is not None:
@@ -734,6 +739,15 @@ class Ctx:
                 global useful_frac
                 useful_frac = x.useful
                 self.weight_grads(x.data, dy, x.geom, W, None if out.bias_done else b, k, up2)
+                if bias_via_ones is not None and b is not None:
+                    tap, ch = bias_via_ones
+                    gw = W.grad.view(W.cout, W.taps, W.cin)
+                    if b.grad_written:
+                        b.grad.add_(gw[:, tap, ch])
+                    else:
+                        b.grad.copy_(gw[:, tap, ch])
+                        b.grad_written = True
+                    gw[:, :, ch].zero_()          # the slot's weights are structural zeros and must stay zero
                 self.dgrad_into(x, dy, W, k, down2=up2)
                 useful_frac = 1.0
                 if residual is not None:

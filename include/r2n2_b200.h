@@ -138,8 +138,10 @@ int r2n2_nchw_to_nhwc(const float* x, void* y, int N, int C, int H, int W, int C
                       int xoff, int out_dtype, void* stream);
 
 /* first-layer variant: y[n,h,w, kx*C + c] = x[n,c,h, w + kx - (kw-1)/2], zero outside the image and
- * for channels >= kw*C, so that the kh x kw conv1 (models/res_gru_net.py:33) becomes a kh x 1
- * convolution over Cpack channels (weights packed accordingly by the host mirror). */
+ * for channels > kw*C, so that the kh x kw conv1 (models/res_gru_net.py:33) becomes a kh x 1
+ * convolution over Cpack channels (weights packed accordingly by the host mirror).  If kw*C < Cpack, channel
+ * kw*C of every pixel holds 1.0 (round 2): with zero weights there the forward pass is unchanged, and the weight
+ * gradient of the centre tap at that channel is sum_p dy[p, co] -- the layer's BIAS gradient, for free. */
 int r2n2_nchw_to_rowpack(const float* x, void* y, int N, int C, int H, int W, int kw, int Cpack,
                          int out_dtype, void* stream);
 

@@ -124,6 +124,8 @@ def nchw_to_rowpack(x, y, kw, cpack):
     o = torch.zeros(N, H, W, cpack, dtype=y.dtype)
     for kx in range(kw):
         o[..., kx * C:(kx + 1) * C] = xp[:, :, :, kx:kx + W].permute(0, 2, 3, 1).to(y.dtype)
+    if kw * C < cpack:
+        o[..., kw * C] = 1.0            # constant-one channel (bias gradient through the weight gradient)
     y.copy_(o.reshape(-1))
     return y
 
