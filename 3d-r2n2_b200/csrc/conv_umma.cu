@@ -506,6 +506,11 @@ struct UmmaWgradParams {
   int* err_word;
 };
 
+// NKT / GT / SEGT > 0: K16 steps per stage, taps per CTA and (dx-halo mode) K16 steps per image row are compile-time, so
+// the MMA issue sequence of a stage is straight-line code with hoisted descriptor offsets.  Round 2 (tools/waitstat.py):
+// the generic loop kept the issuing thread busy 96 % of the kernel at ~85 cycles per N = 96 MMA (56 back to back) --
+// like the forward kernels before their issue sequences were specialised, the weight gradients were issue-bound.
+template <int NKT, int GT, int SEGT>
 __global__ void __launch_bounds__(kUmmaThreads)
 conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                        float* __restrict__ dw, const UmmaWgradParams p) {
@@ -675,7 +680,26 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full0 + 8u * s, ph, abort_flag, p.err_word);
         tc_fence_after();
-        if (elect_one()) {
+        if (NKT > 0 && ntap == GT) {
+          // compile-time issue sequence (every tap group of this CTA is full, NKT K16 steps per stage)
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
+            const uint64_t da0 = da_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+            const uint64_t db0 = db_hi | (uint64_t)(((a_addr + p.b_off) & 0x3FFFF) >> 4);
+            const uint32_t a_step16 = a_step >> 4, b_step16 = (p.dxh ? (uint32_t)rb_b : b_step) >> 4;
+            const uint32_t row_skip16 = (uint32_t)(2 * rb_b) >> 4;         // dx-halo: the x tile is 2 pixels wider per image row
+#pragma unroll
+            for (int g = 0; g < (GT > 0 ? GT : 1); ++g) {
+#pragma unroll
+              for (int k = 0; k < (NKT > 0 ? NKT : 1); ++k) {
+                const uint32_t koff = kbs * (uint32_t)k + (SEGT > 0 ? (uint32_t)(k / (SEGT > 0 ? SEGT : 1)) * row_skip16 : 0u);
+                umma_bf16(tmem_base + (uint32_t)(g * p.ci_cols), da0 + (uint64_t)(ka * (uint32_t)k + a_step16 * (uint32_t)g),
+                          db0 + (uint64_t)(koff + b_step16 * (uint32_t)g), idesc, k == 0 ? acc : 1u);
+              }
+            }
+            umma_commit(empty0 + 8u * s);
+          }
+        } else if (elect_one()) {
           uint32_t a_addr = smem_base + (uint32_t)(s * p.stage_bytes);
           uint32_t b_addr = a_addr + p.b_off;
           uint32_t d_tmem = tmem_base;
@@ -743,6 +767,21 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }
+}
+
+template <int NKT, int GT, int SEGT>
+static int launch_wgrad(const CUtensorMap& map_dy, const CUtensorMap& map_x, float* dw, const UmmaWgradParams& p, dim3 grid,
+                        size_t smem_bytes, cudaStream_t st) {
+  auto kern = conv_wgrad_umma_kernel<NKT, GT, SEGT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_wgrad[umma]: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaError_t le = r2n2::launch_k((kern), grid, dim3(kUmmaThreads), smem_bytes, st, 0, map_dy, map_x, dw, p);
+  R2N2_CHECK_ARG(le == cudaSuccess, R2N2_ERR_CUDA, "conv_wgrad[umma]: launch: %s", cudaGetErrorString(le));
+  return R2N2_OK;
 }
 
 // pixel box for the K loop: rows = bw*bh*bd*bn must be a multiple of 16 and <= max_rows;
@@ -978,14 +1017,6 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
   }
   if (!accumulate)
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.taps * Cin, st);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    R2N2_CHECK_ARG(e == cudaSuccess, R2N2_ERR_CUDA, "conv_wgrad[umma]: smem attribute: %s",
-                   cudaGetErrorString(e));
-    attr_set = true;
-  }
   // the M=128 A view of the LAST stage may run past its tile (narrow Cout): keep it inside the window
   const int a_span_slack = p.rows * 256 > p.stage_bytes ? p.rows * 256 - p.stage_bytes : 0;
   const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 256 + 1024 + a_span_slack;
@@ -995,7 +1026,25 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
             "smem %zu grid %ux%ux%u tmem %d ci_cols %d\n", Cin, Cout, p.taps, p.G, p.bw, p.bh, p.bd, p.bn, p.rows, p.dxh,
             p.ystack, p.up2, p.stage_bytes, p.stages, smem_bytes, grid.x, grid.y, grid.z, p.tmem_cols, p.ci_cols);
   R2N2_CHECK_ARG(smem_bytes <= 200 * 1024, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma]: smem %zu too large", smem_bytes);
-  r2n2::launch_k((conv_wgrad_umma_kernel), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0, map_dy, map_x, dw, p);
+  // compile-time issue sequences for the configurations of the training step (anything else: the generic loop)
+  const int nk = p.rows >> 4, seg = p.dxh ? p.segs : 0;
+  const bool gen = getenv("R2N2_UMMA_WGRAD_GENERIC") != nullptr;
+  int rc;
+#define R2N2_WG(NK_, G_, SEG_) (!gen && nk == NK_ && p.G == G_ && seg == SEG_) rc = launch_wgrad<NK_, G_, SEG_>(map_dy, map_x, dw, p, grid, smem_bytes, st)
+  if R2N2_WG(8, 3, 8);          // conv1b (128-pixel rows)
+  else if R2N2_WG(6, 3, 2);     // conv2a / conv2b
+  else if R2N2_WG(6, 3, 1);     // conv8a / conv8b
+  else if R2N2_WG(8, 3, 2);     // conv9a
+  else if R2N2_WG(9, 3, 1);     // conv9a data-gradient shape (UP2 layers)
+  else if R2N2_WG(3, 3, 0);     // conv3a
+  else if R2N2_WG(3, 2, 0);     // conv3b, conv4, conv5, conv6
+  else if R2N2_WG(3, 4, 0);     // recurrent unit, conv7
+  else if R2N2_WG(13, 1, 0);    // row-packed conv1a (y-stacked taps)
+  else if R2N2_WG(8, 1, 0);     // 1x1 convolutions, 128-pixel boxes
+  else if R2N2_WG(4, 1, 0);     // FC layers / x-projections (64-sample boxes)
+  else rc = launch_wgrad<0, 0, 0>(map_dy, map_x, dw, p, grid, smem_bytes, st);
+#undef R2N2_WG
+  if (rc != R2N2_OK) return rc;
   R2N2_CHECK_LAUNCH("conv_wgrad[umma]");
   return R2N2_OK;
 }
