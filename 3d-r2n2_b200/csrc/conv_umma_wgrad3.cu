@@ -19,6 +19,10 @@
 //     the M side with the descriptor's leading-dimension stride set to ONE ROW: M chunk j (cs
 //     channels) then reads the tile shifted by j pixels, i.e. one MMA computes 128/cs dx-taps at
 //     once with all 128 lanes busy.  N = channels of the other tensor.
+//   * STACKED dy TAPS (round 2, `nstack`).  The other tensor O = x carries the halo rows, and the N
+//     operand's leading-dimension stride is ONE IMAGE ROW (P flat rows): N chunk k reads the x tile
+//     shifted by k image rows, so ONE MMA with N = 3 * Cin yields the 3 dy x (128/cs) dx taps of a
+//     filter plane: 32 + 3*Cin/4 cycles per K16 instead of 3 x (32 + Cin/4) (SS-operand read bound).
 // grid = (pixel splits, 3 dz planes); each CTA accumulates 3 dy x 3 dx taps in TMEM over all its
 // units and reduces into dw with fp32 red.global.add at the end.
 #include "umma.cuh"
@@ -32,6 +36,7 @@ struct Wgrad3Params {
   int s_is_x;                              // stacked (M side) tensor: 1 = x, 0 = dy
   int cs, co;                              // channels of the stacked / the other tensor
   int nshift, nmma;                        // dx shifts per MMA (128/cs), MMAs per dy (ceil(3/nshift))
+  int nstack;                              // 1: the 3 dy taps are chunks of the N operand (O = x, chunk stride = P rows)
   int acc_cols, tmem_cols;
   int rb_s, rb_o;                          // row bytes
   int s_off, o_off, stage_bytes, stages;   // S tile / O tile offsets inside a stage
@@ -138,12 +143,15 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     // ================================ MMA issuer ============================================
     if (n_valid > 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(p.co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)((p.nstack ? 3 * p.co : p.co) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const int nd = p.nstack ? 1 : 3;                                   // MMA groups per stage along dy
       const uint32_t lt_s = (p.rb_s == 128) ? 2u : (p.rb_s == 64 ? 4u : 6u);
       const uint32_t lt_o = (p.rb_o == 128) ? 2u : (p.rb_o == 64 ? 4u : 6u);
       // stacked operand: leading-dimension (chunk) stride = ONE ROW -> chunk j is the tile shifted by j pixels
       const uint64_t ds_hi = make_mnmajor_desc(0, (uint32_t)p.rb_s, 8u * (uint32_t)p.rb_s, lt_s);
-      const uint64_t do_hi = make_mnmajor_desc(0, 8u * (uint32_t)p.rb_o, 8u * (uint32_t)p.rb_o, lt_o);
+      // other operand, dy-stacked: chunk k of N is the tile shifted by k image rows (P flat rows)
+      const uint64_t do_hi = make_mnmajor_desc(0, (p.nstack ? (uint32_t)p.P : 8u) * (uint32_t)p.rb_o,
+                                               8u * (uint32_t)p.rb_o, lt_o);
       const uint32_t ks = (uint32_t)p.rb_s, ko = (uint32_t)p.rb_o;       // descriptor step per K16 (16 rows >> 4)
       // row offsets of the views for dy index dyi: the x tile starts one image row above the dy tile
       const int s_dy = p.s_is_x ? p.P : 0, o_dy = p.s_is_x ? 0 : p.P;
@@ -155,7 +163,7 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         tc_fence_after();
         const uint32_t stage = smem_base + (uint32_t)(s * p.stage_bytes);
         if (elect_one()) {
-          for (int dyi = 0; dyi < 3; ++dyi) {
+          for (int dyi = 0; dyi < nd; ++dyi) {
             const uint32_t o_addr = stage + (uint32_t)p.o_off + (uint32_t)(dyi * o_dy * p.rb_o);
             const uint64_t db0 = do_hi | (uint64_t)((o_addr & 0x3FFFF) >> 4);
             for (int m = 0; m < p.nmma; ++m) {
@@ -190,6 +198,8 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int dyi = 0; dyi < 3; ++dyi)
       for (int m = 0; m < p.nmma; ++m) {
+        // accumulator columns of (dy, m): separate accumulators, or the dy-th chunk of MMA m's 3*co columns
+        const int acol = p.nstack ? m * p.acc_cols + dyi * p.co : (dyi * p.nmma + m) * p.acc_cols;
         const int sg = m * p.nshift + j;                  // shift index: pixel offset sg - 1 of the stacked tensor
         const bool valid = sg < 3;
         // stacked x: x[p + sg - 1] meets dy[p] -> dx = sg - 1; stacked dy: dy[p + sg - 1] meets x[p] -> dx = 1 - sg
@@ -197,7 +207,7 @@ conv_wgrad3_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         const int tap = (dzi * 3 + dyi) * 3 + tx;
         for (int c = 0; c < p.co; c += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)((dyi * p.nmma + m) * p.acc_cols + c), v);
+          tmem_ld16(taddr + (uint32_t)(acol + c), v);
           if (!valid) continue;
           if (p.s_is_x) {
             // lanes = ci (contiguous in dw), columns = co
@@ -270,9 +280,18 @@ int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int
   p.rb_o = p.co * 2;
   p.nshift = 128 / p.cs;
   p.nmma = (3 + p.nshift - 1) / p.nshift;
-  p.acc_cols = p.co < 32 ? 32 : p.co;
+  // dy taps stacked on N (one MMA per filter plane and dx group): needs the halo rows on the N side (O = x)
+  p.nstack = getenv("R2N2_WGRAD3_NO_NSTACK") ? 0 : 1;
+  if (p.nstack && p.s_is_x) {
+    p.s_is_x = 0;
+    p.cs = Cout; p.co = Cin;
+    p.rb_s = p.cs * 2; p.rb_o = p.co * 2;
+    p.nshift = 128 / p.cs;
+    p.nmma = (3 + p.nshift - 1) / p.nshift;
+  }
+  p.acc_cols = p.nstack ? 3 * p.co : (p.co < 32 ? 32 : p.co);
   p.tmem_cols = 32;
-  while (p.tmem_cols < 3 * p.nmma * p.acc_cols) p.tmem_cols *= 2;
+  while (p.tmem_cols < (p.nstack ? 1 : 3) * p.nmma * p.acc_cols) p.tmem_cols *= 2;
   R2N2_CHECK_ARG(p.tmem_cols <= 512, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma3]: accumulators exceed TMEM");
   // band height: fewest wasted MMA rows / image rows, then the tallest band whose stage is <= 56 KB
   int bestY = 0;
@@ -339,8 +358,8 @@ int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int
   const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_wgrad[umma3]: smem %zu too large", smem_bytes);
   if (getenv("R2N2_UMMA_DBG"))
-    fprintf(stderr, "[umma wgrad3] Cin %d Cout %d stack %s cs %d nshift %d nmma %d Y %d bands %d R %d nk %d stage %d x %d "
-            "units %lld per cta %lld grid %lldx3 tmem %d\n", Cin, Cout, p.s_is_x ? "x" : "dy", p.cs, p.nshift, p.nmma,
+    fprintf(stderr, "[umma wgrad3] Cin %d Cout %d nstack %d stack %s cs %d nshift %d nmma %d Y %d bands %d R %d nk %d stage %d x %d "
+            "units %lld per cta %lld grid %lldx3 tmem %d\n", Cin, Cout, p.nstack, p.s_is_x ? "x" : "dy", p.cs, p.nshift, p.nmma,
             p.Y, p.bands, p.R, p.nk, p.stage_bytes, p.stages, p.units, p.units_per_cta, splits, p.tmem_cols);
   dim3 grid((unsigned)splits, 3);
   r2n2::launch_k((conv_wgrad3_umma_kernel), dim3(grid), dim3(kUmmaThreads), smem_bytes, (cudaStream_t)(st), 0, map_dy, map_x, dw, p);
