@@ -16,6 +16,7 @@ EPI_RES_PRE = 64
 CONV_UP2, CONV_DOWN2 = 16, 32
 WGRAD_ACCUMULATE, WGRAD_UP2 = 1, 2
 ALGO_SIMT, ALGO_UMMA = 0, 1
+GRU_UR, GRU_BLEND, GRU_RBWD, GRU_OBWD = 1, 2, 3, 4
 ALGO_SPLIT = 2      # host-level only: three ALGO_UMMA passes over hi/lo split operands (COMPUTE='bf16x3')
 ELT_SIGMOID, ELT_TANH, ELT_COMPLEMENT, ELT_MUL = 0, 1, 2, 3
 ELT_SIGMOID_BWD, ELT_TANH_BWD, ELT_NEG = 4, 5, 6
@@ -26,6 +27,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 PROTOTYPES = {
     'r2n2_conv_fwd': [_p, _p, _p, _p, _p, _p] + [_i] * 9 + [_i, _i, _i, _i, _p],
     'r2n2_conv_fwd_colsum': [_p, _p, _p, _p, _p, _p] + [_i] * 9 + [_i, _i, _i, _i, _p, _p],
+    'r2n2_conv_fwd_gru': [_i] + [_p] * 10 + [_i] * 10 + [_p],
     'r2n2_conv_wgrad': [_p, _p, _p] + [_i] * 9 + [_i, _i, _i, _p],
     'r2n2_bias_grad': [_p, _p, _ll, _i, _i, _i, _p],
     'r2n2_weight_transpose': [_p, _p, _i, _i, _i, _i, _p],

@@ -32,6 +32,13 @@ void set_error(const char* fmt, ...);
 
 constexpr float kLeak = 0.01f;  // LeakyReLU leakiness, lib/layers.py:630
 
+// operands of a fused conv-GRU gate epilogue (r2n2_conv_fwd_gru): mode = R2N2_GRU_*
+struct GruEpi {
+  int mode;
+  const void* in[4];
+  void* out[3];
+};
+
 // ---- 4-element vector load/store with conversion to/from float -------------------------
 template <typename T>
 struct Vec4;

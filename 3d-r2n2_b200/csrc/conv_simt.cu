@@ -405,7 +405,8 @@ int conv_wgrad_simt(const void* x, const void* dy, float* dw, int N, int D, int 
 // implemented in conv_umma.cu
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
-                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st);
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st,
+                  const GruEpi* gru = nullptr);
 int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,
                     int Cout, int kd, int kh, int kw, int dtype, int accumulate, cudaStream_t st);
 
@@ -452,6 +453,31 @@ int r2n2_conv_fwd_colsum(const void* x, const void* w, const float* bias, const 
   R2N2_CHECK_ARG(colsum != nullptr, R2N2_ERR_BAD_SHAPE, "conv_fwd_colsum: null colsum");
   return conv_fwd_dispatch(x, w, bias, mask_src, residual, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, in_dtype,
                            out_dtype, algo, colsum, stream);
+}
+
+int r2n2_conv_fwd_gru(int mode, const void* x, const void* w, const float* bias, const void* in0, const void* in1,
+                      const void* in2, const void* in3, void* out0, void* out1, void* out2, int N, int D, int H,
+                      int W, int Cin, int Cout, int kd, int kh, int kw, int dtype, void* stream) {
+  using namespace r2n2;
+  R2N2_CHECK_ARG(mode >= R2N2_GRU_UR && mode <= R2N2_GRU_OBWD, R2N2_ERR_UNSUPPORTED, "conv_fwd_gru: unknown mode %d", mode);
+  R2N2_CHECK_ARG(dtype == R2N2_BF16, R2N2_ERR_BAD_DTYPE, "conv_fwd_gru: bf16 tensors only (the fp32 path keeps the gate kernels)");
+  R2N2_CHECK_ARG(x && w && in0 && in1 && out0 && out1, R2N2_ERR_BAD_SHAPE, "conv_fwd_gru: null pointer");
+  const bool fwd = mode == R2N2_GRU_UR || mode == R2N2_GRU_BLEND;
+  R2N2_CHECK_ARG(!fwd || bias, R2N2_ERR_BAD_SHAPE, "conv_fwd_gru: forward modes need the gate bias");
+  R2N2_CHECK_ARG(mode == R2N2_GRU_RBWD || (mode == R2N2_GRU_BLEND ? in2 != nullptr : out2 != nullptr), R2N2_ERR_BAD_SHAPE,
+                 "conv_fwd_gru: null pointer");
+  R2N2_CHECK_ARG(mode != R2N2_GRU_OBWD || in2, R2N2_ERR_BAD_SHAPE, "conv_fwd_gru: null pointer");
+  R2N2_CHECK_ARG(Cout % 32 == 0 && Cin % 16 == 0, R2N2_ERR_BAD_SHAPE, "conv_fwd_gru: Cout %d must be a multiple of 32", Cout);
+  const void* ptrs[7] = {in0, in1, in2, in3, out0, out1, out2};
+  for (int i = 0; i < 7; ++i)
+    R2N2_CHECK_ARG((reinterpret_cast<uintptr_t>(ptrs[i]) & 31) == 0, R2N2_ERR_BAD_ALIGN,
+                   "conv_fwd_gru: gate tensors must be 32-byte aligned");
+  GruEpi g;
+  g.mode = mode;
+  g.in[0] = in0; g.in[1] = in1; g.in[2] = in2; g.in[3] = in3;
+  g.out[0] = out0; g.out[1] = out1; g.out[2] = out2;
+  return conv_fwd_umma(x, w, bias, nullptr, nullptr, out0, N, D, H, W, Cin, Cout, kd, kh, kw, fwd ? R2N2_EPI_BIAS : 0,
+                       R2N2_BF16, R2N2_BF16, nullptr, (cudaStream_t)stream, &g);
 }
 
 int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,

@@ -41,6 +41,11 @@ struct FwdParams {
   int mode;                                // 0 plain, 1 UP2 (zero-stuffed x2 input, 8 parity classes), 2 DOWN2
   int cls_tiles;                           // tiles per parity class (= m_tiles * n_tiles)
   int* err_word;
+  // conv-GRU gate math fused into the register epilogue (R2N2_GRU_*; r2n2_conv_fwd_gru): no y tensor, the accumulator row of
+  // a hidden-grid position feeds the gate formulas directly (models/res_gru_net.py:130-151 and their gradients)
+  int gru;
+  const void* gin[4];
+  void* gout[3];
 };
 
 // Filter taps that hit non-zero input along one axis.  Plain / DOWN2: all k taps, input offset
@@ -74,13 +79,116 @@ static __device__ __forceinline__ TileCoord decode_tile(const FwdParams& p, int 
   return c;
 }
 
+// Gate epilogue of one accumulator row (hidden-grid position pr) over the 16-column chunks [c_begin, c_end) of a tile.
+// HC = hidden channels.  Inputs are fetched BEFORE the TMEM load of the chunk; every lane executes the tcgen05.ld.
+//   UR    (Cout = 2 HC): s = sigmoid(acc + xp[pr,co] + b[co]); co < HC: u = s; else r = s, rh = s * h
+//   BLEND (Cout = HC):   c = tanh(acc + xp[pr,co] + b[co]); h' = u h + (1 - u) c
+//   RBWD  (Cout = HC):   g = acc (= d(r h)); da_r = g h r (1 - r) -> da_ur[pr, HC + co]; dh_prev += g r
+//   OBWD  (Cout = HC):   dh = acc + dh_in; da_c = dh (1 - u)(1 - c^2); da_u = dh (h - c) u (1 - u) -> da_ur[pr, co]; dh_prev = dh u
+template <typename T>
+struct GruIn {
+  Row16<T> a0, a1, a2, a3;
+};
+// operand rows of one 16-column chunk (issued BEFORE the accumulator-ready wait for the first chunk of a tile)
+template <typename T>
+static __device__ __forceinline__ void gru_fetch(GruIn<T>& g, const FwdParams& p, int co, bool ok, long long pr) {
+  const int mode = p.gru;
+  const int HC = mode == R2N2_GRU_UR ? (p.Cout >> 1) : p.Cout;
+  g.a0.zero(); g.a1.zero(); g.a2.zero(); g.a3.zero();
+  if (!ok || co >= p.Cout) return;
+  const T* in0 = static_cast<const T*>(p.gin[0]);
+  const T* in1 = static_cast<const T*>(p.gin[1]);
+  const T* in2 = static_cast<const T*>(p.gin[2]);
+  const T* in3 = static_cast<const T*>(p.gin[3]);
+  const int ch = (mode == R2N2_GRU_UR && co >= HC) ? co - HC : co;      // hidden channel
+  const long long hoff = pr * HC + ch;
+  if (mode == R2N2_GRU_UR) {
+    g.a0.load(in0 + pr * p.Cout + co);
+    if (co >= HC) g.a1.load(in1 + hoff);
+  } else if (mode == R2N2_GRU_BLEND) {
+    g.a0.load(in0 + hoff); g.a1.load(in1 + hoff); g.a2.load(in2 + hoff);
+  } else if (mode == R2N2_GRU_RBWD) {
+    g.a0.load(in0 + hoff); g.a1.load(in1 + hoff); g.a2.load(static_cast<const T*>(p.gout[1]) + hoff);
+  } else {
+    g.a0.load(in0 + hoff); g.a1.load(in1 + hoff); g.a2.load(in2 + hoff);
+    if (in3) g.a3.load(in3 + hoff);
+  }
+}
+template <typename T>
+static __device__ __forceinline__ void epi_row_gru(GruIn<T>& pf, const FwdParams& p, uint32_t taddr, int c_begin, int c_end,
+                                                    int co0, bool ok, long long pr, const float* __restrict__ bias) {
+  const int mode = p.gru;
+  const int HC = mode == R2N2_GRU_UR ? (p.Cout >> 1) : p.Cout;
+  T* out0 = static_cast<T*>(p.gout[0]);
+  T* out1 = static_cast<T*>(p.gout[1]);
+  T* out2 = static_cast<T*>(p.gout[2]);
+  for (int c = c_begin; c < c_end; c += 16) {
+    const int co = co0 + c;
+    const bool act = ok && co < p.Cout;
+    const int ch = (mode == R2N2_GRU_UR && co >= HC) ? co - HC : co;      // hidden channel
+    const long long hoff = pr * HC + ch;
+    const GruIn<T> cur = pf;
+    if (c + 16 < c_end) gru_fetch(pf, p, co + 16, ok, pr);
+    uint32_t v[16];
+    tmem_ld16(taddr + (uint32_t)c, v);
+    if (!act) continue;
+    float f[16], q0[16], q1[16], q2[16], q3[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    cur.a0.unpack(q0); cur.a1.unpack(q1); cur.a2.unpack(q2); cur.a3.unpack(q3);
+    if (mode == R2N2_GRU_UR || mode == R2N2_GRU_BLEND) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+        f[j] += q0[j] + b4.x; f[j + 1] += q0[j + 1] + b4.y; f[j + 2] += q0[j + 2] + b4.z; f[j + 3] += q0[j + 3] + b4.w;
+      }
+    }
+    if (mode == R2N2_GRU_UR) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = sigmoidf_(f[j]);
+      if (co < HC) {
+        store16(out0 + hoff, f);
+      } else {
+        store16(out1 + hoff, f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] *= q1[j];
+        store16(out2 + hoff, f);
+      }
+    } else if (mode == R2N2_GRU_BLEND) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = tanhf(f[j]);
+      store16(out0 + hoff, f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = q1[j] * q2[j] + (1.f - q1[j]) * f[j];
+      store16(out1 + hoff, f);
+    } else if (mode == R2N2_GRU_RBWD) {
+      float d[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { d[j] = f[j] * q0[j] * q1[j] * (1.f - q1[j]); f[j] = q2[j] + f[j] * q1[j]; }
+      store16(out0 + pr * (2 * HC) + HC + ch, d);
+      store16(out1 + hoff, f);
+    } else {
+      float d[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { f[j] += q0[j]; d[j] = f[j] * (1.f - q1[j]) * (1.f - q2[j] * q2[j]); }
+      store16(out0 + hoff, d);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[j] = f[j] * (q3[j] - q2[j]) * q1[j] * (1.f - q1[j]);
+      store16(out1 + pr * (2 * HC) + ch, d);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] *= q1[j];
+      store16(out2 + hoff, f);
+    }
+  }
+}
+
 constexpr int kFwdThreads = 64 + 32 * kEpiWarps;
 
 // NK16 / NSUB > 0: K16 steps per sub-block and sub-blocks per stage are compile-time (every stage full, every
 // channel chunk full): the MMA issue sequence of a stage is straight-line code with immediate descriptor
 // offsets -- the issuing thread, not the tensor pipe, sets the pace when it spends ~17 instructions per MMA.
-template <typename TOut, int NK16, int NSUB, int MC>
-__global__ void __launch_bounds__(kFwdThreads, MC ? 1 : 2)
+template <typename TOut, int NK16, int NSUB, int MC, int GRU = 0>
+__global__ void __launch_bounds__(kFwdThreads, (MC || GRU) ? 1 : 2)
 conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_res,
                          const __grid_constant__ CUtensorMap map_mask,
@@ -434,12 +542,20 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
       }
       const int col0 = tc.nt * p.BN;
       const long long off = pix * p.Cout;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
+      if constexpr (GRU) {
+        GruIn<TOut> gpf;
+        gru_fetch(gpf, p, col0 + c_begin, valid, pix);
+        mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
+        tc_fence_after();
+        epi_row_gru<TOut>(gpf, p, taddr, c_begin, c_end, col0, valid, pix, bias);
+      } else {
       EpiPrefetch<TOut> pf;
       epi_prefetch(pf, p.flags, valid, res + off, mask + off, col0 + c_begin, p.Cout);
       mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.bn_cols);
       epi_row(pf, taddr, c_begin, c_end, col0, p.Cout, valid, empty_acc, p.flags, bias, res + off, mask + off, y + off);
+      }
       // this warp has finished reading the accumulator: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -466,9 +582,9 @@ struct FwdLaunch {
   const FwdParams& p;
   int grid; size_t smem; cudaStream_t st;
 };
-template <typename TOut, int NK16, int NSUB, int MC>
+template <typename TOut, int NK16, int NSUB, int MC, int GRU = 0>
 static int launch_fwd_k(const FwdLaunch& L) {
-  auto kern = conv_fwd_umma_persistent<TOut, NK16, NSUB, MC>;
+  auto kern = conv_fwd_umma_persistent<TOut, NK16, NSUB, MC, GRU>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -482,6 +598,15 @@ static int launch_fwd_k(const FwdLaunch& L) {
 }
 template <typename TOut, int NK16, int NSUB>
 static int launch_fwd(const FwdLaunch& L) {
+  // fused gate epilogues: the generic and the (4, 3) issue sequence (the hidden convolutions at small batch) are instantiated
+  if (L.p.gru) {
+    if constexpr (sizeof(TOut) == 2) {
+      if constexpr (NK16 == 4 && NSUB == 3) return launch_fwd_k<TOut, 4, 3, 0, 1>(L);
+      else return launch_fwd_k<TOut, 0, 0, 0, 1>(L);
+    } else {
+      R2N2_CHECK_ARG(false, R2N2_ERR_BAD_DTYPE, "conv_fwd_gru[umma]: bf16 tensors only");
+    }
+  }
   // multicast clusters: only the generic and the (4, 2) / (4, 3) / (4, 4) issue sequences are instantiated
   if (L.p.mc > 1) {
     if constexpr (NK16 == 4 && (NSUB == 2 || NSUB == 3 || NSUB == 4)) return launch_fwd_k<TOut, NK16, NSUB, 1>(L);
@@ -551,7 +676,8 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
 // whose output gradient this call produces; fused into the TMA epilogue where possible, else a second pass
 int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* mask,
                   const void* res, void* y, int N, int D, int H, int W, int Cin, int Cout, int kd,
-                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st) {
+                  int kh, int kw, int flags, int in_dtype, int out_dtype, float* colsum, cudaStream_t st,
+                  const GruEpi* gru) {
   const int mode = (flags & R2N2_CONV_UP2) ? 1 : ((flags & R2N2_CONV_DOWN2) ? 2 : 0);
   R2N2_CHECK_ARG(!((flags & R2N2_CONV_UP2) && (flags & R2N2_CONV_DOWN2)), R2N2_ERR_BAD_SHAPE,
                  "conv_fwd[umma]: UP2 and DOWN2 are exclusive");
@@ -574,7 +700,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
                      (!(flags & R2N2_EPI_MASK) || (reinterpret_cast<uintptr_t>(mask) & 31) == 0),
                  R2N2_ERR_BAD_ALIGN, "conv_fwd[umma]: y / residual / mask must be 32-byte aligned");
   // 3x3 / 3x3x3 layers with <= 128 output channels: input loaded once, taps as descriptor views
-  if (mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw)) {
+  if (gru) {
+    R2N2_CHECK_ARG(mode == 0 && !colsum && out_dtype == R2N2_BF16 && (flags & ~R2N2_EPI_BIAS) == 0, R2N2_ERR_UNSUPPORTED,
+                   "conv_fwd_gru[umma]: plain geometry, bf16 tensors, no other epilogue flags");
+  }
+  if (!gru && mode == 0 && N > 0 && D > 0 && H > 0 && W > 0 && conv_fwd3_applicable(N, D, H, W, Cin, Cout, kd, kh, kw)) {
     int rc = conv_fwd3_umma(x, w, bias, mask, res, y, N, D, H, W, Cin, Cout, kd, kh, kw, flags, out_dtype, st);
     if (rc == R2N2_OK && colsum) rc = r2n2_bias_grad(y, colsum, out_rows, Cout, out_dtype, 1, (void*)st);
     return rc;
@@ -606,7 +736,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   // MEASURED (CUDA-graph replay, no host launch time): no gain -- GRU hidden conv 13 us with or without (only C = 2 leaves
   // all 72 clusters resident), fc7 10 -> 11 us with C = 8, x-projection 17 -> 18 us: at ~10 us these kernels sit on their
   // launch + prologue + first-load latency floor, not on the A traffic.  Kept as an opt-in (R2N2_UMMA_MC=1), parity-tested.
-  if (mode == 0 && getenv("R2N2_UMMA_MC") && atoi(getenv("R2N2_UMMA_MC")) && !getenv("R2N2_UMMA_BN")) {
+  if (!gru && mode == 0 && getenv("R2N2_UMMA_MC") && atoi(getenv("R2N2_UMMA_MC")) && !getenv("R2N2_UMMA_BN")) {
     const int rows = p.bw * p.bh * p.bd * p.bn, c3 = p.bw * p.bh * p.bd, c2 = p.bw * p.bh;
     double best_traffic = 1e30;
     int bBN = 0, bC = 0;
@@ -676,7 +806,11 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
     // pass it saves -- conv1b dgrad 0.68 + 0.20 -> 0.97 ms, conv3b dgrad 0.19 + 0.03 -> 0.26 ms -- so the sum
     // is fused only where the TMA epilogue is chosen anyway)
     if (getenv("R2N2_FORCE_COLSUM_FUSE") && colsum && out_dtype == R2N2_BF16 && mode != 1 && Cout <= p.BN) p.tma_epi = 1;
+    if (gru) p.tma_epi = 0;                 // the gate math lives in the register epilogue
   }
+  p.gru = gru ? gru->mode : 0;
+  for (int i = 0; i < 4; ++i) p.gin[i] = gru ? gru->in[i] : nullptr;
+  for (int i = 0; i < 3; ++i) p.gout[i] = gru ? gru->out[i] : nullptr;
   const bool fuse_colsum = colsum && p.tma_epi && Cout <= p.BN && !getenv("R2N2_NO_COLSUM_FUSE");
   p.SC = (p.BN % 64 == 0 && ctas == 1) ? 64 : (p.BN % 32 == 0 ? 32 : 16);
   p.slab_bytes = 128 * p.SC * 2;

@@ -300,6 +300,7 @@ struct Row16;
 template <>
 struct Row16<__nv_bfloat16> {
   uint4 a, b;
+  __device__ __forceinline__ void zero() { a = make_uint4(0, 0, 0, 0); b = a; }
   __device__ __forceinline__ void load(const __nv_bfloat16* p) {
     asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -318,6 +319,7 @@ struct Row16<__nv_bfloat16> {
 template <>
 struct Row16<float> {
   float4 q[4];
+  __device__ __forceinline__ void zero() { q[0] = q[1] = q[2] = q[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void load(const float* p) {
 #pragma unroll
     for (int j = 0; j < 2; ++j)

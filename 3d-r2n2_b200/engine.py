@@ -30,6 +30,8 @@ N_DECONV = [128, 128, 128, 64, 32, 2]
 N_GRU_VOX = 4
 HID_POS = N_GRU_VOX ** 3          # 64 cells
 HID_C = N_DECONV[0]               # 128 channels
+# conv-GRU gate math in the epilogue of the hidden convolutions (tcgen05 path); R2N2_NO_GRU_FUSE=1: separate gate kernels
+FUSE_GRU_EPILOGUE = not os.environ.get('R2N2_NO_GRU_FUSE')
 
 NETS = ('GRUNet', 'ResidualGRUNet', 'ResidualLSTMNet')
 
@@ -402,6 +404,9 @@ class Engine:
         h = ctx.empty(T * B * hn, f.data)
         sl = lambda buf, t, width=hn: buf[t * B * width:(t + 1) * B * width]
         geom_h = (B, g4, g4, g4, HID_C)
+        # tcgen05 path: the gate math runs in the epilogue of the hidden convolutions (r2n2_conv_fwd_gru) -- no conv
+        # output tensor, no separate gate launches except for the first view (h = 0: nothing to convolve)
+        fused = FUSE_GRU_EPILOGUE and ctx.algo == L.ALGO_UMMA and f.data.dtype == torch.bfloat16
         for t in range(T):
             if t == 0:
                 ops.gru_ur_fwd(None, sl(xp_ur, 0, 2 * hn), P['rnn.b_ur'].data, None, sl(u, 0), sl(r, 0),
@@ -410,6 +415,12 @@ class Engine:
                                 sl(h, 0), B)
                 continue
             hp = sl(h, t - 1)
+            if fused:
+                ops.conv_fwd_gru(L.GRU_UR, hp, P['rnn.Wh_ur'].operand(), P['rnn.b_ur'].data,
+                                 (sl(xp_ur, t, 2 * hn), hp), (sl(u, t), sl(r, t), sl(rh, t)), geom_h, 2 * HID_C, (3, 3, 3))
+                ops.conv_fwd_gru(L.GRU_BLEND, sl(rh, t), P['rnn.Wh_c'].operand(), P['rnn.b_c'].data,
+                                 (sl(xp_c, t), sl(u, t), hp), (sl(c, t), sl(h, t)), geom_h, HID_C, (3, 3, 3))
+                continue
             a_ur = ctx.empty(B * 2 * hn, f.data)
             ops.conv_fwd_x(hp, P['rnn.Wh_ur'].operand(), None, None, None, a_ur, geom_h, 2 * HID_C,
                          (3, 3, 3), 0, ctx.algo)
@@ -430,13 +441,27 @@ class Engine:
                 dxp_c = ctx.empty(T * B * hn, f.data)
                 dh = h_last.grad
                 geom_ur = (B, g4, g4, g4, 2 * HID_C)
+                out_bwd_done = False            # fused: step t's gate gradients came out of step t+1's last epilogue
                 for t in range(T - 1, -1, -1):
                     hp = sl(h, t - 1) if t > 0 else None
-                    dh_prev = ctx.empty(B * hn, f.data)
-                    ops.gru_out_bwd(dh, sl(u, t), sl(c, t), hp, sl(dxp_ur, t, 2 * hn), sl(dxp_c, t),
-                                    dh_prev, B)
+                    if not out_bwd_done:
+                        dh_prev = ctx.empty(B * hn, f.data)
+                        ops.gru_out_bwd(dh, sl(u, t), sl(c, t), hp, sl(dxp_ur, t, 2 * hn), sl(dxp_c, t),
+                                        dh_prev, B)
                     if t == 0:
                         break
+                    if fused:
+                        # d(r*h) = conv(d pre-tanh; Wh_c^T) with the reset-gate gradient in its epilogue, then
+                        # dh_{t-1} = conv(d pre-sigmoid; Wh_ur^T) + dh_prev with step t-1's gate gradients in ITS epilogue
+                        ops.conv_fwd_gru(L.GRU_RBWD, sl(dxp_c, t), P['rnn.Wh_c'].operand_t(), None, (hp, sl(r, t)),
+                                         (sl(dxp_ur, t, 2 * hn), dh_prev), geom_h, HID_C, (3, 3, 3))
+                        dh_next = ctx.empty(B * hn, f.data)
+                        ops.conv_fwd_gru(L.GRU_OBWD, sl(dxp_ur, t, 2 * hn), P['rnn.Wh_ur'].operand_t(), None,
+                                         (dh_prev, sl(u, t - 1), sl(c, t - 1), sl(h, t - 2) if t > 1 else None),
+                                         (sl(dxp_c, t - 1), sl(dxp_ur, t - 1, 2 * hn), dh_next), geom_ur, HID_C, (3, 3, 3))
+                        dh_prev = dh_next
+                        out_bwd_done = True
+                        continue
                     d_rh = ctx.empty(B * hn, f.data)
                     ops.conv_fwd_x(sl(dxp_c, t), P['rnn.Wh_c'].operand_t(), None, None, None, d_rh,
                                  geom_h, HID_C, (3, 3, 3), 0, ctx.algo)

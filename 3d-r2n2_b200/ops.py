@@ -415,6 +415,23 @@ def eltwise(op, a, b, y):
     _call('r2n2_eltwise', op, _ptr(a), _ptr(b), _ptr(y), a.numel(), _DT[a.dtype], _stream())
 
 
+def conv_fwd_gru(mode, x, w, bias, ins, outs, geom, cout, k):
+    """Hidden-state convolution of the conv-GRU with the gate math in its epilogue (r2n2_conv_fwd_gru, tcgen05 path, bf16):
+    mode = L.GRU_UR / GRU_BLEND / GRU_RBWD / GRU_OBWD; ins (<= 4) / outs (<= 3) as documented in include/r2n2_b200.h."""
+    N, D, H, W, Cin = geom
+    ins = list(ins) + [None] * (4 - len(ins))
+    outs = list(outs) + [None] * (3 - len(outs))
+    for t in [x, w] + ins + outs:
+        _check(t, torch.bfloat16)
+    _check(bias, torch.float32)
+    assert x.numel() == N * D * H * W * Cin and w.numel() == cout * k[0] * k[1] * k[2] * Cin
+    global _next_tag
+    _work(2.0 * N * D * H * W * Cin * cout * k[0] * k[1] * k[2], [x, w] + ins + outs)
+    _next_tag = 'M%dxN%dxK%d' % (N * D * H * W, cout, k[0] * k[1] * k[2] * Cin)
+    _call('r2n2_conv_fwd_gru', mode, _ptr(x), _ptr(w), _ptr(bias), *[_ptr(t) for t in ins], *[_ptr(t) for t in outs],
+          N, D, H, W, Cin, cout, k[0], k[1], k[2], L.BF16, _stream())
+
+
 def gru_ur_fwd(conv_ur, xp_ur, bias_ur, h, u, r, rh, B):
     _work(0.0, (conv_ur, xp_ur, h, u, r, rh))
     _call('r2n2_gru_gates_ur_fwd', _ptr(conv_ur), _ptr(xp_ur), _ptr(bias_ur), _ptr(h), _ptr(u),

@@ -357,13 +357,13 @@ def run_ours(args):
         # forward / data-gradient launches of the implicit-GEMM kernels (the _colsum entry point is the same
         # kernels plus the producing layer's bias gradient, fused or as a second pass: counted in, conservatively)
         conv = dict(ms=0.0, flops=0.0, calls=0, bytes=0.0)
-        for name in ('r2n2_conv_fwd', 'r2n2_conv_fwd_colsum'):
+        for name in ('r2n2_conv_fwd', 'r2n2_conv_fwd_colsum', 'r2n2_conv_fwd_gru'):
             for k_ in conv:
                 conv[k_] += table.get(name, {}).get(k_, 0)
         if conv['ms'] > 0:
             ach = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
             traffic, tdetail = ncu_traffic(conv['calls'])
-            roofline = {'bound': 'tensor', 'kernel': 'r2n2_conv_fwd (implicit-GEMM conv/FC fwd + dgrad)',
+            roofline = {'bound': 'tensor', 'kernel': 'r2n2_conv_fwd / _colsum / _gru (implicit-GEMM conv/FC fwd + dgrad)',
                         'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops'],
                         'traffic': traffic,
                         'traffic_note': None if tdetail is None else

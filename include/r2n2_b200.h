@@ -93,6 +93,29 @@ int r2n2_conv_fwd_colsum(const void* x, const void* w, const float* bias, const 
                          int kd, int kh, int kw, int flags, int in_dtype, int out_dtype, int algo,
                          float* colsum, void* stream);
 
+/* r2n2_conv_fwd_gru (tcgen05 path, bf16 tensors): a hidden-state convolution of the conv-GRU (FCConv3DLayer's
+ * `conv3d(h, Wh)`, lib/layers.py:504) with the gate math of models/res_gru_net.py:130-151 -- or of its gradient
+ * (tensor.grad, models/net.py:58) -- applied to the accumulator in the epilogue instead of a separate gate
+ * kernel; no convolution output is written.  pr = hidden-grid position (row of [N*D*H*W]), HC = hidden channels:
+ *   R2N2_GRU_UR    x = h_prev, Cout = 2 HC: s = sigmoid(acc + in0[pr,co] + bias[co])   (in0 = x-projection, [.,2HC])
+ *                  co < HC: out0[pr,co] = s (update gate); else c = co-HC: out1[pr,c] = s (reset gate),
+ *                  out2[pr,c] = s * in1[pr,c]   (in1 = h_prev)
+ *   R2N2_GRU_BLEND x = r*h, Cout = HC: t = tanh(acc + in0[pr,c] + bias[c]); out0 = t;
+ *                  out1 = in1 * in2 + (1 - in1) * t   (in1 = update gate, in2 = h_prev; out1 = h_new)
+ *   R2N2_GRU_RBWD  x = d(pre-tanh), w = Wh_c transposed, Cout = HC: g = acc; out0[pr, HC + c] = g * in0 * in1 * (1 - in1)
+ *                  (in0 = h_prev, in1 = reset gate; out0 = d(pre-sigmoid) [.,2HC]); out1[pr,c] += g * in1   (dh_prev)
+ *   R2N2_GRU_OBWD  x = d(pre-sigmoid) [.,2HC], w = Wh_ur transposed, Cout = HC: dh = acc + in0[pr,c]; with u = in1,
+ *                  cand = in2, hp = in3 (or 0 when NULL) of the EARLIER step: out0 = dh (1-u)(1-cand^2),
+ *                  out1[pr,c] = dh (hp - cand) u (1-u)  ([.,2HC] rows), out2 = dh * u.
+ * The standalone gate kernels (r2n2_gru_gates_*) remain for the first view (h = 0: no convolution) and the fp32 path. */
+#define R2N2_GRU_UR 1
+#define R2N2_GRU_BLEND 2
+#define R2N2_GRU_RBWD 3
+#define R2N2_GRU_OBWD 4
+int r2n2_conv_fwd_gru(int mode, const void* x, const void* w, const float* bias, const void* in0, const void* in1,
+                      const void* in2, const void* in3, void* out0, void* out1, void* out2, int N, int D, int H,
+                      int W, int Cin, int Cout, int kd, int kh, int kw, int dtype, void* stream);
+
 /* r2n2_conv_wgrad: dw[co][tap][ci] (+)= sum_p dy[p,co] * x[p+tap-centre,ci]  (fp32 output in
  * packed layout).  tensor.grad of the call sites above w.r.t. W / Wh / Wx. */
 int r2n2_conv_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Cin,

@@ -247,6 +247,25 @@ def gru_r_bwd(d_rh, h, r, da_ur, dh_prev, B):
     dh_prev.copy_((_f(dh_prev).view(-1, 128) + g * rr).reshape(-1).to(dh_prev.dtype))
 
 
+def conv_fwd_gru(mode, x, w, bias, ins, outs, geom, cout, k):
+    """r2n2_conv_fwd_gru: hidden convolution (kept in float64, no rounding of the conv output) + gate math."""
+    N, D, H, W, Cin = geom
+    B = N * D * H * W // 64
+    ins = list(ins) + [None] * (4 - len(ins))
+    outs = list(outs) + [None] * (3 - len(outs))
+    a = torch.empty(N * D * H * W * cout, dtype=torch.float64)
+    conv_fwd(x, w, None, None, None, a, geom, cout, k, 0, 0)
+    if mode == 1:
+        gru_ur_fwd(a, ins[0], bias, ins[1], outs[0], outs[1], outs[2], B)
+    elif mode == 2:
+        gru_out_fwd(a, ins[0], bias, ins[1], ins[2], outs[0], outs[1], B)
+    elif mode == 3:
+        gru_r_bwd(a, ins[0], ins[1], outs[0], outs[1], B)
+    else:
+        dh = a + _f(ins[0])
+        gru_out_bwd(dh, ins[1], ins[2], ins[3], outs[1], outs[0], outs[2], B)
+
+
 def lstm_fwd(conv, xp, bias, s, fig, s_new, h_new, B):
     a = _f(xp).view(B * 64, 384) + _f(bias).view(1, 384)
     if conv is not None:
@@ -312,7 +331,7 @@ def voxel_eval(pred, gt, thresh):
     return torch.stack([f(occ ^ g1), f(occ & g1), f(occ | g1), f(occ & g0), f(~occ & g1)], 1)
 
 
-ALL = ['conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'split_bf16', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
+ALL = ['conv_fwd_gru', 'conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'split_bf16', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
        'maxpool_fwd', 'maxpool_bwd', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
        'eltwise', 'gru_ur_fwd', 'gru_out_fwd', 'gru_out_bwd', 'gru_r_bwd', 'lstm_fwd', 'lstm_bwd',
        'softmax_ce3d', 'adam', 'sgd', 'voxel_eval']
