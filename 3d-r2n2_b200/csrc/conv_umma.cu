@@ -503,6 +503,8 @@ struct UmmaWgradParams {
   int P, segs, chunk_bx;                   //   ONE x box that is 2 pixels wider (pitch P = bw+2); tap dx = view shifted by dx rows
   int ystack;                              // kh x 1 filter over one channel chunk (row-packed conv1a): ONE x box with kh-1 halo
                                            //   rows; the kh taps are stacked along N (B chunk stride = one image row): 1 MMA per K16
+  int plain_store;                         // one pixel split and no accumulation: every dw element has exactly one writer ->
+                                           //   plain 16-byte stores instead of memset + red.global.add (FC / x-projection layers)
   int* err_word;
 };
 
@@ -751,10 +753,17 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)(g * p.ci_cols + c), v);
         if (!valid) continue;
+        if (p.plain_store) {
+          float f16[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 16; ++j) f16[j] = __uint_as_float(v[j]);
+          store16(dst + c, f16);                           // two 256-bit stores: whole 32-byte sectors
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            red_add_v4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
       }
     }
   }
@@ -1015,7 +1024,9 @@ int conv_wgrad_umma(const void* x, const void* dy, float* dw, int N, int D, int 
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_wgrad[umma]: cuTensorMapEncodeTiled(x) failed (%d)",
                    (int)r);
   }
-  if (!accumulate)
+  p.plain_store = (!accumulate && splits == 1 && (reinterpret_cast<uintptr_t>(dw) & 31) == 0 &&
+                   !getenv("R2N2_WGRAD_NO_PLAIN_STORE")) ? 1 : 0;
+  if (!accumulate && !p.plain_store)
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.taps * Cin, st);
   // the M=128 A view of the LAST stage may run past its tile (narrow Cout): keep it inside the window
   const int a_span_slack = p.rows * 256 > p.stage_bytes ? p.rows * 256 - p.stage_bytes : 0;
