@@ -299,7 +299,9 @@ int conv_wgrad3_umma(const void* x, const void* dy, float* dw, int N, int D, int
   for (int Y = 1; Y <= H && Y <= 64; ++Y) {
     if ((Y + 2) > 256) break;
     Wgrad3Params q = p;
-    if (plan_stage(q, Y) > 56 * 1024) break;
+    // two CTAs per SM need two 2-stage pipelines in 111 KB; a layer whose accumulators take the whole TMEM (conv9b) is
+    // alone on its SM anyway and may use two 100 KB stages (measured: Y = 8 instead of 4, 0.240 -> 0.222 ms)
+    if (plan_stage(q, Y) > (p.tmem_cols > 256 ? 100 : 56) * 1024) break;
     const int bands = (H + Y - 1) / Y;
     const double eff = ((double)H / (bands * Y)) * ((double)q.R / (q.nk * 16)) * ((double)Y / (Y + 2) * 0.25 + 0.75);
     if (eff > best + 1e-9 || (eff > best - 1e-9 && Y > bestY)) { best = eff; bestY = Y; }

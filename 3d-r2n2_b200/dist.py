@@ -118,6 +118,7 @@ def init_from_env(backend=None):
     if world <= 1:
         return 0, 1, 0
     rank, local = int(os.environ['RANK']), int(os.environ.get('LOCAL_RANK', '0'))
+    bind_to_gpu_numa(local)
     # SM partition between the step's persistent kernels and the overlapped all-reduce (GradSync._set_limit):
     # NCCL gets at most NCCL_MAX_CTAS channels (= SMs); must be set before the communicator exists; explicit settings win.
     reserve = int(os.environ.get('R2N2_COMM_SMS', '0'))
@@ -132,6 +133,36 @@ def init_from_env(backend=None):
         else:
             dist.init_process_group(backend)
     return rank, world, local
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and the threads it starts later: data staging, workers) to the CPU cores of the NUMA node
+    the GPU hangs off (sysfs `local_cpulist` of the GPU's PCI function).  With one process per GPU on a two-socket
+    host the pinned staging buffers are then first-touched on the GPU's own socket and the per-step host-to-device
+    copies do not cross the inter-socket link.  Returns the core set, or None when the topology cannot be read
+    (single-socket host, container without sysfs, R2N2_NO_NUMA_BIND=1): nothing is changed then."""
+    import os
+    if os.environ.get('R2N2_NO_NUMA_BIND') or not torch.cuda.is_available() or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bdf) as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(','):
+            if not part:
+                continue
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def shard(items, rank, world):
