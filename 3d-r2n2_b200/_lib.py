@@ -40,6 +40,8 @@ PROTOTYPES = {
     'r2n2_maxpool2d_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     'r2n2_maxpool2d_bwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_maxpool2d_bwd_fused': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    'r2n2_maxpool2d_fwd_code': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'r2n2_maxpool2d_bwd_code': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_unpool3d_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_unpool3d_bwd': [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     'r2n2_add': [_p, _p, _p, _ll, _i, _p],

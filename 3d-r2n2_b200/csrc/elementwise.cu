@@ -128,10 +128,36 @@ __device__ __forceinline__ float round_as<float>(float x) { return x; }
 template <>
 __device__ __forceinline__ float round_as<__nv_bfloat16>(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <typename T, bool HAS_B>
-__global__ void __launch_bounds__(256, 4)
+// CODE: additionally one byte per output element for the backward pass (r2n2_maxpool2d_bwd_code): bit k (k = 2 dh + dw,
+// window position (2 ho - 1 + dh, 2 wo - 1 + dw)) = position k attains the maximum (ties: every such bit is set, like
+// the `==` of maxpool_bwd_kernel); bit 4 + k = the mask source (b if given, else a) is > 0 at position k.  The
+// backward pass then reads N*Ho*Wo*C bytes instead of re-reading a (and b): 1/8 (1/16) of their bf16 bytes.
+// flat index -> (channel group, wo, ho, image).  32-bit divisions where the index fits (always, for this network):
+// a 64-bit division by a run-time value is ~80 instructions, three of them per 16-byte vector rivalled the payload
+__device__ __forceinline__ void pool_decode(long long i, int CG, int Wo, int Ho, int& cg, int& wo, int& ho, int& n) {
+  if (i <= 0x7fffffffLL) {
+    const unsigned u = (unsigned)i;
+    const unsigned q1 = u / (unsigned)CG;
+    cg = (int)(u - q1 * (unsigned)CG);
+    const unsigned q2 = q1 / (unsigned)Wo;
+    wo = (int)(q1 - q2 * (unsigned)Wo);
+    const unsigned q3 = q2 / (unsigned)Ho;
+    ho = (int)(q2 - q3 * (unsigned)Ho);
+    n = (int)q3;
+  } else {
+    cg = (int)(i % CG);
+    long long t = i / CG;
+    wo = (int)(t % Wo);
+    t /= Wo;
+    ho = (int)(t % Ho);
+    n = (int)(t / Ho);
+  }
+}
+
+template <typename T, bool HAS_B, bool CODE = false>
+__global__ void __launch_bounds__(256, (CODE && HAS_B) ? 3 : 4)
 maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int N, int H, int W, int C,
-                   int Ho, int Wo) {
+                   int Ho, int Wo, unsigned char* __restrict__ code = nullptr) {
   r2n2::pdl_trigger();
   r2n2::pdl_wait();
   // one thread per (output pixel, 16-byte channel group); the window's vectors are loaded raw, all before
@@ -144,12 +170,8 @@ maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restri
   for (int e = 0; e < PN; ++e) { sa[e] = 0.f; sb[e] = 0.f; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long t = i / CG;
-    int wo = (int)(t % Wo);
-    t /= Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+    int cg, wo, ho, n;
+    pool_decode(i, CG, Wo, Ho, cg, wo, ho, n);
     uint4 ra[4], rb[4];
     bool valid[4];
 #pragma unroll
@@ -180,6 +202,199 @@ maxpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restri
       for (int e = 0; e < PN; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
     }
     m.store(y + i * PN);
+    if (CODE) {
+      if constexpr (sizeof(T) == 2) {
+        // packed: word j of t holds the code of channel 2j in bits 0..7 and of channel 2j+1 in bits 16..23
+        uint32_t t4[4] = {0u, 0u, 0u, 0u};
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        if constexpr (!HAS_B) {
+          // a alone: the maximum of bf16 values is a bf16 value -> compare the raw pairs (2 channels per instruction)
+          uint32_t m2[4];
+          {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(m.v[0], m.v[1]);   // (exact: m holds bf16 values)
+            m2[0] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+#pragma unroll
+          for (int j = 1; j < 4; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(m.v[2 * j], m.v[2 * j + 1]);
+            m2[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (!valid[k]) continue;
+            const uint32_t aw[4] = {ra[k].x, ra[k].y, ra[k].z, ra[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 av2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[j]);
+              const uint32_t eq = __heq2_mask(av2, *reinterpret_cast<const __nv_bfloat162*>(&m2[j]));
+              const uint32_t sg = __hgt2_mask(av2, zero2);
+              t4[j] |= (eq & (0x00010001u << k)) | (sg & (0x00100010u << k));
+            }
+          }
+        } else {
+          // a + b is compared in fp32 (the sums are not bf16 values); the signs of b pairwise
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (!valid[k]) continue;
+            const Pack<T> av = unpack16<T>(ra[k]);
+            const Pack<T> bv = unpack16<T>(rb[k]);
+            const uint32_t bw[4] = {rb[k].x, rb[k].y, rb[k].z, rb[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t sg = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]), zero2);
+              uint32_t w = sg & (0x00100010u << k);
+              w |= (av.v[2 * j] + bv.v[2 * j] == m.v[2 * j]) ? (1u << k) : 0u;
+              w |= (av.v[2 * j + 1] + bv.v[2 * j + 1] == m.v[2 * j + 1]) ? (0x10000u << k) : 0u;
+              t4[j] |= w;
+            }
+          }
+        }
+        *reinterpret_cast<uint2*>(code + i * PN) = make_uint2(__byte_perm(t4[0], t4[1], 0x6420), __byte_perm(t4[2], t4[3], 0x6420));
+      } else {
+        uint32_t cb[PN];
+#pragma unroll
+        for (int e = 0; e < PN; ++e) cb[e] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!valid[k]) continue;
+          Pack<T> v = unpack16<T>(ra[k]);
+          Pack<T> src = v;
+          if (HAS_B) {
+            src = unpack16<T>(rb[k]);
+#pragma unroll
+            for (int e = 0; e < PN; ++e) v.v[e] += src.v[e];
+          }
+#pragma unroll
+          for (int e = 0; e < PN; ++e)
+            cb[e] |= (v.v[e] == m.v[e] ? (1u << k) : 0u) | (src.v[e] > 0.f ? (16u << k) : 0u);
+        }
+        *reinterpret_cast<uint32_t*>(code + i * PN) = cb[0] | (cb[1] << 8) | (cb[2] << 16) | (cb[3] << 24);
+      }
+    }
+  }
+}
+
+// Max-pool backward from the forward pass's code bytes (see maxpool_fwd_kernel<.., CODE>): dx = dy where the position
+// attained the maximum, times LeakyReLU' of the recorded sign when lrelu_mask (code recorded WITHOUT b); dxb (code
+// recorded WITH b) = dx * LeakyReLU'(b); column sums as in maxpool_bwd_kernel<.., EXTRA>.  Reads dy + code only.
+template <typename T, bool EXTRA>
+__global__ void __launch_bounds__(256, 3)
+maxpool_bwd_code_kernel(const unsigned char* __restrict__ code, const T* __restrict__ dy, T* __restrict__ dx,
+                        int N, int H, int W, int C, int Ho, int Wo, int lrelu_mask, T* __restrict__ dxb,
+                        float* __restrict__ colsum_a, float* __restrict__ colsum_b) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
+  constexpr int PN = Pack<T>::N;
+  int CG = C / PN;
+  long long total = (long long)N * Ho * Wo * CG;
+  float sa[PN], sb[PN];
+#pragma unroll
+  for (int e = 0; e < PN; ++e) { sa[e] = 0.f; sb[e] = 0.f; }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cg, wo, ho, n;
+    pool_decode(i, CG, Wo, Ho, cg, wo, ho, n);
+    const uint4 rg = *reinterpret_cast<const uint4*>(dy + i * PN);
+    uint32_t cw[2];
+    if (PN == 8) {
+      const uint2 c2 = *reinterpret_cast<const uint2*>(code + i * PN);
+      cw[0] = c2.x; cw[1] = c2.y;
+    } else {
+      cw[0] = *reinterpret_cast<const uint32_t*>(code + i * PN); cw[1] = 0u;
+    }
+    if constexpr (sizeof(T) == 2) {
+      // packed: two channels per 32-bit word.  t4[j]: code of channel 2j in bits 0..7, of channel 2j+1 in bits 16..23
+      const uint32_t gw[4] = {rg.x, rg.y, rg.z, rg.w};
+      const uint32_t t4[4] = {__byte_perm(cw[0], 0u, 0x4140), __byte_perm(cw[0], 0u, 0x4342),
+                              __byte_perm(cw[1], 0u, 0x4140), __byte_perm(cw[1], 0u, 0x4342)};
+      const bool need_slope = lrelu_mask || dxb != nullptr;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
+        if (!(h >= 0 && h < H && w >= 0 && w < W)) continue;
+        const long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+        uint32_t ow[4], sw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ow[j] = gw[j] & (((t4[j] >> k) & 0x00010001u) * 0xFFFFu);         // dy where the position attained the maximum
+          sw[j] = ow[j];
+        }
+        if (need_slope) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // LeakyReLU': x 0.01 (fp32 product rounded to bf16, like the unpacked kernels) where the recorded sign is <= 0
+            const float lo = __uint_as_float(ow[j] << 16) * kLeak, hi = __uint_as_float(ow[j] & 0xFFFF0000u) * kLeak;
+            const __nv_bfloat162 sc = __floats2bfloat162_rn(lo, hi);
+            const uint32_t pos = ((t4[j] >> (4 + k)) & 0x00010001u) * 0xFFFFu;
+            sw[j] = (ow[j] & pos) | (*reinterpret_cast<const uint32_t*>(&sc) & ~pos);
+          }
+        }
+        const uint32_t* xw = lrelu_mask ? sw : ow;
+        *reinterpret_cast<uint4*>(dx + off) = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+        if (dxb) *reinterpret_cast<uint4*>(dxb + off) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+        if (EXTRA) {
+          if (colsum_a) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sa[2 * j] += __uint_as_float(xw[j] << 16);
+              sa[2 * j + 1] += __uint_as_float(xw[j] & 0xFFFF0000u);
+            }
+          }
+          if (colsum_b) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sb[2 * j] += __uint_as_float(sw[j] << 16);
+              sb[2 * j + 1] += __uint_as_float(sw[j] & 0xFFFF0000u);
+            }
+          }
+        }
+      }
+    } else {
+    const Pack<T> g = unpack16<T>(rg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int h = 2 * ho - 1 + (k >> 1), w = 2 * wo - 1 + (k & 1);
+      if (!(h >= 0 && h < H && w >= 0 && w < W)) continue;
+      const long long off = (((long long)n * H + h) * W + w) * C + cg * PN;
+      Pack<T> o, ob;
+#pragma unroll
+      for (int e = 0; e < PN; ++e) {
+        const uint32_t cb = (cw[e >> 2] >> (8 * (e & 3))) & 0xffu;
+        const float slope = ((cb >> (4 + k)) & 1u) ? 1.f : kLeak;
+        o.v[e] = ((cb >> k) & 1u) ? g.v[e] : 0.f;
+        ob.v[e] = o.v[e] * slope;
+        if (lrelu_mask) o.v[e] = ob.v[e];
+      }
+      o.store(dx + off);
+      if (dxb) ob.store(dxb + off);
+      if (EXTRA) {
+        if (colsum_a) {
+#pragma unroll
+          for (int e = 0; e < PN; ++e) sa[e] += round_as<T>(o.v[e]);
+        }
+        if (colsum_b) {
+#pragma unroll
+          for (int e = 0; e < PN; ++e) sb[e] += round_as<T>(ob.v[e]);
+        }
+      }
+    }
+    }
+  }
+  if (EXTRA) {
+    __shared__ float red[2][512];
+    for (int c = threadIdx.x; c < 2 * 512; c += blockDim.x) (&red[0][0])[c] = 0.f;
+    __syncthreads();
+    const int cg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % CG);
+#pragma unroll
+    for (int e = 0; e < PN; ++e) {
+      if (colsum_a) atomicAdd(&red[0][cg * PN + e], sa[e]);
+      if (colsum_b) atomicAdd(&red[1][cg * PN + e], sb[e]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (colsum_a) atomicAdd(colsum_a + c, red[0][c]);
+      if (colsum_b) atomicAdd(colsum_b + c, red[1][c]);
+    }
   }
 }
 
@@ -206,12 +421,8 @@ maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __
   for (int e = 0; e < PN; ++e) { sa[e] = 0.f; sb[e] = 0.f; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long t = i / CG;
-    int wo = (int)(t % Wo);
-    t /= Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+    int cg, wo, ho, n;
+    pool_decode(i, CG, Wo, Ho, cg, wo, ho, n);
     uint4 ra[4], rb[4];
     long long off[4];
     bool valid[4];
@@ -1243,13 +1454,68 @@ int r2n2_maxpool2d_fwd(const void* a, const void* b, void* y, int N, int H, int 
   R2N2_DISPATCH_DTYPE(dtype, T, {
     if (b) {
       r2n2::launch_k((maxpool_fwd_kernel<T, true>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
-        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo, (unsigned char*)nullptr);
     } else {
       r2n2::launch_k((maxpool_fwd_kernel<T, false>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
-        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo);
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo, (unsigned char*)nullptr);
     }
   })
   R2N2_CHECK_LAUNCH("maxpool2d_fwd");
+  return R2N2_OK;
+}
+
+int r2n2_maxpool2d_fwd_code(const void* a, const void* b, void* y, unsigned char* code, int N, int H, int W, int C,
+                            int dtype, void* stream) {
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % (dtype == R2N2_BF16 ? 8 : 4)) == 0,
+                 R2N2_ERR_BAD_SHAPE, "maxpool2d_fwd_code: C must be a multiple of 4 (fp32) / 8 (bf16), got %d", C);
+  R2N2_CHECK_ARG(code != nullptr && (reinterpret_cast<uintptr_t>(code) & 7) == 0, R2N2_ERR_BAD_ALIGN,
+                 "maxpool2d_fwd_code: code must be 8-byte aligned");
+  int Ho = H / 2 + 1, Wo = W / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C / (dtype == R2N2_BF16 ? 8 : 4));
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    if (b) {
+      r2n2::launch_k((maxpool_fwd_kernel<T, true, true>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo, code);
+    } else {
+      r2n2::launch_k((maxpool_fwd_kernel<T, false, true>), dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
+        (const T*)a, (const T*)b, (T*)y, N, H, W, C, Ho, Wo, code);
+    }
+  })
+  R2N2_CHECK_LAUNCH("maxpool2d_fwd_code");
+  return R2N2_OK;
+}
+
+int r2n2_maxpool2d_bwd_code(const unsigned char* code, const void* dy, void* dx, void* dxb, float* colsum_a,
+                            float* colsum_b, int N, int H, int W, int C, int lrelu_mask, int dtype, void* stream) {
+  const int pn = dtype == R2N2_BF16 ? 8 : 4;
+  R2N2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % pn) == 0,
+                 R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd_code: C must be a multiple of 4 (fp32) / 8 (bf16), got %d", C);
+  R2N2_CHECK_ARG(code && dy && dx, R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd_code: null pointer");
+  R2N2_CHECK_ARG(!(lrelu_mask && dxb), R2N2_ERR_UNSUPPORTED,
+                 "maxpool2d_bwd_code: the code holds ONE sign per position (a's without b, b's with b)");
+  R2N2_CHECK_ARG(dxb || !colsum_b, R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd_code: colsum_b is the column sum of dxb");
+  int Ho = H / 2 + 1, Wo = W / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C / pn);
+  const bool extra = colsum_a || colsum_b;
+  unsigned grid = grid_for(total, 256);
+  if (extra) {
+    R2N2_CHECK_ARG(C <= 512, R2N2_ERR_BAD_SHAPE, "maxpool2d_bwd_code: fused column sums support C <= 512, got %d", C);
+    int cg = C / pn, g = 256, r = cg;
+    while (r) { int t = g % r; g = r; r = t; }                 // g = gcd(256, cg)
+    const unsigned m = (unsigned)(cg / g);
+    const unsigned wave = (unsigned)num_sms() * 3u;            // one resident wave: see r2n2_maxpool2d_bwd_fused
+    if (grid > wave) grid = wave;
+    grid = (grid + m - 1) / m * m;
+  }
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    if (extra)
+      r2n2::launch_k((maxpool_bwd_code_kernel<T, true>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
+        code, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, (T*)dxb, colsum_a, colsum_b);
+    else
+      r2n2::launch_k((maxpool_bwd_code_kernel<T, false>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
+        code, (const T*)dy, (T*)dx, N, H, W, C, Ho, Wo, lrelu_mask, (T*)dxb, nullptr, nullptr);
+  })
+  R2N2_CHECK_LAUNCH("maxpool2d_bwd_code");
   return R2N2_OK;
 }
 

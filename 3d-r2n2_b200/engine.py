@@ -564,6 +564,8 @@ class Engine:
             xin = ctx.empty(TB * img * img * rp, x)
             ys = [ctx.empty(TB * img * img * P[n + '.W'].cout, x) for n in names]
             pooled = ctx.empty(TB * po * po * P[names[-1] + '.W'].cout, x)
+            pcode = (torch.empty(pooled.numel(), dtype=torch.uint8, device=x.device)
+                     if (training and ops.POOL_CODES) else None)
             for t in range(T):
                 cur.wait_event(x_events[t])
                 sl = lambda buf, per: buf[t * B * per:(t + 1) * B * per]
@@ -578,8 +580,9 @@ class Engine:
                                  L.EPI_BIAS | L.EPI_LRELU, ctx.algo)
                     ops.useful_frac = 1.0
                     src, cin = dst, W_.cout
-                ops.maxpool_fwd(src, None, sl(pooled, po * po * cin), B, img, img, cin)
-            head = (xin, ys, pooled)
+                ops.maxpool_fwd(src, None, sl(pooled, po * po * cin), B, img, img, cin,
+                                None if pcode is None else sl(pcode, po * po * cin))
+            head = (xin, ys, pooled, pcode)
         elif x_events is not None:
             # host inputs staged on a side stream (Net._stage_inputs) but no chunked head on this path
             # (fp32 FFMA kernels): every view must have landed before the first kernel reads x
@@ -621,7 +624,7 @@ class Engine:
 
         if self.residual:
             if head is not None:
-                pool1 = ctx.pool(c2h('conv1b', c2h('conv1a', a, 0), 1), out_data=head[2])
+                pool1 = ctx.pool(c2h('conv1b', c2h('conv1a', a, 0), 1), out_data=head[2], out_code=head[3])
             else:
                 pool1 = ctx.pool(c2('conv1b', c2('conv1a', a, True), True))
             if self.debug is not None:
@@ -641,7 +644,7 @@ class Engine:
                 if i == 3:
                     mark_hi = len(ctx.tape)
                 if i == 0 and head is not None:
-                    t_ = ctx.pool(c2h('conv1', t_, 0), out_data=head[2])
+                    t_ = ctx.pool(c2h('conv1', t_, 0), out_data=head[2], out_code=head[3])
                 else:
                     t_ = ctx.pool(c2('conv%d' % (i + 1), t_, True))
             pool6 = t_

@@ -6,6 +6,8 @@ torch is used for device memory and streams only: every FLOP and every byte move
 hot path goes through libr2n2_b200.so.  There is no CPU path here: tensors must be CUDA
 tensors and the library must load.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -84,6 +86,7 @@ WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
 FUSE_BIAS_GRAD = True     # bias gradients as column sums of the data-gradient epilogue that produces dy
 TRANSPOSE_FROM_MIRROR = True   # data-gradient operands are transposed from the bf16 mirror (half the reads)
 FUSE_POOL_BWD = True      # max-pool backward also writes the rectified branch's pre-activation gradient + bias sums
+POOL_CODES = not os.environ.get('R2N2_NO_POOL_CODES')   # training: max-pool backward from arg-max/sign bytes (no re-read of a, b)
 ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
                          # useful (1/8 on zero-stuffed Unpool3D inputs, 3/Cpad on the padded RGB)
@@ -355,10 +358,32 @@ def nchw_to_rowpack(x, y, kw, cpack):
     return y
 
 
-def maxpool_fwd(a, b, y, N, H, W, C):
+def maxpool_fwd(a, b, y, N, H, W, C, code=None):
+    """code (uint8 [N,Ho,Wo,C], optional): arg-max / sign byte per output element for maxpool_bwd_code."""
     _check(a), _check(b), _check(y)
+    if code is not None:
+        _check(code, torch.uint8)
+        assert code.numel() == y.numel()
+        _work(0.0, (a, b, y, code))
+        _call('r2n2_maxpool2d_fwd_code', _ptr(a), _ptr(b), _ptr(y), _ptr(code), N, H, W, C, _DT[a.dtype], _stream())
+        return
     _work(0.0, (a, b, y))
     _call('r2n2_maxpool2d_fwd', _ptr(a), _ptr(b), _ptr(y), N, H, W, C, _DT[a.dtype], _stream())
+
+
+def maxpool_bwd_code(code, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
+    """maxpool_bwd from the forward pass's code bytes: neither a nor b is read again."""
+    _check(code, torch.uint8)
+    for t in (dy, dx, dxb):
+        _check(t)
+    for t in (colsum_a, colsum_b):
+        if t is not None:
+            _check(t, torch.float32)
+            assert t.numel() == C
+    assert code.numel() == dy.numel()
+    _work(0.0, (code, dy, dx, dxb))
+    _call('r2n2_maxpool2d_bwd_code', _ptr(code), _ptr(dy), _ptr(dx), _ptr(dxb), _ptr(colsum_a), _ptr(colsum_b),
+          N, H, W, C, 1 if lrelu_mask else 0, _DT[dy.dtype], _stream())
 
 
 def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
@@ -773,16 +798,21 @@ class Ctx:
             self.tape.append(bwd)
         return out
 
-    def pool(self, a, b=None, out_data=None):
-        """2x2/2 max-pool (pad 1) of a (+ b).  out_data: already computed (chunked head)."""
+    def pool(self, a, b=None, out_data=None, out_code=None):
+        """2x2/2 max-pool (pad 1) of a (+ b).  out_data (+ out_code): already computed (chunked head).
+        Training: the forward pass records one code byte per output element (which window positions attain the
+        maximum, sign of the rectified operand) and the backward pass runs from dy + code alone (POOL_CODES)."""
         N, D, H, W, C = a.geom
         assert D == 1
         Ho, Wo = H // 2 + 1, W // 2 + 1
+        code = None
         if out_data is not None:
-            y = out_data
+            y, code = out_data, out_code
         else:
             y = self.empty(N * Ho * Wo * C, a.data)
-            maxpool_fwd(a.data, None if b is None else b.data, y, N, H, W, C)
+            if self.training and POOL_CODES:
+                code = torch.empty(N * Ho * Wo * C, dtype=torch.uint8, device=a.data.device)
+            maxpool_fwd(a.data, None if b is None else b.data, y, N, H, W, C, code)
         out = Act(y, (N, 1, Ho, Wo, C), requires_grad=self.training,
                   lrelu_out=(b is None and a.lrelu_out))
         if self.training:
@@ -808,7 +838,10 @@ class Ctx:
                     return None
                 if b is None:
                     preact = fuse or out.grad_preact or not a.lrelu_out
-                    maxpool_bwd(a.data, None, out.grad, dx, N, H, W, C, fuse, colsum_a=bias_sum(a, preact))
+                    if code is not None:
+                        maxpool_bwd_code(code, out.grad, dx, N, H, W, C, fuse, colsum_a=bias_sum(a, preact))
+                    else:
+                        maxpool_bwd(a.data, None, out.grad, dx, N, H, W, C, fuse, colsum_a=bias_sum(a, preact))
                     if out.grad_preact:         # mask already applied downstream (on the max)
                         assert a.n_cons == 1
                         a.grad_preact = True
@@ -821,8 +854,9 @@ class Ctx:
                     split = (FUSE_POOL_BWD and b.requires_grad and b.lrelu_out and not b.grad_preact
                              and b.n_recv == 0 and b.n_cons == 1)
                     dxb = torch.empty_like(b.data) if split else None
-                    maxpool_bwd(a.data, b.data, out.grad, dx, N, H, W, C, False, dxb=dxb,
-                                colsum_a=bias_sum(a, not a.lrelu_out), colsum_b=bias_sum(b, True) if split else None)
+                    (maxpool_bwd_code if code is not None else maxpool_bwd)(
+                        *((code,) if code is not None else (a.data, b.data)), out.grad, dx, N, H, W, C, False, dxb=dxb,
+                        colsum_a=bias_sum(a, not a.lrelu_out), colsum_b=bias_sum(b, True) if split else None)
                     if split:
                         self.accumulate(a, dx)
                         b.grad_preact = True

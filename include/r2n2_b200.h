@@ -185,6 +185,19 @@ int r2n2_maxpool2d_bwd(const void* a, const void* b, const void* dy, void* dx, i
 int r2n2_maxpool2d_bwd_fused(const void* a, const void* b, const void* dy, void* dx, void* dxb, float* colsum_a,
                              float* colsum_b, int N, int H, int W, int C, int lrelu_mask, int dtype, void* stream);
 
+/* Training variant of the pair above that does not re-read the pooled tensors in the backward pass:
+ * r2n2_maxpool2d_fwd_code additionally writes one byte per OUTPUT element, code[N,Ho,Wo,C]: bit k (k = 2 dh + dw for
+ * the window position (2 ho - 1 + dh, 2 wo - 1 + dw)) = position k attains the maximum (every tied position, as
+ * above); bit 4 + k = the mask source -- b if given, else a -- is > 0 at position k.
+ * r2n2_maxpool2d_bwd_code computes the same dx / dxb / colsum_a / colsum_b as r2n2_maxpool2d_bwd_fused from dy and the
+ * code alone (bit-identical results): lrelu_mask uses the recorded sign and is therefore only valid for a code
+ * recorded WITHOUT b, dxb only for a code recorded WITH b (both at once: R2N2_ERR_UNSUPPORTED).  HBM traffic of the
+ * backward pass: dy + code + dx (+ dxb) instead of a (+ b) + dy + dx (+ dxb). */
+int r2n2_maxpool2d_fwd_code(const void* a, const void* b, void* y, unsigned char* code, int N, int H, int W, int C,
+                            int dtype, void* stream);
+int r2n2_maxpool2d_bwd_code(const unsigned char* code, const void* dy, void* dx, void* dxb, float* colsum_a,
+                            float* colsum_b, int N, int H, int W, int C, int lrelu_mask, int dtype, void* stream);
+
 /* Unpool3DLayer (lib/layers.py:375-385): y[B,2D,2H,2W,C], value at the even corner, zeros
  * elsewhere; input is a+b if b != NULL (AddLayer res7/res8, models/res_gru_net.py:171-178). */
 int r2n2_unpool3d_fwd(const void* a, const void* b, void* y, int B, int D, int H, int W, int C,

@@ -137,9 +137,46 @@ def _pool_in(a, b, N, H, W, C):
     return s
 
 
-def maxpool_fwd(a, b, y, N, H, W, C):
+def maxpool_fwd(a, b, y, N, H, W, C, code=None):
     s = _pool_in(a, b, N, H, W, C).permute(0, 3, 1, 2)
     y.copy_(F.max_pool2d(s, 2, 2, 1).permute(0, 2, 3, 1).reshape(-1).to(y.dtype))
+    if code is not None:        # r2n2_maxpool2d_fwd_code: bit k = window position k attains the maximum, bit 4+k = sign
+        s = _pool_in(a, b, N, H, W, C)
+        src = _f(a if b is None else b).view(N, H, W, C)
+        Ho, Wo = H // 2 + 1, W // 2 + 1
+        padding = (0, 0, 1, 2 * Wo - W - 1, 1, 2 * Ho - H - 1)
+        win = F.pad(s, padding, value=float('-inf')).view(N, Ho, 2, Wo, 2, C)
+        sg = F.pad(src, padding, value=0.0).view(N, Ho, 2, Wo, 2, C) > 0
+        eq = win == win.amax(dim=(2, 4), keepdim=True)
+        cb = torch.zeros(N, Ho, Wo, C, dtype=torch.int64)
+        for dh in range(2):
+            for dw in range(2):
+                k = 2 * dh + dw
+                cb |= eq[:, :, dh, :, dw].long() << k
+                cb |= sg[:, :, dh, :, dw].long() << (4 + k)
+        code.copy_(cb.reshape(-1).to(torch.uint8))
+
+
+def maxpool_bwd_code(code, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
+    Ho, Wo = H // 2 + 1, W // 2 + 1
+    cb = code.view(N, Ho, Wo, C).long()
+    g = _f(dy).view(N, Ho, Wo, C)
+    d = torch.zeros(N, Ho, 2, Wo, 2, C, dtype=g.dtype)
+    sl = torch.zeros(N, Ho, 2, Wo, 2, C, dtype=g.dtype)
+    for dh in range(2):
+        for dw in range(2):
+            k = 2 * dh + dw
+            d[:, :, dh, :, dw] = torch.where(((cb >> k) & 1) == 1, g, torch.zeros_like(g))
+            sl[:, :, dh, :, dw] = torch.where(((cb >> (4 + k)) & 1) == 1, torch.ones_like(g), torch.full_like(g, LEAK))
+    d = d.reshape(N, 2 * Ho, 2 * Wo, C)[:, 1:1 + H, 1:1 + W]
+    sl = sl.reshape(N, 2 * Ho, 2 * Wo, C)[:, 1:1 + H, 1:1 + W]
+    dx.copy_((d * sl if lrelu_mask else d).reshape(-1).to(dx.dtype))
+    if colsum_a is not None:
+        colsum_a += _f(dx).view(-1, C).sum(0).to(colsum_a.dtype)
+    if dxb is not None:
+        dxb.copy_((d * sl).reshape(-1).to(dxb.dtype))
+        if colsum_b is not None:
+            colsum_b += _f(dxb).view(-1, C).sum(0).to(colsum_b.dtype)
 
 
 def maxpool_bwd(a, b, dy, dx, N, H, W, C, lrelu_mask, dxb=None, colsum_a=None, colsum_b=None):
@@ -332,7 +369,7 @@ def voxel_eval(pred, gt, thresh):
 
 
 ALL = ['conv_fwd_gru', 'conv_fwd', 'conv_wgrad', 'bias_grad', 'weight_transpose', 'cast', 'split_bf16', 'fill_zero', 'nchw_to_nhwc', 'nchw_to_rowpack',
-       'maxpool_fwd', 'maxpool_bwd', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
+       'maxpool_fwd', 'maxpool_bwd', 'maxpool_bwd_code', 'unpool_fwd', 'unpool_bwd', 'add', 'lrelu_fwd', 'lrelu_bwd',
        'eltwise', 'gru_ur_fwd', 'gru_out_fwd', 'gru_out_bwd', 'gru_r_bwd', 'lstm_fwd', 'lstm_bwd',
        'softmax_ce3d', 'adam', 'sgd', 'voxel_eval']
 

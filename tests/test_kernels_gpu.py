@@ -153,6 +153,51 @@ def test_pool_bwd_fused(dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_pool_codes(dtype):
+    """r2n2_maxpool2d_fwd_code / _bwd_code: the backward pass from dy + one code byte per output element (arg-max
+    positions incl. ties, sign of the rectified operand) is BIT-IDENTICAL to r2n2_maxpool2d_bwd_fused on a, b, dy;
+    the code bytes equal the emulated ones.  Values are quantised so that ties do occur."""
+    for (N, H, W, C) in [(2, 64, 64, 96), (3, 33, 33, 128), (2, 9, 9, 256), (5, 127, 127, 96), (1, 3, 3, 8), (2, 17, 17, 40),
+                         (1, 4, 6, 512)]:
+        q = lambda t: (t * 4).round() / 4           # coarse grid: many exact ties and exact zeros
+        a, b = q(_r(N * H * W * C, seed=1)).to(dtype), q(_r(N * H * W * C, seed=2)).to(dtype)
+        Ho, Wo = H // 2 + 1, W // 2 + 1
+        dy = _r(N * Ho * Wo * C, seed=3).to(dtype)
+        for bb, mask in ((b, False), (None, True), (None, False)):
+            y0 = torch.empty(N * Ho * Wo * C, dtype=dtype, device=DEV)
+            y1 = torch.empty_like(y0)
+            code = torch.full((N * Ho * Wo * C,), 255, dtype=torch.uint8, device=DEV)
+            ad, bd = a.to(DEV), None if bb is None else bb.to(DEV)
+            ops.maxpool_fwd(ad, bd, y0, N, H, W, C)
+            ops.maxpool_fwd(ad, bd, y1, N, H, W, C, code)
+            assert torch.equal(y0, y1)
+            wy, wcode = torch.empty(N * Ho * Wo * C, dtype=dtype), torch.empty(N * Ho * Wo * C, dtype=torch.uint8)
+            emu.maxpool_fwd(a, bb, wy, N, H, W, C, wcode)
+            assert torch.equal(code.cpu(), wcode), 'code bytes'
+            for with_b_out, with_sums in ((True, True), (True, False), (False, True), (False, False)):
+                if with_b_out and bb is None:
+                    continue
+                dx0, dx1 = torch.full_like(ad, float('nan')), torch.full_like(ad, float('nan'))
+                dxb0 = torch.full_like(ad, float('nan')) if with_b_out else None
+                dxb1 = torch.full_like(ad, float('nan')) if with_b_out else None
+                sa0 = torch.full((C,), 0.5, device=DEV) if with_sums else None
+                sa1 = torch.full((C,), 0.5, device=DEV) if with_sums else None
+                sb0 = torch.zeros(C, device=DEV) if (with_sums and with_b_out) else None
+                sb1 = torch.zeros(C, device=DEV) if (with_sums and with_b_out) else None
+                ops.maxpool_bwd(ad, bd, dy.to(DEV), dx0, N, H, W, C, mask, dxb0, sa0, sb0)
+                ops.maxpool_bwd_code(code, dy.to(DEV), dx1, N, H, W, C, mask, dxb1, sa1, sb1)
+                assert torch.equal(dx0, dx1), 'dx from codes'
+                if with_b_out:
+                    assert torch.equal(dxb0, dxb1), 'dxb from codes'
+                if with_sums:
+                    assert (sa0 - sa1).abs().max().item() <= 1e-3 * max(1.0, float(sa0.abs().max()))
+                    if with_b_out:
+                        assert (sb0 - sb1).abs().max().item() <= 1e-3 * max(1.0, float(sb0.abs().max()))
+    with pytest.raises(RuntimeError):       # one sign per position: lrelu_mask and dxb together are refused
+        ops.maxpool_bwd_code(code, dy.to(DEV), dx1, N, H, W, C, True, torch.empty_like(dx1), None, None)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_pool_unpool(dtype):
     tol = 1e-6 if dtype == torch.float32 else 1e-2
     for (N, H, W, C) in [(2, 127, 127, 8), (3, 33, 33, 16), (2, 5, 5, 256), (1, 3, 3, 4), (1, 64, 64, 96)]:
