@@ -47,6 +47,7 @@ PROTOTYPES = {
     'r2n2_add': [_p, _p, _p, _ll, _i, _p],
     'r2n2_lrelu_fwd': [_p, _p, _ll, _i, _p],
     'r2n2_lrelu_bwd': [_p, _p, _p, _p, _ll, _i, _p],
+    'r2n2_lrelu_bwd_colsum': [_p, _p, _p, _p, _ll, _i, _p, _i, _p],
     'r2n2_eltwise': [_i, _p, _p, _p, _ll, _i, _p],
     'r2n2_gru_gates_ur_fwd': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     'r2n2_gru_gates_out_fwd': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],

@@ -609,6 +609,47 @@ __global__ void lrelu_bwd_kernel(const T* a, const T* dy,
   }
 }
 
+// lrelu_bwd over a [rows, C] tensor that also accumulates the column sums of dx (as stored) into colsum[C] (fp32): dx is
+// the pre-activation gradient of a convolution output, its column sums are that convolution's bias gradient -- no
+// separate r2n2_bias_grad pass over dx.  16-byte vectors; gridDim * blockDim is a multiple of C / PN, so a thread
+// keeps its channel group and sums in registers (one resident wave, per-block shared-memory reduction, C atomics per block).
+template <typename T>
+__global__ void __launch_bounds__(256)
+lrelu_bwd_colsum_kernel(const T* __restrict__ a, const T* __restrict__ dy, const T* __restrict__ addend, T* __restrict__ dx,
+                        long long nvec, int C, float* __restrict__ colsum) {
+  r2n2::pdl_trigger();
+  r2n2::pdl_wait();
+  constexpr int PN = Pack<T>::N;
+  const int CG = C / PN;
+  float sa[PN];
+#pragma unroll
+  for (int e = 0; e < PN; ++e) sa[e] = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const Pack<T> av = unpack16<T>(*reinterpret_cast<const uint4*>(a + i * PN));
+    const Pack<T> g = unpack16<T>(*reinterpret_cast<const uint4*>(dy + i * PN));
+    Pack<T> o;
+#pragma unroll
+    for (int e = 0; e < PN; ++e) o.v[e] = g.v[e] * lrelu_slope(av.v[e]);
+    if (addend) {
+      const Pack<T> ad = unpack16<T>(*reinterpret_cast<const uint4*>(addend + i * PN));
+#pragma unroll
+      for (int e = 0; e < PN; ++e) o.v[e] += ad.v[e];
+    }
+    o.store(dx + i * PN);
+#pragma unroll
+    for (int e = 0; e < PN; ++e) sa[e] += round_as<T>(o.v[e]);
+  }
+  __shared__ float red[512];
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  const int cg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % CG);
+#pragma unroll
+  for (int e = 0; e < PN; ++e) atomicAdd(&red[cg * PN + e], sa[e]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(colsum + c, red[c]);
+}
+
 // SigmoidLayer / TanhLayer / ComplementLayer / EltwiseMultiplyLayer (lib/layers.py:217-225,649-676)
 template <typename T>
 __global__ void eltwise_kernel(int op, const T* __restrict__ a, const T* __restrict__ b,
@@ -1622,6 +1663,30 @@ int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, 
         (const T*)a, (const T*)dy, (const T*)addend, (T*)dx, n >> 2);
   })
   R2N2_CHECK_LAUNCH("lrelu_bwd");
+  return R2N2_OK;
+}
+
+int r2n2_lrelu_bwd_colsum(const void* a, const void* dy, const void* addend, void* dx, long long rows, int C,
+                          float* colsum, int dtype, void* stream) {
+  const int pn = dtype == R2N2_BF16 ? 8 : 4;
+  R2N2_CHECK_ARG(rows > 0 && C > 0 && C % pn == 0 && C <= 512, R2N2_ERR_BAD_SHAPE,
+                 "lrelu_bwd_colsum: C (%d) must be a multiple of %d and <= 512", C, pn);
+  R2N2_CHECK_ARG(a && dy && dx && colsum, R2N2_ERR_BAD_SHAPE, "lrelu_bwd_colsum: null pointer");
+  const long long nvec = rows * (C / pn);
+  unsigned grid = grid_for(nvec, 256);
+  {
+    int cg = C / pn, g = 256, r = cg;
+    while (r) { int t = g % r; g = r; r = t; }                 // g = gcd(256, cg)
+    const unsigned m = (unsigned)(cg / g);
+    const unsigned wave = (unsigned)num_sms() * 4u;
+    if (grid > wave) grid = wave;
+    grid = (grid + m - 1) / m * m;
+  }
+  R2N2_DISPATCH_DTYPE(dtype, T, {
+    r2n2::launch_k((lrelu_bwd_colsum_kernel<T>), dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), 0,
+        (const T*)a, (const T*)dy, (const T*)addend, (T*)dx, nvec, C, colsum);
+  })
+  R2N2_CHECK_LAUNCH("lrelu_bwd_colsum");
   return R2N2_OK;
 }
 

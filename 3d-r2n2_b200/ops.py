@@ -86,6 +86,7 @@ WGRAD_UMMA = True        # tcgen05 weight-gradient kernel available
 FUSE_BIAS_GRAD = True     # bias gradients as column sums of the data-gradient epilogue that produces dy
 TRANSPOSE_FROM_MIRROR = True   # data-gradient operands are transposed from the bf16 mirror (half the reads)
 FUSE_POOL_BWD = True      # max-pool backward also writes the rectified branch's pre-activation gradient + bias sums
+FUSE_LRELU_BIAS = not os.environ.get('R2N2_NO_LRELU_BIAS')    # standalone LeakyReLU' passes also emit the bias column sums
 POOL_CODES = not os.environ.get('R2N2_NO_POOL_CODES')   # training: max-pool backward from arg-max/sign bytes (no re-read of a, b)
 ZERO_SKIP_ANY_DTYPE = False   # host-logic tests on the emulated ABI only (the kernels are bf16)
 useful_frac = 1.0        # fraction of the dense MACs of the next conv that are algorithmically
@@ -427,10 +428,17 @@ def lrelu_fwd(x, y):
     _call('r2n2_lrelu_fwd', _ptr(x), _ptr(y), x.numel(), _DT[x.dtype], _stream())
 
 
-def lrelu_bwd(a, dy, addend, dx):
+def lrelu_bwd(a, dy, addend, dx, colsum=None, C=None):
+    """colsum (fp32 [C], optional; a is then [rows, C]): += column sums of dx (bias gradient of the conv that produced a)."""
     for t in (a, dy, addend, dx):
         _check(t)
     _work(0.0, (a, dy, addend, dx))
+    if colsum is not None:
+        _check(colsum, torch.float32)
+        assert colsum.numel() == C and a.numel() % C == 0
+        _call('r2n2_lrelu_bwd_colsum', _ptr(a), _ptr(dy), _ptr(addend), _ptr(dx), a.numel() // C, C, _ptr(colsum),
+              _DT[a.dtype], _stream())
+        return
     _call('r2n2_lrelu_bwd', _ptr(a), _ptr(dy), _ptr(addend), _ptr(dx), a.numel(), _DT[a.dtype],
           _stream())
 
@@ -671,7 +679,16 @@ class Ctx:
         """out.grad currently holds dL/d(out); turn it into dL/dz where out = LeakyReLU(z)."""
         if out.lrelu_out and not out.grad_preact:
             dst = torch.empty_like(out.grad) if out.grad_shared else out.grad
-            lrelu_bwd(out.data, out.grad, None, dst)
+            # dst is the complete pre-activation gradient: its column sums are the bias gradient of the convolution
+            # that produced `out` -- taken in the same pass instead of a bias_grad pass over dst
+            C = out.geom[4]
+            b = getattr(out, 'bias', None)
+            if (FUSE_BIAS_GRAD and FUSE_LRELU_BIAS and b is not None and not out.bias_done and b.grad_written
+                    and C <= 512 and C % (8 if out.data.dtype == torch.bfloat16 else 4) == 0 and b.grad.numel() == C):
+                lrelu_bwd(out.data, out.grad, None, dst, colsum=b.grad, C=C)
+                out.bias_done = True
+            else:
+                lrelu_bwd(out.data, out.grad, None, dst)
             split_invalidate(dst)
             out.grad, out.grad_shared, out.grad_preact = dst, False, True
 

@@ -211,6 +211,11 @@ int r2n2_add(const void* a, const void* b, void* y, long long n, int dtype, void
 int r2n2_lrelu_fwd(const void* x, void* y, long long n, int dtype, void* stream);
 int r2n2_lrelu_bwd(const void* a, const void* dy, const void* addend, void* dx, long long n,
                    int dtype, void* stream);
+/* The same over a [rows, C] tensor, plus colsum[c] += sum over rows of dx[row, c] (fp32, the values as stored): dx is
+ * the gradient of a convolution's pre-activation, so colsum is that convolution's bias gradient (`+ b.dimshuffle(...)`,
+ * lib/layers.py:442) -- no separate r2n2_bias_grad pass over dx. */
+int r2n2_lrelu_bwd_colsum(const void* a, const void* dy, const void* addend, void* dx, long long rows, int C,
+                          float* colsum, int dtype, void* stream);
 
 /* SigmoidLayer / TanhLayer / ComplementLayer (1-x) / EltwiseMultiplyLayer (a*b) as standalone
  * kernels (lib/layers.py:649-676, 217-225) for the layer-by-layer API; the fused GRU kernels

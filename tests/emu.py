@@ -224,12 +224,14 @@ def lrelu_fwd(x, y):
     y.copy_(torch.where(v > 0, v, LEAK * v).to(y.dtype))
 
 
-def lrelu_bwd(a, dy, addend, dx):
+def lrelu_bwd(a, dy, addend, dx, colsum=None, C=None):
     av = _f(a)
     o = _f(dy) * torch.where(av > 0, torch.ones_like(av), torch.full_like(av, LEAK))
     if addend is not None:
         o = o + _f(addend)
     dx.copy_(o.to(dx.dtype))
+    if colsum is not None:                          # sums of the values as stored
+        colsum += _f(dx).view(-1, C).sum(0).to(colsum.dtype)
 
 
 def eltwise(op, a, b, y):

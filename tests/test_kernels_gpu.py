@@ -230,6 +230,26 @@ def test_pool_unpool(dtype):
         _cmp(dx, wdx, 0.0 if dtype == torch.float32 else tol, 'unpool bwd')
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_lrelu_bwd_colsum(dtype):
+    """r2n2_lrelu_bwd_colsum: dx bit-identical to r2n2_lrelu_bwd, column sums of the stored dx accumulate into fp32."""
+    for rows, C in [(1237, 32), (36 * 64, 128), (5000, 64), (7, 8), (20011, 40), (333, 512)]:
+        a, g, ad = _r(rows * C, seed=1).to(dtype), _r(rows * C, seed=2).to(dtype), _r(rows * C, seed=3).to(dtype)
+        for addend in (None, ad):
+            dx0 = torch.empty(rows * C, dtype=dtype, device=DEV)
+            dx1 = torch.full((rows * C,), float('nan'), dtype=dtype, device=DEV)
+            cs = torch.full((C,), 0.25, device=DEV)
+            add_d = None if addend is None else addend.to(DEV)
+            ops.lrelu_bwd(a.to(DEV), g.to(DEV), add_d, dx0)
+            ops.lrelu_bwd(a.to(DEV), g.to(DEV), add_d, dx1, colsum=cs, C=C)
+            assert torch.equal(dx0, dx1)
+            want = dx0.double().view(rows, C).sum(0).cpu() + 0.25
+            assert (cs.cpu().double() - want).abs().max().item() <= 1e-4 * max(1.0, float(want.abs().max()))
+            wdx, wcs = torch.empty(rows * C, dtype=dtype), torch.full((C,), 0.25)
+            emu.lrelu_bwd(a, g, addend, wdx, wcs, C)
+            _cmp(dx1, wdx, 1e-6 if dtype == torch.float32 else 1e-2, 'lrelu_bwd_colsum')
+
+
 def test_pointwise_and_layout():
     n = 4 * 1237
     a, b = _r(n, seed=1), _r(n, seed=2)
