@@ -49,6 +49,8 @@ class GradSync:
             self.ranges[last] = self.ranges[last] + [(st.n_decay, st.n)]
         self.pending = []
         self.launched = set()
+        self.works = {}                # stage -> its all-reduce handles
+        self.last_stage = last
         # OPTIONAL SM partition while an all-reduce is in flight (csrc: r2n2_set_sm_limit): the compute grids leave
         # `reserve` TPCs (2 SMs each: the CTA-pair kernels need whole TPCs) to the NCCL kernels, which init_from_env caps
         # at NCCL_MAX_CTAS = reserve channels.  Measured on 8 x B200 (profiles/r02_scaling_experiments.txt): no gain --
@@ -80,9 +82,10 @@ class GradSync:
             return
         self.launched.add(stage)
         g = self.engine.store.g
-        for lo, hi in self.ranges[stage]:
-            self.pending.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
-                                                async_op=True))
+        ws = [dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+              for lo, hi in self.ranges[stage]]
+        self.works[stage] = ws
+        self.pending.extend(ws)
         self._set_limit(True)
 
     def __call__(self, g):
@@ -91,9 +94,40 @@ class GradSync:
                 self.stage_done(stage)
             for w in self.pending:
                 w.wait()
-        self.pending, self.launched = [], set()
+        self.pending, self.launched, self.works = [], set(), {}
         self._set_limit(False)
         return 1.0 / self.world
+
+    # The last stage's buckets (conv1a / conv1b and all biases, 0.4 MB) are launched after the final backward kernel: nothing
+    # of the backward pass is left to hide them.  OPT-IN (R2N2_SPLIT_UPDATE=1): Solver runs the optimiser in two passes --
+    # everything else right away (wait_early), the last stage's ranges once their all-reduce has landed (wait_late).
+    # Measured slower than the single pass (see Solver._step), kept as a tested experiment.
+    def wait_early(self):
+        """-> (scale, early_ranges, late_ranges); the last stage's all-reduce may still be in flight."""
+        n = self.engine.store.p.numel()
+        if self.world == 1:
+            return 1.0, [(0, n)], []
+        for stage in self.ranges:
+            self.stage_done(stage)
+        late = sorted(self.ranges[self.last_stage])
+        for stage, ws in self.works.items():
+            if stage != self.last_stage:
+                for w in ws:
+                    w.wait()
+        early, pos = [], 0
+        for lo, hi in late:
+            if lo > pos:
+                early.append((pos, lo))
+            pos = hi
+        if pos < n:
+            early.append((pos, n))
+        return 1.0 / self.world, early, late
+
+    def wait_late(self):
+        for w in self.works.get(self.last_stage, []):
+            w.wait()
+        self.pending, self.launched, self.works = [], set(), {}
+        self._set_limit(False)
 
 
 def attach(solver, group=None):

@@ -32,7 +32,19 @@ def _worker(rank, world, port, q):
     eng.store.p.fill_(float(rank + 1))
     broadcast_params(eng, src=0)
     ok_bc = bool((eng.store.p == 1.0).all())
-    q.put((rank, ok_cov, ok_sum, scale, ok_bc, list(sync.ranges.keys())))
+    # split update (Solver._step): everything but the last stage is final after wait_early, the last stage after wait_late;
+    # early + late ranges tile the store, and the last stage's all-reduce result is complete after wait_late
+    g.copy_(torch.arange(g.numel(), dtype=torch.float32) % 89 + rank * 10.0)
+    expect2 = (torch.arange(g.numel(), dtype=torch.float32) % 89) * world + 10.0 * sum(range(world))
+    scale2, early, late = sync.wait_early()
+    ok_early = all(torch.equal(g[lo:hi], expect2[lo:hi]) for lo, hi in early)
+    tiles = sorted(early + late)
+    ok_tiles = tiles[0][0] == 0 and tiles[-1][1] == g.numel() and all(a[1] == b[0] for a, b in zip(tiles, tiles[1:]))
+    ok_late_is_last = sorted(late) == sorted(sync.ranges['enc_lo'])
+    sync.wait_late()
+    ok_all = torch.equal(g, expect2) and not sync.pending and not sync.works
+    q.put((rank, ok_cov, ok_sum, scale, ok_bc, list(sync.ranges.keys()),
+           (scale2, ok_early, ok_tiles, ok_late_is_last, ok_all)))
     dist.destroy_process_group()
 
 
@@ -47,7 +59,8 @@ def test_gradsync_world2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok_cov, ok_sum, scale, ok_bc, stages in res:
+    for rank, ok_cov, ok_sum, scale, ok_bc, stages, split in res:
+        assert split == (0.5, True, True, True, True), 'split update protocol: %r' % (split,)
         assert ok_cov, 'buckets must tile the flat buffer exactly once'
         assert ok_sum, 'all-reduce(sum) result wrong on rank %d' % rank
         assert scale == 0.5 and ok_bc

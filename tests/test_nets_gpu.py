@@ -127,6 +127,36 @@ def test_adam_training_steps_fp32():
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize('compute', ['fp32', 'bf16'])
+def test_optimiser_pass_in_ranges_equals_one_pass(compute):
+    """Solver._apply_updates(ranges=...) (the optional data-parallel split update, dist.GradSync.wait_early): updating the
+    flat store range by range leaves parameters, moments and the bf16 operand mirror bit-identical to the single launch,
+    wherever the cuts fall relative to the L2-decay boundary.  (Same gradient buffer for both: the weight-gradient kernels
+    accumulate with atomics, two backward passes differ in the last bits.)"""
+    net, _ = _build('GRUNet', 2, compute)
+    solver = Solver(net)
+    solver.set_lr(1e-3)
+    x, y = rt.synthetic_batch(2, 2)
+    st = net.engine.store
+    n = st.p.numel()
+    cuts = [(0, 64 * 1000), (64 * 1000, st.n_decay - 64 * 3), (st.n_decay - 64 * 3, st.n_decay + 64), (st.n_decay + 64, n)]
+    names = ['p', 'm', 'v'] + (['mirror'] if st.mirror is not None else [])
+    for it in range(2):
+        solver.iteration = np.float32(solver.iteration + 1)
+        net.forward_backward(x, y)
+        st.ensure_moments()
+        before = {k: getattr(st, k).clone() for k in names}
+        solver._apply_updates(1.0)
+        one = {k: getattr(st, k).clone() for k in names}
+        for k in names:
+            getattr(st, k).copy_(before[k])
+        solver._apply_updates(1.0, ranges=cuts[2:], finish=False)       # late ranges first: order must not matter
+        solver._apply_updates(1.0, ranges=cuts[:2])
+        for k in names:
+            assert torch.equal(one[k], getattr(st, k)), (it, k)
+        assert not torch.equal(one['p'], before['p'])
+
+
 def test_load_weights_file_written_the_reference_way(tmp_path):
     """f-2: a checkpoint written exactly as /root/reference/models/net.py:60-67 writes it --
     `np.save(filename, [param.val.get_value() for param in self.params])`, i.e. a pickled OBJECT array of ragged
