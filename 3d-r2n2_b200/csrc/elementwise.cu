@@ -512,6 +512,29 @@ maxpool_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __
 }
 
 // ------------------------------------------------------------------ Unpool3D (zero stuffing x2)
+// flat index -> (channel group, x, y, z, image): 32-bit divisions where the index fits (see pool_decode)
+__device__ __forceinline__ void grid_decode(long long i, int CG, int W, int H, int D, int& cg, int& x, int& y, int& z, int& n) {
+  if (i <= 0x7fffffffLL) {
+    const unsigned u = (unsigned)i;
+    const unsigned q1 = u / (unsigned)CG;
+    cg = (int)(u - q1 * (unsigned)CG);
+    const unsigned q2 = q1 / (unsigned)W;
+    x = (int)(q1 - q2 * (unsigned)W);
+    const unsigned q3 = q2 / (unsigned)H;
+    y = (int)(q2 - q3 * (unsigned)H);
+    const unsigned q4 = q3 / (unsigned)D;
+    z = (int)(q3 - q4 * (unsigned)D);
+    n = (int)q4;
+  } else {
+    cg = (int)(i % CG);
+    long long t = i / CG;
+    x = (int)(t % W); t /= W;
+    y = (int)(t % H); t /= H;
+    z = (int)(t % D);
+    n = (int)(t / D);
+  }
+}
+
 template <typename T>
 __global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                   T* __restrict__ y, int B, int D, int H, int W, int C) {
@@ -523,12 +546,8 @@ __global__ void unpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__
   long long total = (long long)B * D2 * H2 * W2 * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long t = i / CG;
-    int x = (int)(t % W2); t /= W2;
-    int yy = (int)(t % H2); t /= H2;
-    int z = (int)(t % D2);
-    int n = (int)(t / D2);
+    int cg, x, yy, z, n;
+    grid_decode(i, CG, W2, H2, D2, cg, x, yy, z, n);
     Pack<T> v;
 #pragma unroll
     for (int e = 0; e < PN; ++e) v.v[e] = 0.f;
@@ -555,12 +574,8 @@ __global__ void unpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, 
   long long total = (long long)B * D * H * W * CG;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % CG);
-    long long t = i / CG;
-    int x = (int)(t % W); t /= W;
-    int yy = (int)(t % H); t /= H;
-    int z = (int)(t % D);
-    int n = (int)(t / D);
+    int cg, x, yy, z, n;
+    grid_decode(i, CG, W, H, D, cg, x, yy, z, n);
     long long off =
         ((((long long)n * 2 * D + 2 * z) * 2 * H + 2 * yy) * 2 * W + 2 * x) * C + cg * PN;
     Pack<T>::load(dy + off).store(dx + i * PN);
@@ -1167,6 +1182,36 @@ __global__ void weight_transpose_batch_bf16_kernel(const __nv_bfloat16* __restri
   const int co0 = (int)(local % tiles_co) * 64; local /= tiles_co;
   const int t = (int)local;
   const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  // 16-byte path (every layer of the networks: channel counts and offsets are multiples of 8): 2 vector loads and 2
+  // vector stores per thread instead of 8 + 8 four-byte accesses -- the 4-byte version moved 144 MB at 1.9 TB/s
+  if ((Cin & 7) == 0 && (Cout & 7) == 0 && ((__ldg(row + 0) | __ldg(row + 1)) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt_base) & 15) == 0) {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+#pragma unroll
+    for (int q = tid; q < 512; q += 256) {
+      const int j = q >> 3, vi = q & 7;
+      const int co = co0 + j, ci = ci0 + vi * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (co < Cout && ci < Cin) v = *reinterpret_cast<const uint4*>(w + ((long long)co * taps + t) * Cin + ci);
+      uint32_t* tp = reinterpret_cast<uint32_t*>(&tile[j][vi * 8]);      // (row pitch 132 bytes: 4-byte aligned)
+      tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = tid; q < 512; q += 256) {
+      const int j = q >> 3, vo = q & 7;
+      const int ci = ci0 + j, co = co0 + vo * 8;
+      if (ci >= Cin || co >= Cout) continue;
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = __halves2bfloat162(tile[vo * 8 + 2 * e][j], tile[vo * 8 + 2 * e + 1][j]);
+        o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(wt + ((long long)ci * taps + (taps - 1 - t)) * Cout + co) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
   for (int j = threadIdx.y; j < 64; j += 8) {
     const int co = co0 + j, ci = ci0 + 2 * threadIdx.x;
     __nv_bfloat162 v = __halves2bfloat162(zero, zero);
