@@ -75,6 +75,9 @@ def main():
             if what == 'fwd':
                 fn = lambda: ops.conv_fwd(x, w, bias, None, None, y, (N, D, H, W, cin), cout, k,
                                           L.EPI_BIAS | L.EPI_LRELU, L.ALGO_UMMA)
+            elif what == 'dgrad':
+                # data-gradient form: no bias, LeakyReLU' mask of the producing layer's output in the epilogue
+                fn = lambda: ops.conv_fwd(x, w, None, dy, None, y, (N, D, H, W, cin), cout, k, L.EPI_MASK, L.ALGO_UMMA)
             else:
                 fn = lambda: ops.conv_wgrad(x, dy, dw, (N, D, H, W, cin), cout, k, L.ALGO_UMMA, False)
             fn()
