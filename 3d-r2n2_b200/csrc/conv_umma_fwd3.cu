@@ -696,6 +696,13 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t u_g = (uint32_t)(lane % NU);           // its 16-byte unit
     const bool has_res = (p.flags & R2N2_EPI_RESIDUAL) != 0, has_mask = (p.flags & R2N2_EPI_MASK) != 0;
     const bool res_pre = (p.flags & R2N2_EPI_RES_PRE) != 0;
+    // bias in shared memory: with ~220 KB of the SM carved out as shared memory the L1 keeps nothing, so the four bias
+    // loads of a round came from L2 (~250 cycles; ncu source view of conv1a: 11 % of the kernel's stall samples sat on
+    // the first FADD behind them)
+    float* bias_s = reinterpret_cast<float*>(smem + p.stg_off + 16 * 1024);
+    if (p.flags & R2N2_EPI_BIAS)
+      for (int i = (warp - 2) * 32 + lane; i < p.BN; i += 32 * EW) bias_s[i] = bias[i];
+    named_bar_sync(3, 32 * EW);
     int step = 0;
     for (long long it = cid; it < pitems; it += ncta) {
       const Item3 c = decode_item_pair<PAIR>(p, it, crank);
@@ -802,7 +809,8 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
             for (int q = 0; q < RC; q += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + rd * RC + q));
+              const float4 b4 = (p.skip & 64) ? __ldg(reinterpret_cast<const float4*>(bias + rd * RC + q))   // (A/B timing)
+                                              : *reinterpret_cast<const float4*>(bias_s + rd * RC + q);
               f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
             }
           }
@@ -945,7 +953,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
     // (with 256-bit thread-per-pixel accesses the other widths are as fast or faster without staging: conv2a 0.171 vs 0.179 ms)
     int want_stage = (!p.stk && want_tma_epi != 2 && p.BN * out_bytes == 192) ? 1 : 0;
     if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
-    if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
+    if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024 + 512; }   // staging tiles + bias copy
     p.ew = (p.stage_epi && out_bytes == 2 && !(getenv("R2N2_FWD3_EW") && atoi(getenv("R2N2_FWD3_EW")) == 8)) ? 16 : 8;
   }
   p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
@@ -1194,7 +1202,7 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
   const size_t smem_bytes = p.tma_epi
       ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) || p.nslab == 2 ? 2 : 1) * p.slab_bytes + 1024
       : (p.stk ? (size_t)p.xch_off + (size_t)p.xch_bytes + 1024
-               : (p.stage_epi ? (size_t)p.stg_off + 16 * 1024 + 1024
+               : (p.stage_epi ? (size_t)p.stg_off + 16 * 1024 + 512 + 1024
                               : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024));
   CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
   if (p.tma_epi) {
