@@ -43,6 +43,7 @@ struct FwdParams {
   int* err_word;
   // conv-GRU gate math fused into the register epilogue (R2N2_GRU_*; r2n2_conv_fwd_gru): no y tensor, the accumulator row of
   // a hidden-grid position feeds the gate formulas directly (models/res_gru_net.py:130-151 and their gradients)
+  int bias_off;                            // smem offset of the epilogue warps' bias copy (Cout floats), or -1: read global
   int gru;
   const void* gin[4];
   void* gout[3];
@@ -139,7 +140,7 @@ static __device__ __forceinline__ void epi_row_gru(GruIn<T>& pf, const FwdParams
     if (mode == R2N2_GRU_UR || mode == R2N2_GRU_BLEND) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + co + j);
         f[j] += q0[j] + b4.x; f[j + 1] += q0[j + 1] + b4.y; f[j + 2] += q0[j + 2] + b4.z; f[j + 3] += q0[j + 3] + b4.w;
       }
     }
@@ -376,6 +377,15 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
     // ================================ epilogue (warps 2..9) =================================
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
+    // bias copy in shared memory: the L1 keeps nothing beside ~200 KB of shared memory, every 16-column chunk paid an
+    // L2 round trip for its bias values (measured on the flat-halo kernel's staged epilogue: conv1a -6 %)
+    const float* bsrc = bias;                           // (generic pointer: global, or the shared-memory copy)
+    if (p.bias_off >= 0) {
+      float* bs = reinterpret_cast<float*>(smem + p.bias_off);
+      for (int i = (warp - 2) * 32 + lane; i < p.Cout; i += 32 * kEpiWarps) bs[i] = bias[i];
+      named_bar_sync(3, 32 * kEpiWarps);
+      bsrc = bs;
+    }
     if (p.tma_epi) {
       // Two teams of 4 warps; team t drains accumulator buffer t (every other tile).  A thread-per-pixel
       // global access touches 32 different 128-byte lines per instruction (32 L1 wavefronts): on layers
@@ -443,7 +453,7 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
               if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                  float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+                  const float4 b4 = *reinterpret_cast<const float4*>(bsrc + co + j);
                   f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                 }
               }
@@ -548,13 +558,13 @@ conv_fwd_umma_persistent(const __grid_constant__ CUtensorMap map_a, const __grid
         gru_fetch(gpf, p, col0 + c_begin, valid, pix);
         mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
         tc_fence_after();
-        epi_row_gru<TOut>(gpf, p, taddr, c_begin, c_end, col0, valid, pix, bias);
+        epi_row_gru<TOut>(gpf, p, taddr, c_begin, c_end, col0, valid, pix, bsrc);
       } else {
       EpiPrefetch<TOut> pf;
       epi_prefetch(pf, p.flags, valid, res + off, mask + off, col0 + c_begin, p.Cout);
       mbar_wait(tfull0 + 8u * buf, use & 1u, abort_flag, p.err_word);
       tc_fence_after();
-      epi_row(pf, taddr, c_begin, c_end, col0, p.Cout, valid, empty_acc, p.flags, bias, res + off, mask + off, y + off);
+      epi_row(pf, taddr, c_begin, c_end, col0, p.Cout, valid, empty_acc, p.flags, bsrc, res + off, mask + off, y + off);
       }
       // this warp has finished reading the accumulator: hand it back to the MMA warp
       tc_fence_before();
@@ -815,7 +825,8 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   p.SC = (p.BN % 64 == 0 && ctas == 1) ? 64 : (p.BN % 32 == 0 ? 32 : 16);
   p.slab_bytes = 128 * p.SC * 2;
   const int slab_region = p.tma_epi ? ((flags & R2N2_EPI_MASK) ? 4 : 2) * p.slab_bytes : 0;
-  const int epi_bytes = slab_region + (fuse_colsum ? 2 * p.BN * 4 : 0);
+  const int bias_bytes = ((flags & R2N2_EPI_BIAS) && Cout <= 1024 && !getenv("R2N2_NO_SMEM_BIAS")) ? (Cout * 4 + 15) / 16 * 16 : 0;
+  const int epi_bytes = slab_region + (fuse_colsum ? 2 * p.BN * 4 : 0) + bias_bytes;
   p.colsum = fuse_colsum ? colsum : nullptr;
   const int smem_budget = (ctas == 2 ? 104 : 208) * 1024 - epi_bytes;
   const int stage_cap = ctas == 2 ? (smem_budget / 2 < 48 * 1024 ? smem_budget / 2 : 48 * 1024) : 64 * 1024;
@@ -850,6 +861,7 @@ int conv_fwd_umma(const void* x, const void* w, const float* bias, const void* m
   // [stages][barriers ...][1024-aligned epilogue slabs]
   p.epi_off = (int)(((size_t)p.stages * p.stage_bytes + (2 * p.stages + 6) * 8 + 16 + 1023) / 1024 * 1024);
   p.csum_off = p.epi_off + slab_region;
+  p.bias_off = bias_bytes ? p.csum_off + (fuse_colsum ? 2 * p.BN * 4 : 0) : -1;
   const size_t smem_bytes = (size_t)p.epi_off + epi_bytes + 1024;
   R2N2_CHECK_ARG(smem_bytes <= 227 * 1024, R2N2_ERR_UNSUPPORTED, "conv_fwd[umma]: pipeline does not fit smem");
 

@@ -52,6 +52,7 @@ struct Fwd3Params {
   int out_bytes;                           // sizeof(output element)
   int ew;                                  // epilogue warps (8, or 16 on the warp-staged bf16 epilogue)
   unsigned P_magic;                        // ceil(2^32 / P): r / P == __umulhi(r, P_magic) for r, P < 2^16
+  int bias_off;                            // smem offset of the epilogue warps' bias copy (BN floats)
   int stage_epi, stg_off;                  // warp-staged epilogue: per-warp 32 pixels x 64 bytes staging tiles at this smem offset
   int pair;                                // CTA-pair mode (cluster of 2, cta_group::2 MMAs with M = 256, each CTA holds half of the filter rows)
   int skip;                                // TIMING EXPERIMENTS ONLY (R2N2_FWD3_SKIP bit mask): 1 no plane loads, 2 no weight loads,
@@ -435,6 +436,13 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp >= 2 && warp < 2 + EW) {
     // ================================ epilogue ==============================================
     const int quad = warp & 3;
+    // bias in shared memory (every epilogue variant): with ~220 KB of the SM carved out as shared memory the L1 keeps
+    // nothing, so the bias loads of every chunk / round came from L2 (~250 cycles; ncu source view of conv1a: 11 % of the
+    // kernel's stall samples sat on the first FADD behind them).  conv1a 0.264 -> 0.248 ms, conv1b 0.431 -> 0.422 ms.
+    float* bias_s = reinterpret_cast<float*>(smem + p.bias_off);
+    if (p.flags & R2N2_EPI_BIAS)
+      for (int i = (warp - 2) * 32 + lane; i < p.BN; i += 32 * EW) bias_s[i] = bias[i];
+    named_bar_sync(3, 32 * EW);
     if (p.tma_epi) {
       // TMA epilogue (see conv_umma_fwd.cu): the block's outputs are gathered DENSELY (junk columns dropped)
       // into a swizzled smem slab of Yb x Xb pixels x SC channels; residual / mask slabs arrive by TMA load,
@@ -499,7 +507,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                   if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
                     for (int q = 0; q < 16; q += 4) {
-                      float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + sc + cc + q));
+                      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + sc + cc + q);
                       f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
                     }
                   }
@@ -636,7 +644,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
               for (int q = 0; q < 16; q += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cc + q));
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc + q);
                 f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
               }
             }
@@ -696,13 +704,6 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t u_g = (uint32_t)(lane % NU);           // its 16-byte unit
     const bool has_res = (p.flags & R2N2_EPI_RESIDUAL) != 0, has_mask = (p.flags & R2N2_EPI_MASK) != 0;
     const bool res_pre = (p.flags & R2N2_EPI_RES_PRE) != 0;
-    // bias in shared memory: with ~220 KB of the SM carved out as shared memory the L1 keeps nothing, so the four bias
-    // loads of a round came from L2 (~250 cycles; ncu source view of conv1a: 11 % of the kernel's stall samples sat on
-    // the first FADD behind them)
-    float* bias_s = reinterpret_cast<float*>(smem + p.stg_off + 16 * 1024);
-    if (p.flags & R2N2_EPI_BIAS)
-      for (int i = (warp - 2) * 32 + lane; i < p.BN; i += 32 * EW) bias_s[i] = bias[i];
-    named_bar_sync(3, 32 * EW);
     int step = 0;
     for (long long it = cid; it < pitems; it += ncta) {
       const Item3 c = decode_item_pair<PAIR>(p, it, crank);
@@ -809,8 +810,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (p.flags & R2N2_EPI_BIAS) {
 #pragma unroll
             for (int q = 0; q < RC; q += 4) {
-              const float4 b4 = (p.skip & 64) ? __ldg(reinterpret_cast<const float4*>(bias + rd * RC + q))   // (A/B timing)
-                                              : *reinterpret_cast<const float4*>(bias_s + rd * RC + q);
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + rd * RC + q);
               f[q] += b4.x; f[q + 1] += b4.y; f[q + 2] += b4.z; f[q + 3] += b4.w;
             }
           }
@@ -887,7 +887,7 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             first = false;
           }
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * T_ + t) * p.bn_cols);
-          epi_row(pf, taddr, c_begin, c_end, 0, p.Cout, valid, false, p.flags, bias, res + off, mask + off, y + off);
+          epi_row(pf, taddr, c_begin, c_end, 0, p.Cout, valid, false, p.flags, bias_s, res + off, mask + off, y + off);
         }
         tc_fence_before();
         __syncwarp();
@@ -918,7 +918,7 @@ static inline int ru(int v, int m) { return (v + m - 1) / m * m; }
 // (caller falls back to the per-tap kernel).
 // want_tma_epi: 0 never, 1 if it pays (heuristic), 2 always (bf16 outputs only; decided by the caller)
 static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
-  int budget = 222 * 1024;
+  int budget = 222 * 1024 - 512;          // (512 bytes: the epilogue warps' bias copy, Fwd3Params::bias_off)
   p.tma_epi = 0; p.SC = 32; p.slab_bytes = 0; p.epi_off = 0; p.nslab = 1;
   // channel chunk = TMA box / swizzle width; 96 = 3 x 32 (no zero-filled half chunk: 25 % less smem + traffic)
   p.kbox = p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16);
@@ -953,7 +953,7 @@ static bool plan_fwd3(Fwd3Params& p, int want_tma_epi = 0, int want_stk = 1) {
     // (with 256-bit thread-per-pixel accesses the other widths are as fast or faster without staging: conv2a 0.171 vs 0.179 ms)
     int want_stage = (!p.stk && want_tma_epi != 2 && p.BN * out_bytes == 192) ? 1 : 0;
     if (const char* e = getenv("R2N2_FWD3_STAGE_EPI")) want_stage = (atoi(e) != 0 && !p.stk && (p.BN * out_bytes) % 64 == 0) ? 1 : 0;
-    if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024 + 512; }   // staging tiles + bias copy
+    if (want_stage) { p.stage_epi = 1; want_tma_epi = 0; budget -= 16 * 1024; }
     p.ew = (p.stage_epi && out_bytes == 2 && !(getenv("R2N2_FWD3_EW") && atoi(getenv("R2N2_FWD3_EW")) == 8)) ? 16 : 8;
   }
   p.bn_cols = ru(p.stk ? 3 * p.BN : p.BN, 32);
@@ -1199,11 +1199,13 @@ int conv_fwd3_umma(const void* x, const void* w, const float* bias, const void* 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     R2N2_CHECK_ARG(r == CUDA_SUCCESS, R2N2_ERR_CUDA, "conv_fwd[umma3]: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
   }
-  const size_t smem_bytes = p.tma_epi
-      ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) || p.nslab == 2 ? 2 : 1) * p.slab_bytes + 1024
-      : (p.stk ? (size_t)p.xch_off + (size_t)p.xch_bytes + 1024
-               : (p.stage_epi ? (size_t)p.stg_off + 16 * 1024 + 512 + 1024
-                              : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16 + 1024));
+  const size_t used_bytes = p.tma_epi
+      ? (size_t)p.epi_off + (size_t)((p.flags & R2N2_EPI_MASK) || p.nslab == 2 ? 2 : 1) * p.slab_bytes
+      : (p.stk ? (size_t)p.xch_off + (size_t)p.xch_bytes
+               : (p.stage_epi ? (size_t)p.stg_off + 16 * 1024
+                              : (size_t)p.w_off + (size_t)p.w_bytes + (2 * p.nring + 2 * p.wstages + 5) * 8 + 16));
+  p.bias_off = (int)((used_bytes + 15) / 16 * 16);
+  const size_t smem_bytes = (size_t)p.bias_off + 512 + 1024;
   CUtensorMap map_y = map_a, map_res = map_a, map_mask = map_a;
   if (p.tma_epi) {
     cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};

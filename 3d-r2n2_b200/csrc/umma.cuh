@@ -375,7 +375,7 @@ static __device__ __forceinline__ void epi_row(EpiPrefetch<TOut>& pf, uint32_t t
     if (flags & R2N2_EPI_BIAS) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co + j));
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + co + j);     // (generic: the kernels pass a shared-memory copy)
         f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
       }
     }
