@@ -7,7 +7,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libr2n2_b200.so')
-if os.environ.get('R2N2_WAITSTAT'):      # diagnostic build with per-warp mbarrier wait statistics (tools/waitstat.py)
+if os.environ.get('R2N2_LIB_PATH'):      # diagnostic A/B runs against another build of the library (never the product's default)
+    LIB_PATH = os.environ['R2N2_LIB_PATH']
+elif os.environ.get('R2N2_WAITSTAT'):      # diagnostic build with per-warp mbarrier wait statistics (tools/waitstat.py)
     LIB_PATH = os.path.join(_HERE, 'libr2n2_b200_ws.so')
 
 F32, BF16 = 0, 1

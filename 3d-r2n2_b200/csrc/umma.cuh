@@ -30,13 +30,26 @@ static __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t 
 }
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the CTA-wide abort flag is
 // raised (every later wait returns at once) and a global error word is set for the host.
+// The abort flag lives in shared memory.  Read through the generic `volatile int*` it became LD.E.STRONG.SYS, a LONG-scoreboard
+// operation: an epilogue warp that had issued its residual / mask loads (global, ~1 us) and then blocked on the
+// accumulator barrier could not evaluate `if (*abort_flag)` before those loads had landed too (ncu source view of the conv1b
+// data gradient: 26 % of the stall samples behind these branches and the first instruction after the wait) -- the
+// prefetch was serialised with the wait it was meant to overlap.  An explicit ld.volatile.shared is a short-scoreboard op.
+static __device__ __forceinline__ int abort_read(volatile int* abort_flag) {
+  int v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];"
+               : "=r"(v)
+               : "r"((uint32_t)__cvta_generic_to_shared(const_cast<int*>(abort_flag)))
+               : "memory");
+  return v;
+}
 static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag,
                                           int* err_word) {
   if (mbar_try_wait(bar, parity)) return;
-  if (*abort_flag) return;
+  if (abort_read(abort_flag)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL || *abort_flag) {
+    if (clock64() - t0 > 2000000000LL || abort_read(abort_flag)) {
       *abort_flag = 1;
       if (err_word) atomicExch(err_word, 1);
       return;
@@ -166,7 +179,10 @@ static __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_b
                : "memory");
 }
 static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // relaxed: the arrivals that use this (accumulator hand-backs of the pair kernel's epilogue warps) order TMEM reads, which
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync already did; `.release.cluster` made every hand-back a MEMBAR that
+  // waited for the warp's outstanding global STORES (ncu source view: 10 % of the conv1b data gradient's stall samples)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA loads into THIS CTA's shared memory whose completion is signalled on an mbarrier of the pair's leader CTA
 static __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
