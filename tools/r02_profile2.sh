@@ -13,7 +13,7 @@ echo "ncu traffic rc $?"
 N="ncu --profile-from-start off --set full --clock-control none"
 timeout 1200 $N -k regex:'conv_fwd3_umma_kernel' -c 16 -o gpurun_out/r02c_ncu_fwd3 python tools/one_step.py > gpurun_out/ncu_fwd3.log 2>&1; echo "fwd3 rc $?"
 timeout 1200 $N -k regex:'conv_fwd_umma_persistent' -c 12 -o gpurun_out/r02c_ncu_fwd python tools/one_step.py > gpurun_out/ncu_fwd.log 2>&1; echo "fwd rc $?"
-# (the fused-GRU variants of the persistent kernel: launches 27.. of that kernel in a step)
+# (persistent-kernel launches 27-30 of a step)
 timeout 1200 $N -k regex:'conv_fwd_umma_persistent' --launch-skip 26 -c 4 -o gpurun_out/r02c_ncu_gru python tools/one_step.py > gpurun_out/ncu_gru.log 2>&1; echo "gru rc $?"
 timeout 1200 $N -k regex:'conv_wgrad' -c 31 -o gpurun_out/r02c_ncu_wgrad python tools/one_step.py > gpurun_out/ncu_wgrad.log 2>&1; echo "wgrad rc $?"
 timeout 1200 $N -k regex:'maxpool_|lrelu_bwd_colsum' -c 16 -o gpurun_out/r02c_ncu_bw python tools/one_step.py > gpurun_out/ncu_bw.log 2>&1; echo "bw rc $?"
