@@ -692,7 +692,9 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int PPA = 32 / NU;                          // pixels per global access
     static_assert(EW == 8 || sizeof(TOut) == 2, "16 epilogue warps: bf16 outputs");
     const int nrounds = p.BN / RC;
-    const int sub = (warp - 2) >> 2, nsubw = EW / 4;     // this warp among the warps of its quadrant
+    const unsigned nr_magic = (unsigned)((0x100000000ULL + (unsigned)nrounds - 1) / (unsigned)nrounds);
+    const int sub = (warp - 2) >> 2;
+    constexpr int nsubw = EW / 4;                         // this warp among the warps of its quadrant
     const uint32_t stg = smem_base + (uint32_t)p.stg_off + (uint32_t)(warp - 2) * (32u * RB);
     // XOR swizzle of the 16-byte unit index: conflict-free for the owner pattern (32 rows, fixed unit) and for the
     // global-access pattern (PPA rows x NU units)
@@ -716,8 +718,12 @@ conv_fwd3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const bool by_tile = (T_ % nsubw) == 0;
         for (int wi0 = sub; wi0 < ((p.skip & 4) ? 0 : nitems); wi0 += nsubw) {
           // by_tile: warp `sub` takes the tiles t = sub, sub + nsubw, ... with all their rounds
-          const int t = by_tile ? (wi0 / (nrounds * nsubw)) * nsubw + sub : wi0 / nrounds;
-          const int rd = by_tile ? (wi0 / nsubw) % nrounds : wi0 - (wi0 / nrounds) * nrounds;
+          // (x / nrounds by multiply-high: the run-time divisions were ~5 % of conv1a's stall samples in ncu's source view)
+          const int q_ = by_tile ? wi0 / nsubw : wi0;                            // nsubw is a compile-time power of two
+          const int qd = nrounds == 1 ? q_ : (int)__umulhi((unsigned)q_, nr_magic);   // q_ / nrounds, exact for q_ < 2^16
+                                                                                // (nrounds = 1: the magic number is 2^32)
+          const int t = by_tile ? qd * nsubw + sub : qd;
+          const int rd = q_ - qd * nrounds;
           R2N2_WS_T0();
           // the NU pixels whose 16-byte unit u_g this lane loads / stores: rows q = PPA k + q_lo of the warp's 32
           long long goff0[NU];
