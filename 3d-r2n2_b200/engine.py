@@ -406,7 +406,9 @@ class Engine:
         geom_h = (B, g4, g4, g4, HID_C)
         # tcgen05 path: the gate math runs in the epilogue of the hidden convolutions (r2n2_conv_fwd_gru) -- no conv
         # output tensor, no separate gate launches except for the first view (h = 0: nothing to convolve)
-        fused = FUSE_GRU_EPILOGUE and ctx.algo == L.ALGO_UMMA and f.data.dtype == torch.bfloat16
+        # (ops.ZERO_SKIP_ANY_DTYPE: host-logic tests on the emulated ABI run this schedule in fp32 against the oracle)
+        fused = (FUSE_GRU_EPILOGUE and ctx.algo == L.ALGO_UMMA
+                 and (f.data.dtype == torch.bfloat16 or ops.ZERO_SKIP_ANY_DTYPE))
         for t in range(T):
             if t == 0:
                 ops.gru_ur_fwd(None, sl(xp_ur, 0, 2 * hn), P['rnn.b_ur'].data, None, sl(u, 0), sl(r, 0),

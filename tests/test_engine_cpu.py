@@ -44,13 +44,18 @@ def test_engine_forward_backward_matches_oracle(monkeypatch, net_name, T):
         assert _rel(g, rg.numpy()) < 2e-4, (name, _rel(g, rg.numpy()))
 
 
-@pytest.mark.parametrize('net_name', ['GRUNet', 'ResidualGRUNet'])
-def test_engine_tensor_path_schedule_matches_oracle(monkeypatch, net_name):
+@pytest.mark.parametrize('net_name,T', [('GRUNet', 3), ('ResidualGRUNet', 2)])
+def test_engine_tensor_path_schedule_matches_oracle(monkeypatch, net_name, T):
     """The schedule of the tcgen05 path (row-packed conv1, channel padding, fused Unpool3D+Conv3D
-    with UP2 / DOWN2 / WGRAD_UP2, padded logits) on the emulated ABI, in fp32, against the oracle."""
+    with UP2 / DOWN2 / WGRAD_UP2, padded logits, the conv-GRU gate math in the hidden convolutions' epilogues --
+    r2n2_conv_fwd_gru UR / BLEND forward, RBWD / OBWD backward, T = 3: with and without an earlier hidden state --
+    and the max-pool backward from code bytes) on the emulated ABI, in fp32, against the oracle."""
     emu.install(monkeypatch, ops)
     monkeypatch.setattr(ops, 'ZERO_SKIP_ANY_DTYPE', True)
-    B, T = 1, 2
+    calls = []
+    real_gru = ops.conv_fwd_gru
+    monkeypatch.setattr(ops, 'conv_fwd_gru', lambda mode, *a, **k: (calls.append(mode), real_gru(mode, *a, **k))[1])
+    B = 1
     params = rt.init_params(net_name, seed=3)
     x, y = rt.synthetic_batch(T, B)
     eng = Engine(net_name, B, device='cpu', compute='fp32', conv_algo=1, params_only=True)
@@ -66,6 +71,8 @@ def test_engine_tensor_path_schedule_matches_oracle(monkeypatch, net_name):
         assert g.shape == tuple(rg.shape), name
         # fp32 storage between ~40 layers: the first layers' gradients carry the rounding of all of them
         assert _rel(g, rg.numpy()) < 2e-3, (name, _rel(g, rg.numpy()))
+    # every view after the first runs both hidden convolutions with fused gates, forward and backward
+    assert calls == [1, 2] * (T - 1) + [3, 4] * (T - 1), calls
 
 
 def test_solver_adam_steps_match_oracle(monkeypatch):
