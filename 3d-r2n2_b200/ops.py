@@ -871,9 +871,11 @@ class Ctx:
                     split = (FUSE_POOL_BWD and b.requires_grad and b.lrelu_out and not b.grad_preact
                              and b.n_recv == 0 and b.n_cons == 1)
                     dxb = torch.empty_like(b.data) if split else None
-                    (maxpool_bwd_code if code is not None else maxpool_bwd)(
-                        *((code,) if code is not None else (a.data, b.data)), out.grad, dx, N, H, W, C, False, dxb=dxb,
-                        colsum_a=bias_sum(a, not a.lrelu_out), colsum_b=bias_sum(b, True) if split else None)
+                    sums = dict(colsum_a=bias_sum(a, not a.lrelu_out), colsum_b=bias_sum(b, True) if split else None)
+                    if code is not None:
+                        maxpool_bwd_code(code, out.grad, dx, N, H, W, C, False, dxb=dxb, **sums)
+                    else:
+                        maxpool_bwd(a.data, b.data, out.grad, dx, N, H, W, C, False, dxb=dxb, **sums)
                     if split:
                         self.accumulate(a, dx)
                         b.grad_preact = True
