@@ -120,3 +120,15 @@ def test_shared_view_schedule_and_dataset_shards_world2_gloo():
     assert shapes0 == shapes1 == counts0 == counts1
     assert all(1 <= t <= 5 for t in shapes0) and len(set(shapes0)) > 1
     assert mean0 == mean1 == 1.5
+
+
+def test_numa_binding_is_a_noop_without_cuda():
+    """dist.bind_to_gpu_numa only ever narrows the affinity to the GPU's local cores; without CUDA (or when the
+    topology cannot be read) it returns None and leaves the process affinity alone."""
+    sys.path.insert(0, ROOT)
+    import r2n2_b200  # noqa: F401
+    from r2n2_b200 import dist as r2dist
+    before = os.sched_getaffinity(0)
+    assert r2dist.bind_to_gpu_numa(0) is None or torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
